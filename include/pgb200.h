@@ -1,0 +1,127 @@
+/*
+ * pgb200.h — C ABI of libpgb200.so, the B200-native SHIMMER index + read-to-read overlap engine.
+ *
+ * Three groups of entry points; every one is plain C (pointers + sizes, no C++/torch types):
+ *
+ *  (1) the reference's own cffi surface, same names, argument meaning, struct layouts and ownership rules as the
+ *      cdef at py/peregrine/build_shimmer4py.py:8-84 (a library built from this header can be dlopen'ed in place
+ *      of peregrine._shimmer4py's C side);
+ *  (2) the two command-line tools as callable mains — same getopt strings, defaults, file names and messages as
+ *      src/shmr_index.c:37-245 and src/shmr_overlap.c:233-419 — which bin/shmr_index and bin/shmr_overlap wrap;
+ *  (3) a stage-level context API (load reads -> index chunk -> overlap chunk) over host buffers, used by bench.py,
+ *      the tests and the multi-GPU driver; it is what (2) is written on.
+ *
+ * All computation runs in CUDA kernels (sm_100a).  There is no CPU fallback: without a usable CUDA device every
+ * computing entry point prints a message and fails (returns non-zero / exits like the reference does on errors).
+ */
+#ifndef PGB200_H
+#define PGB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ shared types (layouts are ABI) -------- */
+typedef struct { uint64_t x, y; } mm128_t;                  /* src/shimmer.h:24-26 : x = hash<<8|span, y = rid<<32|pos<<1|strand */
+typedef struct { size_t n, m; mm128_t *a; } mm128_v;        /* src/shimmer.h:27-30 : .a is libc realloc memory */
+typedef struct { uint64_t mer; uint32_t count; } mm_count_t;/* src/shimmer.h:61-64 : 16 bytes, 4 trailing pad bytes (zeroed here) */
+typedef int32_t seq_coor_t;                                 /* src/shimmer.h:95 */
+typedef struct {                                            /* src/shimmer.h:97-102 */
+  seq_coor_t m_size, dist;
+  seq_coor_t q_bgn, q_end;
+  seq_coor_t t_bgn, t_end;
+  seq_coor_t t_m_end, q_m_end;
+} ovlp_match_t;
+typedef struct {                                            /* src/shimmer.h:104-110 : 64 bytes; pad bytes 27, 60..63 zeroed */
+  uint64_t y0, y1;
+  uint32_t rl0, rl1;
+  uint8_t strand0, strand1;
+  uint8_t ovlp_type;                                        /* 0 overlap, 1 contains, 2 contained (src/shmr_overlap.c:37-39) */
+  ovlp_match_t match;
+} ovlp_t;
+typedef struct { uint64_t x0, x1, y0, y1; uint8_t direction; } mp256_t;  /* src/shimmer.h:123-126 */
+typedef struct { size_t n, m; mp256_t *a; } mp256_v;
+typedef struct { mm128_v *mmers; void *mmer0_map; void *rlmap; void *mcmap; void *ridmm; } py_mmer_t; /* src/shimmer.h:132-138 */
+typedef uint32_t mm_idx_t;
+typedef struct { size_t n, m; mm_idx_t *a; } mm_idx_v;
+typedef struct { mm_idx_v idx0; mm_idx_v idx1; } shmr_aln_t;            /* src/shimmer.h:144-147 */
+typedef struct { size_t n, m; shmr_aln_t *a; } shmr_aln_v;
+
+/* ------------------------------------------------------------------ (1) reference cffi surface ------------ */
+/* replaces src/shmr_utils.c:56-62 */
+void decode_biseq(uint8_t *src, char *seq, size_t len, uint8_t strand);
+/* replaces src/DWmatch.c:66-204; operands are .seqdb-format bytes; result is calloc'd, free with free_ovlp_match */
+ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_t q_strand, uint8_t *target_seq, seq_coor_t t_len,
+                         uint8_t t_strand, seq_coor_t band_tolerance);
+void free_ovlp_match(ovlp_match_t *match);                 /* src/DWmatch.c:206 */
+/* replaces src/shmr_utils.c:110-123; returned BY VALUE, .a freed by the caller with free() */
+mm128_v read_mmlist(char *fn);
+/* replaces src/mm_sketch.c:70-151; APPENDS to p; is_hpc must be 0 (every reference call site passes 0) */
+void mm_sketch(void *km, const char *str, int len, int w, int k, uint32_t rid, int is_hpc, mm128_v *p);
+/* replaces src/shmr_reduce.c:53-90; appends to out */
+void mm_reduce(mm128_v *in, mm128_v *out, uint8_t rs);
+
+/* ------------------------------------------------------------------ (2) command-line tools ---------------- */
+/* replaces main() of src/shmr_index.c:37-245 : -p seqdb_prefix -o out_prefix -t T -c c [-r 6] [-l 2] [-m 1] [-w 80] [-k 16] */
+int pgb_shmr_index_main(int argc, char **argv);
+/* replaces main() of src/shmr_overlap.c:233-419 : -p seqdb_prefix -l index_prefix -t T -c c -o file [-b 4] [-m 2] [-M 240] [-w 100] [-n 120] */
+int pgb_shmr_overlap_main(int argc, char **argv);
+
+/* ------------------------------------------------------------------ (3) stage-level API ------------------- */
+typedef struct pgb_ctx pgb_ctx;
+
+int pgb_device_count(void);                       /* number of usable CUDA devices (0 => nothing can run) */
+pgb_ctx *pgb_create(int device);                  /* NULL on failure (message on stderr) */
+void pgb_destroy(pgb_ctx *);
+const char *pgb_last_error(pgb_ctx *);            /* "" when the last call succeeded */
+
+/* Read set = .seqdb image + .idx table (src/shmr_mkseqdb.c:108-118).  Rows with rid % total_chunk == mychunk % total_chunk
+ * (src/shmr_index.c:157) are copied to the device and 2-bit packed; total_chunk = 1 selects everything.
+ * seqdb may be pageable or pinned host memory.  keep_raw != 0 keeps the 1-byte/base image in HBM so that
+ * pgb_repack() can redo the packing without another host copy (bench.py's device-resident timing). */
+int pgb_load_reads(pgb_ctx *, const uint8_t *seqdb, size_t seqdb_bytes, const uint32_t *rid, const uint32_t *len,
+                   const uint64_t *offset, size_t n_reads, uint32_t total_chunk, uint32_t mychunk, int keep_raw);
+int pgb_repack(pgb_ctx *);
+/* convenience: parse <prefix>.idx, mmap <prefix>.seqdb, then pgb_load_reads */
+int pgb_load_reads_from_files(pgb_ctx *, const char *seqdb_prefix, uint32_t total_chunk, uint32_t mychunk, int keep_raw);
+
+/* Sketch + hierarchical reduction of the loaded (selected) reads: L0 = mm_sketch(w,k), L1 = mm_reduce(L0,r),
+ * L2 = mm_reduce(L1,r) (src/shmr_index.c:155-216).  levels = 1 or 2.  with_counts: bit i set => also build the
+ * multiplicity table of level i (the -MC- files, src/shmr_index.c:25-32). */
+int pgb_index(pgb_ctx *, int w, int k, int r, int levels, int with_counts);
+size_t pgb_index_size(pgb_ctx *, int level);                    /* number of mm128_t at level 0/1/2 */
+int pgb_index_copy(pgb_ctx *, int level, mm128_t *out);          /* device -> host */
+size_t pgb_index_count_size(pgb_ctx *, int level);              /* distinct mers of that level */
+int pgb_index_count_copy(pgb_ctx *, int level, mm_count_t *out); /* (mer,count), order unspecified (a set) */
+
+/* Overlap input: the concatenated SHIMMER list of all index chunks in file order and all count entries
+ * (src/shmr_overlap.c:359-382).  Host-buffer form, and a device hand-off form that re-uses the level just built by
+ * pgb_index (single-chunk jobs: T_idx == 1). */
+int pgb_set_shimmers(pgb_ctx *, const mm128_t *mmers, size_t n, const mm_count_t *counts, size_t n_counts);
+int pgb_set_shimmers_from_index(pgb_ctx *, int level);
+
+/* build_map + process_overlaps for hash chunk `mychunk` of `total_chunk` (src/shmr_overlap.c:394-397).  Needs ALL reads
+ * loaded (pgb_load_reads with total_chunk = 1).  Records come back in the reference's output order. */
+int pgb_overlap(pgb_ctx *, uint32_t total_chunk, uint32_t mychunk, uint32_t bestn, uint32_t mc_lower, uint32_t mc_upper,
+                uint32_t align_bandwidth, uint32_t ovlp_upper);
+size_t pgb_overlap_size(pgb_ctx *);
+int pgb_overlap_copy(pgb_ctx *, ovlp_t *out);
+
+/* counters for bench.py / profiles */
+typedef struct {
+  uint64_t kernel_launches;      /* launches of this library's kernels since pgb_stats_reset */
+  uint64_t h2d_bytes, d2h_bytes;
+  double ms_pack, ms_sketch, ms_reduce, ms_count, ms_pairs, ms_buckets, ms_host_order, ms_replay, ms_align, ms_emit;
+  uint64_t bases_packed, bases_sketched, n_l0, n_l1, n_l2;
+  uint64_t n_pair_records, n_buckets, n_eligible_buckets, n_candidates;
+  uint64_t n_alignments, n_align_bases, n_replay_passes, n_overlaps;
+} pgb_stats;
+void pgb_stats_reset(pgb_ctx *);
+void pgb_stats_get(pgb_ctx *, pgb_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,210 @@
+// host_util.hpp — host-side (CPU) plumbing of libpgb200: file formats, the read table, and the keys-only
+// emulation of klib's khash that reproduces the reference's bucket *visiting order* (SURVEY App. A-3).
+// Nothing here computes sketches, counts, pairs or alignments; those are CUDA kernels.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <errno.h>
+#include <glob.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "shimmer_core.cuh"
+
+namespace pgb {
+
+[[noreturn]] inline void die(const char *fmt, const char *a = "", const char *b = "") {
+  fprintf(stderr, "pgb200: ");
+  fprintf(stderr, fmt, a, b);
+  fprintf(stderr, "\n");
+  exit(1);
+}
+
+// ------------------------------------------------------------------------------------------------ .idx
+// Text lines "%u %255s %u %lu" = rid name len offset (src/shmr_mkseqdb.c:112, parsed at src/shmr_utils.c:259 and
+// src/shmr_index.c:155).  Rows are kept in file order; by_rid maps rid -> row (last row wins, as kh_put overwrites).
+struct ReadTable {
+  std::vector<uint32_t> rid, len;
+  std::vector<uint64_t> off;
+  std::vector<int64_t> by_rid;  // -1 when absent
+  uint64_t total_bases = 0;
+  size_t n() const { return rid.size(); }
+};
+
+inline bool load_read_table(const char *path, ReadTable *t) {
+  FILE *f = fopen(path, "r");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<char> buf((size_t)sz + 1);
+  size_t got = fread(buf.data(), 1, (size_t)sz, f);
+  fclose(f);
+  buf[got] = 0;
+  const char *p = buf.data(), *e = p + got;
+  auto skipws = [&]() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; };
+  auto num = [&](uint64_t *v) -> bool {
+    skipws();
+    if (p >= e || *p < '0' || *p > '9') return false;
+    uint64_t x = 0;
+    while (p < e && *p >= '0' && *p <= '9') x = x * 10 + (uint64_t)(*p++ - '0');
+    *v = x;
+    return true;
+  };
+  uint64_t max_rid = 0;
+  for (;;) {
+    uint64_t r, l, o;
+    if (!num(&r)) break;
+    skipws();
+    while (p < e && !(*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++;  // name token
+    if (!num(&l) || !num(&o)) break;
+    t->rid.push_back((uint32_t)r);
+    t->len.push_back((uint32_t)l);
+    t->off.push_back(o);
+    t->total_bases += l;
+    if (r > max_rid) max_rid = r;
+  }
+  if (t->n() && max_rid > 8 * (uint64_t)t->n() + (1u << 20)) {
+    fprintf(stderr, "pgb200: read ids in %s are too sparse (max rid %lu for %zu reads)\n", path, (unsigned long)max_rid,
+            t->n());
+    exit(1);
+  }
+  t->by_rid.assign(t->n() ? (size_t)max_rid + 1 : 0, -1);
+  for (size_t i = 0; i < t->n(); i++) t->by_rid[t->rid[i]] = (int64_t)i;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ .dat files
+// mm128 list: size_t n + n x {u64 x, u64 y}   (src/shmr_utils.c:98-123)
+inline void write_mmlist_file(const char *fn, const mm128 *a, size_t n) {
+  FILE *f = fopen(fn, "wb");
+  if (!f) {
+    fprintf(stderr, "file '%s' open error: %s\n", fn, strerror(errno));
+    exit(1);
+  }
+  fwrite(&n, sizeof(size_t), 1, f);
+  if (n) fwrite(a, sizeof(mm128), n, f);
+  fclose(f);
+}
+inline void read_mmlist_file(const char *fn, std::vector<mm128> *out) {  // appends
+  FILE *f = fopen(fn, "rb");
+  if (!f) {
+    fprintf(stderr, "file '%s' open error: %s\n", fn, strerror(errno));
+    exit(1);
+  }
+  size_t n = 0;
+  if (fread(&n, sizeof(size_t), 1, f) != 1) n = 0;
+  size_t base = out->size();
+  out->resize(base + n);
+  if (n && fread(out->data() + base, sizeof(mm128), n, f) != n) die("short read on '%s'", fn);
+  fclose(f);
+}
+// count table: size_t n + n x {u64 mer; u32 count; 4 pad}  (src/shmr_utils.c:178-203, src/shimmer.h:61-64)
+struct mc_rec {
+  uint64_t mer;
+  uint32_t count;
+  uint32_t pad;
+};
+inline void write_mc_file(const char *fn, const mc_rec *a, size_t n) {
+  FILE *f = fopen(fn, "wb");
+  if (!f) {
+    fprintf(stderr, "file '%s' open error: %s\n", fn, strerror(errno));
+    exit(1);
+  }
+  fwrite(&n, sizeof(size_t), 1, f);
+  if (n) fwrite(a, sizeof(mc_rec), n, f);
+  fclose(f);
+}
+inline void read_mc_file(const char *fn, std::vector<mc_rec> *out) {  // appends
+  FILE *f = fopen(fn, "rb");
+  if (!f) {
+    fprintf(stderr, "file '%s' open error: %s\n", fn, strerror(errno));
+    exit(1);
+  }
+  size_t n = 0;
+  if (fread(&n, sizeof(size_t), 1, f) != 1) n = 0;
+  size_t base = out->size();
+  out->resize(base + n);
+  if (n && fread(out->data() + base, sizeof(mc_rec), n, f) != n) die("short read on '%s'", fn);
+  fclose(f);
+}
+// "<prefix>-[0-9]*-of-[0-9]*.dat" in the order wordexp() returns it (sorted), src/shmr_overlap.c:359-382
+inline std::vector<std::string> glob_sorted(const std::string &pattern) {
+  std::vector<std::string> r;
+  glob_t g;
+  memset(&g, 0, sizeof g);
+  if (glob(pattern.c_str(), 0, NULL, &g) == 0)
+    for (size_t i = 0; i < g.gl_pathc; i++) r.push_back(g.gl_pathv[i]);
+  globfree(&g);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------ khash order emulation
+// Keys-only model of klib khash (src/khash.h:218-343) for KHASH_MAP_INIT_INT64 tables that only ever see kh_put of
+// 64-bit keys and no deletions: same hash (khash.h:373), same triangular probing, same 0.77 load-factor growth with
+// the in-place kick-out rehash.  order() returns the keys' indices (in insertion order numbering) by ascending slot,
+// which is the order `for (i = kh_begin; i != kh_end; ++i) if (kh_exist(i))` visits them.
+struct KhashEmu {
+  uint32_t nb = 0, size = 0, nocc = 0, ub = 0;
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> tag;   // insertion number of the key stored in the slot
+  std::vector<uint8_t> used;
+  static inline uint32_t H(uint64_t key) { return (uint32_t)(key >> 33 ^ key ^ key << 11); }
+  void resize(uint32_t m) {
+    --m; m |= m >> 1; m |= m >> 2; m |= m >> 4; m |= m >> 8; m |= m >> 16; ++m;
+    if (m < 4) m = 4;
+    if (size >= (uint32_t)(m * 0.77 + 0.5)) return;
+    std::vector<uint8_t> nused(m, 0);
+    if (nb < m) { keys.resize(m); tag.resize(m); used.resize(m, 0); }
+    uint32_t nmask = m - 1;
+    for (uint32_t j = 0; j != nb; ++j) {
+      if (!used[j]) continue;
+      uint64_t key = keys[j];
+      uint32_t tg = tag[j];
+      used[j] = 0;
+      for (;;) {
+        uint32_t i = H(key) & nmask, step = 0;
+        while (nused[i]) i = (i + (++step)) & nmask;
+        nused[i] = 1;
+        if (i < nb && used[i]) {
+          std::swap(keys[i], key);
+          std::swap(tag[i], tg);
+          used[i] = 0;
+        } else {
+          keys[i] = key;
+          tag[i] = tg;
+          break;
+        }
+      }
+    }
+    if (nb > m) { keys.resize(m); tag.resize(m); }
+    used.swap(nused);
+    nb = m;
+    nocc = size;
+    ub = (uint32_t)(nb * 0.77 + 0.5);
+  }
+  // the caller guarantees `key` was not inserted before
+  void put_new(uint64_t key, uint32_t t) {
+    if (nocc >= ub) {
+      if (nb > (size << 1)) resize(nb - 1);
+      else resize(nb + 1);
+    }
+    uint32_t mask = nb - 1, i = H(key) & mask, step = 0;
+    while (used[i]) i = (i + (++step)) & mask;
+    keys[i] = key;
+    tag[i] = t;
+    used[i] = 1;
+    ++size;
+    ++nocc;
+  }
+  template <class F>
+  void for_each_in_slot_order(F &&f) const {
+    for (uint32_t i = 0; i < nb; i++)
+      if (used[i]) f(keys[i], tag[i]);
+  }
+  void clear() { nb = size = nocc = ub = 0; keys.clear(); tag.clear(); used.clear(); }
+};
+
+}  // namespace pgb

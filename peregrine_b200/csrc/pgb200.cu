@@ -1,0 +1,955 @@
+// pgb200.cu — host orchestration + C ABI of libpgb200.so (see include/pgb200.h).
+// All results are produced by the kernels in kernels.cuh; the host code here moves bytes, sizes buffers, replays the
+// keys-only khash model that fixes the bucket visiting order, and drives the replay/align fix-point loop.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <getopt.h>
+#include <assert.h>
+#include <chrono>
+#include <unordered_map>
+#include "../../include/pgb200.h"
+#include "host_util.hpp"
+#include "kernels.cuh"
+
+using namespace pgb;
+
+static_assert(sizeof(ovlp_t) == 64 && sizeof(ovlp_rec) == 64, "ovlp_t layout");
+static_assert(sizeof(mm_count_t) == 16 && sizeof(mc_entry) == 16, "mm_count_t layout");
+static_assert(sizeof(mm128_t) == 16 && sizeof(ovlp_match_t) == 32, "mm128_t / ovlp_match_t layout");
+
+#define CU(call)                                                                                             \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess) {                                                                                 \
+      fprintf(stderr, "pgb200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_));                        \
+    }                                                                                                        \
+  } while (0)
+
+static inline uint32_t pow2_at_least(uint64_t v) {
+  uint64_t p = 1024;
+  while (p < v) p <<= 1;
+  if (p > (1ull << 31)) throw std::runtime_error("hash table too large");
+  return (uint32_t)p;
+}
+static inline unsigned nblk(size_t n, unsigned bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+static inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct pgb_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  std::string err;
+  pgb_stats stats;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // ---- reads
+  size_t n_rows = 0;        // selected rows
+  uint32_t max_rid = 0;
+  uint64_t n_words = 0;     // packed words incl. guards
+  uint64_t sel_bases = 0;
+  uint8_t *d_raw = nullptr; size_t raw_bytes = 0;
+  uint64_t *d_w = nullptr; uint32_t *d_nm = nullptr;
+  uint32_t *d_rlen_by_rid = nullptr, *d_hasn_by_rid = nullptr; uint64_t *d_woff_by_rid = nullptr;
+  uint32_t *d_row_rid = nullptr, *d_row_len = nullptr; uint64_t *d_row_woff = nullptr, *d_row_raw_off = nullptr;
+  uint32_t *d_sel_rows = nullptr;  // identity 0..n_rows-1 (rows are already the selected ones)
+  // ---- index levels
+  mm128 *d_level[3] = {nullptr, nullptr, nullptr};
+  uint64_t *d_level_off[3] = {nullptr, nullptr, nullptr};
+  size_t level_n[3] = {0, 0, 0};
+  std::vector<mc_entry> level_mc[3];
+  // ---- overlap inputs
+  mm128 *d_shm = nullptr; size_t n_shm = 0; bool shm_owned = false;
+  uint64_t *d_mckeys = nullptr; uint32_t *d_mcvals = nullptr; uint32_t mcmask = 0;
+  // ---- overlap output
+  ovlp_rec *d_ovl = nullptr; size_t n_ovl = 0;
+  int *d_err = nullptr;
+
+  template <class T> T *alloc(size_t n) {
+    void *p = nullptr;
+    CU(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st));
+    return (T *)p;
+  }
+  template <class T> void release(T *&p) {
+    if (p) { cudaFreeAsync((void *)p, st); p = nullptr; }
+  }
+  void sync() { CU(cudaStreamSynchronize(st)); }
+  void tic() { CU(cudaEventRecord(ev0, st)); }
+  double toc() {
+    CU(cudaEventRecord(ev1, st));
+    CU(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    return ms;
+  }
+  void h2d(void *d, const void *h, size_t bytes) {
+    if (!bytes) return;
+    CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st));
+    stats.h2d_bytes += bytes;
+  }
+  void d2h(void *h, const void *d, size_t bytes) {
+    if (!bytes) return;
+    CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    stats.d2h_bytes += bytes;
+  }
+  int check_err(const char *where) {
+    int e = 0;
+    d2h(&e, d_err, sizeof e);
+    if (e) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "device error flag 0x%x in %s (4=count table full, 8=mer missing from count table, 16=bucket table full, "
+               "32=pair table full, 64=alignment queue full, 128=ovlp_match band state)", e, where);
+      err = buf;
+      int z = 0;
+      h2d(d_err, &z, sizeof z);
+      sync();
+    }
+    return e;
+  }
+  void free_reads() {
+    release(d_raw); release(d_w); release(d_nm); release(d_rlen_by_rid); release(d_hasn_by_rid); release(d_woff_by_rid);
+    release(d_row_rid); release(d_row_len); release(d_row_woff); release(d_row_raw_off); release(d_sel_rows);
+    n_rows = 0;
+  }
+  void free_index() {
+    for (int l = 0; l < 3; l++) {
+      if (d_shm == d_level[l]) { d_shm = nullptr; n_shm = 0; }
+      release(d_level[l]); release(d_level_off[l]); level_n[l] = 0; level_mc[l].clear();
+    }
+  }
+  void free_shimmers() {
+    if (shm_owned) release(d_shm);
+    d_shm = nullptr; n_shm = 0; shm_owned = false;
+    release(d_mckeys); release(d_mcvals);
+  }
+};
+
+#define LAUNCH(ctx, kern, grid, block, ...)                      \
+  do {                                                           \
+    if ((grid) > 0) {                                            \
+      kern<<<(grid), (block), 0, (ctx)->st>>>(__VA_ARGS__);      \
+      (ctx)->stats.kernel_launches++;                            \
+      CU(cudaGetLastError());                                    \
+    }                                                            \
+  } while (0)
+
+// exclusive scan of n+1 u32 (last element must be 0 on input) -> u64 offsets; returns total
+static uint64_t scan_u32_to_u64(pgb_ctx *c, const uint32_t *d_in, uint64_t *d_out, size_t n_plus1) {
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceScan::ExclusiveScan((void *)nullptr, tmp_bytes, d_in, d_out, cub::Sum(), (uint64_t)0, (int)n_plus1, c->st));
+  uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+  CU(cub::DeviceScan::ExclusiveScan((void *)tmp, tmp_bytes, d_in, d_out, cub::Sum(), (uint64_t)0, (int)n_plus1, c->st));
+  c->stats.kernel_launches += 2;
+  c->release(tmp);
+  uint64_t total = 0;
+  c->d2h(&total, d_out + (n_plus1 - 1), sizeof total);
+  return total;
+}
+static uint32_t scan_u32(pgb_ctx *c, const uint32_t *d_in, uint32_t *d_out, size_t n_plus1) {
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceScan::ExclusiveSum((void *)nullptr, tmp_bytes, d_in, d_out, (int)n_plus1, c->st));
+  uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+  CU(cub::DeviceScan::ExclusiveSum((void *)tmp, tmp_bytes, d_in, d_out, (int)n_plus1, c->st));
+  c->stats.kernel_launches += 2;
+  c->release(tmp);
+  uint32_t total = 0;
+  c->d2h(&total, d_out + (n_plus1 - 1), sizeof total);
+  return total;
+}
+
+// ================================================================================================ context
+extern "C" int pgb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+extern "C" pgb_ctx *pgb_create(int device) {
+  int n = pgb_device_count();
+  if (n <= 0) {
+    fprintf(stderr, "pgb200: no CUDA device available; this library has no CPU path\n");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) {
+    fprintf(stderr, "pgb200: device %d out of range (have %d)\n", device, n);
+    return nullptr;
+  }
+  try {
+    CU(cudaSetDevice(device));
+    pgb_ctx *c = new pgb_ctx();
+    c->device = device;
+    memset(&c->stats, 0, sizeof c->stats);
+    CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    c->d_err = c->alloc<int>(1);
+    CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
+    c->sync();
+    return c;
+  } catch (std::exception &e) {
+    fprintf(stderr, "pgb200: pgb_create failed: %s\n", e.what());
+    return nullptr;
+  }
+}
+extern "C" void pgb_destroy(pgb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  c->free_shimmers();
+  c->free_index();
+  c->free_reads();
+  c->release(c->d_ovl);
+  c->release(c->d_err);
+  cudaStreamSynchronize(c->st);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->st);
+  delete c;
+}
+extern "C" const char *pgb_last_error(pgb_ctx *c) { return c ? c->err.c_str() : "null context"; }
+extern "C" void pgb_stats_reset(pgb_ctx *c) { memset(&c->stats, 0, sizeof c->stats); }
+extern "C" void pgb_stats_get(pgb_ctx *c, pgb_stats *out) { *out = c->stats; }
+
+#define API_BEGIN(c)          \
+  if (!(c)) return -1;        \
+  (c)->err.clear();           \
+  try {                       \
+    CU(cudaSetDevice((c)->device));
+#define API_END(c)                \
+  }                               \
+  catch (std::exception & e) {    \
+    (c)->err = e.what();          \
+    return -1;                    \
+  }                               \
+  return (c)->err.empty() ? 0 : -1;
+
+// ================================================================================================ reads
+static void do_pack(pgb_ctx *c) {
+  c->tic();
+  uint64_t body = c->n_words - 4;  // words [2, n_words-2)
+  CU(cudaMemsetAsync(c->d_w, 0, c->n_words * 8, c->st));
+  CU(cudaMemsetAsync(c->d_nm, 0, c->n_words * 4, c->st));
+  CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
+  if (body && c->n_rows)
+    LAUNCH(c, k_pack_reads, nblk(body), 256, c->d_raw, c->d_row_raw_off, c->d_row_len, c->d_row_woff, c->d_row_rid,
+           (uint32_t)c->n_rows, (uint64_t)2, body, c->d_w, c->d_nm, c->d_hasn_by_rid);
+  c->stats.ms_pack += c->toc();
+  c->stats.bases_packed += c->sel_bases;
+}
+
+extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_bytes, const uint32_t *rid, const uint32_t *len,
+                              const uint64_t *offset, size_t n_reads, uint32_t T, uint32_t mychunk, int keep_raw) {
+  API_BEGIN(c)
+  if (T == 0 || mychunk == 0 || mychunk > T) throw std::runtime_error("bad chunk spec");
+  c->free_reads();
+  // the by-rid tables cover every read (lengths are needed for any rid an index file mentions)
+  uint32_t max_rid = 0;
+  for (size_t i = 0; i < n_reads; i++) if (rid[i] > max_rid) max_rid = rid[i];
+  if (n_reads && (uint64_t)max_rid > 8 * (uint64_t)n_reads + (1u << 20)) throw std::runtime_error("read ids too sparse");
+  c->max_rid = max_rid;
+  std::vector<uint32_t> rows;
+  for (size_t i = 0; i < n_reads; i++) {
+    if (offset[i] + len[i] > seqdb_bytes) throw std::runtime_error("read extends past the end of the seqdb image");
+    if (rid[i] % T == mychunk % T) rows.push_back((uint32_t)i);
+  }
+  size_t nsel = rows.size();
+  std::vector<uint32_t> h_rid(nsel), h_len(nsel), h_rlen_by_rid((size_t)max_rid + 1, 0);
+  std::vector<uint64_t> h_woff(nsel), h_rawoff(nsel), h_woff_by_rid((size_t)max_rid + 1, 0);
+  for (size_t i = 0; i < n_reads; i++) h_rlen_by_rid[rid[i]] = len[i];
+  uint64_t words = 2, raw = 0;
+  bool contiguous = true;
+  for (size_t j = 0; j < nsel; j++) {
+    uint32_t i = rows[j];
+    h_rid[j] = rid[i]; h_len[j] = len[i]; h_woff[j] = words; h_rawoff[j] = raw;
+    h_woff_by_rid[rid[i]] = words;
+    if (j && offset[i] != offset[rows[j - 1]] + len[rows[j - 1]]) contiguous = false;
+    words += ((uint64_t)len[i] + 31) / 32;
+    raw += len[i];
+  }
+  words += 2;
+  c->n_rows = nsel; c->n_words = words; c->sel_bases = raw; c->raw_bytes = raw;
+  c->d_raw = c->alloc<uint8_t>(raw + 64);
+  c->d_w = c->alloc<uint64_t>(words); c->d_nm = c->alloc<uint32_t>(words);
+  c->d_rlen_by_rid = c->alloc<uint32_t>((size_t)max_rid + 1); c->d_hasn_by_rid = c->alloc<uint32_t>((size_t)max_rid + 1);
+  c->d_woff_by_rid = c->alloc<uint64_t>((size_t)max_rid + 1);
+  c->d_row_rid = c->alloc<uint32_t>(nsel); c->d_row_len = c->alloc<uint32_t>(nsel);
+  c->d_row_woff = c->alloc<uint64_t>(nsel); c->d_row_raw_off = c->alloc<uint64_t>(nsel); c->d_sel_rows = c->alloc<uint32_t>(nsel);
+  std::vector<uint32_t> ident(nsel);
+  for (size_t j = 0; j < nsel; j++) ident[j] = (uint32_t)j;
+  c->h2d(c->d_rlen_by_rid, h_rlen_by_rid.data(), h_rlen_by_rid.size() * 4);
+  c->h2d(c->d_woff_by_rid, h_woff_by_rid.data(), h_woff_by_rid.size() * 8);
+  c->h2d(c->d_row_rid, h_rid.data(), nsel * 4); c->h2d(c->d_row_len, h_len.data(), nsel * 4);
+  c->h2d(c->d_row_woff, h_woff.data(), nsel * 8); c->h2d(c->d_row_raw_off, h_rawoff.data(), nsel * 8);
+  c->h2d(c->d_sel_rows, ident.data(), nsel * 4);
+  // raw bytes of the selected reads
+  if (nsel) {
+    if (contiguous) {
+      const uint8_t *src = seqdb + offset[rows[0]];
+      const size_t CH = (size_t)256 << 20;
+      for (size_t o = 0; o < raw; o += CH) c->h2d(c->d_raw + o, src + o, std::min(CH, raw - o));
+    } else {
+      // gather through two pinned staging buffers
+      const size_t CH = (size_t)64 << 20;
+      uint8_t *stage[2] = {nullptr, nullptr};
+      cudaEvent_t done[2];
+      for (int b = 0; b < 2; b++) { CU(cudaMallocHost((void **)&stage[b], CH)); CU(cudaEventCreate(&done[b])); }
+      size_t j = 0, dev_o = 0; int b = 0; uint32_t part = 0;
+      while (j < nsel) {
+        CU(cudaEventSynchronize(done[b]));
+        size_t fill = 0;
+        while (j < nsel && fill < CH) {
+          uint32_t i = rows[j];
+          size_t take = std::min((size_t)len[i] - part, CH - fill);
+          memcpy(stage[b] + fill, seqdb + offset[i] + part, take);
+          fill += take; part += (uint32_t)take;
+          if (part == len[i]) { part = 0; j++; }
+        }
+        c->h2d(c->d_raw + dev_o, stage[b], fill);
+        CU(cudaEventRecord(done[b], c->st));
+        dev_o += fill; b ^= 1;
+      }
+      c->sync();
+      for (int q = 0; q < 2; q++) { cudaFreeHost(stage[q]); cudaEventDestroy(done[q]); }
+    }
+  }
+  do_pack(c);
+  c->sync();
+  if (!keep_raw) c->release(c->d_raw);
+  API_END(c)
+}
+
+extern "C" int pgb_repack(pgb_ctx *c) {
+  API_BEGIN(c)
+  if (!c->d_raw) throw std::runtime_error("pgb_repack: raw image was not kept (keep_raw = 0)");
+  do_pack(c);
+  c->sync();
+  API_END(c)
+}
+
+struct MappedFile {
+  const uint8_t *p = nullptr; size_t n = 0; int fd = -1;
+  bool open_ro(const char *path) {
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat sb;
+    if (fstat(fd, &sb) < 0) return false;
+    n = (size_t)sb.st_size;
+    if (n) {
+      void *m = mmap(nullptr, n, PROT_READ, MAP_SHARED, fd, 0);
+      if (m == MAP_FAILED) return false;
+      p = (const uint8_t *)m;
+    }
+    return true;
+  }
+  ~MappedFile() { if (p) munmap((void *)p, n); if (fd >= 0) ::close(fd); }
+};
+
+extern "C" int pgb_load_reads_from_files(pgb_ctx *c, const char *prefix, uint32_t T, uint32_t mychunk, int keep_raw) {
+  if (!c) return -1;
+  ReadTable rt;
+  std::string idx = std::string(prefix) + ".idx", db = std::string(prefix) + ".seqdb";
+  if (!load_read_table(idx.c_str(), &rt)) { c->err = "cannot open " + idx; return -1; }
+  MappedFile mf;
+  if (!mf.open_ro(db.c_str())) { c->err = "cannot open " + db; return -1; }
+  return pgb_load_reads(c, mf.p, mf.n, rt.rid.data(), rt.len.data(), rt.off.data(), rt.n(), T, mychunk, keep_raw);
+}
+
+// ================================================================================================ index
+static void build_level_counts(pgb_ctx *c, int level) {
+  c->tic();
+  size_t n = c->level_n[level];
+  c->level_mc[level].clear();
+  if (!n) { c->stats.ms_count += c->toc(); return; }
+  uint32_t cap = pow2_at_least(2 * (uint64_t)n);
+  uint64_t *keys = c->alloc<uint64_t>(cap);
+  uint32_t *vals = c->alloc<uint32_t>(cap);
+  uint32_t *flags = c->alloc<uint32_t>((size_t)cap + 1), *pos = c->alloc<uint32_t>((size_t)cap + 1);
+  LAUNCH(c, k_fill_u64, 1184, 256, keys, PGB_EMPTY, (size_t)cap);
+  CU(cudaMemsetAsync(vals, 0, (size_t)cap * 4, c->st));
+  CU(cudaMemsetAsync(flags, 0, ((size_t)cap + 1) * 4, c->st));
+  LAUNCH(c, k_mc_insert, nblk(n), 256, c->d_level[level], n, keys, vals, cap - 1, c->d_err);
+  LAUNCH(c, k_mc_flags, nblk(cap), 256, keys, (size_t)cap, flags);
+  uint32_t distinct = scan_u32(c, flags, pos, (size_t)cap + 1);
+  mc_entry *out = c->alloc<mc_entry>(distinct);
+  LAUNCH(c, k_mc_dump, nblk(cap), 256, keys, vals, pos, (size_t)cap, out);
+  c->level_mc[level].resize(distinct);
+  c->d2h(c->level_mc[level].data(), out, (size_t)distinct * sizeof(mc_entry));
+  c->release(out); c->release(keys); c->release(vals); c->release(flags); c->release(pos);
+  c->stats.ms_count += c->toc();
+}
+
+extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_counts) {
+  API_BEGIN(c)
+  if (!(w > 0 && w < 256 && k > 0 && k <= 28)) throw std::runtime_error("mm_sketch needs 0<w<256 and 0<k<=28");  // mm_sketch.c:77
+  if (!(r >= 1 && r < 256)) throw std::runtime_error("reduction factor must be in [1,255]");
+  if (levels < 0 || levels > 2) throw std::runtime_error("levels must be 0, 1 or 2");
+  if (!c->d_w) throw std::runtime_error("no reads loaded");
+  c->free_index();
+  size_t ns = c->n_rows;
+  uint32_t *counts = c->alloc<uint32_t>(ns + 1);
+  // ---- L0
+  c->tic();
+  CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
+  LAUNCH(c, k_sketch_exact<false>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
+         c->d_row_woff, c->d_hasn_by_rid, w, k, counts, (const uint64_t *)nullptr, (mm128 *)nullptr);
+  c->d_level_off[0] = c->alloc<uint64_t>(ns + 1);
+  c->level_n[0] = scan_u32_to_u64(c, counts, c->d_level_off[0], ns + 1);
+  c->d_level[0] = c->alloc<mm128>(c->level_n[0]);
+  LAUNCH(c, k_sketch_exact<true>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
+         c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, c->d_level_off[0], c->d_level[0]);
+  c->stats.ms_sketch += c->toc();
+  c->stats.bases_sketched += c->sel_bases;
+  c->stats.n_l0 += c->level_n[0];
+  // ---- L1, L2
+  for (int l = 1; l <= levels; l++) {
+    c->tic();
+    CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
+    LAUNCH(c, k_reduce<false>, nblk(ns, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r, counts,
+           (const uint64_t *)nullptr, (mm128 *)nullptr);
+    c->d_level_off[l] = c->alloc<uint64_t>(ns + 1);
+    c->level_n[l] = scan_u32_to_u64(c, counts, c->d_level_off[l], ns + 1);
+    c->d_level[l] = c->alloc<mm128>(c->level_n[l]);
+    LAUNCH(c, k_reduce<true>, nblk(ns, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r,
+           (uint32_t *)nullptr, c->d_level_off[l], c->d_level[l]);
+    c->stats.ms_reduce += c->toc();
+    if (l == 1) c->stats.n_l1 += c->level_n[1]; else c->stats.n_l2 += c->level_n[2];
+  }
+  c->release(counts);
+  for (int l = 0; l <= levels; l++)
+    if (with_counts & (1 << l)) build_level_counts(c, l);
+  c->sync();
+  c->check_err("pgb_index");
+  API_END(c)
+}
+
+extern "C" size_t pgb_index_size(pgb_ctx *c, int level) { return (c && level >= 0 && level < 3) ? c->level_n[level] : 0; }
+extern "C" int pgb_index_copy(pgb_ctx *c, int level, mm128_t *out) {
+  API_BEGIN(c)
+  if (level < 0 || level > 2) throw std::runtime_error("bad level");
+  c->d2h(out, c->d_level[level], c->level_n[level] * sizeof(mm128));
+  API_END(c)
+}
+extern "C" size_t pgb_index_count_size(pgb_ctx *c, int level) { return (c && level >= 0 && level < 3) ? c->level_mc[level].size() : 0; }
+extern "C" int pgb_index_count_copy(pgb_ctx *c, int level, mm_count_t *out) {
+  if (!c || level < 0 || level > 2) return -1;
+  memcpy((void *)out, c->level_mc[level].data(), c->level_mc[level].size() * sizeof(mc_entry));
+  return 0;
+}
+
+// ================================================================================================ overlap inputs
+static void build_mc_table(pgb_ctx *c, const mc_entry *d_mc, size_t n_mc) {
+  c->release(c->d_mckeys); c->release(c->d_mcvals);
+  uint32_t cap = pow2_at_least(2 * (uint64_t)n_mc + 16);
+  c->d_mckeys = c->alloc<uint64_t>(cap); c->d_mcvals = c->alloc<uint32_t>(cap); c->mcmask = cap - 1;
+  LAUNCH(c, k_fill_u64, 1184, 256, c->d_mckeys, PGB_EMPTY, (size_t)cap);
+  CU(cudaMemsetAsync(c->d_mcvals, 0, (size_t)cap * 4, c->st));
+  LAUNCH(c, k_mc_add, nblk(n_mc), 256, d_mc, n_mc, c->d_mckeys, c->d_mcvals, cap - 1, c->d_err);
+}
+
+extern "C" int pgb_set_shimmers(pgb_ctx *c, const mm128_t *mmers, size_t n, const mm_count_t *counts, size_t n_counts) {
+  API_BEGIN(c)
+  c->free_shimmers();
+  c->tic();
+  c->d_shm = c->alloc<mm128>(n); c->n_shm = n; c->shm_owned = true;
+  c->h2d(c->d_shm, mmers, n * sizeof(mm128));
+  mc_entry *d_mc = c->alloc<mc_entry>(n_counts);
+  c->h2d(d_mc, counts, n_counts * sizeof(mc_entry));
+  build_mc_table(c, d_mc, n_counts);
+  c->release(d_mc);
+  c->stats.ms_count += c->toc();
+  c->check_err("pgb_set_shimmers");
+  API_END(c)
+}
+
+extern "C" int pgb_set_shimmers_from_index(pgb_ctx *c, int level) {
+  API_BEGIN(c)
+  if (level < 0 || level > 2 || !c->d_level[level]) throw std::runtime_error("level not built");
+  c->free_shimmers();
+  c->tic();
+  c->d_shm = c->d_level[level]; c->n_shm = c->level_n[level]; c->shm_owned = false;
+  // multiplicity table straight from the mmers (what aggregate_mm_count over the chunk's -MC- file yields)
+  size_t n = c->n_shm;
+  uint32_t cap = pow2_at_least(2 * (uint64_t)n + 16);
+  c->d_mckeys = c->alloc<uint64_t>(cap); c->d_mcvals = c->alloc<uint32_t>(cap); c->mcmask = cap - 1;
+  LAUNCH(c, k_fill_u64, 1184, 256, c->d_mckeys, PGB_EMPTY, (size_t)cap);
+  CU(cudaMemsetAsync(c->d_mcvals, 0, (size_t)cap * 4, c->st));
+  LAUNCH(c, k_mc_insert, nblk(n), 256, c->d_shm, n, c->d_mckeys, c->d_mcvals, cap - 1, c->d_err);
+  c->stats.ms_count += c->toc();
+  c->check_err("pgb_set_shimmers_from_index");
+  API_END(c)
+}
+
+// ================================================================================================ overlap
+extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t bestn, uint32_t mc_lower, uint32_t mc_upper,
+                           uint32_t bw, uint32_t ovlp_upper) {
+  API_BEGIN(c)
+  if (T == 0 || mychunk == 0 || mychunk > T) throw std::runtime_error("bad chunk spec");
+  if (!c->d_w) throw std::runtime_error("no reads loaded");
+  if (!c->d_shm && c->n_shm) throw std::runtime_error("no shimmers set");
+  if (bw + 3 > PGB_MAXV) throw std::runtime_error("align bandwidth (-w) above 256 is not supported by this build");
+  if (ovlp_upper > 65535) throw std::runtime_error("ovlp_upper (-n) above 65535 is not supported");
+  bestn &= 0xFF;  // uint8_t bestn = atoi(), src/shmr_overlap.c:245,286
+  c->release(c->d_ovl); c->n_ovl = 0;
+  size_t n = c->n_shm;
+  if (n == 0) { c->sync(); return 0; }
+  if (n >= (1ull << 31)) throw std::runtime_error("more than 2^31 shimmers in one overlap call");
+
+  // ---------------- build_map: kept set, adjacent pairs, records
+  c->tic();
+  uint32_t *cnt = c->alloc<uint32_t>(n);
+  uint32_t *flags = c->alloc<uint32_t>(n + 1), *pos = c->alloc<uint32_t>(n + 1);
+  unsigned long long *d_first = c->alloc<unsigned long long>(1);
+  CU(cudaMemsetAsync(d_first, 0xFF, 8, c->st));
+  CU(cudaMemsetAsync(flags, 0, (n + 1) * 4, c->st));
+  LAUNCH(c, k_count_lookup, nblk(n), 256, c->d_shm, n, c->d_mckeys, c->d_mcvals, c->mcmask, cnt, mc_lower, mc_upper, d_first, c->d_err);
+  LAUNCH(c, k_kept_flags, nblk(n), 256, cnt, n, mc_lower, mc_upper, d_first, flags);
+  uint32_t n_kept = scan_u32(c, flags, pos, n + 1);
+  uint32_t *kept = c->alloc<uint32_t>(n_kept);
+  LAUNCH(c, k_compact_idx, nblk(n), 256, flags, pos, n, kept);
+  c->release(cnt); c->release(flags); c->release(pos); c->release(d_first);
+  uint32_t *n_rec = c->alloc<uint32_t>((size_t)n_kept + 1), *rec_off = c->alloc<uint32_t>((size_t)n_kept + 1);
+  CU(cudaMemsetAsync(n_rec, 0, ((size_t)n_kept + 1) * 4, c->st));
+  LAUNCH(c, k_pair_count, nblk(n_kept), 256, c->d_shm, kept, n_kept, T, mychunk, n_rec);
+  uint32_t nrec = scan_u32(c, n_rec, rec_off, (size_t)n_kept + 1);
+  PairSoA R;
+  R.k0 = c->alloc<uint64_t>(nrec); R.k1 = c->alloc<uint64_t>(nrec); R.y0 = c->alloc<uint64_t>(nrec); R.y1 = c->alloc<uint64_t>(nrec);
+  R.seq = c->alloc<uint32_t>(nrec); R.dir = c->alloc<uint8_t>(nrec);
+  LAUNCH(c, k_pair_write, nblk(n_kept), 256, c->d_shm, kept, n_kept, T, mychunk, rec_off, c->d_rlen_by_rid, R);
+  c->release(kept); c->release(n_rec); c->release(rec_off);
+  c->stats.ms_pairs += c->toc();
+  c->stats.n_pair_records += nrec;
+  auto free_R = [&]() { c->release(R.k0); c->release(R.k1); c->release(R.y0); c->release(R.y1); c->release(R.seq); c->release(R.dir); };
+  if (nrec == 0) { free_R(); c->sync(); c->check_err("pgb_overlap/build_map"); return c->err.empty() ? 0 : -1; }
+
+  // ---------------- bucket tables
+  c->tic();
+  uint32_t xcap = pow2_at_least(4 * (uint64_t)nrec), bcap = pow2_at_least(2 * (uint64_t)nrec);
+  uint64_t *xkeys = c->alloc<uint64_t>(xcap), *bkeys = c->alloc<uint64_t>(bcap);
+  uint32_t *bcount = c->alloc<uint32_t>(bcap), *bfirst = c->alloc<uint32_t>(bcap), *rec_bucket = c->alloc<uint32_t>(nrec);
+  LAUNCH(c, k_fill_u64, 1184, 256, xkeys, PGB_EMPTY, (size_t)xcap);
+  LAUNCH(c, k_fill_u64, 1184, 256, bkeys, PGB_EMPTY, (size_t)bcap);
+  CU(cudaMemsetAsync(bcount, 0, (size_t)bcap * 4, c->st));
+  CU(cudaMemsetAsync(bfirst, 0xFF, (size_t)bcap * 4, c->st));
+  LAUNCH(c, k_bucket_insert, nblk(nrec), 256, R, nrec, xkeys, xcap - 1, bkeys, bcap - 1, bcount, bfirst, rec_bucket, c->d_err);
+  uint32_t *bflags = c->alloc<uint32_t>((size_t)bcap + 1), *bpos = c->alloc<uint32_t>((size_t)bcap + 1);
+  CU(cudaMemsetAsync(bflags, 0, ((size_t)bcap + 1) * 4, c->st));
+  LAUNCH(c, k_mc_flags, nblk(bcap), 256, bkeys, (size_t)bcap, bflags);
+  uint32_t n_buckets = scan_u32(c, bflags, bpos, (size_t)bcap + 1);
+  BucketInfo *d_binfo = c->alloc<BucketInfo>(n_buckets);
+  LAUNCH(c, k_bucket_dump, nblk(bcap), 256, xkeys, bkeys, bcount, bfirst, bpos, (size_t)bcap, d_binfo);
+  std::vector<BucketInfo> binfo(n_buckets);
+  c->d2h(binfo.data(), d_binfo, (size_t)n_buckets * sizeof(BucketInfo));
+  c->release(d_binfo); c->release(bflags); c->release(bpos); c->release(xkeys); c->release(bkeys); c->release(bcount); c->release(bfirst);
+  if (c->check_err("pgb_overlap/buckets")) { free_R(); c->release(rec_bucket); return -1; }
+  c->stats.ms_buckets += c->toc();
+  c->stats.n_buckets += n_buckets;
+
+  // ---------------- visiting order (host): keys-only khash replay, SURVEY App. A-3 / D-1
+  double t_host0 = now_ms();
+  std::vector<uint32_t> order(n_buckets);
+  for (uint32_t i = 0; i < n_buckets; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return binfo[a].first_seq < binfo[b].first_seq; });
+  std::vector<uint32_t> slot2rank(bcap, PGB_NOSLOT), rank_off;
+  uint64_t n_cand = 0;
+  {
+    KhashEmu outer;
+    std::unordered_map<uint64_t, uint32_t> outer_id;
+    outer_id.reserve(n_buckets);
+    std::vector<uint32_t> head, next(n_buckets, PGB_NOSLOT), tail;  // per-outer linked list of buckets in insertion order
+    for (uint32_t oi = 0; oi < n_buckets; oi++) {
+      uint32_t b = order[oi];
+      auto it = outer_id.find(binfo[b].k0);
+      if (it == outer_id.end()) {
+        uint32_t id = (uint32_t)head.size();
+        outer_id.emplace(binfo[b].k0, id);
+        outer.put_new(binfo[b].k0, id);
+        head.push_back(b); tail.push_back(b);
+      } else {
+        next[tail[it->second]] = b; tail[it->second] = b;
+      }
+    }
+    rank_off.push_back(0);
+    KhashEmu inner;
+    outer.for_each_in_slot_order([&](uint64_t, uint32_t id) {
+      inner.clear();
+      for (uint32_t b = head[id]; b != PGB_NOSLOT; b = next[b]) inner.put_new(binfo[b].k1, b);
+      inner.for_each_in_slot_order([&](uint64_t, uint32_t b) {
+        uint32_t nn = binfo[b].count;
+        if (nn <= 2 || nn > ovlp_upper) return;  // src/shmr_overlap.c:216
+        slot2rank[binfo[b].slot] = (uint32_t)rank_off.size() - 1;
+        rank_off.push_back(rank_off.back() + nn);
+        n_cand += (uint64_t)nn * (nn - 1) / 2;
+      });
+    });
+  }
+  uint32_t n_ranks = (uint32_t)rank_off.size() - 1, n_elig = rank_off.back();
+  c->stats.ms_host_order += now_ms() - t_host0;
+  c->stats.n_eligible_buckets += n_ranks; c->stats.n_candidates += n_cand;
+  if (n_ranks == 0) { free_R(); c->release(rec_bucket); c->sync(); return 0; }
+
+  // ---------------- scatter + per-bucket sort
+  c->tic();
+  uint32_t *d_slot2rank = c->alloc<uint32_t>(bcap), *d_rank_off = c->alloc<uint32_t>((size_t)n_ranks + 1), *fill = c->alloc<uint32_t>(n_ranks);
+  c->h2d(d_slot2rank, slot2rank.data(), (size_t)bcap * 4);
+  c->h2d(d_rank_off, rank_off.data(), ((size_t)n_ranks + 1) * 4);
+  CU(cudaMemsetAsync(fill, 0, (size_t)n_ranks * 4, c->st));
+  uint64_t *sy0 = c->alloc<uint64_t>(n_elig), *sy1 = c->alloc<uint64_t>(n_elig);
+  uint32_t *sseq = c->alloc<uint32_t>(n_elig); uint8_t *sdir = c->alloc<uint8_t>(n_elig), *contained = c->alloc<uint8_t>(n_elig);
+  LAUNCH(c, k_scatter, nblk(nrec), 256, R, nrec, rec_bucket, d_slot2rank, d_rank_off, fill, sy0, sy1, sseq, sdir);
+  LAUNCH(c, k_sort_buckets, nblk(n_ranks, 64), 64, n_ranks, d_rank_off, sy0, sy1, sseq, sdir);
+  free_R(); c->release(rec_bucket); c->release(d_slot2rank); c->release(fill);
+  c->stats.ms_buckets += c->toc();
+
+  // ---------------- replay / align fix-point (DESIGN.md "ordered greedy as a fix-point")
+  ReplayState S;
+  uint32_t ecap = pow2_at_least(8 * (uint64_t)n_elig), acap = pow2_at_least(4 * (uint64_t)n_elig);
+  S.emask = ecap - 1; S.amask = acap - 1; S.req_cap = 2 * n_elig + 1024;
+  S.ekeys = c->alloc<uint64_t>(ecap); S.eold = c->alloc<uint64_t>(ecap); S.enew = c->alloc<uint64_t>(ecap);
+  S.akeys = c->alloc<uint64_t>(acap); S.aidx = c->alloc<uint32_t>(acap);
+  S.reqs = c->alloc<AlnReq>(S.req_cap); S.results = c->alloc<match_t>(S.req_cap);
+  S.n_req = c->alloc<uint32_t>(1); S.n_done = 0; S.rlen_by_rid = c->d_rlen_by_rid; S.err = c->d_err;
+  uint32_t *acc = c->alloc<uint32_t>((size_t)n_ranks + 1), *out_off = c->alloc<uint32_t>((size_t)n_ranks + 1);
+  unsigned long long *d_ctr = c->alloc<unsigned long long>(2);  // [0] unknown alignments, [1] table diffs
+  LAUNCH(c, k_fill_u64, 1184, 256, S.ekeys, PGB_EMPTY, (size_t)ecap);
+  LAUNCH(c, k_fill_u64, 1184, 256, S.eold, PGB_EMPTY, (size_t)ecap);
+  LAUNCH(c, k_fill_u64, 1184, 256, S.akeys, PGB_EMPTY, (size_t)acap);
+  CU(cudaMemsetAsync(S.n_req, 0, 4, c->st));
+  CU(cudaMemsetAsync(acc, 0, ((size_t)n_ranks + 1) * 4, c->st));
+  auto free_S = [&]() {
+    c->release(S.ekeys); c->release(S.eold); c->release(S.enew); c->release(S.akeys); c->release(S.aidx); c->release(S.reqs);
+    c->release(S.results); c->release(S.n_req); c->release(acc); c->release(out_off); c->release(d_ctr);
+    c->release(sy0); c->release(sy1); c->release(sseq); c->release(sdir); c->release(contained); c->release(d_rank_off);
+  };
+  bool wet = false, converged = false;
+  uint64_t prev_diffs = ~0ULL;
+  int dry_passes = 0;
+  for (int pass = 0; pass < 400; pass++) {
+    c->tic();
+    LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
+    CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
+    LAUNCH(c, k_replay, nblk(n_ranks, 64), 64, S, n_ranks, d_rank_off, sy0, sdir, contained, bestn, wet ? 1 : 0, 0, acc,
+           (const uint32_t *)nullptr, (ovlp_rec *)nullptr, d_ctr);
+    LAUNCH(c, k_table_diff, 1184, 256, S.eold, S.enew, (size_t)ecap, d_ctr + 1);
+    unsigned long long ctr[2];
+    uint32_t n_req = 0;
+    c->d2h(ctr, d_ctr, 16);
+    c->d2h(&n_req, S.n_req, 4);
+    c->stats.ms_replay += c->toc();
+    c->stats.n_replay_passes++;
+    if (c->check_err("pgb_overlap/replay")) { free_S(); return -1; }
+    if (n_req > S.n_done) {
+      c->tic();
+      uint32_t nn = n_req - S.n_done;
+      LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, S.n_done, nn, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
+             (int)bw, S.results, c->d_err);
+      c->sync();
+      c->stats.ms_align += c->toc();
+      c->stats.n_alignments += nn;
+      if (c->check_err("pgb_overlap/align")) { free_S(); return -1; }
+    }
+    bool new_requests = n_req > S.n_done;
+    S.n_done = n_req;
+    std::swap(S.eold, S.enew);
+    if (getenv("PGB_VERBOSE"))
+      fprintf(stderr, "pgb200: replay pass %d %s: unknown=%llu table_diffs=%llu requests=%u\n", pass, wet ? "wet" : "dry", ctr[0], ctr[1], n_req);
+    if (wet && !new_requests && ctr[0] == 0 && ctr[1] == 0) { converged = true; break; }
+    if (!wet) {
+      // speculative ("dry") passes settle the time-stamped pair table with predicted alignments only; switch to real
+      // alignments once the table is nearly stable or stops improving
+      dry_passes++;
+      if (ctr[1] <= 16 + ctr[0] / 512 || ctr[1] >= prev_diffs || dry_passes >= 12) wet = true;
+      prev_diffs = ctr[1];
+    }
+  }
+  if (!converged) { free_S(); throw std::runtime_error("replay fix-point did not converge in 400 passes"); }
+
+  // ---------------- emission pass in visiting order
+  c->tic();
+  uint32_t n_out = scan_u32(c, acc, out_off, (size_t)n_ranks + 1);
+  c->d_ovl = c->alloc<ovlp_rec>(n_out); c->n_ovl = n_out;
+  LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
+  CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
+  LAUNCH(c, k_replay, nblk(n_ranks, 64), 64, S, n_ranks, d_rank_off, sy0, sdir, contained, bestn, 0, 1, acc, out_off, c->d_ovl, d_ctr);
+  c->sync();
+  c->stats.ms_emit += c->toc();
+  c->stats.n_overlaps += n_out;
+  free_S();
+  c->sync();
+  c->check_err("pgb_overlap/emit");
+  API_END(c)
+}
+
+extern "C" size_t pgb_overlap_size(pgb_ctx *c) { return c ? c->n_ovl : 0; }
+extern "C" int pgb_overlap_copy(pgb_ctx *c, ovlp_t *out) {
+  API_BEGIN(c)
+  c->d2h(out, c->d_ovl, c->n_ovl * sizeof(ovlp_rec));
+  API_END(c)
+}
+
+// ================================================================================================ command-line tools
+static pgb_ctx *cli_ctx() {
+  int dev = 0;
+  const char *e = getenv("PGB_DEVICE");
+  if (e) dev = atoi(e);
+  pgb_ctx *c = pgb_create(dev);
+  if (!c) exit(1);
+  return c;
+}
+#define CLI_CHECK(c, call)                                              \
+  do {                                                                  \
+    if ((call) != 0) {                                                  \
+      fprintf(stderr, "pgb200: %s failed: %s\n", #call, pgb_last_error(c)); \
+      exit(1);                                                          \
+    }                                                                   \
+  } while (0)
+
+extern "C" int pgb_shmr_index_main(int argc, char **argv) {
+  // option handling, defaults, assertions and messages follow src/shmr_index.c:37-131
+  const char *seqdb_prefix = "seq_dataset", *shimmer_prefix = "shimmer";
+  int total_chunk = 1, mychunk = 1, reduction_factor = 6, number_layers = 2, output_L0 = 1, window_size = 80, kmer_size = 16;
+  int ch;
+  opterr = 0; optind = 1;
+  while ((ch = getopt(argc, argv, "p:o:t:c:l:r:m:w:k:")) != -1) {
+    switch (ch) {
+      case 'p': seqdb_prefix = optarg; break;
+      case 'o': shimmer_prefix = optarg; break;
+      case 't': total_chunk = atoi(optarg); break;
+      case 'c': mychunk = atoi(optarg); break;
+      case 'r': reduction_factor = atoi(optarg); break;
+      case 'l': number_layers = atoi(optarg); break;
+      case 'm': output_L0 = atoi(optarg); break;
+      case 'w': window_size = atoi(optarg); break;
+      case 'k': kmer_size = atoi(optarg); break;
+      case '?':
+        if (optopt == 'p') fprintf(stderr, "Option -%c not specified, using 'seq_dataset' as the sequence db prefix\n", optopt);
+        else if (optopt == 'o') fprintf(stderr, "Option -%c not specified, using 'shimmer' as the output prefix\n", optopt);
+        return 1;
+      default: abort();
+    }
+  }
+  assert(total_chunk > 0);
+  assert(mychunk > 0 && mychunk <= total_chunk);
+  assert(reduction_factor < 256);
+  assert(window_size >= 24 && kmer_size >= 12 && window_size > kmer_size);
+  fprintf(stderr, "reduction factor= %d\n", reduction_factor);
+  char path[8400];
+  snprintf(path, sizeof path, "%s.idx", seqdb_prefix);
+  fprintf(stderr, "using index file: %s\n", path);
+  snprintf(path, sizeof path, "%s.seqdb", seqdb_prefix);
+  fprintf(stderr, "using seqdb file: %s\n", path);
+
+  pgb_ctx *c = cli_ctx();
+  CLI_CHECK(c, pgb_load_reads_from_files(c, seqdb_prefix, (uint32_t)total_chunk, (uint32_t)mychunk, 0));
+  int levels = number_layers == 1 ? 1 : (number_layers > 1 ? 2 : 0);
+  int with_counts = (output_L0 == 1 ? 1 : 0) | (levels == 1 ? 2 : 0) | (levels == 2 ? 4 : 0);
+  CLI_CHECK(c, pgb_index(c, window_size, kmer_size, reduction_factor, levels, with_counts));
+  auto write_level = [&](int level, const char *tag, bool data_msg_stderr) {
+    std::vector<mm128_t> v(pgb_index_size(c, level));
+    CLI_CHECK(c, pgb_index_copy(c, level, v.data()));
+    snprintf(path, sizeof path, "%s-%s-%02d-of-%02d.dat", shimmer_prefix, tag, mychunk, total_chunk);
+    if (data_msg_stderr) fprintf(stderr, "output data file: %s\n", path); else printf("output data file: %s\n", path);
+    write_mmlist_file(path, (const mm128 *)v.data(), v.size());
+    std::vector<mm_count_t> mc(pgb_index_count_size(c, level));
+    pgb_index_count_copy(c, level, mc.data());
+    snprintf(path, sizeof path, "%s-%s-MC-%02d-of-%02d.dat", shimmer_prefix, tag, mychunk, total_chunk);
+    printf("output data file: %s\n", path);
+    write_mc_file(path, (const mc_rec *)mc.data(), mc.size());
+  };
+  if (output_L0 == 1) write_level(0, "L0", true);   // src/shmr_index.c:165-197
+  if (levels == 1) write_level(1, "L1", false);      // :201-214
+  if (levels == 2) write_level(2, "L2", true);       // :216-232
+  pgb_destroy(c);
+  return 0;
+}
+
+extern "C" int pgb_shmr_overlap_main(int argc, char **argv) {
+  // option handling, defaults and messages follow src/shmr_overlap.c:233-392
+  const char *seqdb_prefix = "seq_dataset", *shimmer_prefix = "shimmer-L2";
+  char default_out[64];
+  const char *ovlp_file_path = nullptr;
+  uint8_t bestn = 4;
+  uint32_t mc_lower = 2, mc_upper = 240, ovlp_upper = 120, align_bandwidth = 100, total_chunk = 1, mychunk = 1;
+  int ch;
+  opterr = 0; optind = 1;
+  while ((ch = getopt(argc, argv, "p:l:t:c:b:o:m:M:w:n:")) != -1) {
+    switch (ch) {
+      case 'p': seqdb_prefix = optarg; break;
+      case 'l': shimmer_prefix = optarg; break;
+      case 't': total_chunk = atoi(optarg); break;
+      case 'c': mychunk = atoi(optarg); break;
+      case 'b': bestn = (uint8_t)atoi(optarg); break;
+      case 'o': ovlp_file_path = optarg; break;
+      case 'm': mc_lower = atoi(optarg); break;
+      case 'M': mc_upper = atoi(optarg); break;
+      case 'w': align_bandwidth = atoi(optarg); break;
+      case 'n': ovlp_upper = atoi(optarg); break;
+      case '?':
+        if (optopt == 'p') fprintf(stderr, "Option -%c not specified, using 'seq_dataset' as the sequence db prefix\n", optopt);
+        if (optopt == 'l') fprintf(stderr, "Option -%c not specified, using 'shimmer-L2' as the L2 index prefix\n", optopt);
+        if (optopt == 'o') fprintf(stderr, "Option -%c not specified, using 'ovlp.# as default output' \n", optopt);
+        return 1;
+      default: abort();
+    }
+  }
+  assert(total_chunk > 0);
+  assert(mychunk > 0 && mychunk <= total_chunk);
+  if (!ovlp_file_path) { snprintf(default_out, sizeof default_out, "ovlp.%02d", mychunk); ovlp_file_path = default_out; }
+  char path[8400];
+  snprintf(path, sizeof path, "%s.idx", seqdb_prefix);
+  fprintf(stderr, "using index file: %s\n", path);
+  snprintf(path, sizeof path, "%s.seqdb", seqdb_prefix);
+  fprintf(stderr, "using seqdb file: %s\n", path);
+  std::vector<mm128> mmers;
+  for (auto &fn : glob_sorted(std::string(shimmer_prefix) + "-[0-9]*-of-[0-9]*.dat")) {
+    fprintf(stderr, "using shimmer data file: %s\n", fn.c_str());
+    read_mmlist_file(fn.c_str(), &mmers);
+  }
+  std::vector<mc_rec> mc;
+  for (auto &fn : glob_sorted(std::string(shimmer_prefix) + "-MC-[0-9]*-of-[0-9]*.dat")) {
+    fprintf(stderr, "using shimmer count file: %s\n", fn.c_str());
+    read_mc_file(fn.c_str(), &mc);
+  }
+  FILE *out = fopen(ovlp_file_path, "w");
+  if (!out) { fprintf(stderr, "file '%s' open error: %s\n", ovlp_file_path, strerror(errno)); exit(1); }
+  pgb_ctx *c = cli_ctx();
+  CLI_CHECK(c, pgb_load_reads_from_files(c, seqdb_prefix, 1, 1, 0));
+  CLI_CHECK(c, pgb_set_shimmers(c, (const mm128_t *)mmers.data(), mmers.size(), (const mm_count_t *)mc.data(), mc.size()));
+  CLI_CHECK(c, pgb_overlap(c, total_chunk, mychunk, bestn, mc_lower, mc_upper, align_bandwidth, ovlp_upper));
+  std::vector<ovlp_t> recs(pgb_overlap_size(c));
+  CLI_CHECK(c, pgb_overlap_copy(c, recs.data()));
+  if (!recs.empty()) fwrite(recs.data(), sizeof(ovlp_t), recs.size(), out);
+  fclose(out);
+  pgb_destroy(c);
+  return 0;
+}
+
+// ================================================================================================ reference cffi surface
+extern "C" void decode_biseq(uint8_t *src, char *seq, size_t len, uint8_t strand) {
+  // byte-format conversion helper for Python callers (src/shmr_utils.c:53-62); not part of the compute path
+  static const char b2b[16] = {'N', 'A', 'C', 'N', 'G', 'N', 'N', 'N', 'T', 'N', 'N', 'N', 'N', 'N', 'N', 'N'};
+  for (size_t p = 0; p < len; p++) seq[p] = strand == 0 ? b2b[src[p] & 0x0F] : b2b[src[p] >> 4];
+}
+extern "C" void free_ovlp_match(ovlp_match_t *m) { free(m); }
+extern "C" mm128_v read_mmlist(char *fn) {
+  mm128_v p = {0, 0, 0};
+  std::vector<mm128> v;
+  read_mmlist_file(fn, &v);
+  p.n = p.m = v.size();
+  p.a = (mm128_t *)malloc((v.size() ? v.size() : 1) * sizeof(mm128_t));
+  memcpy((void *)p.a, v.data(), v.size() * sizeof(mm128_t));
+  return p;
+}
+
+static pgb_ctx *g_ctx = nullptr;  // lazily created context behind the single-call cffi functions
+static pgb_ctx *shared_ctx() {
+  if (!g_ctx) {
+    g_ctx = cli_ctx();
+  }
+  return g_ctx;
+}
+static void mm128v_append(mm128_v *p, const mm128_t *src, size_t n) {
+  if (p->n + n > p->m) {
+    size_t m = p->m ? p->m : 16;
+    while (m < p->n + n) m <<= 1;
+    p->a = (mm128_t *)realloc(p->a, m * sizeof(mm128_t));
+    p->m = m;
+  }
+  memcpy((void *)(p->a + p->n), src, n * sizeof(mm128_t));
+  p->n += n;
+}
+static inline uint8_t ascii_to_nibble(char ch) {
+  switch (ch) {
+    case 'A': case 'a': return 1;
+    case 'C': case 'c': return 2;
+    case 'G': case 'g': return 4;
+    case 'T': case 't': case 'U': case 'u': return 8;  // seq_nt4_table maps U/u to 3 as well (src/mm_sketch.c:10-21)
+    default: return 0;
+  }
+}
+extern "C" void mm_sketch(void *km, const char *str, int len, int w, int k, uint32_t rid, int is_hpc, mm128_v *p) {
+  (void)km;
+  assert(len > 0 && (w > 0 && w < 256) && (k > 0 && k <= 28));  // src/mm_sketch.c:77-78
+  if (is_hpc) { fprintf(stderr, "pgb200: mm_sketch with is_hpc != 0 is not supported (no reference caller uses it)\n"); exit(1); }
+  pgb_ctx *c = shared_ctx();
+  std::vector<uint8_t> img((size_t)len);
+  for (int i = 0; i < len; i++) img[i] = ascii_to_nibble(str[i]);
+  uint32_t one_rid = 0, one_len = (uint32_t)len; uint64_t one_off = 0;
+  CLI_CHECK(c, pgb_load_reads(c, img.data(), img.size(), &one_rid, &one_len, &one_off, 1, 1, 1, 0));
+  CLI_CHECK(c, pgb_index(c, w, k, 1, 0, 0));
+  std::vector<mm128_t> v(pgb_index_size(c, 0));
+  CLI_CHECK(c, pgb_index_copy(c, 0, v.data()));
+  for (auto &m : v) m.y = (m.y & 0xFFFFFFFFULL) | ((uint64_t)rid << 32);
+  mm128v_append(p, v.data(), v.size());
+}
+
+extern "C" void mm_reduce(mm128_v *in, mm128_v *out, uint8_t rs) {
+  // runs of equal rid are the "reads" of src/shmr_reduce.c:72-77 (the ring is reset whenever the rid changes)
+  if (!in || in->n == 0) return;
+  pgb_ctx *c = shared_ctx();
+  try {
+    CU(cudaSetDevice(c->device));
+    size_t n = in->n;
+    std::vector<uint64_t> off;
+    for (size_t i = 0; i < n; i++)
+      if (i == 0 || (in->a[i].y >> 32) != (in->a[i - 1].y >> 32)) off.push_back(i);
+    size_t runs = off.size();
+    off.push_back(n);
+    mm128 *d_in = c->alloc<mm128>(n);
+    uint64_t *d_off = c->alloc<uint64_t>(runs + 1), *d_ooff = c->alloc<uint64_t>(runs + 1);
+    uint32_t *counts = c->alloc<uint32_t>(runs + 1);
+    c->h2d(d_in, in->a, n * sizeof(mm128));
+    c->h2d(d_off, off.data(), (runs + 1) * 8);
+    CU(cudaMemsetAsync(counts, 0, (runs + 1) * 4, c->st));
+    LAUNCH(c, k_reduce<false>, nblk(runs, 128), 128, d_in, d_off, (uint32_t)runs, (uint32_t)rs, counts, (const uint64_t *)nullptr, (mm128 *)nullptr);
+    uint64_t total = scan_u32_to_u64(c, counts, d_ooff, runs + 1);
+    mm128 *d_out = c->alloc<mm128>(total);
+    LAUNCH(c, k_reduce<true>, nblk(runs, 128), 128, d_in, d_off, (uint32_t)runs, (uint32_t)rs, (uint32_t *)nullptr, d_ooff, d_out);
+    std::vector<mm128_t> v(total);
+    c->d2h(v.data(), d_out, total * sizeof(mm128));
+    c->release(d_in); c->release(d_off); c->release(d_ooff); c->release(counts); c->release(d_out);
+    c->sync();
+    mm128v_append(out, v.data(), v.size());
+  } catch (std::exception &e) {
+    fprintf(stderr, "pgb200: mm_reduce failed: %s\n", e.what());
+    exit(1);
+  }
+}
+
+extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_t q_strand, uint8_t *target_seq, seq_coor_t t_len,
+                                    uint8_t t_strand, seq_coor_t band_tolerance) {
+  // The operands arrive as .seqdb bytes; the strand picks the nibble (src/DWmatch.c:90-91,136-137).  The selected nibbles
+  // are staged as two forward "reads" and one alignment request is run through the same k_align kernel.
+  ovlp_match_t *rtn = (ovlp_match_t *)calloc(1, sizeof(ovlp_match_t));
+  if (q_len <= 0 || t_len <= 0) return rtn;
+  if (band_tolerance + 3 > PGB_MAXV || band_tolerance < 0) { fprintf(stderr, "pgb200: ovlp_match band_tolerance %d unsupported\n", band_tolerance); exit(1); }
+  pgb_ctx *c = shared_ctx();
+  std::vector<uint8_t> img((size_t)q_len + (size_t)t_len);
+  int qs = q_strand == 0 ? 0 : 4, ts = t_strand == 0 ? 0 : 4;
+  for (int i = 0; i < q_len; i++) img[i] = (query_seq[i] >> qs) & 0x0F;
+  for (int i = 0; i < t_len; i++) img[(size_t)q_len + i] = (target_seq[i] >> ts) & 0x0F;
+  uint32_t rids[2] = {0, 1}, lens[2] = {(uint32_t)q_len, (uint32_t)t_len};
+  uint64_t offs[2] = {0, (uint64_t)q_len};
+  CLI_CHECK(c, pgb_load_reads(c, img.data(), img.size(), rids, lens, offs, 2, 1, 1, 0));
+  try {
+    AlnReq q; q.rid0 = 0; q.start0 = 0; q.rid1 = 1; q.strands = 0;
+    AlnReq *d_q = c->alloc<AlnReq>(1);
+    match_t *d_m = c->alloc<match_t>(1);
+    c->h2d(d_q, &q, sizeof q);
+    LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err);
+    c->d2h(rtn, d_m, sizeof(match_t));
+    c->release(d_q); c->release(d_m);
+    if (c->check_err("ovlp_match")) { fprintf(stderr, "pgb200: %s\n", pgb_last_error(c)); exit(1); }
+  } catch (std::exception &e) {
+    fprintf(stderr, "pgb200: ovlp_match failed: %s\n", e.what());
+    exit(1);
+  }
+  return rtn;
+}

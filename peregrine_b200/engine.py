@@ -1,0 +1,195 @@
+"""ctypes binding of libpgb200.so's stage-level API (include/pgb200.h, group 3).
+
+``Engine`` mirrors the two reference tools as method calls over host (numpy) buffers:
+
+    eng = Engine(device=0)
+    eng.load_reads(seqdb_u8, rid, length, offset)          # .seqdb image + .idx table  (src/shmr_index.c:133-163)
+    eng.index(w=80, k=16, r=6, levels=2)                   # mm_sketch + mm_reduce x2   (src/shmr_index.c:155-216)
+    l2 = eng.level(2); mc = eng.level_counts(2)
+    eng.set_shimmers(l2_all_chunks, mc_all_chunks)         # what shmr_overlap globs    (src/shmr_overlap.c:359-382)
+    ov = eng.overlap(total_chunk=1, mychunk=1)             # build_map + process_overlaps (src/shmr_overlap.c:394-397)
+
+Nothing here computes: every call lands in a CUDA kernel.  Without the shared library or without a CUDA device the
+constructor raises (there is deliberately no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import formats
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class NoDeviceError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.environ.get("PGB200_LIB", os.path.join(_HERE, "libpgb200.so"))
+
+
+class _Stats(C.Structure):
+    _fields_ = (
+        [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+        + [(n, C.c_double) for n in ("ms_pack", "ms_sketch", "ms_reduce", "ms_count", "ms_pairs", "ms_buckets",
+                                     "ms_host_order", "ms_replay", "ms_align", "ms_emit")]
+        + [(n, C.c_uint64) for n in ("bases_packed", "bases_sketched", "n_l0", "n_l1", "n_l2", "n_pair_records",
+                                     "n_buckets", "n_eligible_buckets", "n_candidates", "n_alignments",
+                                     "n_align_bases", "n_replay_passes", "n_overlaps")]
+    )
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libpgb200.so and declare the prototypes.  Raises FileNotFoundError if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not found: build it with `make` (or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(p)
+    vp, u8p, u32p, u64p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    L.pgb_device_count.restype = C.c_int
+    L.pgb_create.restype = vp
+    L.pgb_create.argtypes = [C.c_int]
+    L.pgb_destroy.argtypes = [vp]
+    L.pgb_last_error.restype = C.c_char_p
+    L.pgb_last_error.argtypes = [vp]
+    L.pgb_load_reads.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int]
+    L.pgb_repack.argtypes = [vp]
+    L.pgb_load_reads_from_files.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int]
+    L.pgb_index.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pgb_index_size.restype = C.c_size_t
+    L.pgb_index_size.argtypes = [vp, C.c_int]
+    L.pgb_index_copy.argtypes = [vp, C.c_int, vp]
+    L.pgb_index_count_size.restype = C.c_size_t
+    L.pgb_index_count_size.argtypes = [vp, C.c_int]
+    L.pgb_index_count_copy.argtypes = [vp, C.c_int, vp]
+    L.pgb_set_shimmers.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
+    L.pgb_set_shimmers_from_index.argtypes = [vp, C.c_int]
+    L.pgb_overlap.argtypes = [vp] + [C.c_uint32] * 7
+    L.pgb_overlap_size.restype = C.c_size_t
+    L.pgb_overlap_size.argtypes = [vp]
+    L.pgb_overlap_copy.argtypes = [vp, vp]
+    L.pgb_stats_reset.argtypes = [vp]
+    L.pgb_stats_get.argtypes = [vp, C.POINTER(_Stats)]
+    L.pgb_shmr_index_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.pgb_shmr_overlap_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        if self.L.pgb_device_count() <= 0:
+            raise NoDeviceError("libpgb200 needs a CUDA device (sm_100a); none is visible and there is no CPU path")
+        self.h = self.L.pgb_create(device)
+        if not self.h:
+            raise NoDeviceError(f"pgb_create({device}) failed")
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pgb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: {self.L.pgb_last_error(self.h).decode()}")
+
+    # ------------------------------------------------------------------ reads
+    def load_reads(self, seqdb, rid, length, offset, total_chunk=1, mychunk=1, keep_raw=False):
+        """seqdb: uint8 array (numpy, may wrap pinned memory); rid/length/offset as parsed from .idx."""
+        seqdb = np.ascontiguousarray(seqdb, dtype=np.uint8) if not isinstance(seqdb, np.ndarray) else seqdb
+        rid = np.ascontiguousarray(rid, dtype=np.uint32)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        offset = np.ascontiguousarray(offset, dtype=np.uint64)
+        self._ck(self.L.pgb_load_reads(self.h, _ptr(seqdb), seqdb.size, _ptr(rid), _ptr(length), _ptr(offset), len(rid),
+                                       total_chunk, mychunk, int(keep_raw)), "pgb_load_reads")
+
+    def load_reads_ptr(self, seqdb_ptr: int, seqdb_bytes: int, rid, length, offset, total_chunk=1, mychunk=1, keep_raw=False):
+        """Same, from a raw host address (e.g. a pinned torch tensor's data_ptr())."""
+        rid = np.ascontiguousarray(rid, dtype=np.uint32)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        offset = np.ascontiguousarray(offset, dtype=np.uint64)
+        self._ck(self.L.pgb_load_reads(self.h, C.c_void_p(seqdb_ptr), seqdb_bytes, _ptr(rid), _ptr(length), _ptr(offset),
+                                       len(rid), total_chunk, mychunk, int(keep_raw)), "pgb_load_reads")
+
+    def load_reads_from_files(self, prefix, total_chunk=1, mychunk=1, keep_raw=False):
+        self._ck(self.L.pgb_load_reads_from_files(self.h, prefix.encode(), total_chunk, mychunk, int(keep_raw)),
+                 "pgb_load_reads_from_files")
+
+    def repack(self):
+        self._ck(self.L.pgb_repack(self.h), "pgb_repack")
+
+    # ------------------------------------------------------------------ index
+    def index(self, w=80, k=16, r=6, levels=2, with_counts=0):
+        self._ck(self.L.pgb_index(self.h, w, k, r, levels, with_counts), "pgb_index")
+
+    def level(self, level):
+        n = self.L.pgb_index_size(self.h, level)
+        out = np.empty(n, dtype=formats.MM128)
+        if n:
+            self._ck(self.L.pgb_index_copy(self.h, level, _ptr(out)), "pgb_index_copy")
+        return out
+
+    def level_size(self, level):
+        return self.L.pgb_index_size(self.h, level)
+
+    def level_counts(self, level):
+        n = self.L.pgb_index_count_size(self.h, level)
+        out = np.empty(n, dtype=formats.MMCOUNT)
+        if n:
+            self._ck(self.L.pgb_index_count_copy(self.h, level, _ptr(out)), "pgb_index_count_copy")
+        return out
+
+    # ------------------------------------------------------------------ overlap
+    def set_shimmers(self, mmers, counts):
+        mmers = np.ascontiguousarray(mmers, dtype=formats.MM128)
+        counts = np.ascontiguousarray(counts, dtype=formats.MMCOUNT)
+        self._ck(self.L.pgb_set_shimmers(self.h, _ptr(mmers), len(mmers), _ptr(counts), len(counts)), "pgb_set_shimmers")
+
+    def set_shimmers_from_index(self, level=2):
+        self._ck(self.L.pgb_set_shimmers_from_index(self.h, level), "pgb_set_shimmers_from_index")
+
+    def overlap(self, total_chunk=1, mychunk=1, bestn=4, mc_lower=2, mc_upper=240, align_bandwidth=100, ovlp_upper=120,
+                copy=True):
+        self._ck(self.L.pgb_overlap(self.h, total_chunk, mychunk, bestn, mc_lower, mc_upper, align_bandwidth, ovlp_upper),
+                 "pgb_overlap")
+        if not copy:
+            return self.L.pgb_overlap_size(self.h)
+        return self.overlap_records()
+
+    def overlap_records(self):
+        n = self.L.pgb_overlap_size(self.h)
+        out = np.empty(n, dtype=formats.OVLP)
+        if n:
+            self._ck(self.L.pgb_overlap_copy(self.h, _ptr(out)), "pgb_overlap_copy")
+        return out
+
+    # ------------------------------------------------------------------ stats
+    def stats_reset(self):
+        self.L.pgb_stats_reset(self.h)
+
+    def stats(self) -> dict:
+        s = _Stats()
+        self.L.pgb_stats_get(self.h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in _Stats._fields_}

@@ -1,0 +1,395 @@
+// hostsim — CPU simulator of the kernel logic in peregrine_b200/csrc/shimmer_core.cuh.
+//
+// TEST INFRASTRUCTURE ONLY.  There is no GPU in the development container, so the per-item device functions
+// (sketch automaton, reduce pick, packed-word ovlp_match, bucket replay) are compiled for the host here and
+// compared with the real reference (oracle/_ref/libshimmer_ref.so, built from the unmodified sources) before
+// a GPU minute is spent.  libpgb200.so does not contain or call any of this.
+//
+//   hostsim sketch  <seqdb_prefix> <w> <k>            every read: sketch_exact vs reference mm_sketch, reduce x2
+//   hostsim match   <seqdb_prefix> <n_pairs> <bw>     random + adversarial operand pairs vs reference ovlp_match
+//   hostsim overlap <seqdb_prefix> <l2_prefix> <T> <c> <ref_ovlp_file> [jacobi]
+#include <dlfcn.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <unordered_map>
+#include <map>
+#include <array>
+#include <chrono>
+#include "../../peregrine_b200/csrc/host_util.hpp"
+
+using namespace pgb;
+
+// ---- reference ABI (src/shimmer.h) ----
+typedef struct { size_t n, m; mm128 *a; } mm128_v;
+typedef void (*ref_mm_sketch_t)(void *, const char *, int, int, int, uint32_t, int, mm128_v *);
+typedef void (*ref_mm_reduce_t)(mm128_v *, mm128_v *, uint8_t);
+typedef void (*ref_decode_t)(uint8_t *, char *, size_t, uint8_t);
+typedef match_t *(*ref_ovlp_match_t)(uint8_t *, int32_t, uint8_t, uint8_t *, int32_t, uint8_t, int32_t);
+static ref_mm_sketch_t ref_mm_sketch;
+static ref_mm_reduce_t ref_mm_reduce;
+static ref_decode_t ref_decode;
+static ref_ovlp_match_t ref_ovlp_match;
+
+static void load_ref() {
+  const char *p = getenv("PGB_REF_LIB");
+  void *h = dlopen(p ? p : "oracle/_ref/libshimmer_ref.so", RTLD_NOW);
+  if (!h) { fprintf(stderr, "cannot load reference lib: %s\n", dlerror()); exit(2); }
+  ref_mm_sketch = (ref_mm_sketch_t)dlsym(h, "mm_sketch");
+  ref_mm_reduce = (ref_mm_reduce_t)dlsym(h, "mm_reduce");
+  ref_decode = (ref_decode_t)dlsym(h, "decode_biseq");
+  ref_ovlp_match = (ref_ovlp_match_t)dlsym(h, "ovlp_match");
+}
+
+struct Packed {
+  ReadTable rt;
+  std::vector<uint64_t> w;
+  std::vector<uint32_t> nm;
+  std::vector<uint64_t> woff;  // per row
+  std::vector<uint8_t> has_n;
+  const uint8_t *seqdb = nullptr;
+  size_t seqdb_size = 0;
+};
+
+static void load_packed(const char *prefix, Packed *P) {
+  std::string idx = std::string(prefix) + ".idx", db = std::string(prefix) + ".seqdb";
+  if (!load_read_table(idx.c_str(), &P->rt)) die("cannot open %s", idx.c_str());
+  int fd = open(db.c_str(), O_RDONLY);
+  if (fd < 0) die("cannot open %s", db.c_str());
+  struct stat sb; fstat(fd, &sb);
+  P->seqdb = (const uint8_t *)mmap(0, sb.st_size, PROT_READ, MAP_SHARED, fd, 0);
+  P->seqdb_size = sb.st_size;
+  size_t n = P->rt.n();
+  uint64_t words = 2;
+  P->woff.resize(n); P->has_n.resize(n);
+  for (size_t i = 0; i < n; i++) { P->woff[i] = words; words += (P->rt.len[i] + 31) / 32; }
+  words += 2;
+  P->w.assign(words, 0); P->nm.assign(words, 0);
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t *s = P->seqdb + P->rt.off[i];
+    int hn = 0;
+    for (uint32_t p = 0; p < P->rt.len[i]; p++) {
+      uint8_t nib = s[p] & 0xF;
+      uint64_t c = 0; int isn = 0;
+      switch (nib) { case 1: c = 0; break; case 2: c = 1; break; case 4: c = 2; break; case 8: c = 3; break; default: isn = 1; }
+      P->w[P->woff[i] + p / 32] |= c << (2 * (p & 31));
+      if (isn) { P->nm[P->woff[i] + p / 32] |= 1u << (p & 31); hn = 1; }
+    }
+    P->has_n[i] = hn;
+  }
+}
+
+static void sim_reduce(const std::vector<mm128> &in, std::vector<mm128> &out, uint32_t rs) {
+  // per-element formulation (what the kernel does): element e with in-read offset o>=rs-1 emits its pick if it
+  // differs from the pick of e-1 (or if e-1 had no full window / belongs to another read)
+  size_t n = in.size();
+  size_t start = 0;
+  for (size_t e = 0; e < n; e++) {
+    if (e == 0 || (in[e].y >> 32) != (in[e - 1].y >> 32)) start = e;
+    uint32_t o = (uint32_t)(e - start);
+    if (o + 1 < rs) continue;
+    uint32_t t = reduce_pick(in.data() + start, o, rs);
+    bool emit = true;
+    if (o >= rs) {
+      uint32_t tp = reduce_pick(in.data() + start, o - 1, rs);
+      if (in[start + tp].y == in[start + t].y) emit = false;
+    }
+    if (emit) out.push_back(in[start + t]);
+  }
+}
+
+static int cmd_sketch(int argc, char **argv) {
+  if (argc < 5) return 1;
+  Packed P; load_packed(argv[2], &P);
+  int w = atoi(argv[3]), k = atoi(argv[4]);
+  int rs = argc > 5 ? atoi(argv[5]) : 6;
+  std::vector<uint64_t> rx(256); std::vector<uint32_t> rp(256);
+  size_t bad = 0, total = 0;
+  std::vector<mm128> all_mine;
+  mm128_v all_ref = {0, 0, 0};
+  for (size_t i = 0; i < P.rt.n(); i++) {
+    uint32_t len = P.rt.len[i];
+    if (len == 0) continue;
+    std::vector<char> seq(len + 1);
+    ref_decode((uint8_t *)P.seqdb + P.rt.off[i], seq.data(), len, 0);
+    size_t n0 = all_ref.n;
+    ref_mm_sketch(NULL, seq.data(), len, w, k, P.rt.rid[i], 0, &all_ref);
+    size_t m0 = all_mine.size();
+    sketch_exact(P.w.data(), P.has_n[i] ? P.nm.data() : nullptr, P.woff[i], (int)len, w, k, P.rt.rid[i], rx.data(), rp.data(),
+                 [&](uint64_t x, uint64_t y) { all_mine.push_back(mm128{x, y}); });
+    size_t nr = all_ref.n - n0, nmine = all_mine.size() - m0;
+    total += nr;
+    if (nr != nmine || memcmp(all_ref.a + n0, all_mine.data() + m0, nr * 16) != 0) {
+      if (bad < 5) fprintf(stderr, "sketch mismatch read row %zu rid %u len %u: ref %zu mine %zu\n", i, P.rt.rid[i], len, nr, nmine);
+      bad++;
+    }
+  }
+  printf("sketch: reads=%zu L0=%zu mismatching_reads=%zu\n", P.rt.n(), total, bad);
+  // reduce twice
+  mm128_v r1 = {0, 0, 0}, r2 = {0, 0, 0};
+  ref_mm_reduce(&all_ref, &r1, (uint8_t)rs);
+  ref_mm_reduce(&r1, &r2, (uint8_t)rs);
+  std::vector<mm128> m1, m2;
+  sim_reduce(all_mine, m1, rs);
+  sim_reduce(m1, m2, rs);
+  bool ok1 = r1.n == m1.size() && (r1.n == 0 || memcmp(r1.a, m1.data(), r1.n * 16) == 0);
+  bool ok2 = r2.n == m2.size() && (r2.n == 0 || memcmp(r2.a, m2.data(), r2.n * 16) == 0);
+  printf("reduce: L1 ref=%zu mine=%zu %s ; L2 ref=%zu mine=%zu %s\n", r1.n, m1.size(), ok1 ? "OK" : "MISMATCH", r2.n, m2.size(),
+         ok2 ? "OK" : "MISMATCH");
+  return (bad || !ok1 || !ok2) ? 3 : 0;
+}
+
+static uint64_t rng_state = 0x12345;
+static inline uint64_t rnd() {
+  uint64_t z = (rng_state += 0x9E3779B97F4A7C15ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+static bool same_match(const match_t &a, const match_t &b) { return memcmp(&a, &b, sizeof(match_t)) == 0; }
+
+static int one_match(const Packed &P, size_t r0, uint32_t start0, int s0, size_t r1, int s1, int bw, size_t *bad) {
+  uint32_t rlen0 = P.rt.len[r0], rlen1 = P.rt.len[r1];
+  if (start0 >= rlen0) start0 = 0;
+  int qlen = (int)(rlen0 - start0), tlen = (int)rlen1;
+  match_t *ref = ref_ovlp_match((uint8_t *)P.seqdb + P.rt.off[r0] + start0, qlen, (uint8_t)s0, (uint8_t *)P.seqdb + P.rt.off[r1], tlen,
+                                (uint8_t)s1, bw);
+  std::vector<int> Va(bw + 8), Vb(bw + 8);
+  SeqView q = make_view(P.w.data(), P.nm.data(), P.woff[r0], rlen0, start0, s0, P.has_n[r0]);
+  SeqView t = make_view(P.w.data(), P.nm.data(), P.woff[r1], rlen1, 0, s1, P.has_n[r1]);
+  match_t mine; int err = 0;
+  ovlp_match_core(q, qlen, t, tlen, bw, Va.data(), Vb.data(), bw + 8, &mine, &err);
+  int ok = same_match(*ref, mine) && err == 0;
+  if (!ok) {
+    if (*bad < 8)
+      fprintf(stderr, "match mismatch rows %zu(+%u,s%d) %zu(s%d) bw=%d err=%d: ref{%d %d %d %d %d %d %d %d} mine{%d %d %d %d %d %d %d %d}\n", r0,
+              start0, s0, r1, s1, bw, err, ref->m_size, ref->dist, ref->q_bgn, ref->q_end, ref->t_bgn, ref->t_end, ref->t_m_end, ref->q_m_end,
+              mine.m_size, mine.dist, mine.q_bgn, mine.q_end, mine.t_bgn, mine.t_end, mine.t_m_end, mine.q_m_end);
+    (*bad)++;
+  }
+  free(ref);
+  return ok;
+}
+
+static int cmd_match(int argc, char **argv) {
+  if (argc < 5) return 1;
+  Packed P; load_packed(argv[2], &P);
+  size_t npairs = strtoull(argv[3], 0, 10);
+  int bw = atoi(argv[4]);
+  size_t bad = 0, n = P.rt.n();
+  for (size_t it = 0; it < npairs; it++) {
+    size_t r0 = rnd() % n, r1 = rnd() % n;
+    uint32_t st = (uint32_t)(rnd() % (P.rt.len[r0] ? P.rt.len[r0] : 1));
+    if (it % 4 == 0) r1 = r0;  // self alignment at an offset / strand
+    if (it % 4 == 1) st = 0;
+    one_match(P, r0, st, (int)(rnd() & 1), r1, (int)(rnd() & 1), bw, &bad);
+  }
+  printf("match: pairs=%zu mismatches=%zu\n", npairs, bad);
+  return bad ? 3 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------ overlap
+struct PairRec { uint64_t k0, k1, y0, y1; uint32_t seq; uint8_t dir; };
+struct Bucket { uint64_t k0, k1; uint32_t first_seq; std::vector<uint32_t> recs; };
+
+struct HostCtx {
+  const Packed *P;
+  std::unordered_map<uint64_t, uint64_t> *e_old, *e_new;
+  std::unordered_map<uint64_t, match_t> *aln;  // key rank<<32 | i<<16 | j
+  std::vector<std::array<uint32_t, 8>> *requests;
+  std::vector<ovlp_rec> *out;
+  uint32_t rank;
+  bool request_enabled;
+  uint32_t rlen(uint32_t rid) const { return P->rt.len[P->rt.by_rid[rid]]; }
+  uint64_t pair_old(uint64_t p) const { auto it = e_old->find(p); return it == e_old->end() ? ~0ULL : it->second; }
+  bool strict = getenv("PGB_SIM_STRICT") != nullptr;  // pure Jacobi: other buckets' writes of this pass stay invisible
+  uint64_t pair_new(uint64_t p) const {
+    auto it = e_new->find(p);
+    if (it == e_new->end()) return ~0ULL;
+    if (strict && (uint32_t)(it->second >> 2) != rank) return ~0ULL;
+    return it->second;
+  }
+  void pair_set(uint64_t p, uint64_t v) { auto it = e_new->find(p); if (it == e_new->end() || v < it->second) (*e_new)[p] = v; }
+  bool aln_get(uint32_t i, uint32_t j, match_t *m) const {
+    auto it = aln->find(((uint64_t)rank << 32) | (i << 16) | j);
+    if (it == aln->end()) return false;
+    *m = it->second; return true;
+  }
+  void aln_request(uint32_t i, uint32_t j, uint32_t rid0, uint32_t start0, uint32_t s0, uint32_t rid1, uint32_t s1) {
+    if (request_enabled) requests->push_back({rank, i, j, rid0, start0, s0, rid1, s1});
+  }
+  void emit(uint32_t, const ovlp_rec &o) { out->push_back(o); }
+};
+
+static match_t do_align(const Packed &P, uint32_t rid0, uint32_t start0, uint32_t s0, uint32_t rid1, uint32_t s1, int bw) {
+  size_t r0 = P.rt.by_rid[rid0], r1 = P.rt.by_rid[rid1];
+  uint32_t rlen0 = P.rt.len[r0], rlen1 = P.rt.len[r1];
+  static std::vector<int> Va, Vb;
+  Va.resize(bw + 8); Vb.resize(bw + 8);
+  SeqView q = make_view(P.w.data(), P.nm.data(), P.woff[r0], rlen0, start0, s0, P.has_n[r0]);
+  SeqView t = make_view(P.w.data(), P.nm.data(), P.woff[r1], rlen1, 0, s1, P.has_n[r1]);
+  match_t m; int err = 0;
+  ovlp_match_core(q, (int)(rlen0 - start0), t, (int)rlen1, bw, Va.data(), Vb.data(), bw + 8, &m, &err);
+  if (err) fprintf(stderr, "ovlp_match_core err=%d\n", err);
+  return m;
+}
+
+static int cmd_overlap(int argc, char **argv) {
+  if (argc < 7) return 1;
+  Packed P; load_packed(argv[2], &P);
+  std::string l2 = argv[3];
+  uint32_t T = atoi(argv[4]), c = atoi(argv[5]);
+  const char *ref_file = argv[6];
+  bool jacobi = argc > 7 && !strcmp(argv[7], "jacobi");
+  int dry_passes = argc > 8 ? atoi(argv[8]) : 3;
+  uint32_t mc_lower = 2, mc_upper = 240, ovlp_upper = 120, bestn = 4; int bw = 100;
+  std::vector<mm128> mm;
+  for (auto &fn : glob_sorted(l2 + "-[0-9]*-of-[0-9]*.dat")) read_mmlist_file(fn.c_str(), &mm);
+  std::unordered_map<uint64_t, uint32_t> cnt;
+  for (auto &fn : glob_sorted(l2 + "-MC-[0-9]*-of-[0-9]*.dat")) {
+    std::vector<mc_rec> v; read_mc_file(fn.c_str(), &v);
+    for (auto &r : v) cnt[r.mer] += r.count;
+  }
+  printf("L2 mmers=%zu distinct=%zu\n", mm.size(), cnt.size());
+  // kept set (src/shmr_utils.c:310-328)
+  size_t n = mm.size(), s = 0;
+  for (; s < n; s++) { uint32_t mc = cnt[mm[s].x >> 8]; if (mc >= mc_lower && mc < mc_upper) break; }
+  std::vector<uint32_t> kept;
+  if (s < n) kept.push_back((uint32_t)s);
+  for (size_t i = s + 1; i < n; i++) { uint32_t mc = cnt[mm[i].x >> 8]; if (mc < mc_lower || mc > mc_upper) continue; kept.push_back((uint32_t)i); }
+  // pair records
+  std::vector<PairRec> recs;
+  for (size_t t = 0; t + 1 < kept.size(); t++) {
+    const mm128 &m0 = mm[kept[t]], &m1 = mm[kept[t + 1]];
+    if ((m0.y >> 32) != (m1.y >> 32)) continue;
+    if (!pair_far_enough(m0.y, m1.y)) continue;
+    if ((m0.x >> 8) % T == c % T) recs.push_back({m0.x, m1.x, m0.y, m1.y, (uint32_t)(2 * t), 0});
+    if ((m1.x >> 8) % T == c % T) {
+      uint32_t rl0 = P.rt.len[P.rt.by_rid[m1.y >> 32]], rl1 = P.rt.len[P.rt.by_rid[m0.y >> 32]];
+      recs.push_back({m1.x, m0.x, rev_y(m1.y, m1.x, rl0), rev_y(m0.y, m0.x, rl1), (uint32_t)(2 * t + 1), 1});
+    }
+  }
+  printf("kept=%zu pair records=%zu\n", kept.size(), recs.size());
+  // group into buckets (stand-in for the device hash tables), first-seq order
+  std::map<std::pair<uint64_t, uint64_t>, uint32_t> bidx;
+  std::vector<Bucket> buckets;
+  for (uint32_t r = 0; r < recs.size(); r++) {
+    auto key = std::make_pair(recs[r].k0, recs[r].k1);
+    auto it = bidx.find(key);
+    if (it == bidx.end()) { bidx[key] = (uint32_t)buckets.size(); buckets.push_back({recs[r].k0, recs[r].k1, recs[r].seq, {}}); it = bidx.find(key); }
+    buckets[it->second].recs.push_back(r);
+  }
+  // khash visiting order: outer keys by first insertion, inner keys per outer by first insertion
+  // (buckets vector is already in first-seq order because recs are in seq order)
+  KhashEmu outer;
+  std::unordered_map<uint64_t, uint32_t> outer_id;
+  std::vector<std::vector<uint32_t>> inner_lists;
+  for (uint32_t b = 0; b < buckets.size(); b++) {
+    auto it = outer_id.find(buckets[b].k0);
+    if (it == outer_id.end()) {
+      uint32_t id = (uint32_t)inner_lists.size();
+      outer_id[buckets[b].k0] = id;
+      outer.put_new(buckets[b].k0, id);
+      inner_lists.emplace_back();
+      inner_lists[id].push_back(b);
+    } else inner_lists[it->second].push_back(b);
+  }
+  std::vector<uint32_t> visit;  // eligible buckets in visiting order
+  outer.for_each_in_slot_order([&](uint64_t, uint32_t id) {
+    KhashEmu inner;
+    for (uint32_t b : inner_lists[id]) inner.put_new(buckets[b].k1, b);
+    inner.for_each_in_slot_order([&](uint64_t, uint32_t b) {
+      size_t nn = buckets[b].recs.size();
+      if (nn <= 2 || nn > ovlp_upper) return;
+      visit.push_back(b);
+    });
+  });
+  printf("buckets=%zu outer=%zu eligible=%zu\n", buckets.size(), inner_lists.size(), visit.size());
+  // sorted record arrays per eligible bucket: stable, descending position (glibc qsort with mp128_comp)
+  std::vector<std::vector<uint64_t>> by0(visit.size());
+  std::vector<std::vector<uint8_t>> bdir(visit.size());
+  size_t cand = 0;
+  for (size_t r = 0; r < visit.size(); r++) {
+    std::vector<uint32_t> v = buckets[visit[r]].recs;
+    std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) {
+      return ((recs[a].y0 & 0xFFFFFFFFULL) >> 1) > ((recs[b].y0 & 0xFFFFFFFFULL) >> 1);
+    });
+    for (uint32_t a : v) { by0[r].push_back(recs[a].y0); bdir[r].push_back(recs[a].dir); }
+    cand += v.size() * (v.size() - 1) / 2;
+  }
+  printf("candidate (i,j) pairs=%zu\n", cand);
+  // reference output
+  std::vector<ovlp_rec> ref;
+  {
+    FILE *f = fopen(ref_file, "rb");
+    if (!f) die("cannot open %s", ref_file);
+    ovlp_rec o;
+    while (fread(&o, sizeof o, 1, f) == 1) { o.pad0 = 0; o.pad1 = 0; ref.push_back(o); }
+    fclose(f);
+  }
+  std::unordered_map<uint64_t, uint64_t> eA, eB;
+  std::unordered_map<uint64_t, match_t> aln;
+  std::vector<std::array<uint32_t, 8>> requests;
+  std::vector<ovlp_rec> out;
+  std::vector<uint8_t> contained(65536);
+  HostCtx ctx{&P, &eA, &eB, &aln, &requests, &out, 0, true};
+  if (ctx.strict) printf("strict Jacobi simulation\n");
+  size_t n_align = 0;
+  if (!jacobi) {
+    // sequential (Gauss-Seidel with immediate alignment): exactness check of the restated control path
+    for (uint32_t r = 0; r < visit.size(); r++) {
+      // iterate the bucket until it asks for nothing new
+      for (;;) {
+        ctx.rank = r; requests.clear(); out.clear();
+        // e_new must not keep entries of this rank from the previous attempt
+        std::unordered_map<uint64_t, uint64_t> scratch;
+        ctx.e_old = &eA; ctx.e_new = &scratch;
+        uint32_t unk = 0;
+        replay_bucket(ctx, r, by0[r].data(), bdir[r].data(), (uint32_t)by0[r].size(), contained.data(), bestn, true, &unk);
+        if (requests.empty()) { for (auto &kv : scratch) eA[kv.first] = kv.second; break; }
+        for (auto &q : requests) { aln[((uint64_t)q[0] << 32) | (q[1] << 16) | q[2]] = do_align(P, q[3], q[4], q[5], q[6], q[7], bw); n_align++; }
+      }
+      static std::vector<ovlp_rec> all;
+      all.insert(all.end(), out.begin(), out.end());
+      if (r + 1 == visit.size()) out = all;
+    }
+  } else {
+    int pass = 0;
+    for (;; pass++) {
+      bool dry = pass < dry_passes;
+      ctx.request_enabled = !dry;
+      ctx.e_old = &eA; ctx.e_new = &eB; eB.clear(); requests.clear(); out.clear();
+      size_t unk_total = 0;
+      for (uint32_t r = 0; r < visit.size(); r++) {
+        ctx.rank = r; uint32_t unk = 0;
+        replay_bucket(ctx, r, by0[r].data(), bdir[r].data(), (uint32_t)by0[r].size(), contained.data(), bestn, true, &unk);
+        unk_total += unk;
+      }
+      size_t diffs = 0;
+      for (auto &kv : eB) { auto it = eA.find(kv.first); if (it == eA.end() || it->second != kv.second) diffs++; }
+      for (auto &kv : eA) if (eB.find(kv.first) == eB.end()) diffs++;
+      for (auto &q : requests) { aln[((uint64_t)q[0] << 32) | (q[1] << 16) | q[2]] = do_align(P, q[3], q[4], q[5], q[6], q[7], bw); n_align++; }
+      printf("pass %d %s: records=%zu unknown=%zu new_requests=%zu table_diffs=%zu total_aligned=%zu\n", pass, dry ? "dry" : "wet", out.size(),
+             unk_total, requests.size(), diffs, n_align);
+      eA.swap(eB);
+      if (!dry && requests.empty() && diffs == 0 && unk_total == 0) break;
+      if (pass > 200) { printf("no convergence\n"); break; }
+    }
+  }
+  size_t nb = 0;
+  size_t m = std::min(out.size(), ref.size());
+  for (size_t i = 0; i < m; i++) if (memcmp(&out[i], &ref[i], sizeof(ovlp_rec)) != 0) { if (nb < 5) fprintf(stderr, "record %zu differs\n", i); nb++; }
+  printf("overlap: ref=%zu mine=%zu differing=%zu alignments=%zu\n", ref.size(), out.size(), nb, n_align);
+  return (nb || out.size() != ref.size()) ? 3 : 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2) { fprintf(stderr, "usage: hostsim sketch|match|overlap ...\n"); return 1; }
+  load_ref();
+  if (!strcmp(argv[1], "sketch")) return cmd_sketch(argc, argv);
+  if (!strcmp(argv[1], "match")) return cmd_match(argc, argv);
+  if (!strcmp(argv[1], "overlap")) return cmd_overlap(argc, argv);
+  return 1;
+}

@@ -1,0 +1,167 @@
+"""GPU parity tests: the CUDA path (through the drop-in CLI tools and the C ABI) against the UNMODIFIED reference
+compiled into oracle/_ref, on the same inputs.  Bar: byte-identical L0/L1/L2 files, set-identical -MC- files, and
+ovlp files identical field-for-field AND in order (padding bytes masked, SURVEY A-1)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import datasets as D
+from peregrine_b200 import formats as F
+
+pytestmark = pytest.mark.gpu
+
+ROOT = D.ROOT
+BIN = os.path.join(ROOT, "bin")
+
+
+def ours_index(prefix, outdir, T=1, extra=()):
+    os.makedirs(outdir, exist_ok=True)
+    for c in range(1, T + 1):
+        D.run([os.path.join(BIN, "shmr_index"), "-p", prefix, "-t", str(T), "-c", str(c), "-o", os.path.join(outdir, "shmr"), *extra])
+    return os.path.join(outdir, "shmr")
+
+
+def ours_overlap(prefix, idx_prefix, level, outdir, T=1, extra=()):
+    os.makedirs(outdir, exist_ok=True)
+    outs = []
+    for c in range(1, T + 1):
+        o = os.path.join(outdir, f"ovlp.{c:02d}")
+        D.run([os.path.join(BIN, "shmr_overlap"), "-p", prefix, "-l", f"{idx_prefix}-L{level}", "-t", str(T), "-c", str(c), "-o", o, *extra])
+        outs.append(o)
+    return outs
+
+
+def assert_same_bytes(a, b):
+    with open(a, "rb") as fa, open(b, "rb") as fb:
+        da, db = fa.read(), fb.read()
+    assert len(da) == len(db), f"{a} ({len(da)} B) vs {b} ({len(db)} B)"
+    assert da == db, f"{a} differs from {b}"
+
+
+def assert_same_mc(a, b):
+    ma, mb = F.mc_as_sorted_pairs(F.read_mc(a)), F.mc_as_sorted_pairs(F.read_mc(b))
+    assert ma.shape == mb.shape and np.array_equal(ma, mb), f"{a} vs {b}: count tables differ as sets"
+
+
+def assert_same_ovlp(a, b):
+    ra, rb = F.normalise_ovlp(F.read_ovlp(a)), F.normalise_ovlp(F.read_ovlp(b))
+    assert len(ra) == len(rb), f"{a}: {len(ra)} records vs reference {len(rb)}"
+    if len(ra):
+        neq = np.nonzero(ra.view(np.uint8).reshape(-1, 64) != rb.view(np.uint8).reshape(-1, 64))[0]
+        assert neq.size == 0, f"{a}: first differing record {neq[0]}: {ra[neq[0]]} vs {rb[neq[0]]}"
+
+
+def compare_index(ref_p, our_p, T, levels=("L0", "L2")):
+    for c in range(1, T + 1):
+        for lv in levels:
+            sfx = f"{c:02d}-of-{T:02d}.dat"
+            assert_same_bytes(f"{our_p}-{lv}-{sfx}", f"{ref_p}-{lv}-{sfx}")
+            assert_same_mc(f"{our_p}-{lv}-MC-{sfx}", f"{ref_p}-{lv}-MC-{sfx}")
+
+
+@pytest.fixture(scope="module")
+def sim1(workdir):
+    return D.make_sim(workdir, "sim1", genome=1_000_000, cov=20)
+
+
+def test_index_and_overlap_single_chunk(sim1, workdir, ref_dir):
+    """BASELINE.json configs[0] shape: T_idx = T_ovlp = 1, k=16 w=80 r=6 l=2."""
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
+    op = ours_index(sim1, os.path.join(workdir, "sim1/our1"), T=1, extra=["-m", "1"])
+    compare_index(rp, op, 1)
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref1"), T=1)
+    oo = ours_overlap(sim1, op, 2, os.path.join(workdir, "sim1/our1"), T=1)
+    assert_same_ovlp(oo[0], ro[0])
+    assert os.path.getsize(ro[0]) > 64 * 1000
+
+
+def test_multi_chunk(sim1, workdir, ref_dir):
+    """T_idx=3, T_ovlp=2 (exercises rid % T selection, file concatenation order and c % T == 0)."""
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref3"), T=3, extra=["-m", "0"])
+    op = ours_index(sim1, os.path.join(workdir, "sim1/our3"), T=3, extra=["-m", "0"])
+    compare_index(rp, op, 3, levels=("L2",))
+    assert not os.path.exists(f"{op}-L0-01-of-03.dat")
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref3"), T=2)
+    # our overlap reads OUR index files
+    oo = ours_overlap(sim1, op, 2, os.path.join(workdir, "sim1/our3"), T=2)
+    for a, b in zip(oo, ro):
+        assert_same_ovlp(a, b)
+
+
+@pytest.mark.parametrize("k,w,r,l", [(14, 60, 6, 2), (18, 120, 3, 2), (16, 80, 36, 1), (12, 24, 2, 2), (28, 255, 6, 2)])
+def test_index_parameter_sweep(sim1, workdir, ref_dir, k, w, r, l):
+    tag = f"k{k}w{w}r{r}l{l}"
+    ex = ["-k", str(k), "-w", str(w), "-r", str(r), "-l", str(l), "-m", "1"]
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, f"sim1/ref_{tag}"), T=1, extra=ex)
+    op = ours_index(sim1, os.path.join(workdir, f"sim1/our_{tag}"), T=1, extra=ex)
+    compare_index(rp, op, 1, levels=("L0", f"L{l}"))
+
+
+@pytest.mark.parametrize("extra", [["-w", "50"], ["-w", "200"], ["-b", "2", "-n", "40"], ["-m", "3", "-M", "60"], ["-b", "8", "-n", "500", "-M", "1000"]])
+def test_overlap_parameter_sweep(sim1, workdir, ref_dir, extra):
+    tag = "_".join(x.strip("-") for x in extra)
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, f"sim1/refo_{tag}"), T=1, extra=extra)
+    oo = ours_overlap(sim1, rp, 2, os.path.join(workdir, f"sim1/ouro_{tag}"), T=1, extra=extra)
+    assert_same_ovlp(oo[0], ro[0])
+
+
+def test_adversarial_reads(workdir, ref_dir):
+    """N runs, tandem repeats / poly-A (hash ties), palindromic k-mers, reads shorter than k or than one window."""
+    p = D.make_from_fasta(workdir, "adv", D.adversarial_records(), ref_dir)
+    for ex in (["-m", "1"], ["-m", "1", "-k", "12", "-w", "24", "-r", "2"], ["-m", "1", "-k", "18", "-w", "120", "-r", "3"]):
+        tag = "".join(ex).replace("-", "")
+        rp = D.ref_index(ref_dir, p, os.path.join(workdir, f"adv/ref_{tag}"), T=2, extra=ex)
+        op = ours_index(p, os.path.join(workdir, f"adv/our_{tag}"), T=2, extra=ex)
+        compare_index(rp, op, 2)
+        ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, f"adv/ref_{tag}"), T=1)
+        oo = ours_overlap(p, op, 2, os.path.join(workdir, f"adv/our_{tag}"), T=1)
+        assert_same_ovlp(oo[0], ro[0])
+
+
+def test_noisy_reads_one_percent(workdir, ref_dir):
+    """The E. coli test's error rate (1 %, test/ecoli_K12/simulate_reads.py:13): wider live band, more rejected alignments."""
+    p = D.make_sim(workdir, "sim_e1", genome=400_000, cov=25, err=0.01, seed=7)
+    rp = D.ref_index(ref_dir, p, os.path.join(workdir, "sim_e1/ref"), T=1, extra=["-m", "0"])
+    op = ours_index(p, os.path.join(workdir, "sim_e1/our"), T=1, extra=["-m", "0"])
+    compare_index(rp, op, 1, levels=("L2",))
+    for ex in ([], ["-w", "50"]):
+        ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, "sim_e1/ref" + "".join(ex)), T=1, extra=ex)
+        oo = ours_overlap(p, op, 2, os.path.join(workdir, "sim_e1/our" + "".join(ex)), T=1, extra=ex)
+        assert_same_ovlp(oo[0], ro[0])
+
+
+def test_engine_api_matches_cli(sim1, workdir, ref_dir):
+    """Stage-level C ABI (device hand-off of L2, no files) gives the same records as the file-based tools."""
+    from peregrine_b200 import Engine
+
+    rid, ln, off = F.read_idx(sim1 + ".idx")
+    seqdb = np.fromfile(sim1 + ".seqdb", dtype=np.uint8)
+    eng = Engine(0)
+    eng.load_reads(seqdb, rid, ln, off)
+    eng.index(80, 16, 6, 2, with_counts=0b100)
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
+    assert np.array_equal(eng.level(2), F.read_mmlist(rp + "-L2-01-of-01.dat"))
+    assert np.array_equal(F.mc_as_sorted_pairs(eng.level_counts(2)), F.mc_as_sorted_pairs(F.read_mc(rp + "-L2-MC-01-of-01.dat")))
+    eng.set_shimmers_from_index(2)
+    ov = eng.overlap(1, 1)
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref1"), T=1)
+    ref = F.normalise_ovlp(F.read_ovlp(ro[0]))
+    assert len(ov) == len(ref) and ov.tobytes() == ref.tobytes()
+    st = eng.stats()
+    assert st["kernel_launches"] > 10 and st["n_alignments"] >= len(ref)
+    eng.close()
+
+
+def test_empty_and_tiny_inputs(workdir, ref_dir):
+    """Chunks with no reads, reads with no minimizer, and an index with no eligible bucket."""
+    recs = [("t/000000/0_5", "ACGTA"), ("t/000001/0_40", "ACGTTGCAAGGCTTAACCGGTTAACCGGATATCGCGATAT" )]
+    p = D.make_from_fasta(workdir, "tiny", recs, ref_dir)
+    rp = D.ref_index(ref_dir, p, os.path.join(workdir, "tiny/ref"), T=3, extra=["-m", "1"])
+    op = ours_index(p, os.path.join(workdir, "tiny/our"), T=3, extra=["-m", "1"])
+    compare_index(rp, op, 3)
+    ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, "tiny/ref"), T=1)
+    oo = ours_overlap(p, op, 2, os.path.join(workdir, "tiny/our"), T=1)
+    assert_same_ovlp(oo[0], ro[0])
