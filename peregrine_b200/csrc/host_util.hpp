@@ -199,6 +199,15 @@ struct KhashEmu {
     ++size;
     ++nocc;
   }
+  // kh_put of a key that is ALREADY present still runs the load-factor check first (khash.h:289-297), so a put of an
+  // existing key that follows the insertion which filled the table to its upper bound rehashes it.  Only the last such
+  // put matters for the final layout (a pending rehash would otherwise happen, identically, at the next new key).
+  void touch_existing() {
+    if (nocc >= ub) {
+      if (nb > (size << 1)) resize(nb - 1);
+      else resize(nb + 1);
+    }
+  }
   template <class F>
   void for_each_in_slot_order(F &&f) const {
     for (uint32_t i = 0; i < nb; i++)

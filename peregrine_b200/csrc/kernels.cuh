@@ -261,7 +261,7 @@ __global__ void k_pair_write(const mm128 *__restrict__ mm, const uint32_t *__res
 // ------------------------------------------------------------------------------------------------ bucket tables
 // X table: distinct full x values -> slot (a dense id).  B table: (slot(x0)<<32 | slot(x1)) -> bucket.
 __global__ void k_bucket_insert(PairSoA r, uint32_t n_rec, uint64_t *xkeys, uint32_t xmask, uint64_t *bkeys, uint32_t bmask,
-                                uint32_t *bcount, uint32_t *bfirst, uint32_t *rec_bucket, int *err) {
+                                uint32_t *bcount, uint32_t *bfirst, uint32_t *blast, uint32_t *rec_bucket, int *err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rec) return;
   uint32_t s0 = ht_insert(xkeys, xmask, r.k0[i]);
@@ -271,12 +271,13 @@ __global__ void k_bucket_insert(PairSoA r, uint32_t n_rec, uint64_t *xkeys, uint
   if (b == PGB_NOSLOT) { atomicOr(err, 16); return; }
   atomicAdd(&bcount[b], 1u);
   atomicMin(&bfirst[b], r.seq[i]);
+  atomicMax(&blast[b], r.seq[i]);
   rec_bucket[i] = b;
 }
-struct BucketInfo { uint64_t k0, k1; uint32_t first_seq, count, slot, pad; };
+struct BucketInfo { uint64_t k0, k1; uint32_t first_seq, count, slot, last_seq; };
 __global__ void k_bucket_dump(const uint64_t *__restrict__ xkeys, const uint64_t *__restrict__ bkeys,
                               const uint32_t *__restrict__ bcount, const uint32_t *__restrict__ bfirst,
-                              const uint32_t *__restrict__ pos, size_t cap, BucketInfo *out) {
+                              const uint32_t *__restrict__ blast, const uint32_t *__restrict__ pos, size_t cap, BucketInfo *out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap || bkeys[i] == PGB_EMPTY) return;
   BucketInfo b;
@@ -286,7 +287,7 @@ __global__ void k_bucket_dump(const uint64_t *__restrict__ xkeys, const uint64_t
   b.first_seq = bfirst[i];
   b.count = bcount[i];
   b.slot = (uint32_t)i;
-  b.pad = 0;
+  b.last_seq = blast[i];
   out[pos[i]] = b;
 }
 // records of eligible buckets -> rank-ordered arrays (arbitrary order inside the bucket; sorted next)

@@ -533,21 +533,22 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   c->tic();
   uint32_t xcap = pow2_at_least(4 * (uint64_t)nrec), bcap = pow2_at_least(2 * (uint64_t)nrec);
   uint64_t *xkeys = c->alloc<uint64_t>(xcap), *bkeys = c->alloc<uint64_t>(bcap);
-  uint32_t *bcount = c->alloc<uint32_t>(bcap), *bfirst = c->alloc<uint32_t>(bcap), *rec_bucket = c->alloc<uint32_t>(nrec);
+  uint32_t *bcount = c->alloc<uint32_t>(bcap), *bfirst = c->alloc<uint32_t>(bcap), *blast = c->alloc<uint32_t>(bcap), *rec_bucket = c->alloc<uint32_t>(nrec);
   LAUNCH(c, k_fill_u64, 1184, 256, xkeys, PGB_EMPTY, (size_t)xcap);
   LAUNCH(c, k_fill_u64, 1184, 256, bkeys, PGB_EMPTY, (size_t)bcap);
   CU(cudaMemsetAsync(bcount, 0, (size_t)bcap * 4, c->st));
   CU(cudaMemsetAsync(bfirst, 0xFF, (size_t)bcap * 4, c->st));
-  LAUNCH(c, k_bucket_insert, nblk(nrec), 256, R, nrec, xkeys, xcap - 1, bkeys, bcap - 1, bcount, bfirst, rec_bucket, c->d_err);
+  CU(cudaMemsetAsync(blast, 0, (size_t)bcap * 4, c->st));
+  LAUNCH(c, k_bucket_insert, nblk(nrec), 256, R, nrec, xkeys, xcap - 1, bkeys, bcap - 1, bcount, bfirst, blast, rec_bucket, c->d_err);
   uint32_t *bflags = c->alloc<uint32_t>((size_t)bcap + 1), *bpos = c->alloc<uint32_t>((size_t)bcap + 1);
   CU(cudaMemsetAsync(bflags, 0, ((size_t)bcap + 1) * 4, c->st));
   LAUNCH(c, k_mc_flags, nblk(bcap), 256, bkeys, (size_t)bcap, bflags);
   uint32_t n_buckets = scan_u32(c, bflags, bpos, (size_t)bcap + 1);
   BucketInfo *d_binfo = c->alloc<BucketInfo>(n_buckets);
-  LAUNCH(c, k_bucket_dump, nblk(bcap), 256, xkeys, bkeys, bcount, bfirst, bpos, (size_t)bcap, d_binfo);
+  LAUNCH(c, k_bucket_dump, nblk(bcap), 256, xkeys, bkeys, bcount, bfirst, blast, bpos, (size_t)bcap, d_binfo);
   std::vector<BucketInfo> binfo(n_buckets);
   c->d2h(binfo.data(), d_binfo, (size_t)n_buckets * sizeof(BucketInfo));
-  c->release(d_binfo); c->release(bflags); c->release(bpos); c->release(xkeys); c->release(bkeys); c->release(bcount); c->release(bfirst);
+  c->release(d_binfo); c->release(bflags); c->release(bpos); c->release(xkeys); c->release(bkeys); c->release(bcount); c->release(bfirst); c->release(blast);
   if (c->check_err("pgb_overlap/buckets")) { free_R(); c->release(rec_bucket); return -1; }
   c->stats.ms_buckets += c->toc();
   c->stats.n_buckets += n_buckets;
@@ -564,23 +565,31 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     std::unordered_map<uint64_t, uint32_t> outer_id;
     outer_id.reserve(n_buckets);
     std::vector<uint32_t> head, next(n_buckets, PGB_NOSLOT), tail;  // per-outer linked list of buckets in insertion order
+    std::vector<uint32_t> o_last;                                    // per outer key: last put (record sequence number)
+    uint32_t newest_outer_seq = 0, last_seq_all = 0;
     for (uint32_t oi = 0; oi < n_buckets; oi++) {
       uint32_t b = order[oi];
+      last_seq_all = std::max(last_seq_all, binfo[b].last_seq);
       auto it = outer_id.find(binfo[b].k0);
       if (it == outer_id.end()) {
         uint32_t id = (uint32_t)head.size();
         outer_id.emplace(binfo[b].k0, id);
         outer.put_new(binfo[b].k0, id);
-        head.push_back(b); tail.push_back(b);
+        newest_outer_seq = binfo[b].first_seq;
+        head.push_back(b); tail.push_back(b); o_last.push_back(binfo[b].last_seq);
       } else {
         next[tail[it->second]] = b; tail[it->second] = b;
+        o_last[it->second] = std::max(o_last[it->second], binfo[b].last_seq);
       }
     }
+    if (last_seq_all > newest_outer_seq) outer.touch_existing();  // a put of a known outer key followed the last new one
     rank_off.push_back(0);
     KhashEmu inner;
     outer.for_each_in_slot_order([&](uint64_t, uint32_t id) {
       inner.clear();
-      for (uint32_t b = head[id]; b != PGB_NOSLOT; b = next[b]) inner.put_new(binfo[b].k1, b);
+      uint32_t newest_inner_seq = 0;
+      for (uint32_t b = head[id]; b != PGB_NOSLOT; b = next[b]) { inner.put_new(binfo[b].k1, b); newest_inner_seq = binfo[b].first_seq; }
+      if (o_last[id] > newest_inner_seq) inner.touch_existing();
       inner.for_each_in_slot_order([&](uint64_t, uint32_t b) {
         uint32_t nn = binfo[b].count;
         if (nn <= 2 || nn > ovlp_upper) return;  // src/shmr_overlap.c:216

@@ -192,7 +192,7 @@ static int cmd_match(int argc, char **argv) {
 
 // ------------------------------------------------------------------------------------------------------------ overlap
 struct PairRec { uint64_t k0, k1, y0, y1; uint32_t seq; uint8_t dir; };
-struct Bucket { uint64_t k0, k1; uint32_t first_seq; std::vector<uint32_t> recs; };
+struct Bucket { uint64_t k0, k1; uint32_t first_seq; std::vector<uint32_t> recs; uint32_t last_seq = 0; };
 
 struct HostCtx {
   const Packed *P;
@@ -278,28 +278,37 @@ static int cmd_overlap(int argc, char **argv) {
   for (uint32_t r = 0; r < recs.size(); r++) {
     auto key = std::make_pair(recs[r].k0, recs[r].k1);
     auto it = bidx.find(key);
-    if (it == bidx.end()) { bidx[key] = (uint32_t)buckets.size(); buckets.push_back({recs[r].k0, recs[r].k1, recs[r].seq, {}}); it = bidx.find(key); }
+    if (it == bidx.end()) { bidx[key] = (uint32_t)buckets.size(); buckets.push_back(Bucket{recs[r].k0, recs[r].k1, recs[r].seq, {}, 0}); it = bidx.find(key); }
     buckets[it->second].recs.push_back(r);
+    buckets[it->second].last_seq = recs[r].seq;
   }
   // khash visiting order: outer keys by first insertion, inner keys per outer by first insertion
   // (buckets vector is already in first-seq order because recs are in seq order)
   KhashEmu outer;
   std::unordered_map<uint64_t, uint32_t> outer_id;
   std::vector<std::vector<uint32_t>> inner_lists;
+  std::vector<uint32_t> o_last;
+  uint32_t newest_outer_seq = 0, last_seq_all = 0;
   for (uint32_t b = 0; b < buckets.size(); b++) {
+    last_seq_all = std::max(last_seq_all, buckets[b].last_seq);
     auto it = outer_id.find(buckets[b].k0);
     if (it == outer_id.end()) {
       uint32_t id = (uint32_t)inner_lists.size();
       outer_id[buckets[b].k0] = id;
       outer.put_new(buckets[b].k0, id);
+      newest_outer_seq = buckets[b].first_seq;
       inner_lists.emplace_back();
       inner_lists[id].push_back(b);
-    } else inner_lists[it->second].push_back(b);
+      o_last.push_back(buckets[b].last_seq);
+    } else { inner_lists[it->second].push_back(b); o_last[it->second] = std::max(o_last[it->second], buckets[b].last_seq); }
   }
+  if (last_seq_all > newest_outer_seq) outer.touch_existing();
   std::vector<uint32_t> visit;  // eligible buckets in visiting order
   outer.for_each_in_slot_order([&](uint64_t, uint32_t id) {
     KhashEmu inner;
-    for (uint32_t b : inner_lists[id]) inner.put_new(buckets[b].k1, b);
+    uint32_t newest_inner_seq = 0;
+    for (uint32_t b : inner_lists[id]) { inner.put_new(buckets[b].k1, b); newest_inner_seq = buckets[b].first_seq; }
+    if (o_last[id] > newest_inner_seq) inner.touch_existing();
     inner.for_each_in_slot_order([&](uint64_t, uint32_t b) {
       size_t nn = buckets[b].recs.size();
       if (nn <= 2 || nn > ovlp_upper) return;
@@ -307,6 +316,7 @@ static int cmd_overlap(int argc, char **argv) {
     });
   });
   printf("buckets=%zu outer=%zu eligible=%zu\n", buckets.size(), inner_lists.size(), visit.size());
+  if (getenv("PGB_SIM_VISIT")) { FILE *f = fopen(getenv("PGB_SIM_VISIT"), "w"); for (uint32_t b : visit) fprintf(f, "VISIT %lu %lu %zu\n", (unsigned long)buckets[b].k0, (unsigned long)buckets[b].k1, buckets[b].recs.size()); fclose(f); }
   // sorted record arrays per eligible bucket: stable, descending position (glibc qsort with mp128_comp)
   std::vector<std::vector<uint64_t>> by0(visit.size());
   std::vector<std::vector<uint8_t>> bdir(visit.size());
@@ -378,6 +388,7 @@ static int cmd_overlap(int argc, char **argv) {
       if (pass > 200) { printf("no convergence\n"); break; }
     }
   }
+  if (getenv("PGB_SIM_DUMP")) { FILE *f = fopen(getenv("PGB_SIM_DUMP"), "wb"); fwrite(out.data(), 64, out.size(), f); fclose(f); }
   size_t nb = 0;
   size_t m = std::min(out.size(), ref.size());
   for (size_t i = 0; i < m; i++) if (memcmp(&out[i], &ref[i], sizeof(ovlp_rec)) != 0) { if (nb < 5) fprintf(stderr, "record %zu differs\n", i); nb++; }
