@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — SHIMMER index + read-to-read overlap throughput on B200 (BASELINE.json metric: overlaps/s and read-bases/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (pack -> mm_sketch -> mm_reduce x2 -> count -> build_map -> bucket order ->
+replay/ovlp_match fix-point -> ovlp records) over one synthetic read set.  Workload at N=1 = BASELINE.json configs[1]:
+synthetic 50 Mb genome, 30x 15 kb reads at 99.5 % accuracy, k=16 w=80 r=6 l=2, single chunk (T=1).  At N>1 (torchrun)
+the genome grows with N (weak scaling: 50 Mb per GPU) and hash chunk c of T=N is owned by rank c-1.
+
+  value  = overlaps/s with the .seqdb image already resident in HBM (device-resident step, CUDA-event timed)
+  e2e    = the same through the public C ABI with HOST buffers: pinned .seqdb -> H2D -> ... -> ovlp records -> D2H
+  --impl reference : the unmodified reference tools (oracle/_ref, built from /root/reference/src) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+PARAMS = dict(w=80, k=16, r=6, levels=2, bestn=4, mc_lower=2, mc_upper=240, bw=100, ovlp_upper=120)
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def work_dir():
+    d = os.environ.get("PGB_WORK", "/tmp/pgb_bench")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def make_dataset(name, genome, cov, seed=42, err=0.005):
+    import datasets as D
+
+    return D.make_sim(work_dir(), name, genome=genome, cov=cov, err=err, seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.p = device, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=2)
+            except Exception:
+                self.p.kill()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference / cpu legs
+def ref_one(prefix, outdir):
+    """index + overlap of one read set with the unmodified reference tools, T=1 (one core)."""
+    import datasets as D
+
+    t = time.perf_counter()
+    rp = D.ref_index(REF, prefix, outdir, T=1, extra=["-m", "0"])
+    ro = D.ref_overlap(REF, prefix, rp, 2, outdir, T=1)
+    return os.path.getsize(ro[0]) // 64, time.perf_counter() - t
+
+
+def cpu_baseline_single_core(genome=6_000_000, cov=30):
+    from peregrine_b200 import formats as F
+
+    p = make_dataset(f"cpu1_g{genome}", genome, cov, seed=1234)
+    _, ln, _ = F.read_idx(p + ".idx")
+    n, dt = ref_one(p, os.path.join(work_dir(), f"cpu1_g{genome}", "ref"))
+    return {"value": n / dt, "unit": "overlaps/s", "cores": 1, "kind": "reference",
+            "read_bases_per_s": float(ln.sum()) / dt,
+            "sample": f"oracle/_ref shmr_index+shmr_overlap (unmodified reference), {genome/1e6:g} Mb genome {cov:g}x, T=1, one core, {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    from concurrent.futures import ThreadPoolExecutor
+    from peregrine_b200 import formats as F
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    g = int(args.ref_genome_mb * 1e6)
+    sets = [make_dataset(f"ref_g{g}_s{i}", g, args.cov, seed=1000 + i) for i in range(cores)]
+    bases = sum(int(F.read_idx(p + ".idx")[1].sum()) for p in sets)
+
+    def step():
+        t = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            res = list(ex.map(lambda i: ref_one(sets[i], os.path.join(os.path.dirname(sets[i]), "ref")), range(cores)))
+        return sum(r[0] for r in res), time.perf_counter() - t
+
+    for _ in range(args.warmup):
+        step()
+    tot_n, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        n, dt = step()
+        tot_n += n
+        tot_t += dt
+    v = tot_n / tot_t
+    sample = (f"{cores} independent {args.ref_genome_mb:g} Mb genomes at {args.cov:g}x (same read model), one reference process per core, "
+              f"T=1 each; {tot_n // args.steps} overlaps per step")
+    print(json.dumps({
+        "impl": "reference", "metric": "overlaps/s (index+overlap)", "value": v, "unit": "overlaps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "read_bases_per_s": bases * args.steps / tot_t,
+        "config": {"workload": "synthetic 30x 15 kb reads @99.5%, k=16 w=80 r=6 l=2, T=1 (bounded sample of configs[1])", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "overlaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+
+    from peregrine_b200 import Engine, formats as F
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    genome = int(args.genome_mb * 1e6) * world
+    if rank == 0:
+        prefix = make_dataset(f"g{genome}", genome, args.cov)
+    if world > 1:
+        dist.barrier()
+    prefix = os.path.join(work_dir(), f"g{genome}", "seq")
+    rid, ln, off = F.read_idx(prefix + ".idx")
+    nbytes = os.path.getsize(prefix + ".seqdb")
+    pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    seqdb = pinned.numpy()
+    with open(prefix + ".seqdb", "rb") as f:
+        f.readinto(memoryview(seqdb))
+    bases = int(ln.sum())
+    eng = Engine(local)
+    P = PARAMS
+    T = world
+    c = rank + 1
+
+    def compute(copy):
+        eng.index(P["w"], P["k"], P["r"], P["levels"], 0)
+        eng.set_shimmers_from_index(2)
+        return eng.overlap(T, c, P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy=copy)
+
+    if world > 1:
+        raise SystemExit("multi-GPU bench path is wired in a later commit")
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    # ---- end-to-end: host buffers in, host records out (this also warms the allocator pool)
+    def e2e_step():
+        eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False)
+        return compute(copy=True)
+
+    for _ in range(max(args.warmup, 1)):
+        ov = e2e_step()
+    n_ovl = len(ov)
+    eng.stats_reset()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ov = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    st_e2e = eng.stats()
+
+    # ---- device-resident: .seqdb image already in HBM, records stay in HBM; CUDA events on the library's stream
+    eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=True)
+
+    def dev_step():
+        eng.repack()
+        return compute(copy=False)
+
+    for _ in range(args.warmup):
+        dev_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    eng.stats_reset()
+    barrier()
+    eng.event_record(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_dev = dev_step()
+    eng.event_record(1)
+    barrier()
+    dev_wall = (time.perf_counter() - t0) / args.steps
+    dev_ms = eng.event_elapsed_ms(0, 1) / args.steps
+    clocks = sampler.stop()
+    st = eng.stats()
+    eng.close()
+    assert n_dev == n_ovl
+
+    # ---- roofline of the dominant kernel (HBM-bound integer work; algorithmic bytes per SURVEY 8d / DESIGN.md)
+    peak, peak_src = measured_peaks()
+    K = args.steps
+    kern = {
+        "k_sketch_exact<count>": (st["ms_k_sketch_count"], st["n_k_sketch_count"], bases / 4.0),
+        "k_sketch_exact<write>": (st["ms_k_sketch_write"], st["n_k_sketch_write"], bases / 4.0 + 16.0 * st["n_l0"] / K),
+        "k_align": (st["ms_k_align"], st["n_k_align"], (st["n_align_bases"] / 4.0 + 64.0 * st["n_alignments"]) / max(st["n_k_align"], 1)),
+        "k_replay": (st["ms_k_replay"], st["n_k_replay"], 16.0 * st["n_candidates"] / K + 9.0 * st["n_pair_records"] / K),
+    }
+    top = max(kern, key=lambda k_: kern[k_][0])
+    ms_tot, n_l, bytes_per_launch = kern[top]
+    avg_ms = ms_tot / max(n_l, 1)
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_l / K,
+                "kernel_ms_per_step": {k_: v[0] / K for k_, v in kern.items()}}
+    cpu = cpu_baseline_single_core() if (rank == 0 and not args.no_cpu_baseline) else None
+    out = {
+        "metric": "overlaps/s (index+overlap)", "value": n_ovl / (dev_ms * 1e-3), "unit": "overlaps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "read_bases_per_s": bases / (dev_ms * 1e-3),
+        "config": {"workload": f"synthetic {args.genome_mb * world:g} Mb genome, {args.cov:g}x 15 kb reads @99.5%, k=16 w=80 r=6 l=2, T={T}",
+                   "reads": int(len(rid)), "bases": bases, "overlaps_per_step": int(n_ovl), "l2_flush": "inputs (1.5 GB image) exceed the 126 MB L2",
+                   "wall_ms_per_step_device_resident": dev_wall * 1e3},
+        "e2e": {"value": n_ovl / e2e_s, "unit": "overlaps/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"] // K, "d2h_bytes_per_step": st_e2e["d2h_bytes"] // K,
+                "ms_per_step": e2e_s * 1e3, "read_bases_per_s": bases / e2e_s},
+        "gpu_launches": int(st["kernel_launches"]),
+        "clocks": clocks,
+        "roofline": roofline,
+        "stage_ms_per_step": {k_: st[k_] / K for k_ in st if k_.startswith("ms_") and not k_.startswith("ms_k_")},
+        "counts_per_step": {k_: st[k_] // K for k_ in ("n_l0", "n_l1", "n_l2", "n_pair_records", "n_buckets", "n_eligible_buckets", "n_candidates",
+                                                         "n_alignments", "n_replay_passes")},
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome-mb", type=float, default=50.0, help="genome size per GPU (BASELINE.json configs[1]: 50 Mb)")
+    ap.add_argument("--cov", type=float, default=30.0)
+    ap.add_argument("--ref-genome-mb", type=float, default=4.0, help="reference arm: genome size of each per-core sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

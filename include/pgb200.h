@@ -117,8 +117,15 @@ typedef struct {
   uint64_t bases_packed, bases_sketched, n_l0, n_l1, n_l2;
   uint64_t n_pair_records, n_buckets, n_eligible_buckets, n_candidates;
   uint64_t n_alignments, n_align_bases, n_replay_passes, n_overlaps;
+  /* per-kernel CUDA-event time (sum over launches) and launch counts of the three heavy kernels */
+  double ms_k_sketch_count, ms_k_sketch_write, ms_k_align, ms_k_replay;
+  uint64_t n_k_sketch_count, n_k_sketch_write, n_k_align, n_k_replay;
 } pgb_stats;
 void pgb_stats_reset(pgb_ctx *);
+/* CUDA events on the context's stream (the stream every kernel of this library is launched on): record slot 0..7, then
+ * read the device time between two recorded slots. */
+int pgb_event_record(pgb_ctx *, int slot);
+double pgb_event_elapsed_ms(pgb_ctx *, int slot_a, int slot_b);
 void pgb_stats_get(pgb_ctx *, pgb_stats *out);
 
 #ifdef __cplusplus

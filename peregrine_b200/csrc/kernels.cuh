@@ -405,7 +405,7 @@ __global__ void k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__res
 __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint64_t *__restrict__ w,
                         const uint32_t *__restrict__ nm, const uint64_t *__restrict__ woff_by_rid,
                         const uint32_t *__restrict__ rlen_by_rid, const uint32_t *__restrict__ hasn_by_rid, int bw, match_t *results,
-                        int *err) {
+                        int *err, unsigned long long *bases_total) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   AlnReq q = reqs[first + i];
@@ -418,6 +418,8 @@ __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_
   ovlp_match_core(qv, (int)(rl0 - q.start0), tv, (int)rl1, bw, Va, Vb, PGB_MAXV, &m, &e);
   if (e) atomicOr(err, 128 | (e << 8));
   results[first + i] = m;
+  // bases actually compared along the final path (algorithmic-bytes accounting, SURVEY 8d: (q_end + t_end)/4 per alignment)
+  atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
 }
 
 __global__ void k_table_diff(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, size_t n, unsigned long long *diffs) {

@@ -46,7 +46,9 @@ struct pgb_ctx {
   cudaStream_t st = nullptr;
   std::string err;
   pgb_stats stats;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned long long *d_align_bases = nullptr;
 
   // ---- reads
   size_t n_rows = 0;        // selected rows
@@ -85,6 +87,14 @@ struct pgb_ctx {
     CU(cudaEventSynchronize(ev1));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    return ms;
+  }
+  void ktic() { CU(cudaEventRecord(evk0, st)); }
+  double ktoc() {
+    CU(cudaEventRecord(evk1, st));
+    CU(cudaEventSynchronize(evk1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, evk0, evk1));
     return ms;
   }
   void h2d(void *d, const void *h, size_t bytes) {
@@ -187,12 +197,17 @@ extern "C" pgb_ctx *pgb_create(int device) {
     CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreate(&c->evk0));
+    CU(cudaEventCreate(&c->evk1));
+    for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->user_ev[i]));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     c->d_err = c->alloc<int>(1);
     CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
+    c->d_align_bases = c->alloc<unsigned long long>(1);
+    CU(cudaMemsetAsync(c->d_align_bases, 0, 8, c->st));
     c->sync();
     return c;
   } catch (std::exception &e) {
@@ -208,15 +223,32 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   c->free_reads();
   c->release(c->d_ovl);
   c->release(c->d_err);
+  c->release(c->d_align_bases);
   cudaStreamSynchronize(c->st);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->evk0);
+  cudaEventDestroy(c->evk1);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(c->user_ev[i]);
   cudaStreamDestroy(c->st);
   delete c;
 }
 extern "C" const char *pgb_last_error(pgb_ctx *c) { return c ? c->err.c_str() : "null context"; }
 extern "C" void pgb_stats_reset(pgb_ctx *c) { memset(&c->stats, 0, sizeof c->stats); }
 extern "C" void pgb_stats_get(pgb_ctx *c, pgb_stats *out) { *out = c->stats; }
+extern "C" int pgb_event_record(pgb_ctx *c, int slot) {
+  if (!c || slot < 0 || slot > 7) return -1;
+  cudaSetDevice(c->device);
+  return cudaEventRecord(c->user_ev[slot], c->st) == cudaSuccess ? 0 : -1;
+}
+extern "C" double pgb_event_elapsed_ms(pgb_ctx *c, int a, int b) {
+  if (!c || a < 0 || a > 7 || b < 0 || b > 7) return -1.0;
+  cudaSetDevice(c->device);
+  float ms = -1.f;
+  if (cudaEventSynchronize(c->user_ev[b]) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, c->user_ev[a], c->user_ev[b]) != cudaSuccess) return -1.0;
+  return ms;
+}
 
 #define API_BEGIN(c)          \
   if (!(c)) return -1;        \
@@ -398,13 +430,17 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   // ---- L0
   c->tic();
   CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
+  c->ktic();
   LAUNCH(c, k_sketch_exact<false>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
          c->d_row_woff, c->d_hasn_by_rid, w, k, counts, (const uint64_t *)nullptr, (mm128 *)nullptr);
+  c->stats.ms_k_sketch_count += c->ktoc(); c->stats.n_k_sketch_count++;
   c->d_level_off[0] = c->alloc<uint64_t>(ns + 1);
   c->level_n[0] = scan_u32_to_u64(c, counts, c->d_level_off[0], ns + 1);
   c->d_level[0] = c->alloc<mm128>(c->level_n[0]);
+  c->ktic();
   LAUNCH(c, k_sketch_exact<true>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
          c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, c->d_level_off[0], c->d_level[0]);
+  c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
   c->stats.ms_sketch += c->toc();
   c->stats.bases_sketched += c->sel_bases;
   c->stats.n_l0 += c->level_n[0];
@@ -644,8 +680,10 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     c->tic();
     LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
     CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
+    c->ktic();
     LAUNCH(c, k_replay, nblk(n_ranks, 64), 64, S, n_ranks, d_rank_off, sy0, sdir, contained, bestn, wet ? 1 : 0, 0, acc,
            (const uint32_t *)nullptr, (ovlp_rec *)nullptr, d_ctr);
+    c->stats.ms_k_replay += c->ktoc(); c->stats.n_k_replay++;
     LAUNCH(c, k_table_diff, 1184, 256, S.eold, S.enew, (size_t)ecap, d_ctr + 1);
     unsigned long long ctr[2];
     uint32_t n_req = 0;
@@ -657,9 +695,16 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     if (n_req > S.n_done) {
       c->tic();
       uint32_t nn = n_req - S.n_done;
+      c->ktic();
       LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, S.n_done, nn, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
-             (int)bw, S.results, c->d_err);
-      c->sync();
+             (int)bw, S.results, c->d_err, c->d_align_bases);
+      c->stats.ms_k_align += c->ktoc(); c->stats.n_k_align++;
+      {
+        unsigned long long ab = 0;
+        c->d2h(&ab, c->d_align_bases, 8);
+        c->stats.n_align_bases += ab;
+        CU(cudaMemsetAsync(c->d_align_bases, 0, 8, c->st));
+      }
       c->stats.ms_align += c->toc();
       c->stats.n_alignments += nn;
       if (c->check_err("pgb_overlap/align")) { free_S(); return -1; }
@@ -952,7 +997,7 @@ extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_
     AlnReq *d_q = c->alloc<AlnReq>(1);
     match_t *d_m = c->alloc<match_t>(1);
     c->h2d(d_q, &q, sizeof q);
-    LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err);
+    LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err, c->d_align_bases);
     c->d2h(rtn, d_m, sizeof(match_t));
     c->release(d_q); c->release(d_m);
     if (c->check_err("ovlp_match")) { fprintf(stderr, "pgb200: %s\n", pgb_last_error(c)); exit(1); }

@@ -40,6 +40,8 @@ class _Stats(C.Structure):
         + [(n, C.c_uint64) for n in ("bases_packed", "bases_sketched", "n_l0", "n_l1", "n_l2", "n_pair_records",
                                      "n_buckets", "n_eligible_buckets", "n_candidates", "n_alignments",
                                      "n_align_bases", "n_replay_passes", "n_overlaps")]
+        + [(n, C.c_double) for n in ("ms_k_sketch_count", "ms_k_sketch_write", "ms_k_align", "ms_k_replay")]
+        + [(n, C.c_uint64) for n in ("n_k_sketch_count", "n_k_sketch_write", "n_k_align", "n_k_replay")]
     )
 
 
@@ -80,6 +82,9 @@ def load_library():
     L.pgb_overlap_copy.argtypes = [vp, vp]
     L.pgb_stats_reset.argtypes = [vp]
     L.pgb_stats_get.argtypes = [vp, C.POINTER(_Stats)]
+    L.pgb_event_record.argtypes = [vp, C.c_int]
+    L.pgb_event_elapsed_ms.restype = C.c_double
+    L.pgb_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int]
     L.pgb_shmr_index_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     L.pgb_shmr_overlap_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     _lib = L
@@ -186,6 +191,12 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ stats
+    def event_record(self, slot):
+        self.L.pgb_event_record(self.h, slot)
+
+    def event_elapsed_ms(self, a, b):
+        return self.L.pgb_event_elapsed_ms(self.h, a, b)
+
     def stats_reset(self):
         self.L.pgb_stats_reset(self.h)
 
