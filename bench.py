@@ -241,8 +241,7 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     K = args.steps
     kern = {
-        "k_sketch_exact<count>": (st["ms_k_sketch_count"], st["n_k_sketch_count"], bases / 4.0),
-        "k_sketch_exact<write>": (st["ms_k_sketch_write"], st["n_k_sketch_write"], bases / 4.0 + 16.0 * st["n_l0"] / K),
+        "k_sketch_tiled": (st["ms_k_sketch_tiled"], st["n_k_sketch_tiled"], bases / 4.0 + 16.0 * st["n_l0"] / K),
         "k_align": (st["ms_k_align"], st["n_k_align"], (st["n_align_bases"] / 4.0 + 64.0 * st["n_alignments"]) / max(st["n_k_align"], 1)),
         "k_replay": (st["ms_k_replay"], st["n_k_replay"], 16.0 * st["n_candidates"] / K + 9.0 * st["n_pair_records"] / K),
     }

@@ -120,6 +120,8 @@ typedef struct {
   /* per-kernel CUDA-event time (sum over launches) and launch counts of the three heavy kernels */
   double ms_k_sketch_count, ms_k_sketch_write, ms_k_align, ms_k_replay;
   uint64_t n_k_sketch_count, n_k_sketch_write, n_k_align, n_k_replay;
+  double ms_k_sketch_tiled;
+  uint64_t n_k_sketch_tiled, n_sketch_fallback_reads;
 } pgb_stats;
 void pgb_stats_reset(pgb_ctx *);
 /* CUDA events on the context's stream (the stream every kernel of this library is launched on): record slot 0..7, then

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "shimmer_core.cuh"
+#include "sketch_tile.cuh"
+#include "khash_small.cuh"
 
 namespace pgb {
 
@@ -109,22 +111,23 @@ __global__ void k_pack_reads(const uint8_t *__restrict__ raw, const uint64_t *__
 }
 
 // ------------------------------------------------------------------------------------------------ sketch (exact automaton)
-// Thread per read.  WRITE=false: count only.  WRITE=true: write at out + out_off[sel].
+// Thread per read of `list` (row indices).  WRITE=false: cnt_by_row[row] = number of minimizers.  WRITE=true: write at
+// out + off_by_row[row].
 template <bool WRITE>
 __global__ void k_sketch_exact(const uint64_t *__restrict__ w, const uint32_t *__restrict__ nm,
-                               const uint32_t *__restrict__ sel_rows, uint32_t n_sel, const uint32_t *__restrict__ row_rid,
+                               const uint32_t *__restrict__ list, uint32_t n_list, const uint32_t *__restrict__ row_rid,
                                const uint32_t *__restrict__ row_len, const uint64_t *__restrict__ row_woff,
-                               const uint32_t *__restrict__ hasn_by_rid, int wsz, int k, uint32_t *__restrict__ counts,
-                               const uint64_t *__restrict__ out_off, mm128 *__restrict__ out) {
+                               const uint32_t *__restrict__ hasn_by_rid, int wsz, int k, uint32_t *__restrict__ cnt_by_row,
+                               const uint64_t *__restrict__ off_by_row, mm128 *__restrict__ out) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_sel) return;
-  uint32_t row = sel_rows[t];
+  if (t >= n_list) return;
+  uint32_t row = list[t];
   uint32_t rid = row_rid[row];
   int len = (int)row_len[row];
   uint64_t ring_x[256];
   uint32_t ring_p[256];
   uint32_t n = 0;
-  mm128 *dst = WRITE ? out + out_off[t] : nullptr;
+  mm128 *dst = WRITE ? out + off_by_row[row] : nullptr;
   if (len > 0) {
     sketch_exact(w, hasn_by_rid[rid] ? nm : nullptr, row_woff[row], len, wsz, k, rid, ring_x, ring_p,
                  [&](uint64_t x, uint64_t y) {
@@ -135,7 +138,188 @@ __global__ void k_sketch_exact(const uint64_t *__restrict__ w, const uint32_t *_
                    n++;
                  });
   }
-  if (!WRITE) counts[t] = n;
+  if (!WRITE) cnt_by_row[row] = n;
+}
+
+// Segment-parallel form of the exact automaton for the reads the tiled kernel hands back: one thread replays one
+// SEG-position segment of one read (warm-up before it, w slots after it; see sketch_exact_range).
+template <bool WRITE>
+__global__ void k_sketch_exact_seg(const uint64_t *__restrict__ w, const uint32_t *__restrict__ nm, const uint32_t *__restrict__ seg_row,
+                                   const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_first, uint32_t n_seg, int seg_len,
+                                   const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ row_len,
+                                   const uint64_t *__restrict__ row_woff, const uint32_t *__restrict__ hasn_by_rid, int wsz, int k,
+                                   uint32_t *__restrict__ seg_cnt, const uint32_t *__restrict__ seg_pos,
+                                   const uint64_t *__restrict__ off_by_row, mm128 *__restrict__ out) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  const uint32_t row = seg_row[s];
+  const uint32_t rid = row_rid[row];
+  const int len = (int)row_len[row];
+  const int lo = (int)seg_lo[s];
+  const int hi = lo + seg_len < len ? lo + seg_len : len;
+  uint64_t ring_x[256];
+  uint32_t ring_p[256];
+  uint32_t n = 0;
+  mm128 *dst = WRITE ? out + off_by_row[row] + (seg_pos[s] - seg_pos[seg_first[s]]) : nullptr;
+  auto em = [&](uint64_t x, uint64_t y) {
+    if (WRITE) {
+      dst[n].x = x;
+      dst[n].y = y;
+    }
+    n++;
+  };
+  const uint32_t *nmp = hasn_by_rid[rid] ? nm : nullptr;
+  int st = lo - sketch_warmup_len(wsz, k);
+  if (st < 0) st = 0;
+  if (!sketch_exact_range(w, nmp, row_woff[row], len, wsz, k, rid, st, lo, hi, ring_x, ring_p, em)) {
+    n = 0;  // warm-up too short (palindrome-dense stretch): replay from the read start
+    sketch_exact_range(w, nmp, row_woff[row], len, wsz, k, rid, 0, lo, hi, ring_x, ring_p, em);
+  }
+  if (!WRITE) seg_cnt[s] = n;
+}
+__global__ void k_seg_row_counts(const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_first_seg, uint32_t n_list,
+                                 const uint32_t *__restrict__ seg_pos, uint32_t *cnt_by_row) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_list) return;
+  cnt_by_row[list[i]] = seg_pos[list_first_seg[i + 1]] - seg_pos[list_first_seg[i]];
+}
+
+// ------------------------------------------------------------------------------------------------ sketch (tiled fast path)
+// exclusive block scan of one u32 per thread (256 threads); returns the prefix, *total gets the block sum
+__device__ __forceinline__ uint32_t block_exscan_256(uint32_t v, uint32_t *scratch /* >= 9 u32 */, uint32_t *total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) scratch[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t t = lane < 8 ? scratch[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, t, d);
+      if (lane >= d) t += y;
+    }
+    if (lane < 8) scratch[lane] = t;  // inclusive warp totals
+  }
+  __syncthreads();
+  uint32_t base = wid ? scratch[wid - 1] : 0;
+  *total = scratch[7];
+  __syncthreads();  // scratch may be reused by the caller
+  return base + x - v;
+}
+
+// One CTA = one tile of one read.  tile_off[row] = first tile of the row (exclusive prefix, n_rows+1 entries).
+// Output: tile_cnt[tile] records in tmp[tile * SK_CAP ...] (position order); row_flags[row] |= reason when the read must be
+// redone by the exact automaton (the tile then reports 0 records).
+template <class HT>
+__global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__restrict__ w, const uint32_t *__restrict__ tile_off, uint32_t n_rows,
+                                                             const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ row_len,
+                                                             const uint64_t *__restrict__ row_woff, const uint32_t *__restrict__ hasn_by_rid,
+                                                             int wsz, int k, uint32_t *__restrict__ tile_cnt, uint32_t *row_flags,
+                                                             mm128 *__restrict__ tmp, uint32_t tile_cap) {
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  SkShared<HT> &sh = *reinterpret_cast<SkShared<HT> *>(sk_smem);
+  const uint32_t tile = blockIdx.x;
+  const int tid = threadIdx.x;
+  // owning row: last row with tile_off[row] <= tile
+  uint32_t lo = 0, hi = n_rows;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const uint32_t row = lo;
+  const int j = (int)(tile - tile_off[row]);
+  SkParams p;
+  p.w = w; p.word_off = row_woff[row]; p.len = (int)row_len[row]; p.rid = row_rid[row]; p.wsz = wsz; p.k = k;
+  const int H = sk_halo(wsz), TILE = sk_tile_len(wsz);
+  p.r0 = j * TILE - H; p.first_tile = j == 0;
+  if (hasn_by_rid[p.rid] || p.len < sk_min_len(wsz, k)) {  // block-uniform
+    if (tid == 0) {
+      atomicOr(&row_flags[row], hasn_by_rid[p.rid] ? (uint32_t)SK_FLAG_N : (uint32_t)SK_FLAG_SHORT);
+      tile_cnt[tile] = 0;
+    }
+    return;
+  }
+  if (tid == 0) { sh.n_pal = 0; sh.n_halo_slots = 0; sh.flags = 0; }
+  __syncthreads();
+  HT hv[SK_G];
+  uint16_t ps[SK_G];
+  uint32_t slot_mask, np, hs;
+  sk_phase1<HT>(tid, p, H, hv, ps, &slot_mask, &np, &hs);
+  if (np) atomicAdd(&sh.n_pal, np);
+  if (hs) atomicAdd(&sh.n_halo_slots, hs);
+  uint32_t total = 0;
+  const uint32_t slot_base = block_exscan_256((uint32_t)__popc(slot_mask), sh.scan, &total);
+  if (tid == 0) sh.n_slots = total;
+  __syncthreads();
+  if (sh.n_pal > SK_PALPAD) {
+    if (tid == 0) { atomicOr(&row_flags[row], (uint32_t)SK_FLAG_PAL); tile_cnt[tile] = 0; }
+    return;
+  }
+  sk_phase2_write<HT>(sh, hv, ps, slot_mask, slot_base);
+  __syncthreads();
+  sk_phase3_group<HT>(tid, sh);
+  if (tid + SK_THREADS < SK_NG) sk_phase3_group<HT>(tid + SK_THREADS, sh);
+  __syncthreads();
+  int s_eval, s_emit, s_first_full;
+  sk_ranges(p, sh.n_halo_slots, &s_eval, &s_emit, &s_first_full);
+  uint32_t tie = sk_phase4_group<HT>(tid, sh, wsz, s_eval);
+  if (tid + SK_THREADS < SK_NG) tie |= sk_phase4_group<HT>(tid + SK_THREADS, sh, wsz, s_eval);
+  if (tie) atomicOr(&sh.flags, (uint32_t)SK_FLAG_TIE);
+  __syncthreads();
+  if (sh.flags) {
+    if (tid == 0) { atomicOr(&row_flags[row], sh.flags); tile_cnt[tile] = 0; }
+    return;
+  }
+  // groups tid (first stride) precede groups tid+256 (second stride) in slot order: scan both counts in one packed word
+  const uint32_t cA = sk_phase5_group<HT, false>(tid, sh, p, s_emit, s_first_full, nullptr);
+  const uint32_t cB = (tid + SK_THREADS < SK_NG) ? sk_phase5_group<HT, false>(tid + SK_THREADS, sh, p, s_emit, s_first_full, nullptr) : 0u;
+  uint32_t packed_total = 0;
+  const uint32_t pre = block_exscan_256(cA | (cB << 16), sh.scan, &packed_total);
+  const uint32_t totA = packed_total & 0xFFFFu, totB = packed_total >> 16;
+  if (totA + totB > tile_cap) {
+    if (tid == 0) { atomicOr(&row_flags[row], (uint32_t)SK_FLAG_OVERFLOW); tile_cnt[tile] = 0; }
+    return;
+  }
+  mm128 *dst = tmp + (size_t)tile * tile_cap;
+  if (cA) sk_phase5_group<HT, true>(tid, sh, p, s_emit, s_first_full, dst + (pre & 0xFFFFu));
+  if (cB) sk_phase5_group<HT, true>(tid + SK_THREADS, sh, p, s_emit, s_first_full, dst + totA + (pre >> 16));
+  if (tid == 0) tile_cnt[tile] = totA + totB;
+}
+
+// per row: minimizer count from its tiles, or mark it for the exact automaton
+__global__ void k_row_counts(const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ row_flags,
+                             uint32_t n_rows, uint32_t *cnt_by_row, uint32_t *exact_flag) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  if (row_flags[row]) { cnt_by_row[row] = 0; exact_flag[row] = 1; return; }
+  uint32_t n = 0;
+  for (uint32_t t = tile_off[row]; t < tile_off[row + 1]; t++) n += tile_cnt[t];
+  cnt_by_row[row] = n;
+  exact_flag[row] = 0;
+}
+// 64 threads per tile copy its records to their final place
+__global__ void k_tile_gather(const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_cnt, const uint32_t *__restrict__ row_flags,
+                              uint32_t n_rows, uint32_t n_tiles, const uint64_t *__restrict__ off_by_row, const mm128 *__restrict__ tmp,
+                              uint32_t tile_cap, mm128 *__restrict__ out) {
+  const uint32_t tile = blockIdx.x * (blockDim.x / 64) + threadIdx.x / 64;
+  if (tile >= n_tiles) return;
+  uint32_t lo = 0, hi = n_rows;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const uint32_t row = lo;
+  if (row_flags[row]) return;
+  uint64_t at = off_by_row[row];
+  for (uint32_t t = tile_off[row]; t < tile; t++) at += tile_cnt[t];
+  const uint32_t n = tile_cnt[tile];
+  const mm128 *src = tmp + (size_t)tile * tile_cap;
+  for (uint32_t i = threadIdx.x % 64; i < n; i += 64) out[at + i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------ reduce
@@ -261,7 +445,7 @@ __global__ void k_pair_write(const mm128 *__restrict__ mm, const uint32_t *__res
 // ------------------------------------------------------------------------------------------------ bucket tables
 // X table: distinct full x values -> slot (a dense id).  B table: (slot(x0)<<32 | slot(x1)) -> bucket.
 __global__ void k_bucket_insert(PairSoA r, uint32_t n_rec, uint64_t *xkeys, uint32_t xmask, uint64_t *bkeys, uint32_t bmask,
-                                uint32_t *bcount, uint32_t *bfirst, uint32_t *blast, uint32_t *rec_bucket, int *err) {
+                                uint32_t *bcount, uint32_t *bfirst, uint32_t *blast, uint32_t *xfirst, uint32_t *rec_bucket, int *err) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rec) return;
   uint32_t s0 = ht_insert(xkeys, xmask, r.k0[i]);
@@ -272,24 +456,120 @@ __global__ void k_bucket_insert(PairSoA r, uint32_t n_rec, uint64_t *xkeys, uint
   atomicAdd(&bcount[b], 1u);
   atomicMin(&bfirst[b], r.seq[i]);
   atomicMax(&blast[b], r.seq[i]);
+  atomicMin(&xfirst[s0], r.seq[i]);  // first put of this x as an OUTER key (kh_put(MMER0, ..), src/shmr_utils.c:338,363)
   rec_bucket[i] = b;
 }
-struct BucketInfo { uint64_t k0, k1; uint32_t first_seq, count, slot, last_seq; };
-__global__ void k_bucket_dump(const uint64_t *__restrict__ xkeys, const uint64_t *__restrict__ bkeys,
-                              const uint32_t *__restrict__ bcount, const uint32_t *__restrict__ bfirst,
-                              const uint32_t *__restrict__ blast, const uint32_t *__restrict__ pos, size_t cap, BucketInfo *out) {
+// ---- visiting order of the buckets, computed on the GPU (DESIGN.md "bucket order")
+// occupied bucket slots -> compact list + their first-insertion sequence numbers (sort keys)
+__global__ void k_bucket_list(const uint64_t *__restrict__ bkeys, const uint32_t *__restrict__ bfirst, const uint32_t *__restrict__ pos,
+                              size_t cap, uint32_t *slot_out, uint32_t *key_out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap || bkeys[i] == PGB_EMPTY) return;
-  BucketInfo b;
-  uint64_t key = bkeys[i];
-  b.k0 = xkeys[(uint32_t)(key >> 32)];
-  b.k1 = xkeys[(uint32_t)key];
-  b.first_seq = bfirst[i];
-  b.count = bcount[i];
-  b.slot = (uint32_t)i;
-  b.last_seq = blast[i];
-  out[pos[i]] = b;
+  slot_out[pos[i]] = (uint32_t)i;
+  key_out[pos[i]] = bfirst[i];
 }
+// buckets sorted by first sequence: is this bucket the one that inserted its outer key?
+__global__ void k_outer_first(const uint32_t *__restrict__ sslot, uint32_t n, const uint64_t *__restrict__ bkeys,
+                              const uint32_t *__restrict__ bfirst, const uint32_t *__restrict__ xfirst, uint32_t *isfirst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t slot = sslot[i];
+  uint32_t s0 = (uint32_t)(bkeys[slot] >> 32);
+  isfirst[i] = bfirst[slot] == xfirst[s0];
+}
+// outer id = number of distinct outer keys inserted before (first-insertion order)
+__global__ void k_outer_id_first(const uint32_t *__restrict__ sslot, uint32_t n, const uint64_t *__restrict__ bkeys,
+                                 const uint32_t *__restrict__ isfirst, const uint32_t *__restrict__ firstpos, uint32_t *xid) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !isfirst[i]) return;
+  xid[(uint32_t)(bkeys[sslot[i]] >> 32)] = firstpos[i];
+}
+__global__ void k_outer_id_all(const uint32_t *__restrict__ sslot, uint32_t n, const uint64_t *__restrict__ bkeys,
+                               const uint32_t *__restrict__ xid, uint32_t *oid, uint32_t *idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  oid[i] = xid[(uint32_t)(bkeys[sslot[i]] >> 32)];
+  idx[i] = i;
+}
+// grouped order (stable sort by outer id): gather per-bucket attributes, mark group starts
+struct GroupedBuckets {
+  uint32_t *slot, *first, *last, *count, *oid;
+  uint64_t *k1;
+};
+__global__ void k_group_gather(const uint32_t *__restrict__ gidx, const uint32_t *__restrict__ goid_sorted, uint32_t n,
+                               const uint32_t *__restrict__ sslot, const uint64_t *__restrict__ bkeys, const uint64_t *__restrict__ xkeys,
+                               const uint32_t *__restrict__ bfirst, const uint32_t *__restrict__ blast, const uint32_t *__restrict__ bcount,
+                               GroupedBuckets g, uint32_t *goff, uint32_t n_outer, uint64_t *okey, unsigned int *last_seq_all) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint32_t slot = sslot[gidx[j]];
+  uint64_t key = bkeys[slot];
+  uint32_t o = goid_sorted[j];
+  g.slot[j] = slot;
+  g.first[j] = bfirst[slot];
+  g.last[j] = blast[slot];
+  g.count[j] = bcount[slot];
+  g.oid[j] = o;
+  g.k1[j] = xkeys[(uint32_t)key];
+  if (j == 0 || goid_sorted[j - 1] != o) {
+    goff[o] = j;
+    okey[o] = xkeys[(uint32_t)(key >> 32)];
+  }
+  if (j == n - 1) goff[n_outer] = n;
+  atomicMax(last_seq_all, blast[slot]);
+}
+// one thread per outer key: replay its inner khash, write each bucket's visiting position inside the group
+__global__ void k_inner_order(const uint32_t *__restrict__ goff, uint32_t n_outer, GroupedBuckets g, uint32_t *ipos, uint32_t *big_list,
+                              uint32_t *n_big) {
+  uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_outer) return;
+  uint32_t b = goff[o], n = goff[o + 1] - b;
+  if (n == 1) { ipos[b] = 0; return; }
+  if (n > KHS_MAX_KEYS) {  // replayed on the host
+    big_list[atomicAdd(n_big, 1u)] = o;
+    return;
+  }
+  uint64_t keys[KHS_MAX_KEYS];
+  uint8_t rank[KHS_MAX_KEYS];
+  uint32_t last = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    keys[i] = g.k1[b + i];
+    uint32_t l = g.last[b + i];
+    if (l > last) last = l;
+  }
+  khs_order(keys, n, last > g.first[b + n - 1], rank);
+  for (uint32_t i = 0; i < n; i++) ipos[b + i] = rank[i];
+}
+// group sizes in outer visiting order
+__global__ void k_group_sizes_by_rank(const uint32_t *__restrict__ goff, const uint32_t *__restrict__ orank, uint32_t n_outer, uint32_t *size_by_rank) {
+  uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_outer) return;
+  size_by_rank[orank[o]] = goff[o + 1] - goff[o];
+}
+// place every bucket at its visiting position; eligibility per src/shmr_overlap.c:216
+__global__ void k_visit_place(GroupedBuckets g, uint32_t n, const uint32_t *__restrict__ orank, const uint32_t *__restrict__ vstart,
+                              const uint32_t *__restrict__ ipos, uint32_t ovlp_upper, uint32_t *vis_slot, uint32_t *vis_elig, uint32_t *vis_cnt,
+                              unsigned long long *n_cand) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  uint32_t v = vstart[orank[g.oid[j]]] + ipos[j];
+  uint32_t c = g.count[j];
+  bool el = !(c <= 2 || c > ovlp_upper);
+  vis_slot[v] = g.slot[j];
+  vis_elig[v] = el;
+  vis_cnt[v] = el ? c : 0;
+  if (el) atomicAdd(n_cand, (unsigned long long)c * (c - 1) / 2);
+}
+__global__ void k_visit_rank(const uint32_t *__restrict__ vis_slot, const uint32_t *__restrict__ vis_elig, const uint32_t *__restrict__ rank_of,
+                             const uint32_t *__restrict__ off_of, uint32_t n, uint32_t *slot2rank, uint32_t *rank_off) {
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  if (vis_elig[v]) {
+    slot2rank[vis_slot[v]] = rank_of[v];
+    rank_off[rank_of[v]] = off_of[v];
+  }
+}
+
 // records of eligible buckets -> rank-ordered arrays (arbitrary order inside the bucket; sorted next)
 __global__ void k_scatter(PairSoA r, uint32_t n_rec, const uint32_t *__restrict__ rec_bucket, const uint32_t *__restrict__ slot2rank,
                           const uint32_t *__restrict__ rank_off, uint32_t *fill, uint64_t *sy0, uint64_t *sy1, uint32_t *sseq,

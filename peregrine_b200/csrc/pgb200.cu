@@ -3,6 +3,7 @@
 // keys-only khash model that fixes the bucket visiting order, and drives the replay/align fix-point loop.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <fcntl.h>
@@ -60,6 +61,7 @@ struct pgb_ctx {
   uint32_t *d_rlen_by_rid = nullptr, *d_hasn_by_rid = nullptr; uint64_t *d_woff_by_rid = nullptr;
   uint32_t *d_row_rid = nullptr, *d_row_len = nullptr; uint64_t *d_row_woff = nullptr, *d_row_raw_off = nullptr;
   uint32_t *d_sel_rows = nullptr;  // identity 0..n_rows-1 (rows are already the selected ones)
+  std::vector<uint32_t> h_row_len;
   // ---- index levels
   mm128 *d_level[3] = {nullptr, nullptr, nullptr};
   uint64_t *d_level_off[3] = {nullptr, nullptr, nullptr};
@@ -72,13 +74,53 @@ struct pgb_ctx {
   ovlp_rec *d_ovl = nullptr; size_t n_ovl = 0;
   int *d_err = nullptr;
 
-  template <class T> T *alloc(size_t n) {
+  // persistent device memory (reads, index levels, overlap output)
+  template <class T> T *palloc(size_t n) {
     void *p = nullptr;
     CU(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st));
     return (T *)p;
   }
+  // stage temporaries: bump allocation out of slabs that are kept for the lifetime of the context, reset at the end of every
+  // API call (no per-step cudaMalloc/cudaFree traffic once the slabs have reached their steady-state size)
+  struct Slab { char *base; size_t cap, used; };
+  std::vector<Slab> slabs;
+  template <class T> T *alloc(size_t n) {
+    size_t bytes = ((n ? n : 1) * sizeof(T) + 255) & ~(size_t)255;
+    for (auto &sl : slabs)
+      if (sl.cap - sl.used >= bytes) { T *p = (T *)(sl.base + sl.used); sl.used += bytes; return p; }
+    size_t cap = std::max(bytes, (size_t)512 << 20);
+    void *b = nullptr;
+    CU(cudaMalloc(&b, cap));
+    slabs.push_back(Slab{(char *)b, cap, bytes});
+    return (T *)b;
+  }
+  bool in_scratch(const void *p) const {
+    for (auto &sl : slabs)
+      if ((const char *)p >= sl.base && (const char *)p < sl.base + sl.cap) return true;
+    return false;
+  }
+  void scratch_reset() {
+    // coalesce into one slab once the total demand of a call is known, so later calls never allocate again
+    size_t total = 0, used = 0;
+    for (auto &sl : slabs) { total += sl.cap; used += sl.used; }
+    if (slabs.size() > 1) {
+      cudaStreamSynchronize(st);
+      for (auto &sl : slabs) cudaFree(sl.base);
+      slabs.clear();
+      void *b = nullptr;
+      size_t cap = used + (used >> 3) + ((size_t)64 << 20);
+      if (cudaMalloc(&b, cap) == cudaSuccess) slabs.push_back(Slab{(char *)b, cap, 0});
+    }
+    for (auto &sl : slabs) sl.used = 0;
+    (void)total;
+  }
+  void scratch_free() {
+    for (auto &sl : slabs) cudaFree(sl.base);
+    slabs.clear();
+  }
   template <class T> void release(T *&p) {
-    if (p) { cudaFreeAsync((void *)p, st); p = nullptr; }
+    if (p && !in_scratch((const void *)p)) cudaFreeAsync((void *)p, st);
+    p = nullptr;
   }
   void sync() { CU(cudaStreamSynchronize(st)); }
   void tic() { CU(cudaEventRecord(ev0, st)); }
@@ -173,6 +215,17 @@ static uint32_t scan_u32(pgb_ctx *c, const uint32_t *d_in, uint32_t *d_out, size
   return total;
 }
 
+// stable LSD radix sort of (u32 key, u32 value) pairs (cub::DeviceRadixSort is stable)
+static void sort_pairs_u32(pgb_ctx *c, const uint32_t *kin, uint32_t *kout, const uint32_t *vin, uint32_t *vout, uint32_t n) {
+  if (!n) return;
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, kin, kout, vin, vout, (int)n, 0, 32, c->st));
+  uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+  CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, kin, kout, vin, vout, (int)n, 0, 32, c->st));
+  c->stats.kernel_launches += 9;  // histogram + 4 x (scan, downsweep) passes of 8 bits
+  c->release(tmp);
+}
+
 // ================================================================================================ context
 extern "C" int pgb_device_count(void) {
   int n = 0;
@@ -204,9 +257,9 @@ extern "C" pgb_ctx *pgb_create(int device) {
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    c->d_err = c->alloc<int>(1);
+    c->d_err = c->palloc<int>(1);
     CU(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->st));
-    c->d_align_bases = c->alloc<unsigned long long>(1);
+    c->d_align_bases = c->palloc<unsigned long long>(1);
     CU(cudaMemsetAsync(c->d_align_bases, 0, 8, c->st));
     c->sync();
     return c;
@@ -225,6 +278,7 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   c->release(c->d_err);
   c->release(c->d_align_bases);
   cudaStreamSynchronize(c->st);
+  c->scratch_free();
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaEventDestroy(c->evk0);
@@ -259,8 +313,12 @@ extern "C" double pgb_event_elapsed_ms(pgb_ctx *c, int a, int b) {
   }                               \
   catch (std::exception & e) {    \
     (c)->err = e.what();          \
+    cudaStreamSynchronize((c)->st); \
+    (c)->scratch_reset();         \
     return -1;                    \
   }                               \
+  cudaStreamSynchronize((c)->st); \
+  (c)->scratch_reset();           \
   return (c)->err.empty() ? 0 : -1;
 
 // ================================================================================================ reads
@@ -308,12 +366,13 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
   }
   words += 2;
   c->n_rows = nsel; c->n_words = words; c->sel_bases = raw; c->raw_bytes = raw;
-  c->d_raw = c->alloc<uint8_t>(raw + 64);
-  c->d_w = c->alloc<uint64_t>(words); c->d_nm = c->alloc<uint32_t>(words);
-  c->d_rlen_by_rid = c->alloc<uint32_t>((size_t)max_rid + 1); c->d_hasn_by_rid = c->alloc<uint32_t>((size_t)max_rid + 1);
-  c->d_woff_by_rid = c->alloc<uint64_t>((size_t)max_rid + 1);
-  c->d_row_rid = c->alloc<uint32_t>(nsel); c->d_row_len = c->alloc<uint32_t>(nsel);
-  c->d_row_woff = c->alloc<uint64_t>(nsel); c->d_row_raw_off = c->alloc<uint64_t>(nsel); c->d_sel_rows = c->alloc<uint32_t>(nsel);
+  c->h_row_len = h_len;
+  c->d_raw = c->palloc<uint8_t>(raw + 64);
+  c->d_w = c->palloc<uint64_t>(words); c->d_nm = c->palloc<uint32_t>(words);
+  c->d_rlen_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1); c->d_hasn_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1);
+  c->d_woff_by_rid = c->palloc<uint64_t>((size_t)max_rid + 1);
+  c->d_row_rid = c->palloc<uint32_t>(nsel); c->d_row_len = c->palloc<uint32_t>(nsel);
+  c->d_row_woff = c->palloc<uint64_t>(nsel); c->d_row_raw_off = c->palloc<uint64_t>(nsel); c->d_sel_rows = c->palloc<uint32_t>(nsel);
   std::vector<uint32_t> ident(nsel);
   for (size_t j = 0; j < nsel; j++) ident[j] = (uint32_t)j;
   c->h2d(c->d_rlen_by_rid, h_rlen_by_rid.data(), h_rlen_by_rid.size() * 4);
@@ -430,17 +489,104 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   // ---- L0
   c->tic();
   CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
-  c->ktic();
-  LAUNCH(c, k_sketch_exact<false>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
-         c->d_row_woff, c->d_hasn_by_rid, w, k, counts, (const uint64_t *)nullptr, (mm128 *)nullptr);
-  c->stats.ms_k_sketch_count += c->ktoc(); c->stats.n_k_sketch_count++;
-  c->d_level_off[0] = c->alloc<uint64_t>(ns + 1);
-  c->level_n[0] = scan_u32_to_u64(c, counts, c->d_level_off[0], ns + 1);
-  c->d_level[0] = c->alloc<mm128>(c->level_n[0]);
-  c->ktic();
-  LAUNCH(c, k_sketch_exact<true>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
-         c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, c->d_level_off[0], c->d_level[0]);
-  c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
+  c->d_level_off[0] = c->palloc<uint64_t>(ns + 1);
+  const char *force = getenv("PGB_SKETCH");
+  const bool use_tiled = w >= SK_GS + 1 && !(force && !strcmp(force, "exact")) && ns > 0;
+  if (!use_tiled) {
+    // exact automaton for every read (tiny windows, or PGB_SKETCH=exact)
+    c->ktic();
+    LAUNCH(c, k_sketch_exact<false>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
+           c->d_row_woff, c->d_hasn_by_rid, w, k, counts, (const uint64_t *)nullptr, (mm128 *)nullptr);
+    c->stats.ms_k_sketch_count += c->ktoc(); c->stats.n_k_sketch_count++;
+    c->level_n[0] = scan_u32_to_u64(c, counts, c->d_level_off[0], ns + 1);
+    c->d_level[0] = c->palloc<mm128>(c->level_n[0]);
+    c->ktic();
+    LAUNCH(c, k_sketch_exact<true>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
+           c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, c->d_level_off[0], c->d_level[0]);
+    c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
+  } else {
+    // tiled fast path; reads it flags (N, ties, palindrome-dense, short, overflow) are redone by the exact automaton
+    const int TILE = sk_tile_len(w);
+    std::vector<uint32_t> h_tile_off(ns + 1);
+    uint64_t nt = 0;
+    for (size_t i = 0; i < ns; i++) { h_tile_off[i] = (uint32_t)nt; nt += (c->h_row_len[i] + (uint32_t)TILE - 1) / (uint32_t)TILE; }
+    h_tile_off[ns] = (uint32_t)nt;
+    if (nt >= (1ull << 31)) throw std::runtime_error("too many sketch tiles in one pgb_index call");
+    const uint32_t n_tiles = (uint32_t)nt;
+    uint32_t *tile_off = c->alloc<uint32_t>(ns + 1), *tile_cnt = c->alloc<uint32_t>(n_tiles), *row_flags = c->alloc<uint32_t>(ns);
+    uint32_t *exact_flag = c->alloc<uint32_t>(ns + 1), *exact_pos = c->alloc<uint32_t>(ns + 1);
+    // per-tile record budget: 3x the expected 2/(w+1) density, at most SK_CAP
+    uint32_t tile_cap = (uint32_t)((3 * 2 * TILE) / (w + 1) + 31) & ~31u;
+    if (tile_cap < 64) tile_cap = 64;
+    if (tile_cap > SK_CAP) tile_cap = SK_CAP;
+    mm128 *tmp = c->alloc<mm128>((size_t)n_tiles * tile_cap);
+    c->h2d(tile_off, h_tile_off.data(), (ns + 1) * 4);
+    CU(cudaMemsetAsync(row_flags, 0, ns * 4, c->st));
+    CU(cudaMemsetAsync(exact_flag, 0, (ns + 1) * 4, c->st));
+    c->ktic();
+    if (k <= 16) {
+      size_t smem = sizeof(SkShared<uint32_t>);
+      CU(cudaFuncSetAttribute(k_sketch_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (n_tiles) {
+        k_sketch_tiled<uint32_t><<<n_tiles, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
+                                                                       c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap);
+        c->stats.kernel_launches++;
+        CU(cudaGetLastError());
+      }
+    } else {
+      size_t smem = sizeof(SkShared<uint64_t>);
+      CU(cudaFuncSetAttribute(k_sketch_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (n_tiles) {
+        k_sketch_tiled<uint64_t><<<n_tiles, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
+                                                                       c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap);
+        c->stats.kernel_launches++;
+        CU(cudaGetLastError());
+      }
+    }
+    c->stats.ms_k_sketch_tiled += c->ktoc(); c->stats.n_k_sketch_tiled++;
+    LAUNCH(c, k_row_counts, nblk(ns), 256, tile_off, tile_cnt, row_flags, (uint32_t)ns, counts, exact_flag);
+    uint32_t n_exact = scan_u32(c, exact_flag, exact_pos, ns + 1);
+    uint32_t *exact_list = nullptr, *seg_row = nullptr, *seg_lo = nullptr, *seg_first = nullptr, *list_first = nullptr, *seg_cnt = nullptr, *seg_pos = nullptr;
+    uint32_t n_seg = 0;
+    const int SEG = 1024;
+    if (n_exact) {
+      exact_list = c->alloc<uint32_t>(n_exact);
+      LAUNCH(c, k_compact_idx, nblk(ns), 256, exact_flag, exact_pos, ns, exact_list);
+      std::vector<uint32_t> h_list(n_exact), h_seg_row, h_seg_lo, h_seg_first, h_list_first(n_exact + 1);
+      c->d2h(h_list.data(), exact_list, (size_t)n_exact * 4);
+      for (uint32_t i = 0; i < n_exact; i++) {
+        uint32_t row = h_list[i], len = c->h_row_len[row];
+        h_list_first[i] = (uint32_t)h_seg_row.size();
+        for (uint32_t lo = 0; lo < len; lo += SEG) { h_seg_row.push_back(row); h_seg_lo.push_back(lo); h_seg_first.push_back(h_list_first[i]); }
+      }
+      n_seg = (uint32_t)h_seg_row.size();
+      h_list_first[n_exact] = n_seg;
+      seg_row = c->alloc<uint32_t>(n_seg); seg_lo = c->alloc<uint32_t>(n_seg); seg_first = c->alloc<uint32_t>(n_seg);
+      list_first = c->alloc<uint32_t>((size_t)n_exact + 1); seg_cnt = c->alloc<uint32_t>((size_t)n_seg + 1); seg_pos = c->alloc<uint32_t>((size_t)n_seg + 1);
+      c->h2d(seg_row, h_seg_row.data(), (size_t)n_seg * 4); c->h2d(seg_lo, h_seg_lo.data(), (size_t)n_seg * 4);
+      c->h2d(seg_first, h_seg_first.data(), (size_t)n_seg * 4); c->h2d(list_first, h_list_first.data(), ((size_t)n_exact + 1) * 4);
+      CU(cudaMemsetAsync(seg_cnt, 0, ((size_t)n_seg + 1) * 4, c->st));
+      c->ktic();
+      LAUNCH(c, k_sketch_exact_seg<false>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
+             c->d_row_woff, c->d_hasn_by_rid, w, k, seg_cnt, (const uint32_t *)nullptr, (const uint64_t *)nullptr, (mm128 *)nullptr);
+      c->stats.ms_k_sketch_count += c->ktoc(); c->stats.n_k_sketch_count++;
+      scan_u32(c, seg_cnt, seg_pos, (size_t)n_seg + 1);
+      LAUNCH(c, k_seg_row_counts, nblk(n_exact), 256, exact_list, list_first, n_exact, seg_pos, counts);
+    }
+    c->stats.n_sketch_fallback_reads += n_exact;
+    c->level_n[0] = scan_u32_to_u64(c, counts, c->d_level_off[0], ns + 1);
+    c->d_level[0] = c->palloc<mm128>(c->level_n[0]);
+    LAUNCH(c, k_tile_gather, nblk((size_t)n_tiles * 64, 256), 256, tile_off, tile_cnt, row_flags, (uint32_t)ns, n_tiles, c->d_level_off[0], tmp,
+           tile_cap, c->d_level[0]);
+    if (n_exact) {
+      c->ktic();
+      LAUNCH(c, k_sketch_exact_seg<true>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
+             c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, seg_pos, c->d_level_off[0], c->d_level[0]);
+      c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
+      c->release(exact_list); c->release(seg_row); c->release(seg_lo); c->release(seg_first); c->release(list_first); c->release(seg_cnt); c->release(seg_pos);
+    }
+    c->release(tile_off); c->release(tile_cnt); c->release(row_flags); c->release(exact_flag); c->release(exact_pos); c->release(tmp);
+  }
   c->stats.ms_sketch += c->toc();
   c->stats.bases_sketched += c->sel_bases;
   c->stats.n_l0 += c->level_n[0];
@@ -450,9 +596,9 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
     LAUNCH(c, k_reduce<false>, nblk(ns, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r, counts,
            (const uint64_t *)nullptr, (mm128 *)nullptr);
-    c->d_level_off[l] = c->alloc<uint64_t>(ns + 1);
+    c->d_level_off[l] = c->palloc<uint64_t>(ns + 1);
     c->level_n[l] = scan_u32_to_u64(c, counts, c->d_level_off[l], ns + 1);
-    c->d_level[l] = c->alloc<mm128>(c->level_n[l]);
+    c->d_level[l] = c->palloc<mm128>(c->level_n[l]);
     LAUNCH(c, k_reduce<true>, nblk(ns, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r,
            (uint32_t *)nullptr, c->d_level_off[l], c->d_level[l]);
     c->stats.ms_reduce += c->toc();
@@ -484,7 +630,7 @@ extern "C" int pgb_index_count_copy(pgb_ctx *c, int level, mm_count_t *out) {
 static void build_mc_table(pgb_ctx *c, const mc_entry *d_mc, size_t n_mc) {
   c->release(c->d_mckeys); c->release(c->d_mcvals);
   uint32_t cap = pow2_at_least(2 * (uint64_t)n_mc + 16);
-  c->d_mckeys = c->alloc<uint64_t>(cap); c->d_mcvals = c->alloc<uint32_t>(cap); c->mcmask = cap - 1;
+  c->d_mckeys = c->palloc<uint64_t>(cap); c->d_mcvals = c->palloc<uint32_t>(cap); c->mcmask = cap - 1;
   LAUNCH(c, k_fill_u64, 1184, 256, c->d_mckeys, PGB_EMPTY, (size_t)cap);
   CU(cudaMemsetAsync(c->d_mcvals, 0, (size_t)cap * 4, c->st));
   LAUNCH(c, k_mc_add, nblk(n_mc), 256, d_mc, n_mc, c->d_mckeys, c->d_mcvals, cap - 1, c->d_err);
@@ -494,7 +640,7 @@ extern "C" int pgb_set_shimmers(pgb_ctx *c, const mm128_t *mmers, size_t n, cons
   API_BEGIN(c)
   c->free_shimmers();
   c->tic();
-  c->d_shm = c->alloc<mm128>(n); c->n_shm = n; c->shm_owned = true;
+  c->d_shm = c->palloc<mm128>(n); c->n_shm = n; c->shm_owned = true;
   c->h2d(c->d_shm, mmers, n * sizeof(mm128));
   mc_entry *d_mc = c->alloc<mc_entry>(n_counts);
   c->h2d(d_mc, counts, n_counts * sizeof(mc_entry));
@@ -514,7 +660,7 @@ extern "C" int pgb_set_shimmers_from_index(pgb_ctx *c, int level) {
   // multiplicity table straight from the mmers (what aggregate_mm_count over the chunk's -MC- file yields)
   size_t n = c->n_shm;
   uint32_t cap = pow2_at_least(2 * (uint64_t)n + 16);
-  c->d_mckeys = c->alloc<uint64_t>(cap); c->d_mcvals = c->alloc<uint32_t>(cap); c->mcmask = cap - 1;
+  c->d_mckeys = c->palloc<uint64_t>(cap); c->d_mcvals = c->palloc<uint32_t>(cap); c->mcmask = cap - 1;
   LAUNCH(c, k_fill_u64, 1184, 256, c->d_mckeys, PGB_EMPTY, (size_t)cap);
   CU(cudaMemsetAsync(c->d_mcvals, 0, (size_t)cap * 4, c->st));
   LAUNCH(c, k_mc_insert, nblk(n), 256, c->d_shm, n, c->d_mckeys, c->d_mcvals, cap - 1, c->d_err);
@@ -570,81 +716,135 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   uint32_t xcap = pow2_at_least(4 * (uint64_t)nrec), bcap = pow2_at_least(2 * (uint64_t)nrec);
   uint64_t *xkeys = c->alloc<uint64_t>(xcap), *bkeys = c->alloc<uint64_t>(bcap);
   uint32_t *bcount = c->alloc<uint32_t>(bcap), *bfirst = c->alloc<uint32_t>(bcap), *blast = c->alloc<uint32_t>(bcap), *rec_bucket = c->alloc<uint32_t>(nrec);
+  uint32_t *xfirst = c->alloc<uint32_t>(xcap), *xid = c->alloc<uint32_t>(xcap);
   LAUNCH(c, k_fill_u64, 1184, 256, xkeys, PGB_EMPTY, (size_t)xcap);
   LAUNCH(c, k_fill_u64, 1184, 256, bkeys, PGB_EMPTY, (size_t)bcap);
   CU(cudaMemsetAsync(bcount, 0, (size_t)bcap * 4, c->st));
   CU(cudaMemsetAsync(bfirst, 0xFF, (size_t)bcap * 4, c->st));
   CU(cudaMemsetAsync(blast, 0, (size_t)bcap * 4, c->st));
-  LAUNCH(c, k_bucket_insert, nblk(nrec), 256, R, nrec, xkeys, xcap - 1, bkeys, bcap - 1, bcount, bfirst, blast, rec_bucket, c->d_err);
+  CU(cudaMemsetAsync(xfirst, 0xFF, (size_t)xcap * 4, c->st));
+  LAUNCH(c, k_bucket_insert, nblk(nrec), 256, R, nrec, xkeys, xcap - 1, bkeys, bcap - 1, bcount, bfirst, blast, xfirst, rec_bucket, c->d_err);
   uint32_t *bflags = c->alloc<uint32_t>((size_t)bcap + 1), *bpos = c->alloc<uint32_t>((size_t)bcap + 1);
   CU(cudaMemsetAsync(bflags, 0, ((size_t)bcap + 1) * 4, c->st));
   LAUNCH(c, k_mc_flags, nblk(bcap), 256, bkeys, (size_t)bcap, bflags);
   uint32_t n_buckets = scan_u32(c, bflags, bpos, (size_t)bcap + 1);
-  BucketInfo *d_binfo = c->alloc<BucketInfo>(n_buckets);
-  LAUNCH(c, k_bucket_dump, nblk(bcap), 256, xkeys, bkeys, bcount, bfirst, blast, bpos, (size_t)bcap, d_binfo);
-  std::vector<BucketInfo> binfo(n_buckets);
-  c->d2h(binfo.data(), d_binfo, (size_t)n_buckets * sizeof(BucketInfo));
-  c->release(d_binfo); c->release(bflags); c->release(bpos); c->release(xkeys); c->release(bkeys); c->release(bcount); c->release(bfirst); c->release(blast);
-  if (c->check_err("pgb_overlap/buckets")) { free_R(); c->release(rec_bucket); return -1; }
-  c->stats.ms_buckets += c->toc();
+  auto free_tables = [&]() {
+    c->release(bflags); c->release(bpos); c->release(xkeys); c->release(bkeys); c->release(bcount); c->release(bfirst); c->release(blast);
+    c->release(xfirst); c->release(xid);
+  };
+  if (c->check_err("pgb_overlap/buckets")) { free_tables(); free_R(); c->release(rec_bucket); return -1; }
   c->stats.n_buckets += n_buckets;
 
-  // ---------------- visiting order (host): keys-only khash replay, SURVEY App. A-3 / D-1
+  // ---------------- visiting order: everything on the GPU except the replay of the OUTER khash
+  // (a) buckets in first-insertion order
+  uint32_t *lslot = c->alloc<uint32_t>(n_buckets), *lkey = c->alloc<uint32_t>(n_buckets);
+  uint32_t *sslot = c->alloc<uint32_t>(n_buckets), *skey = c->alloc<uint32_t>(n_buckets);
+  LAUNCH(c, k_bucket_list, nblk(bcap), 256, bkeys, bfirst, bpos, (size_t)bcap, lslot, lkey);
+  sort_pairs_u32(c, lkey, skey, lslot, sslot, n_buckets);
+  // (b) outer ids in first-insertion order
+  uint32_t *isfirst = c->alloc<uint32_t>((size_t)n_buckets + 1), *firstpos = c->alloc<uint32_t>((size_t)n_buckets + 1);
+  CU(cudaMemsetAsync(isfirst, 0, ((size_t)n_buckets + 1) * 4, c->st));
+  LAUNCH(c, k_outer_first, nblk(n_buckets), 256, sslot, n_buckets, bkeys, bfirst, xfirst, isfirst);
+  uint32_t n_outer = scan_u32(c, isfirst, firstpos, (size_t)n_buckets + 1);
+  LAUNCH(c, k_outer_id_first, nblk(n_buckets), 256, sslot, n_buckets, bkeys, isfirst, firstpos, xid);
+  uint32_t *oid = lkey, *idx = lslot;  // reuse
+  LAUNCH(c, k_outer_id_all, nblk(n_buckets), 256, sslot, n_buckets, bkeys, xid, oid, idx);
+  // (c) group by outer id (stable: inner first-insertion order is kept inside a group)
+  uint32_t *goid_sorted = skey, *gidx = c->alloc<uint32_t>(n_buckets);
+  sort_pairs_u32(c, oid, goid_sorted, idx, gidx, n_buckets);
+  GroupedBuckets G;
+  G.slot = c->alloc<uint32_t>(n_buckets); G.first = c->alloc<uint32_t>(n_buckets); G.last = c->alloc<uint32_t>(n_buckets);
+  G.count = c->alloc<uint32_t>(n_buckets); G.oid = c->alloc<uint32_t>(n_buckets); G.k1 = c->alloc<uint64_t>(n_buckets);
+  uint32_t *goff = c->alloc<uint32_t>((size_t)n_outer + 1), *ipos = c->alloc<uint32_t>(n_buckets), *big_list = c->alloc<uint32_t>((size_t)n_outer + 1);
+  uint64_t *okey = c->alloc<uint64_t>((size_t)n_outer + 1);
+  unsigned int *d_small = c->alloc<unsigned int>(2);  // [0] last_seq_all, [1] n_big
+  unsigned long long *d_ncand = c->alloc<unsigned long long>(1);
+  CU(cudaMemsetAsync(d_small, 0, 8, c->st));
+  CU(cudaMemsetAsync(d_ncand, 0, 8, c->st));
+  LAUNCH(c, k_group_gather, nblk(n_buckets), 256, gidx, goid_sorted, n_buckets, sslot, bkeys, xkeys, bfirst, blast, bcount, G, goff, n_outer, okey,
+         d_small);
+  // (d) inner khash replay, one thread per outer key
+  LAUNCH(c, k_inner_order, nblk(n_outer, 128), 128, goff, n_outer, G, ipos, big_list, d_small + 1);
+  std::vector<uint64_t> h_okey(n_outer);
+  std::vector<uint32_t> h_goff_last(2);
+  unsigned int h_small[2];
+  c->d2h(h_okey.data(), okey, (size_t)n_outer * 8);
+  c->d2h(h_small, d_small, 8);
+  uint32_t newest_outer_seq = 0;
+  {
+    uint32_t last_group_start = 0;
+    c->d2h(&last_group_start, goff + (n_outer - 1), 4);
+    c->d2h(&newest_outer_seq, G.first + last_group_start, 4);
+  }
+  c->stats.ms_buckets += c->toc();
+  // (e) host: outer khash replay (keys only) -> visiting rank of every outer key; inner replay of the few oversized groups
   double t_host0 = now_ms();
-  std::vector<uint32_t> order(n_buckets);
-  for (uint32_t i = 0; i < n_buckets; i++) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return binfo[a].first_seq < binfo[b].first_seq; });
-  std::vector<uint32_t> slot2rank(bcap, PGB_NOSLOT), rank_off;
-  uint64_t n_cand = 0;
+  std::vector<uint32_t> orank(n_outer);
   {
     KhashEmu outer;
-    std::unordered_map<uint64_t, uint32_t> outer_id;
-    outer_id.reserve(n_buckets);
-    std::vector<uint32_t> head, next(n_buckets, PGB_NOSLOT), tail;  // per-outer linked list of buckets in insertion order
-    std::vector<uint32_t> o_last;                                    // per outer key: last put (record sequence number)
-    uint32_t newest_outer_seq = 0, last_seq_all = 0;
-    for (uint32_t oi = 0; oi < n_buckets; oi++) {
-      uint32_t b = order[oi];
-      last_seq_all = std::max(last_seq_all, binfo[b].last_seq);
-      auto it = outer_id.find(binfo[b].k0);
-      if (it == outer_id.end()) {
-        uint32_t id = (uint32_t)head.size();
-        outer_id.emplace(binfo[b].k0, id);
-        outer.put_new(binfo[b].k0, id);
-        newest_outer_seq = binfo[b].first_seq;
-        head.push_back(b); tail.push_back(b); o_last.push_back(binfo[b].last_seq);
-      } else {
-        next[tail[it->second]] = b; tail[it->second] = b;
-        o_last[it->second] = std::max(o_last[it->second], binfo[b].last_seq);
-      }
-    }
-    if (last_seq_all > newest_outer_seq) outer.touch_existing();  // a put of a known outer key followed the last new one
-    rank_off.push_back(0);
-    KhashEmu inner;
-    outer.for_each_in_slot_order([&](uint64_t, uint32_t id) {
-      inner.clear();
-      uint32_t newest_inner_seq = 0;
-      for (uint32_t b = head[id]; b != PGB_NOSLOT; b = next[b]) { inner.put_new(binfo[b].k1, b); newest_inner_seq = binfo[b].first_seq; }
-      if (o_last[id] > newest_inner_seq) inner.touch_existing();
-      inner.for_each_in_slot_order([&](uint64_t, uint32_t b) {
-        uint32_t nn = binfo[b].count;
-        if (nn <= 2 || nn > ovlp_upper) return;  // src/shmr_overlap.c:216
-        slot2rank[binfo[b].slot] = (uint32_t)rank_off.size() - 1;
-        rank_off.push_back(rank_off.back() + nn);
-        n_cand += (uint64_t)nn * (nn - 1) / 2;
-      });
-    });
+    for (uint32_t o = 0; o < n_outer; o++) outer.put_new(h_okey[o], o);
+    if (h_small[0] > newest_outer_seq) outer.touch_existing();  // a put of a known outer key followed the last new one
+    uint32_t r = 0;
+    outer.for_each_in_slot_order([&](uint64_t, uint32_t o) { orank[o] = r++; });
   }
-  uint32_t n_ranks = (uint32_t)rank_off.size() - 1, n_elig = rank_off.back();
+  if (h_small[1]) {
+    std::vector<uint32_t> big(h_small[1]), h_goff((size_t)n_outer + 1);
+    c->d2h(big.data(), big_list, (size_t)h_small[1] * 4);
+    c->d2h(h_goff.data(), goff, ((size_t)n_outer + 1) * 4);
+    KhashEmu inner;
+    for (uint32_t o : big) {
+      uint32_t b = h_goff[o], n = h_goff[o + 1] - b;
+      std::vector<uint64_t> k1(n);
+      std::vector<uint32_t> fi(n), la(n), pos(n);
+      c->d2h(k1.data(), G.k1 + b, (size_t)n * 8);
+      c->d2h(fi.data(), G.first + b, (size_t)n * 4);
+      c->d2h(la.data(), G.last + b, (size_t)n * 4);
+      inner.clear();
+      uint32_t last = 0;
+      for (uint32_t i = 0; i < n; i++) { inner.put_new(k1[i], i); last = std::max(last, la[i]); }
+      if (last > fi[n - 1]) inner.touch_existing();
+      uint32_t r = 0;
+      inner.for_each_in_slot_order([&](uint64_t, uint32_t i) { pos[i] = r++; });
+      c->h2d(ipos + b, pos.data(), (size_t)n * 4);
+      c->sync();
+    }
+  }
   c->stats.ms_host_order += now_ms() - t_host0;
+  // (f) visiting positions, eligibility, ranks
+  c->tic();
+  uint32_t *d_orank = c->alloc<uint32_t>(n_outer), *size_by_rank = c->alloc<uint32_t>((size_t)n_outer + 1), *vstart = c->alloc<uint32_t>((size_t)n_outer + 1);
+  c->h2d(d_orank, orank.data(), (size_t)n_outer * 4);
+  CU(cudaMemsetAsync(size_by_rank, 0, ((size_t)n_outer + 1) * 4, c->st));
+  LAUNCH(c, k_group_sizes_by_rank, nblk(n_outer), 256, goff, d_orank, n_outer, size_by_rank);
+  scan_u32(c, size_by_rank, vstart, (size_t)n_outer + 1);
+  uint32_t *vis_slot = c->alloc<uint32_t>(n_buckets), *vis_elig = c->alloc<uint32_t>((size_t)n_buckets + 1), *vis_cnt = c->alloc<uint32_t>((size_t)n_buckets + 1);
+  uint32_t *rank_of = c->alloc<uint32_t>((size_t)n_buckets + 1), *off_of = c->alloc<uint32_t>((size_t)n_buckets + 1);
+  CU(cudaMemsetAsync(vis_elig, 0, ((size_t)n_buckets + 1) * 4, c->st));
+  CU(cudaMemsetAsync(vis_cnt, 0, ((size_t)n_buckets + 1) * 4, c->st));
+  LAUNCH(c, k_visit_place, nblk(n_buckets), 256, G, n_buckets, d_orank, vstart, ipos, ovlp_upper, vis_slot, vis_elig, vis_cnt, d_ncand);
+  uint32_t n_ranks = scan_u32(c, vis_elig, rank_of, (size_t)n_buckets + 1);
+  uint32_t n_elig = scan_u32(c, vis_cnt, off_of, (size_t)n_buckets + 1);
+  unsigned long long n_cand = 0;
+  c->d2h(&n_cand, d_ncand, 8);
   c->stats.n_eligible_buckets += n_ranks; c->stats.n_candidates += n_cand;
-  if (n_ranks == 0) { free_R(); c->release(rec_bucket); c->sync(); return 0; }
+  uint32_t *d_slot2rank = c->alloc<uint32_t>(bcap), *d_rank_off = c->alloc<uint32_t>((size_t)n_ranks + 1);
+  LAUNCH(c, k_fill_u32, 1184, 256, d_slot2rank, PGB_NOSLOT, (size_t)bcap);
+  LAUNCH(c, k_visit_rank, nblk(n_buckets), 256, vis_slot, vis_elig, rank_of, off_of, n_buckets, d_slot2rank, d_rank_off);
+  CU(cudaMemcpyAsync(d_rank_off + n_ranks, &n_elig, 4, cudaMemcpyHostToDevice, c->st));
+  c->sync();
+  auto free_order = [&]() {
+    c->release(lslot); c->release(lkey); c->release(sslot); c->release(skey); c->release(isfirst); c->release(firstpos); c->release(gidx);
+    c->release(G.slot); c->release(G.first); c->release(G.last); c->release(G.count); c->release(G.oid); c->release(G.k1);
+    c->release(goff); c->release(ipos); c->release(big_list); c->release(okey); c->release(d_small); c->release(d_ncand);
+    c->release(d_orank); c->release(size_by_rank); c->release(vstart); c->release(vis_slot); c->release(vis_elig); c->release(vis_cnt);
+    c->release(rank_of); c->release(off_of);
+  };
+  free_order();
+  free_tables();
+  if (n_ranks == 0) { free_R(); c->release(rec_bucket); c->release(d_slot2rank); c->release(d_rank_off); c->sync(); return 0; }
 
   // ---------------- scatter + per-bucket sort
-  c->tic();
-  uint32_t *d_slot2rank = c->alloc<uint32_t>(bcap), *d_rank_off = c->alloc<uint32_t>((size_t)n_ranks + 1), *fill = c->alloc<uint32_t>(n_ranks);
-  c->h2d(d_slot2rank, slot2rank.data(), (size_t)bcap * 4);
-  c->h2d(d_rank_off, rank_off.data(), ((size_t)n_ranks + 1) * 4);
+  uint32_t *fill = c->alloc<uint32_t>(n_ranks);
   CU(cudaMemsetAsync(fill, 0, (size_t)n_ranks * 4, c->st));
   uint64_t *sy0 = c->alloc<uint64_t>(n_elig), *sy1 = c->alloc<uint64_t>(n_elig);
   uint32_t *sseq = c->alloc<uint32_t>(n_elig); uint8_t *sdir = c->alloc<uint8_t>(n_elig), *contained = c->alloc<uint8_t>(n_elig);
@@ -728,7 +928,7 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   // ---------------- emission pass in visiting order
   c->tic();
   uint32_t n_out = scan_u32(c, acc, out_off, (size_t)n_ranks + 1);
-  c->d_ovl = c->alloc<ovlp_rec>(n_out); c->n_ovl = n_out;
+  c->d_ovl = c->palloc<ovlp_rec>(n_out); c->n_ovl = n_out;
   LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
   CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
   LAUNCH(c, k_replay, nblk(n_ranks, 64), 64, S, n_ranks, d_rank_off, sy0, sdir, contained, bestn, 0, 1, acc, out_off, c->d_ovl, d_ctr);
@@ -970,6 +1170,7 @@ extern "C" void mm_reduce(mm128_v *in, mm128_v *out, uint8_t rs) {
     c->d2h(v.data(), d_out, total * sizeof(mm128));
     c->release(d_in); c->release(d_off); c->release(d_ooff); c->release(counts); c->release(d_out);
     c->sync();
+    c->scratch_reset();
     mm128v_append(out, v.data(), v.size());
   } catch (std::exception &e) {
     fprintf(stderr, "pgb200: mm_reduce failed: %s\n", e.what());
@@ -1000,6 +1201,8 @@ extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_
     LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err, c->d_align_bases);
     c->d2h(rtn, d_m, sizeof(match_t));
     c->release(d_q); c->release(d_m);
+    c->sync();
+    c->scratch_reset();
     if (c->check_err("ovlp_match")) { fprintf(stderr, "pgb200: %s\n", pgb_last_error(c)); exit(1); }
   } catch (std::exception &e) {
     fprintf(stderr, "pgb200: ovlp_match failed: %s\n", e.what());

@@ -349,6 +349,108 @@ PGB_HD void sketch_exact(const uint64_t *w, const uint32_t *nm, uint64_t word_of
   if (min_x != XMAX) emit(min_x, ridhi | min_p);  // mm_sketch.c:150
 }
 
+// ---------------------------------------------------------------------------------------------- mm_sketch (exact, one segment)
+// The automaton's state after a base depends only on the last w ring slots and on l (capped at w+k), so a read can be cut
+// into segments that are replayed independently: start `start_pos` early enough that by position seg_lo (a) at least w
+// slots were written (ring identical to the full run) and (b) l is either >= w+k in both runs or was reset by an N inside
+// the warm-up (identical in both runs).  Records are attributed by POSITION: only minimizers with seg_lo <= pos < seg_hi
+// are reported; the replay continues until w slots past seg_hi (an entry leaves the ring, and can no longer be emitted,
+// w slots after it entered) or to the end of the read (final flush, mm_sketch.c:150).
+// Returns false when start_pos > 0 and the warm-up condition was not met (caller retries with start_pos = 0).
+template <class Emit>
+PGB_HD bool sketch_exact_range(const uint64_t *w, const uint32_t *nm, uint64_t word_off, int len, int wsz, int k, uint32_t rid,
+                               int start_pos, int seg_lo, int seg_hi, uint64_t *ring_x, uint32_t *ring_p, Emit &&emit) {
+  const uint64_t shift1 = 2 * (uint64_t)(k - 1), mask = (1ULL << 2 * k) - 1;
+  const uint64_t XMAX = ~0ULL;
+  const uint32_t PMAX = ~0u;
+  uint64_t kmer0 = 0, kmer1 = 0;
+  int l = 0, buf_pos = 0, min_pos = 0;
+  uint64_t min_x = XMAX;
+  uint32_t min_p = PMAX;
+  for (int j = 0; j < wsz; j++) {
+    ring_x[j] = XMAX;
+    ring_p[j] = PMAX;
+  }
+  const uint64_t ridhi = (uint64_t)rid << 32;
+  const uint32_t plo = (uint32_t)seg_lo << 1, phi = (uint32_t)seg_hi << 1;
+#define PGB_EMIT_IF(x_, p_) do { uint32_t pp_ = (p_); if (pp_ >= plo && pp_ < phi) emit((x_), ridhi | pp_); } while (0)
+  uint64_t cw = 0;
+  uint32_t cn = 0;
+  int slots_before = 0, slots_after = 0;
+  bool saw_n = false, warm_checked = start_pos == 0;
+  int i = start_pos;
+  if (i < len) {
+    cw = w[word_off + (i >> 5)];
+    cn = nm ? nm[word_off + (i >> 5)] : 0u;
+  }
+  for (; i < len; ++i) {
+    if ((i & 31) == 0) {
+      cw = w[word_off + (i >> 5)];
+      cn = nm ? nm[word_off + (i >> 5)] : 0u;
+    }
+    if (!warm_checked && i >= seg_lo) {
+      if (!(slots_before >= wsz && (saw_n || l >= wsz + k))) { return false; }
+      warm_checked = true;
+    }
+    if (slots_after >= wsz) break;  // every entry with pos < seg_hi has left the ring
+    int c = (int)((cw >> (2 * (i & 31))) & 3);
+    int isn = (int)((cn >> (i & 31)) & 1);
+    uint64_t info_x = XMAX;
+    uint32_t info_p = PMAX;
+    if (!isn) {
+      kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
+      kmer1 = (kmer1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+      if (kmer0 == kmer1) continue;
+      int z = kmer0 < kmer1 ? 0 : 1;
+      ++l;
+      if (l >= k) {
+        info_x = hash64(z ? kmer1 : kmer0, mask) << 8 | (uint64_t)k;
+        info_p = (uint32_t)i << 1 | (uint32_t)z;
+      }
+    } else {
+      l = 0;
+      saw_n = true;
+    }
+    if (i < seg_lo) slots_before++;
+    if (i >= seg_hi) slots_after++;
+    ring_x[buf_pos] = info_x;
+    ring_p[buf_pos] = info_p;
+    if (l == wsz + k - 1 && min_x != XMAX) {
+      for (int j = buf_pos + 1; j < wsz; ++j)
+        if (min_x == ring_x[j] && ring_p[j] != min_p) PGB_EMIT_IF(ring_x[j], ring_p[j]);
+      for (int j = 0; j < buf_pos; ++j)
+        if (min_x == ring_x[j] && ring_p[j] != min_p) PGB_EMIT_IF(ring_x[j], ring_p[j]);
+    }
+    if (info_x <= min_x) {
+      if (l >= wsz + k && min_x != XMAX) PGB_EMIT_IF(min_x, min_p);
+      min_x = info_x;
+      min_p = info_p;
+      min_pos = buf_pos;
+    } else if (buf_pos == min_pos) {
+      if (l >= wsz + k - 1 && min_x != XMAX) PGB_EMIT_IF(min_x, min_p);
+      min_x = XMAX;
+      for (int j = buf_pos + 1; j < wsz; ++j)
+        if (min_x >= ring_x[j]) min_x = ring_x[j], min_p = ring_p[j], min_pos = j;
+      for (int j = 0; j <= buf_pos; ++j)
+        if (min_x >= ring_x[j]) min_x = ring_x[j], min_p = ring_p[j], min_pos = j;
+      if (l >= wsz + k - 1 && min_x != XMAX) {
+        for (int j = buf_pos + 1; j < wsz; ++j)
+          if (min_x == ring_x[j] && min_p != ring_p[j]) PGB_EMIT_IF(ring_x[j], ring_p[j]);
+        for (int j = 0; j <= buf_pos; ++j)
+          if (min_x == ring_x[j] && min_p != ring_p[j]) PGB_EMIT_IF(ring_x[j], ring_p[j]);
+      }
+    }
+    if (++buf_pos == wsz) buf_pos = 0;
+  }
+  if (!warm_checked) {  // the read ended inside the warm-up (seg_lo >= len cannot happen for a valid segment)
+    if (!(slots_before >= wsz && (saw_n || l >= wsz + k))) return false;
+  }
+  if (i >= len && min_x != XMAX) PGB_EMIT_IF(min_x, min_p);  // final flush only when the read's end was reached
+#undef PGB_EMIT_IF
+  return true;
+}
+PGB_HD int sketch_warmup_len(int wsz, int k) { return 2 * (wsz + k) + 64; }
+
 // ---------------------------------------------------------------------------------------------- mm_reduce
 // Window pick for the element at in-read offset o (o >= rs-1), src/shmr_reduce.c:33-50,79-88: the ring slot of
 // the element with offset t is t % rs; slots are scanned 0..rs-1 with strict '<' on x>>8, so ties go to the lowest

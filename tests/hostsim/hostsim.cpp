@@ -18,6 +18,8 @@
 #include <array>
 #include <chrono>
 #include "../../peregrine_b200/csrc/host_util.hpp"
+#include "../../peregrine_b200/csrc/sketch_tile.cuh"
+#include "../../peregrine_b200/csrc/khash_small.cuh"
 
 using namespace pgb;
 
@@ -99,13 +101,62 @@ static void sim_reduce(const std::vector<mm128> &in, std::vector<mm128> &out, ui
   }
 }
 
+
+// ---- CPU execution of the tiled sketch kernel's phases (peregrine_b200/csrc/sketch_tile.cuh): one "CTA" at a time,
+// the 256 threads of each phase run sequentially, block scans are plain loops.  Returns flags != 0 if the read must
+// take the exact automaton instead.
+template <class HT>
+static uint32_t sketch_tiled_host(const Packed &P, size_t row, int wsz, int k, std::vector<mm128> &out) {
+  const int len = (int)P.rt.len[row];
+  if (P.has_n[row]) return SK_FLAG_N;
+  if (len < sk_min_len(wsz, k)) return SK_FLAG_SHORT;
+  const int H = sk_halo(wsz), TILE = sk_tile_len(wsz);
+  const int n_tiles = (len + TILE - 1) / TILE;
+  static SkShared<HT> sh;
+  std::vector<mm128> rec;
+  for (int j = 0; j < n_tiles; j++) {
+    SkParams p;
+    p.w = P.w.data(); p.word_off = P.woff[row]; p.len = len; p.rid = P.rt.rid[row]; p.wsz = wsz; p.k = k;
+    p.r0 = j * TILE - H; p.first_tile = j == 0;
+    static HT hv[SK_THREADS][SK_G];
+    static uint16_t ps[SK_THREADS][SK_G];
+    uint32_t mask[SK_THREADS], base[SK_THREADS];
+    sh.n_pal = 0; sh.n_halo_slots = 0; sh.flags = 0;
+    uint32_t tot = 0;
+    for (int t = 0; t < SK_THREADS; t++) {
+      uint32_t np, hs;
+      sk_phase1<HT>(t, p, H, hv[t], ps[t], &mask[t], &np, &hs);
+      sh.n_pal += np; sh.n_halo_slots += hs;
+      base[t] = tot; tot += (uint32_t)sk_popc(mask[t]);
+    }
+    sh.n_slots = tot;
+    if (sh.n_pal > SK_PALPAD) return SK_FLAG_PAL;
+    for (int t = 0; t < SK_THREADS; t++) sk_phase2_write<HT>(sh, hv[t], ps[t], mask[t], base[t]);
+    for (int t = 0; t < SK_THREADS; t++) for (int g = t; g < SK_NG; g += SK_THREADS) sk_phase3_group<HT>(g, sh);
+    int s_eval, s_emit, s_first_full;
+    sk_ranges(p, sh.n_halo_slots, &s_eval, &s_emit, &s_first_full);
+    uint32_t tie = 0;
+    for (int t = 0; t < SK_THREADS; t++) for (int g = t; g < SK_NG; g += SK_THREADS) tie |= sk_phase4_group<HT>(g, sh, wsz, s_eval);
+    if (tie) return SK_FLAG_TIE;
+    uint32_t total = 0;
+    for (int g = 0; g < SK_NG; g++) total += sk_phase5_group<HT, false>(g, sh, p, s_emit, s_first_full, nullptr);
+    if (total > SK_CAP) return SK_FLAG_OVERFLOW;
+    size_t at = rec.size();
+    rec.resize(at + total);
+    uint32_t o = 0;
+    for (int g = 0; g < SK_NG; g++) o += sk_phase5_group<HT, true>(g, sh, p, s_emit, s_first_full, rec.data() + at + o);
+  }
+  out.insert(out.end(), rec.begin(), rec.end());
+  return 0;
+}
+
 static int cmd_sketch(int argc, char **argv) {
   if (argc < 5) return 1;
   Packed P; load_packed(argv[2], &P);
   int w = atoi(argv[3]), k = atoi(argv[4]);
   int rs = argc > 5 ? atoi(argv[5]) : 6;
   std::vector<uint64_t> rx(256); std::vector<uint32_t> rp(256);
-  size_t bad = 0, total = 0;
+  size_t bad = 0, total = 0, bad_tiled = 0, n_fallback = 0, bad_seg = 0, n_seg_retry = 0; uint32_t fallback_flags = 0;
   std::vector<mm128> all_mine;
   mm128_v all_ref = {0, 0, 0};
   for (size_t i = 0; i < P.rt.n(); i++) {
@@ -120,12 +171,43 @@ static int cmd_sketch(int argc, char **argv) {
                  [&](uint64_t x, uint64_t y) { all_mine.push_back(mm128{x, y}); });
     size_t nr = all_ref.n - n0, nmine = all_mine.size() - m0;
     total += nr;
+    {  // segment-parallel exact automaton: cut the read into segments, replay each independently, concatenate
+      for (int seg : {257, 1024}) {
+        std::vector<mm128> segout;
+        for (int lo = 0; lo < (int)len; lo += seg) {
+          int hi = std::min<int>(lo + seg, (int)len);
+          int st = std::max(0, lo - sketch_warmup_len(w, k));
+          auto em = [&](uint64_t x, uint64_t y) { segout.push_back(mm128{x, y}); };
+          size_t mark = segout.size();
+          if (!sketch_exact_range(P.w.data(), P.has_n[i] ? P.nm.data() : nullptr, P.woff[i], (int)len, w, k, P.rt.rid[i], st, lo, hi, rx.data(), rp.data(), em)) {
+            segout.resize(mark); n_seg_retry++;
+            sketch_exact_range(P.w.data(), P.has_n[i] ? P.nm.data() : nullptr, P.woff[i], (int)len, w, k, P.rt.rid[i], 0, lo, hi, rx.data(), rp.data(), em);
+          }
+        }
+        if (segout.size() != nr || memcmp(all_ref.a + n0, segout.data(), nr * 16) != 0) {
+          if (bad_seg < 5) fprintf(stderr, "SEGMENT sketch mismatch read row %zu len %u seg %d: ref %zu seg %zu\n", i, len, seg, nr, segout.size());
+          bad_seg++;
+        }
+      }
+    }
+    if (w >= SK_GS + 1) {
+      std::vector<mm128> tiled;
+      uint32_t fl = (k <= 16) ? sketch_tiled_host<uint32_t>(P, i, w, k, tiled) : sketch_tiled_host<uint64_t>(P, i, w, k, tiled);
+      if (fl) { n_fallback++; fallback_flags |= fl; }
+      else if (tiled.size() != nr || memcmp(all_ref.a + n0, tiled.data(), nr * 16) != 0) {
+        if (bad_tiled < 5) {
+          fprintf(stderr, "TILED sketch mismatch read row %zu rid %u len %u: ref %zu tiled %zu\n", i, P.rt.rid[i], len, nr, tiled.size());
+          for (size_t q = 0; q < std::min(nr, tiled.size()); q++) if (memcmp(&all_ref.a[n0 + q], &tiled[q], 16)) { fprintf(stderr, "  first diff at %zu: ref pos %u tiled pos %u\n", q, (uint32_t)(all_ref.a[n0+q].y & 0xFFFFFFFF) >> 1, (uint32_t)(tiled[q].y & 0xFFFFFFFF) >> 1); break; }
+        }
+        bad_tiled++;
+      }
+    }
     if (nr != nmine || memcmp(all_ref.a + n0, all_mine.data() + m0, nr * 16) != 0) {
       if (bad < 5) fprintf(stderr, "sketch mismatch read row %zu rid %u len %u: ref %zu mine %zu\n", i, P.rt.rid[i], len, nr, nmine);
       bad++;
     }
   }
-  printf("sketch: reads=%zu L0=%zu mismatching_reads=%zu\n", P.rt.n(), total, bad);
+  printf("sketch: reads=%zu L0=%zu mismatching_reads=%zu ; tiled kernel: mismatching=%zu fallback_reads=%zu (flags 0x%x) ; segmented exact: mismatching=%zu retries=%zu\n", P.rt.n(), total, bad, bad_tiled, n_fallback, fallback_flags, bad_seg, n_seg_retry);
   // reduce twice
   mm128_v r1 = {0, 0, 0}, r2 = {0, 0, 0};
   ref_mm_reduce(&all_ref, &r1, (uint8_t)rs);
@@ -137,7 +219,7 @@ static int cmd_sketch(int argc, char **argv) {
   bool ok2 = r2.n == m2.size() && (r2.n == 0 || memcmp(r2.a, m2.data(), r2.n * 16) == 0);
   printf("reduce: L1 ref=%zu mine=%zu %s ; L2 ref=%zu mine=%zu %s\n", r1.n, m1.size(), ok1 ? "OK" : "MISMATCH", r2.n, m2.size(),
          ok2 ? "OK" : "MISMATCH");
-  return (bad || !ok1 || !ok2) ? 3 : 0;
+  return (bad || bad_tiled || bad_seg || !ok1 || !ok2) ? 3 : 0;
 }
 
 static uint64_t rng_state = 0x12345;
@@ -303,19 +385,29 @@ static int cmd_overlap(int argc, char **argv) {
     } else { inner_lists[it->second].push_back(b); o_last[it->second] = std::max(o_last[it->second], buckets[b].last_seq); }
   }
   if (last_seq_all > newest_outer_seq) outer.touch_existing();
+  size_t n_khs_checked = 0;
   std::vector<uint32_t> visit;  // eligible buckets in visiting order
   outer.for_each_in_slot_order([&](uint64_t, uint32_t id) {
     KhashEmu inner;
     uint32_t newest_inner_seq = 0;
     for (uint32_t b : inner_lists[id]) { inner.put_new(buckets[b].k1, b); newest_inner_seq = buckets[b].first_seq; }
     if (o_last[id] > newest_inner_seq) inner.touch_existing();
+    if (inner_lists[id].size() <= KHS_MAX_KEYS) {  // the fixed-capacity device model must agree with the unbounded one
+      uint64_t kk[KHS_MAX_KEYS]; uint8_t rk[KHS_MAX_KEYS];
+      for (size_t q = 0; q < inner_lists[id].size(); q++) kk[q] = buckets[inner_lists[id][q]].k1;
+      khs_order(kk, (uint32_t)inner_lists[id].size(), o_last[id] > newest_inner_seq, rk);
+      uint32_t r = 0; bool okk = true;
+      inner.for_each_in_slot_order([&](uint64_t, uint32_t b) { size_t q = 0; while (inner_lists[id][q] != b) q++; if (rk[q] != r) okk = false; r++; });
+      if (!okk) { fprintf(stderr, "khs_order disagrees with KhashEmu for outer id %u (%zu keys)\n", id, inner_lists[id].size()); exit(4); }
+      n_khs_checked++;
+    }
     inner.for_each_in_slot_order([&](uint64_t, uint32_t b) {
       size_t nn = buckets[b].recs.size();
       if (nn <= 2 || nn > ovlp_upper) return;
       visit.push_back(b);
     });
   });
-  printf("buckets=%zu outer=%zu eligible=%zu\n", buckets.size(), inner_lists.size(), visit.size());
+  printf("buckets=%zu outer=%zu eligible=%zu khs_checked=%zu\n", buckets.size(), inner_lists.size(), visit.size(), n_khs_checked);
   if (getenv("PGB_SIM_VISIT")) { FILE *f = fopen(getenv("PGB_SIM_VISIT"), "w"); for (uint32_t b : visit) fprintf(f, "VISIT %lu %lu %zu\n", (unsigned long)buckets[b].k0, (unsigned long)buckets[b].k1, buckets[b].recs.size()); fclose(f); }
   // sorted record arrays per eligible bucket: stable, descending position (glibc qsort with mp128_comp)
   std::vector<std::vector<uint64_t>> by0(visit.size());

@@ -165,3 +165,28 @@ def test_empty_and_tiny_inputs(workdir, ref_dir):
     ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, "tiny/ref"), T=1)
     oo = ours_overlap(p, op, 2, os.path.join(workdir, "tiny/our"), T=1)
     assert_same_ovlp(oo[0], ro[0])
+
+
+def test_exact_automaton_path_on_all_reads(sim1, workdir, ref_dir, monkeypatch):
+    """PGB_SKETCH=exact forces every read through k_sketch_exact (normally only the reads the tiled kernel flags)."""
+    monkeypatch.setenv("PGB_SKETCH", "exact")
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
+    op = ours_index(sim1, os.path.join(workdir, "sim1/our_exact"), T=1, extra=["-m", "1"])
+    compare_index(rp, op, 1)
+
+
+def test_tiled_sketch_reports_fallbacks(workdir, ref_dir):
+    """The tiled kernel hands flagged reads (N, ties, palindromes, short) to the exact automaton and says how many."""
+    from peregrine_b200 import Engine
+
+    p = D.make_from_fasta(workdir, "adv", D.adversarial_records(), ref_dir)
+    rid, ln, off = F.read_idx(p + ".idx")
+    seqdb = np.fromfile(p + ".seqdb", dtype=np.uint8)
+    eng = Engine(0)
+    eng.load_reads(seqdb, rid, ln, off)
+    eng.index(80, 16, 6, 2)
+    st = eng.stats()
+    assert st["n_k_sketch_tiled"] == 1 and 0 < st["n_sketch_fallback_reads"] < len(rid)
+    rp = D.ref_index(ref_dir, p, os.path.join(workdir, "adv/ref_T1"), T=1, extra=["-m", "1"])
+    assert np.array_equal(eng.level(0), F.read_mmlist(rp + "-L0-01-of-01.dat"))
+    eng.close()
