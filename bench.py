@@ -172,70 +172,137 @@ def run_ours(args):
         dist.barrier()
     prefix = os.path.join(work_dir(), f"g{genome}", "seq")
     rid, ln, off = F.read_idx(prefix + ".idx")
-    nbytes = os.path.getsize(prefix + ".seqdb")
-    pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    seqdb = pinned.numpy()
-    with open(prefix + ".seqdb", "rb") as f:
-        f.readinto(memoryview(seqdb))
     bases = int(ln.sum())
-    eng = Engine(local)
+    if world == 1:
+        nbytes = os.path.getsize(prefix + ".seqdb")
+        pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        seqdb = pinned.numpy()
+        with open(prefix + ".seqdb", "rb") as f:
+            f.readinto(memoryview(seqdb))
+    else:
+        # this rank's share of the read set (rid % N == (rank+1) % N, src/shmr_index.c:157) as its own pinned host image
+        mm = np.memmap(prefix + ".seqdb", dtype=np.uint8, mode="r")
+        sel = np.nonzero(rid % world == (rank + 1) % world)[0]
+        rid, ln_all, off_all = rid[sel], ln[sel], off[sel]
+        ln = ln_all
+        new_off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
+        pinned = torch.empty(int(ln.astype(np.uint64).sum()), dtype=torch.uint8, pin_memory=True)
+        seqdb = pinned.numpy()
+        for i in range(len(sel)):
+            seqdb[int(new_off[i]): int(new_off[i]) + int(ln[i])] = mm[int(off_all[i]): int(off_all[i]) + int(ln[i])]
+        off = new_off
+        del mm
     P = PARAMS
     T = world
     c = rank + 1
-
-    def compute(copy):
-        eng.index(P["w"], P["k"], P["r"], P["levels"], 0)
-        eng.set_shimmers_from_index(2)
-        return eng.overlap(T, c, P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy=copy)
-
-    if world > 1:
-        raise SystemExit("multi-GPU bench path is wired in a later commit")
+    sampler = ClockSampler(local)
 
     def barrier():
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
 
-    # ---- end-to-end: host buffers in, host records out (this also warms the allocator pool)
-    def e2e_step():
-        eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False)
-        return compute(copy=True)
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    if world == 1:
+        eng = Engine(local)
+        engines = [eng]
+
+        def compute(copy):
+            eng.index(P["w"], P["k"], P["r"], P["levels"], 0)
+            eng.set_shimmers_from_index(2)
+            return eng.overlap(1, 1, P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy=copy)
+
+        def e2e_step():  # host buffers in, host records out
+            eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False)
+            return len(compute(copy=True))
+
+        def dev_prepare():
+            eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=True)
+
+        def dev_step():  # .seqdb image resident in HBM, records stay in HBM
+            eng.repack()
+            return compute(copy=False)
+    else:
+        from peregrine_b200 import multigpu as M
+
+        idx_eng, ovl_eng = Engine(local), Engine(local)
+        engines = [idx_eng, ovl_eng]
+        job = M.ShardedJob(idx_eng, ovl_eng, rank, world, torch.device("cuda", local))
+
+        def e2e_step():  # this rank's share of the .seqdb from pinned host memory, its chunk's records back to the host
+            idx_eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False)
+            job.index_and_exchange(P["w"], P["k"], P["r"])
+            return len(job.overlap(P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy=True))
+
+        def dev_prepare():
+            idx_eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=True)
+
+        def dev_step():
+            idx_eng.repack()
+            job.index_and_exchange(P["w"], P["k"], P["r"])
+            return job.overlap(P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy=False)
+
+    def all_stats():
+        out = {}
+        for e in engines:
+            for k_, v in e.stats().items():
+                out[k_] = out.get(k_, 0) + v
+        return out
+
+    # ---- end-to-end (this also warms the allocator pool)
     for _ in range(max(args.warmup, 1)):
-        ov = e2e_step()
-    n_ovl = len(ov)
-    eng.stats_reset()
+        n_mine = e2e_step()
+    for e in engines:
+        e.stats_reset()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ov = e2e_step()
+        n_mine = e2e_step()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    st_e2e = eng.stats()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    st_e2e = all_stats()
+    n_ovl = int(sum_over_ranks(n_mine))
 
-    # ---- device-resident: .seqdb image already in HBM, records stay in HBM; CUDA events on the library's stream
-    eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=True)
-
-    def dev_step():
-        eng.repack()
-        return compute(copy=False)
-
+    # ---- device-resident; CUDA events on the library's stream (+ wall clock, which includes the NCCL exchange at N > 1)
+    dev_prepare()
     for _ in range(args.warmup):
         dev_step()
-    sampler = ClockSampler(local)
     sampler.start()
-    eng.stats_reset()
+    for e in engines:
+        e.stats_reset()
     barrier()
-    eng.event_record(0)
+    engines[-1].event_record(0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         n_dev = dev_step()
-    eng.event_record(1)
+    engines[-1].event_record(1)
     barrier()
-    dev_wall = (time.perf_counter() - t0) / args.steps
-    dev_ms = eng.event_elapsed_ms(0, 1) / args.steps
+    dev_wall = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    dev_ms = max_over_ranks(engines[-1].event_elapsed_ms(0, 1) / args.steps)
     clocks = sampler.stop()
-    st = eng.stats()
-    eng.close()
-    assert n_dev == n_ovl
+    st = all_stats()
+    for e in engines:
+        e.close()
+    assert int(sum_over_ranks(n_dev)) == n_ovl
+    bases_total = bases
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- roofline of the dominant kernel (HBM-bound integer work; algorithmic bytes per SURVEY 8d / DESIGN.md)
     peak, peak_src = measured_peaks()
@@ -252,14 +319,15 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_l / K,
                 "kernel_ms_per_step": {k_: v[0] / K for k_, v in kern.items()}}
-    cpu = cpu_baseline_single_core() if (rank == 0 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline_single_core() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     out = {
         "metric": "overlaps/s (index+overlap)", "value": n_ovl / (dev_ms * 1e-3), "unit": "overlaps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "read_bases_per_s": bases / (dev_ms * 1e-3),
         "config": {"workload": f"synthetic {args.genome_mb * world:g} Mb genome, {args.cov:g}x 15 kb reads @99.5%, k=16 w=80 r=6 l=2, T={T}",
-                   "reads": int(len(rid)), "bases": bases, "overlaps_per_step": int(n_ovl), "l2_flush": "inputs (1.5 GB image) exceed the 126 MB L2",
-                   "wall_ms_per_step_device_resident": dev_wall * 1e3},
+                   "reads_per_rank": int(len(rid)), "bases": bases, "overlaps_per_step": int(n_ovl), "l2_flush": "inputs (1.5 GB image) exceed the 126 MB L2",
+                   "wall_ms_per_step_device_resident": dev_wall * 1e3,
+                   "sharding": "reads by rid % N for the index, SHIMMER-hash chunk c of T=N for the overlap; NCCL all-gather of packed reads + L2 lists" if world > 1 else "single GPU"},
         "e2e": {"value": n_ovl / e2e_s, "unit": "overlaps/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"] // K, "d2h_bytes_per_step": st_e2e["d2h_bytes"] // K,
                 "ms_per_step": e2e_s * 1e3, "read_bases_per_s": bases / e2e_s},
         "gpu_launches": int(st["kernel_launches"]),
@@ -272,6 +340,9 @@ def run_ours(args):
     if cpu:
         out["cpu_baseline"] = cpu
     print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -109,6 +109,29 @@ int pgb_overlap(pgb_ctx *, uint32_t total_chunk, uint32_t mychunk, uint32_t best
 size_t pgb_overlap_size(pgb_ctx *);
 int pgb_overlap_copy(pgb_ctx *, ovlp_t *out);
 
+/* ---- multi-GPU plumbing (one process per GPU; the collective itself is the caller's, e.g. torch.distributed / NCCL) ----
+ * A rank sketches the reads of ITS index chunk, then the ranks all-gather (a) the packed reads + read table so that any rank
+ * can align any pair and (b) the SHIMMER lists (chunk order = file order of src/shmr_overlap.c:359-369).  These calls move
+ * the library's device buffers to / from caller-owned DEVICE buffers; every call synchronises the library's stream. */
+enum pgb_buffer {
+  PGB_BUF_WORDS = 0,    /* uint64[n]: 2-bit packed reads of the loaded rows, incl. 2 guard words at each end          */
+  PGB_BUF_NMASK = 1,    /* uint32[n]: N mask, parallel to PGB_BUF_WORDS                                               */
+  PGB_BUF_ROW_RID = 2,  /* uint32[rows]                                                                                */
+  PGB_BUF_ROW_LEN = 3,  /* uint32[rows]                                                                                */
+  PGB_BUF_ROW_WOFF = 4, /* uint64[rows]: word offset of each row inside PGB_BUF_WORDS                                  */
+  PGB_BUF_ROW_HASN = 5, /* uint32[rows]: 1 if the read contains a non-ACGT base                                        */
+  PGB_BUF_LEVEL0 = 8, PGB_BUF_LEVEL1 = 9, PGB_BUF_LEVEL2 = 10 /* mm128_t[n] of the index level                        */
+};
+size_t pgb_buffer_elems(pgb_ctx *, int which);                       /* element count of a buffer                      */
+int pgb_buffer_copy_out(pgb_ctx *, int which, void *dst_device);     /* device -> caller's device buffer               */
+/* Replace the context's read set by an already packed one (device pointers, e.g. the concatenation of every rank's
+ * buffers with row_woff rebased to the concatenated word array). */
+int pgb_load_packed_device(pgb_ctx *, const uint64_t *words, const uint32_t *nmask, size_t n_words, const uint32_t *row_rid,
+                           const uint32_t *row_len, const uint64_t *row_woff, const uint32_t *row_hasn, size_t n_rows);
+/* Overlap input from a DEVICE array of mm128_t (all chunks concatenated in chunk order); the multiplicity table is rebuilt
+ * from it, which equals summing the per-chunk -MC- files (src/shmr_utils.c:162-176). */
+int pgb_set_shimmers_device(pgb_ctx *, const mm128_t *mmers_device, size_t n);
+
 /* counters for bench.py / profiles */
 typedef struct {
   uint64_t kernel_launches;      /* launches of this library's kernels since pgb_stats_reset */
@@ -122,6 +145,7 @@ typedef struct {
   uint64_t n_k_sketch_count, n_k_sketch_write, n_k_align, n_k_replay;
   double ms_k_sketch_tiled;
   uint64_t n_k_sketch_tiled, n_sketch_fallback_reads;
+  uint64_t n_replay_buckets;     /* buckets replayed, summed over passes (incremental passes replay only dirty buckets) */
 } pgb_stats;
 void pgb_stats_reset(pgb_ctx *);
 /* CUDA events on the context's stream (the stream every kernel of this library is launched on): record slot 0..7, then

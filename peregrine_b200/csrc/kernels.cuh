@@ -110,6 +110,28 @@ __global__ void k_pack_reads(const uint8_t *__restrict__ raw, const uint64_t *__
   if (nmask) atomicOr(&hasn_by_rid[row_rid[row]], 1u);
 }
 
+// ------------------------------------------------------------------------------------------------ read-table helpers
+__global__ void k_rows_hasn(const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ hasn_by_rid, uint32_t n, uint32_t *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hasn_by_rid[row_rid[i]];
+}
+__global__ void k_rows_to_rid_tables(const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ row_len, const uint64_t *__restrict__ row_woff,
+                                     const uint32_t *__restrict__ row_hasn, uint32_t n, uint32_t *rlen_by_rid, uint64_t *woff_by_rid,
+                                     uint32_t *hasn_by_rid) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t rid = row_rid[i];
+  rlen_by_rid[rid] = row_len[i];
+  woff_by_rid[rid] = row_woff[i];
+  hasn_by_rid[rid] = row_hasn[i];
+}
+__global__ void k_max_u32(const uint32_t *__restrict__ a, uint32_t n, uint32_t *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = i < n ? a[i] : 0;
+  v = __reduce_max_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, v);
+}
+
 // ------------------------------------------------------------------------------------------------ sketch (exact automaton)
 // Thread per read of `list` (row indices).  WRITE=false: cnt_by_row[row] = number of minimizers.  WRITE=true: write at
 // out + off_by_row[row].
@@ -663,12 +685,14 @@ struct DevReplayCtx {
   __device__ void emit(uint32_t n, const ovlp_rec &o) { out[n] = o; }
 };
 
-__global__ void k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ rank_off, const uint64_t *__restrict__ sy0,
-                         const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn, int request_enabled, int do_emit,
-                         uint32_t *acc_count, const uint32_t *__restrict__ out_off, ovlp_rec *out,
-                         unsigned long long *n_unknown_total) {
+// list != nullptr: only the n_ranks buckets named in list are replayed (incremental passes)
+__global__ void k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ list, const uint32_t *__restrict__ rank_off,
+                         const uint64_t *__restrict__ sy0, const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn,
+                         int request_enabled, int do_emit, uint32_t *acc_count, const uint32_t *__restrict__ out_off, ovlp_rec *out,
+                         unsigned long long *n_unknown_total, uint8_t *unk_flag) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_ranks) return;
+  if (list) r = list[r];
   uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
   DevReplayCtx c;
   c.s = st;
@@ -678,28 +702,245 @@ __global__ void k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__res
   uint32_t unk = 0;
   uint32_t acc = replay_bucket(c, r, sy0 + b, sdir + b, n, contained + b, bestn, do_emit != 0, &unk);
   acc_count[r] = acc;
+  unk_flag[r] = unk != 0;
   if (unk) atomicAdd(n_unknown_total, (unsigned long long)unk);
 }
 
+// Warp-cooperative form of the same scan (one warp = one bucket): the candidates j of a row i are classified by 32 lanes
+// in parallel (pair-table lookups, alignment-cache lookups, acceptance test), then the row's sequential semantics are
+// restored with ballots: a lane is "reached" iff overlap_count (prefix over earlier lanes) is still below bestn and no
+// earlier lane ended the row (CONTAINED, src/shmr_overlap.c:176); only reached lanes apply side effects (pair_set,
+// contained[], alignment requests, record emission, in lane order).  A lane whose read also occurs in an earlier
+// still-unresolved lane of the same chunk is deferred to the next round so that it sees that lane's pair_set.
+__global__ void __launch_bounds__(128) k_replay_warp(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ rank_off,
+                                                     const uint64_t *__restrict__ sy0, const uint8_t *__restrict__ sdir, uint8_t *contained,
+                                                     uint32_t bestn, int request_enabled, int do_emit, uint32_t *acc_count,
+                                                     const uint32_t *__restrict__ out_off, ovlp_rec *out, unsigned long long *n_unknown_total,
+                                                     uint8_t *unk_flag, const uint32_t *__restrict__ list) {
+  uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (r >= n_ranks) return;
+  if (list) r = list[r];
+  const uint32_t FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+  const uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
+  const uint64_t *y0s = sy0 + b;
+  const uint8_t *dirs = sdir + b;
+  uint8_t *cont = contained + b;
+  DevReplayCtx c;
+  c.s = st;
+  c.rank = r;
+  c.request_enabled = request_enabled != 0;
+  c.out = do_emit ? out + out_off[r] : nullptr;
+  for (uint32_t t = lane; t < n; t += 32) cont[t] = 0;
+  __syncwarp();
+  uint32_t n_acc = 0, n_unk = 0;
+  const uint64_t NONE = ~0ULL;
+  for (uint32_t k0 = n - 1; k0 > 0; k0--) {
+    const uint32_t i = k0 - 1;
+    if (cont[i]) continue;  // warp-uniform
+    const uint64_t y0 = y0s[i];
+    const uint32_t rid0 = (uint32_t)(y0 >> 32);
+    const uint32_t pos0 = (uint32_t)((y0 & 0xFFFFFFFFULL) >> 1) + 1;
+    const uint32_t rlen0 = c.rlen(rid0);
+    const uint32_t strand0 = dirs[i];
+    uint32_t oc = 0;
+    bool row_done = false;
+    uint32_t j0 = i + 1;
+    while (j0 < n && !row_done) {
+      const uint32_t j = j0 + lane;
+      // ---- phase A: classify (no side effects)
+      int kind = 0;  // 0 skip, 1 pair-table hit, 2 evaluate alignment
+      uint32_t type = 0, rid1 = 0, rlen1 = 0, strand1 = 0, start0 = 0;
+      uint64_t y1 = 0, ridp = 0;
+      bool accepted = false, known = true;
+      match_t m;
+      m.m_size = m.dist = m.q_bgn = m.q_end = m.t_bgn = m.t_end = m.t_m_end = m.q_m_end = 0;
+      if (j < n && !cont[j]) {
+        y1 = y0s[j];
+        rid1 = (uint32_t)(y1 >> 32);
+        if (rid1 != rid0) {
+          ridp = rid0 < rid1 ? ((uint64_t)rid0 << 32) | rid1 : ((uint64_t)rid1 << 32) | rid0;
+          uint64_t v = c.pair_old(ridp);
+          bool hit = (v != NONE) && ((uint32_t)(v >> 2) < r);
+          if (!hit) {
+            v = c.pair_new(ridp);
+            hit = (v != NONE) && ((uint32_t)(v >> 2) <= r);
+          }
+          if (hit) {
+            kind = 1;
+            type = (uint32_t)(v & 3);
+          } else {
+            kind = 2;
+            const uint32_t pos1 = (uint32_t)((y1 & 0xFFFFFFFFULL) >> 1) + 1;
+            rlen1 = c.rlen(rid1);
+            strand1 = dirs[j];
+            start0 = pos0 - pos1;
+            const uint32_t slen0 = rlen0 - pos0 + pos1, slen1 = rlen1;
+            known = c.aln_get(i, j, &m);
+            if (!known) predict_match(rlen0, rlen1, start0, &m);
+            const int64_t q_bgn = m.q_bgn, q_end = m.q_end, t_bgn = m.t_bgn, t_end = m.t_end;
+            int64_t dq = (int64_t)slen0 - q_end, dt = (int64_t)slen1 - t_end;
+            if (dq < 0) dq = -dq;
+            if (dt < 0) dt = -dt;
+            if (q_bgn < READ_END_FUZZINESS && t_bgn < READ_END_FUZZINESS && (dq < READ_END_FUZZINESS || dt < READ_END_FUZZINESS) &&
+                q_end > 500 && t_end > 500) {
+              accepted = true;
+              int64_t c0 = (int64_t)rlen0 - (q_end - q_bgn), c1 = (int64_t)rlen1 - (t_end - t_bgn);
+              if (c0 < 0) c0 = -c0;
+              if (c1 < 0) c1 = -c1;
+              if (c0 < READ_END_FUZZINESS * 2 || c1 < READ_END_FUZZINESS * 2) type = rlen0 >= rlen1 ? OVL_CONTAINS : OVL_CONTAINED;
+              else type = OVL_OVERLAP;
+            }
+          }
+        }
+      }
+      // ---- a lane that repeats the read of an earlier evaluate-lane must wait for that lane's pair_set
+      const uint32_t k2mask = __ballot_sync(FULL, kind == 2);
+      const uint32_t peers = __match_any_sync(FULL, kind ? rid1 : (0xF0000000u | lane));  // skip lanes never match each other
+      const bool dependent = kind != 0 && ((peers & lt & k2mask) != 0);
+      const uint32_t depmask = __ballot_sync(FULL, dependent);
+      const uint32_t live = depmask ? ((1u << (__ffs(depmask) - 1)) - 1u) : FULL;  // lanes handled this round
+      const bool mine = (live >> lane) & 1u;
+      // ---- phase B: sequential semantics
+      const bool inc = mine && ((kind == 1 && type == OVL_OVERLAP) || (kind == 2 && accepted && type == OVL_OVERLAP));
+      const bool stop = mine && kind == 2 && accepted && type == OVL_CONTAINED;
+      const uint32_t incmask = __ballot_sync(FULL, inc), stopmask = __ballot_sync(FULL, stop);
+      const bool reached = mine && (oc + __popc(incmask & lt) < bestn) && ((stopmask & lt) == 0);
+      const uint32_t reachmask = __ballot_sync(FULL, reached);
+      const bool acc = reached && kind == 2 && accepted;
+      const uint32_t accmask = __ballot_sync(FULL, acc);
+      if (reached && kind == 2) {
+        if (!known) {
+          n_unk++;
+          c.aln_request(i, j, rid0, start0, strand0, rid1, strand1);
+        }
+        if (accepted) {
+          if (type == OVL_CONTAINS) cont[j] = 1;
+          else if (type == OVL_CONTAINED) cont[i] = 1;
+          c.pair_set(ridp, ((uint64_t)r << 2) | type);
+          if (do_emit) {
+            ovlp_rec o;
+            o.y0 = y0; o.y1 = y1; o.rl0 = rlen0; o.rl1 = rlen1;
+            o.strand0 = (uint8_t)strand0; o.strand1 = (uint8_t)strand1; o.ovlp_type = (uint8_t)type; o.pad0 = 0;
+            o.match = m; o.pad1 = 0;
+            c.out[n_acc + __popc(accmask & lt)] = o;
+          }
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      n_acc += __popc(accmask);
+      oc += __popc(incmask & reachmask);
+      const uint32_t handled = depmask ? (uint32_t)(__ffs(depmask) - 1) : 32u;
+      // the row ends when bestn overlaps were counted, a CONTAINED record was reached, or a handled lane was not reached
+      if (oc >= bestn || (stopmask & reachmask) != 0) row_done = true;
+      j0 += handled;
+    }
+  }
+  if (lane == 0) acc_count[r] = n_acc;
+  const uint32_t unk_total = __reduce_add_sync(FULL, n_unk);
+  if (lane == 0) unk_flag[r] = unk_total != 0;
+  if (lane == 0 && unk_total) atomicAdd(n_unknown_total, (unsigned long long)unk_total);
+}
+
 #define PGB_MAXV 264  // supports band_tolerance <= 256
-__global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint64_t *__restrict__ w,
-                        const uint32_t *__restrict__ nm, const uint64_t *__restrict__ woff_by_rid,
+// sort key of an alignment request = predicted overlap length in 256-base units: warps then hold alignments of similar
+// length and finish together
+__global__ void k_align_keys(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint32_t *__restrict__ rlen_by_rid,
+                             uint32_t *keys, uint32_t *idx) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  AlnReq q = reqs[first + i];
+  uint32_t a = rlen_by_rid[q.rid0] - q.start0, b = rlen_by_rid[q.rid1];
+  uint32_t e = (a < b ? a : b) >> 8;
+  keys[i] = e > 255 ? 255 : e;
+  idx[i] = i;
+}
+// 1 thread = 1 alignment, flattened state machine (ovlp_match_flat); perm (optional) = processing order
+__global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint32_t *__restrict__ perm,
+                        const uint64_t *__restrict__ w, const uint32_t *__restrict__ nm, const uint64_t *__restrict__ woff_by_rid,
                         const uint32_t *__restrict__ rlen_by_rid, const uint32_t *__restrict__ hasn_by_rid, int bw, match_t *results,
                         int *err, unsigned long long *bases_total) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (perm) i = perm[i];
   AlnReq q = reqs[first + i];
   uint32_t rl0 = rlen_by_rid[q.rid0], rl1 = rlen_by_rid[q.rid1];
   SeqView qv = make_view(w, nm, woff_by_rid[q.rid0], rl0, q.start0, q.strands & 1, (int)hasn_by_rid[q.rid0]);
   SeqView tv = make_view(w, nm, woff_by_rid[q.rid1], rl1, 0, (q.strands >> 1) & 1, (int)hasn_by_rid[q.rid1]);
-  int Va[PGB_MAXV], Vb[PGB_MAXV];
+  int V[2 * PGB_MAXV];
   match_t m;
   int e = 0;
-  ovlp_match_core(qv, (int)(rl0 - q.start0), tv, (int)rl1, bw, Va, Vb, PGB_MAXV, &m, &e);
+  ovlp_match_flat(qv, (int)(rl0 - q.start0), tv, (int)rl1, bw, V, PGB_MAXV, &m, &e);
   if (e) atomicOr(err, 128 | (e << 8));
   results[first + i] = m;
-  // bases actually compared along the final path (algorithmic-bytes accounting, SURVEY 8d: (q_end + t_end)/4 per alignment)
+  // bases compared along the final path (algorithmic-bytes accounting, SURVEY 8d: (q_end + t_end)/4 per alignment)
   atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
+}
+
+// ---- incremental replay (DESIGN.md "dirty buckets"): a bucket has to be replayed again only if it still had predicted
+// alignments, or if the time-stamped pair table changed for a pair of reads that both occur in it.
+__device__ __forceinline__ uint32_t bloom_bit(uint32_t rid) { return ht_mix(rid) & 255u; }
+// per eligible bucket: (rid, rank) of every record + a 256-bit Bloom filter of its read ids
+__global__ void k_bucket_reads(uint32_t n_ranks, const uint32_t *__restrict__ rank_off, const uint64_t *__restrict__ sy0, uint32_t *rec_rid,
+                               uint32_t *rec_rank, uint64_t *bloom) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_ranks) return;
+  uint64_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  for (uint32_t t = rank_off[r]; t < rank_off[r + 1]; t++) {
+    uint32_t rid = (uint32_t)(sy0[t] >> 32);
+    rec_rid[t] = rid;
+    rec_rank[t] = r;
+    uint32_t bit = bloom_bit(rid);
+    uint64_t m = 1ULL << (bit & 63);
+    if ((bit >> 6) == 0) b0 |= m; else if ((bit >> 6) == 1) b1 |= m; else if ((bit >> 6) == 2) b2 |= m; else b3 |= m;
+  }
+  bloom[4 * (size_t)r] = b0; bloom[4 * (size_t)r + 1] = b1; bloom[4 * (size_t)r + 2] = b2; bloom[4 * (size_t)r + 3] = b3;
+}
+// table diff that also lists the changed pairs (up to cap)
+__global__ void k_table_diff_list(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, const uint64_t *__restrict__ keys, size_t n,
+                                  unsigned long long *diffs, uint64_t *changed, uint32_t cap) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    if (a[i] != b[i]) {
+      unsigned long long at = atomicAdd(diffs, 1ULL);
+      if (at < cap) changed[at] = keys[i];
+    }
+}
+// thread per changed pair: every bucket holding read a that may also hold read b becomes dirty
+__global__ void k_mark_dirty_pairs(const uint64_t *__restrict__ changed, uint32_t n_changed, const uint32_t *__restrict__ rid_sorted,
+                                   const uint32_t *__restrict__ rank_sorted, uint32_t n_rec, const uint64_t *__restrict__ bloom, uint8_t *dirty) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_changed) return;
+  const uint32_t a = (uint32_t)(changed[i] >> 32), b = (uint32_t)changed[i];
+  uint32_t lo = 0, hi = n_rec;  // lower_bound(a)
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (rid_sorted[mid] < a) lo = mid + 1; else hi = mid;
+  }
+  const uint32_t bit = bloom_bit(b);
+  for (uint32_t t = lo; t < n_rec && rid_sorted[t] == a; t++) {
+    uint32_t r = rank_sorted[t];
+    if (bloom[4 * (size_t)r + (bit >> 6)] >> (bit & 63) & 1ULL) dirty[r] = 1;
+  }
+}
+__global__ void k_dirty_from_unknown(const uint8_t *__restrict__ unk_flag, uint32_t n_ranks, uint8_t *dirty) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_ranks) dirty[r] = unk_flag[r];
+}
+__global__ void k_dirty_flags32(const uint8_t *__restrict__ dirty, uint32_t n_ranks, uint32_t *flags) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_ranks) flags[r] = dirty[r];
+}
+// entries owned by clean buckets are carried over, entries owned by dirty buckets are rebuilt by their replay
+__global__ void k_table_carry(const uint64_t *__restrict__ eold, uint64_t *enew, size_t n, const uint8_t *__restrict__ dirty) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint64_t v = eold[i];
+    enew[i] = (v != PGB_EMPTY && !dirty[(uint32_t)(v >> 2)]) ? v : PGB_EMPTY;
+  }
 }
 
 __global__ void k_table_diff(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, size_t n, unsigned long long *diffs) {

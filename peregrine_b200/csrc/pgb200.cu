@@ -669,6 +669,92 @@ extern "C" int pgb_set_shimmers_from_index(pgb_ctx *c, int level) {
   API_END(c)
 }
 
+// ================================================================================================ multi-GPU plumbing
+extern "C" size_t pgb_buffer_elems(pgb_ctx *c, int which) {
+  if (!c) return 0;
+  switch (which) {
+    case PGB_BUF_WORDS: case PGB_BUF_NMASK: return c->d_w ? (size_t)c->n_words : 0;
+    case PGB_BUF_ROW_RID: case PGB_BUF_ROW_LEN: case PGB_BUF_ROW_WOFF: case PGB_BUF_ROW_HASN: return c->n_rows;
+    case PGB_BUF_LEVEL0: case PGB_BUF_LEVEL1: case PGB_BUF_LEVEL2: return c->level_n[which - PGB_BUF_LEVEL0];
+    default: return 0;
+  }
+}
+extern "C" int pgb_buffer_copy_out(pgb_ctx *c, int which, void *dst) {
+  API_BEGIN(c)
+  size_t n = pgb_buffer_elems(c, which);
+  const void *src = nullptr;
+  size_t esz = 0;
+  uint32_t *tmp = nullptr;
+  switch (which) {
+    case PGB_BUF_WORDS: src = c->d_w; esz = 8; break;
+    case PGB_BUF_NMASK: src = c->d_nm; esz = 4; break;
+    case PGB_BUF_ROW_RID: src = c->d_row_rid; esz = 4; break;
+    case PGB_BUF_ROW_LEN: src = c->d_row_len; esz = 4; break;
+    case PGB_BUF_ROW_WOFF: src = c->d_row_woff; esz = 8; break;
+    case PGB_BUF_ROW_HASN:
+      tmp = c->alloc<uint32_t>(n);
+      LAUNCH(c, k_rows_hasn, nblk(n), 256, c->d_row_rid, c->d_hasn_by_rid, (uint32_t)n, tmp);
+      src = tmp; esz = 4; break;
+    case PGB_BUF_LEVEL0: case PGB_BUF_LEVEL1: case PGB_BUF_LEVEL2: src = c->d_level[which - PGB_BUF_LEVEL0]; esz = 16; break;
+    default: throw std::runtime_error("unknown buffer id");
+  }
+  if (n) CU(cudaMemcpyAsync(dst, src, n * esz, cudaMemcpyDeviceToDevice, c->st));
+  c->sync();
+  API_END(c)
+}
+extern "C" int pgb_load_packed_device(pgb_ctx *c, const uint64_t *words, const uint32_t *nmask, size_t n_words, const uint32_t *row_rid,
+                                      const uint32_t *row_len, const uint64_t *row_woff, const uint32_t *row_hasn, size_t n_rows) {
+  API_BEGIN(c)
+  c->free_reads();
+  if (n_words < 4) throw std::runtime_error("packed word array must include its guard words");
+  uint32_t *d_max = c->alloc<uint32_t>(1);
+  CU(cudaMemsetAsync(d_max, 0, 4, c->st));
+  LAUNCH(c, k_max_u32, nblk(n_rows), 256, row_rid, (uint32_t)n_rows, d_max);
+  uint32_t max_rid = 0;
+  c->d2h(&max_rid, d_max, 4);
+  if (n_rows && (uint64_t)max_rid > 8 * (uint64_t)n_rows + (1u << 20)) throw std::runtime_error("read ids too sparse");
+  c->max_rid = max_rid; c->n_rows = n_rows; c->n_words = n_words;
+  c->d_w = c->palloc<uint64_t>(n_words); c->d_nm = c->palloc<uint32_t>(n_words);
+  c->d_rlen_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1); c->d_hasn_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1);
+  c->d_woff_by_rid = c->palloc<uint64_t>((size_t)max_rid + 1);
+  c->d_row_rid = c->palloc<uint32_t>(n_rows); c->d_row_len = c->palloc<uint32_t>(n_rows); c->d_row_woff = c->palloc<uint64_t>(n_rows);
+  c->d_sel_rows = c->palloc<uint32_t>(n_rows);
+  CU(cudaMemcpyAsync(c->d_w, words, n_words * 8, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemcpyAsync(c->d_nm, nmask, n_words * 4, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemcpyAsync(c->d_row_rid, row_rid, n_rows * 4, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemcpyAsync(c->d_row_len, row_len, n_rows * 4, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemcpyAsync(c->d_row_woff, row_woff, n_rows * 8, cudaMemcpyDeviceToDevice, c->st));
+  CU(cudaMemsetAsync(c->d_rlen_by_rid, 0, ((size_t)max_rid + 1) * 4, c->st));
+  CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)max_rid + 1) * 4, c->st));
+  CU(cudaMemsetAsync(c->d_woff_by_rid, 0, ((size_t)max_rid + 1) * 8, c->st));
+  LAUNCH(c, k_rows_to_rid_tables, nblk(n_rows), 256, row_rid, row_len, row_woff, row_hasn, (uint32_t)n_rows, c->d_rlen_by_rid, c->d_woff_by_rid,
+         c->d_hasn_by_rid);
+  c->h_row_len.resize(n_rows);
+  c->d2h(c->h_row_len.data(), c->d_row_len, n_rows * 4);
+  std::vector<uint32_t> ident(n_rows);
+  for (size_t j = 0; j < n_rows; j++) ident[j] = (uint32_t)j;
+  c->h2d(c->d_sel_rows, ident.data(), n_rows * 4);
+  c->sel_bases = 0;
+  for (uint32_t l : c->h_row_len) c->sel_bases += l;
+  c->sync();
+  API_END(c)
+}
+extern "C" int pgb_set_shimmers_device(pgb_ctx *c, const mm128_t *mmers, size_t n) {
+  API_BEGIN(c)
+  c->free_shimmers();
+  c->tic();
+  c->d_shm = c->palloc<mm128>(n); c->n_shm = n; c->shm_owned = true;
+  if (n) CU(cudaMemcpyAsync(c->d_shm, mmers, n * sizeof(mm128), cudaMemcpyDeviceToDevice, c->st));
+  uint32_t cap = pow2_at_least(2 * (uint64_t)n + 16);
+  c->d_mckeys = c->palloc<uint64_t>(cap); c->d_mcvals = c->palloc<uint32_t>(cap); c->mcmask = cap - 1;
+  LAUNCH(c, k_fill_u64, 1184, 256, c->d_mckeys, PGB_EMPTY, (size_t)cap);
+  CU(cudaMemsetAsync(c->d_mcvals, 0, (size_t)cap * 4, c->st));
+  LAUNCH(c, k_mc_insert, nblk(n), 256, c->d_shm, n, c->d_mckeys, c->d_mcvals, cap - 1, c->d_err);
+  c->stats.ms_count += c->toc();
+  c->check_err("pgb_set_shimmers_device");
+  API_END(c)
+}
+
 // ================================================================================================ overlap
 extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t bestn, uint32_t mc_lower, uint32_t mc_upper,
                            uint32_t bw, uint32_t ovlp_upper) {
@@ -874,17 +960,51 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     c->release(sy0); c->release(sy1); c->release(sseq); c->release(sdir); c->release(contained); c->release(d_rank_off);
   };
   bool wet = false, converged = false;
-  uint64_t prev_diffs = ~0ULL;
+  const char *rp_env = getenv("PGB_REPLAY");
+  const bool warp_replay = rp_env && !strcmp(rp_env, "warp");  // default: one thread per bucket (the warp form issues ~30x more instructions)
+  const bool incremental = !(getenv("PGB_REPLAY_FULL"));        // PGB_REPLAY_FULL=1: replay every bucket in every pass
+  // incremental passes: (rid, rank) index of the eligible records sorted by rid + per-bucket Bloom filter of read ids
+  const uint32_t CHANGED_CAP = 16384;
+  uint32_t *rid_sorted = c->alloc<uint32_t>(n_elig), *rank_sorted = c->alloc<uint32_t>(n_elig);
+  uint64_t *bloom = c->alloc<uint64_t>(4 * (size_t)n_ranks), *changed = c->alloc<uint64_t>(CHANGED_CAP);
+  uint8_t *unk_flag = c->alloc<uint8_t>(n_ranks), *dirty = c->alloc<uint8_t>(n_ranks);
+  uint32_t *dflags = c->alloc<uint32_t>((size_t)n_ranks + 1), *dpos = c->alloc<uint32_t>((size_t)n_ranks + 1), *dlist = c->alloc<uint32_t>(n_ranks);
+  {
+    uint32_t *rr = c->alloc<uint32_t>(n_elig), *rk = c->alloc<uint32_t>(n_elig);
+    LAUNCH(c, k_bucket_reads, nblk(n_ranks, 128), 128, n_ranks, d_rank_off, sy0, rr, rk, bloom);
+    sort_pairs_u32(c, rr, rid_sorted, rk, rank_sorted, n_elig);
+    CU(cudaMemsetAsync(unk_flag, 0, n_ranks, c->st));
+    CU(cudaMemsetAsync(dflags, 0, ((size_t)n_ranks + 1) * 4, c->st));
+  }
+  uint64_t prev_diffs = ~0ULL, last_diffs = ~0ULL;
   int dry_passes = 0;
   for (int pass = 0; pass < 400; pass++) {
     c->tic();
-    LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
     CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
+    // which buckets run in this pass
+    uint32_t n_run = n_ranks;
+    const uint32_t *run_list = nullptr;
+    const bool partial = incremental && pass > 0 && last_diffs <= CHANGED_CAP;
+    if (partial) {
+      LAUNCH(c, k_dirty_from_unknown, nblk(n_ranks), 256, unk_flag, n_ranks, dirty);
+      if (last_diffs) LAUNCH(c, k_mark_dirty_pairs, nblk(last_diffs), 256, changed, (uint32_t)last_diffs, rid_sorted, rank_sorted, n_elig, bloom, dirty);
+      LAUNCH(c, k_dirty_flags32, nblk(n_ranks), 256, dirty, n_ranks, dflags);
+      n_run = scan_u32(c, dflags, dpos, (size_t)n_ranks + 1);
+      LAUNCH(c, k_compact_idx, nblk(n_ranks), 256, dflags, dpos, (size_t)n_ranks, dlist);
+      LAUNCH(c, k_table_carry, 1184, 256, S.eold, S.enew, (size_t)ecap, dirty);
+      run_list = dlist;
+    } else {
+      LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
+    }
     c->ktic();
-    LAUNCH(c, k_replay, nblk(n_ranks, 64), 64, S, n_ranks, d_rank_off, sy0, sdir, contained, bestn, wet ? 1 : 0, 0, acc,
-           (const uint32_t *)nullptr, (ovlp_rec *)nullptr, d_ctr);
+    if (warp_replay)
+      LAUNCH(c, k_replay_warp, nblk((size_t)n_run * 32, 128), 128, S, n_run, d_rank_off, sy0, sdir, contained, bestn, wet ? 1 : 0, 0, acc,
+             (const uint32_t *)nullptr, (ovlp_rec *)nullptr, d_ctr, unk_flag, run_list);
+    else
+      LAUNCH(c, k_replay, nblk(n_run, 64), 64, S, n_run, run_list, d_rank_off, sy0, sdir, contained, bestn, wet ? 1 : 0, 0, acc,
+             (const uint32_t *)nullptr, (ovlp_rec *)nullptr, d_ctr, unk_flag);
     c->stats.ms_k_replay += c->ktoc(); c->stats.n_k_replay++;
-    LAUNCH(c, k_table_diff, 1184, 256, S.eold, S.enew, (size_t)ecap, d_ctr + 1);
+    LAUNCH(c, k_table_diff_list, 1184, 256, S.eold, S.enew, S.ekeys, (size_t)ecap, d_ctr + 1, changed, CHANGED_CAP);
     unsigned long long ctr[2];
     uint32_t n_req = 0;
     c->d2h(ctr, d_ctr, 16);
@@ -895,8 +1015,19 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     if (n_req > S.n_done) {
       c->tic();
       uint32_t nn = n_req - S.n_done;
+      uint32_t *perm = nullptr;
+      if (nn > 8192) {  // group alignments of similar predicted length into the same warps
+        uint32_t *keys = c->alloc<uint32_t>(nn), *keys2 = c->alloc<uint32_t>(nn), *idx0 = c->alloc<uint32_t>(nn);
+        perm = c->alloc<uint32_t>(nn);
+        LAUNCH(c, k_align_keys, nblk(nn), 256, S.reqs, S.n_done, nn, c->d_rlen_by_rid, keys, idx0);
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
+        uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+        CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
+        c->stats.kernel_launches += 3;
+      }
       c->ktic();
-      LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, S.n_done, nn, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
+      LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, S.n_done, nn, perm, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
              (int)bw, S.results, c->d_err, c->d_align_bases);
       c->stats.ms_k_align += c->ktoc(); c->stats.n_k_align++;
       {
@@ -913,7 +1044,10 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     S.n_done = n_req;
     std::swap(S.eold, S.enew);
     if (getenv("PGB_VERBOSE"))
-      fprintf(stderr, "pgb200: replay pass %d %s: unknown=%llu table_diffs=%llu requests=%u\n", pass, wet ? "wet" : "dry", ctr[0], ctr[1], n_req);
+      fprintf(stderr, "pgb200: replay pass %d %s: buckets=%u/%u unknown=%llu table_diffs=%llu requests=%u\n", pass, wet ? "wet" : "dry", n_run, n_ranks,
+              ctr[0], ctr[1], n_req);
+    last_diffs = ctr[1];
+    c->stats.n_replay_buckets += n_run;
     if (wet && !new_requests && ctr[0] == 0 && ctr[1] == 0) { converged = true; break; }
     if (!wet) {
       // speculative ("dry") passes settle the time-stamped pair table with predicted alignments only; switch to real
@@ -931,7 +1065,12 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   c->d_ovl = c->palloc<ovlp_rec>(n_out); c->n_ovl = n_out;
   LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
   CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
-  LAUNCH(c, k_replay, nblk(n_ranks, 64), 64, S, n_ranks, d_rank_off, sy0, sdir, contained, bestn, 0, 1, acc, out_off, c->d_ovl, d_ctr);
+  if (warp_replay)
+    LAUNCH(c, k_replay_warp, nblk((size_t)n_ranks * 32, 128), 128, S, n_ranks, d_rank_off, sy0, sdir, contained, bestn, 0, 1, acc, out_off, c->d_ovl, d_ctr,
+           unk_flag, (const uint32_t *)nullptr);
+  else
+    LAUNCH(c, k_replay, nblk(n_ranks, 64), 64, S, n_ranks, (const uint32_t *)nullptr, d_rank_off, sy0, sdir, contained, bestn, 0, 1, acc, out_off, c->d_ovl,
+           d_ctr, unk_flag);
   c->sync();
   c->stats.ms_emit += c->toc();
   c->stats.n_overlaps += n_out;
@@ -1198,7 +1337,7 @@ extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_
     AlnReq *d_q = c->alloc<AlnReq>(1);
     match_t *d_m = c->alloc<match_t>(1);
     c->h2d(d_q, &q, sizeof q);
-    LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err, c->d_align_bases);
+    LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, (const uint32_t *)nullptr, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err, c->d_align_bases);
     c->d2h(rtn, d_m, sizeof(match_t));
     c->release(d_q); c->release(d_m);
     c->sync();

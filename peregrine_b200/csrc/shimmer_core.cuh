@@ -273,6 +273,109 @@ PGB_HD void ovlp_match_core(const SeqView &q, int q_len, const SeqView &t, int t
   *out = r;
 }
 
+// ---------------------------------------------------------------------------------------------- ovlp_match, flattened
+// Same algorithm and results as ovlp_match_core, restructured for SIMT: ONE loop whose every iteration performs one
+// 32-base snake word-step, preceded by the cell set-up when a new diagonal starts and followed by the cell / edit-distance
+// bookkeeping when the snake ended.  All lanes of a warp therefore run the same instruction stream whatever (d, k) they are
+// at; only the short band-trimming loop at the end of an edit distance remains data dependent.
+// V: caller scratch of 2*cap ints (two rows used alternately).
+PGB_HD void ovlp_match_flat(const SeqView &q, int q_len, const SeqView &t, int t_len, int band_tolerance, int *V, int cap,
+                            match_t *out, int *err) {
+  match_t r;
+  r.m_size = r.dist = r.q_bgn = r.q_end = r.t_bgn = r.t_end = r.t_m_end = r.q_m_end = 0;
+  const int max_d = (int)(0.3 * (double)(q_len + t_len));
+  const int band_size = band_tolerance * 2;
+  const int has_n = q.has_n | t.has_n;
+  uint32_t longest_match = 0;
+  bool start = false, matched = false;
+  int best_m = -1, min_k = 0, max_k = 0, pbase = 0;
+  int d = 0, k = 0, idx = 0, x = 0, y = 0, x1 = 0, y1 = 0;
+  int cur = 0;              // V + cur*cap is the row being written, the other row holds d-1
+  bool new_cell = true;
+  bool running = max_d > 0;  // d = 0: band is a single diagonal, always within band_size
+  while (running) {
+    int *Vc = V + cur * cap;
+    const int *Vp = V + (cur ^ 1) * cap;
+    if (new_cell) {  // DWmatch.c:125-131
+      if (d == 0) x = 0;
+      else if (k == min_k) x = Vp[(k + 1 - pbase) >> 1];
+      else if (k == max_k) x = Vp[(k - 1 - pbase) >> 1] + 1;
+      else {
+        const int vm = Vp[(k - 1 - pbase) >> 1], vp = Vp[(k + 1 - pbase) >> 1];
+        x = (vm < vp) ? vp : vm + 1;
+      }
+      y = x - k;
+      x1 = x;
+      y1 = y;
+      new_cell = false;
+    }
+    // one snake word-step (DWmatch.c:135-140)
+    int rem = q_len - x;
+    if (t_len - y < rem) rem = t_len - y;
+    bool more = false;
+    if (rem > 0) {
+      uint64_t df = fetch32(q, x) ^ fetch32(t, y);
+      df = (df | (df >> 1)) & 0x5555555555555555ULL;
+      if (has_n) {
+        const uint32_t qn = q.has_n ? fetchn32(q, x) : 0u, tn = t.has_n ? fetchn32(t, y) : 0u;
+        uint64_t both = qn & tn, one = qn ^ tn;  // N equals only N (nibble 0 == nibble 0 in the reference)
+        both = (both | (both << 16)) & 0x0000FFFF0000FFFFULL; one = (one | (one << 16)) & 0x0000FFFF0000FFFFULL;
+        both = (both | (both << 8)) & 0x00FF00FF00FF00FFULL;  one = (one | (one << 8)) & 0x00FF00FF00FF00FFULL;
+        both = (both | (both << 4)) & 0x0F0F0F0F0F0F0F0FULL;  one = (one | (one << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+        both = (both | (both << 2)) & 0x3333333333333333ULL;  one = (one | (one << 2)) & 0x3333333333333333ULL;
+        both = (both | (both << 1)) & 0x5555555555555555ULL;  one = (one | (one << 1)) & 0x5555555555555555ULL;
+        df = (df & ~both) | one;
+      }
+      int n = df ? (ctz64(df) >> 1) : 32;
+      if (n > rem) n = rem;
+      x += n;
+      y += n;
+      more = (n == 32) && (rem > 32);
+    }
+    if (more) continue;
+    // ---- the snake of cell (d, k) ended
+    if ((x - x1 > 16) && !start) { r.q_bgn = x1; r.t_bgn = y1; start = true; }             // DWmatch.c:142-146
+    if ((uint32_t)(x - x1) > longest_match) { longest_match = (uint32_t)(x - x1); r.q_m_end = x; r.t_m_end = y; }  // :148-152
+    Vc[idx] = x;
+    if (x + y > best_m) best_m = x + y;
+    if (x >= q_len || y >= t_len) {  // :161-164, :185-194
+      matched = true;
+      r.q_end = x;
+      r.t_end = y;
+      r.dist = d;
+      r.m_size = (r.q_end - r.q_bgn + r.t_end - r.t_bgn + 2 * d) / 2;
+      break;
+    }
+    new_cell = true;
+    if (k + 2 <= max_k) {
+      k += 2;
+      idx++;
+      continue;
+    }
+    // ---- end of edit distance d: trim the band (DWmatch.c:168-183), advance d
+    int new_min_k = max_k, new_max_k = min_k, i2 = 0;
+    for (int k2 = min_k; k2 <= max_k; k2 += 2, i2++) {
+      if (2 * Vc[i2] - k2 >= best_m - band_tolerance) {
+        if (k2 < new_min_k) new_min_k = k2;
+        if (k2 > new_max_k) new_max_k = k2;
+      }
+    }
+    pbase = min_k;
+    max_k = new_max_k + 1;
+    min_k = new_min_k - 1;
+    cur ^= 1;
+    d++;
+    k = min_k;
+    idx = 0;
+    if (d >= max_d) break;
+    if (max_k - min_k > band_size) break;  // DWmatch.c:120-122
+    if (min_k > max_k) { *err |= 1; break; }
+    if (((max_k - min_k) >> 1) + 1 > cap) { *err |= 2; break; }
+  }
+  if (!matched) { r.q_bgn = 0; r.t_bgn = 0; }
+  *out = r;
+}
+
 // ---------------------------------------------------------------------------------------------- mm_sketch (exact automaton)
 // One read, forward strand, sequential — a literal restatement of src/mm_sketch.c:84-150 for is_hpc == 0 over the
 // packed representation.  Used (a) for reads the tiled fast kernel flags (N, hash ties, palindrome-dense halos) and

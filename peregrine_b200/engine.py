@@ -42,7 +42,8 @@ class _Stats(C.Structure):
                                      "n_align_bases", "n_replay_passes", "n_overlaps")]
         + [(n, C.c_double) for n in ("ms_k_sketch_count", "ms_k_sketch_write", "ms_k_align", "ms_k_replay")]
         + [(n, C.c_uint64) for n in ("n_k_sketch_count", "n_k_sketch_write", "n_k_align", "n_k_replay")]
-        + [("ms_k_sketch_tiled", C.c_double), ("n_k_sketch_tiled", C.c_uint64), ("n_sketch_fallback_reads", C.c_uint64)]
+        + [("ms_k_sketch_tiled", C.c_double), ("n_k_sketch_tiled", C.c_uint64), ("n_sketch_fallback_reads", C.c_uint64),
+           ("n_replay_buckets", C.c_uint64)]
     )
 
 
@@ -81,6 +82,11 @@ def load_library():
     L.pgb_overlap_size.restype = C.c_size_t
     L.pgb_overlap_size.argtypes = [vp]
     L.pgb_overlap_copy.argtypes = [vp, vp]
+    L.pgb_buffer_elems.restype = C.c_size_t
+    L.pgb_buffer_elems.argtypes = [vp, C.c_int]
+    L.pgb_buffer_copy_out.argtypes = [vp, C.c_int, vp]
+    L.pgb_load_packed_device.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp, vp, C.c_size_t]
+    L.pgb_set_shimmers_device.argtypes = [vp, vp, C.c_size_t]
     L.pgb_stats_reset.argtypes = [vp]
     L.pgb_stats_get.argtypes = [vp, C.POINTER(_Stats)]
     L.pgb_event_record.argtypes = [vp, C.c_int]
@@ -190,6 +196,24 @@ class Engine:
         if n:
             self._ck(self.L.pgb_overlap_copy(self.h, _ptr(out)), "pgb_overlap_copy")
         return out
+
+    # ------------------------------------------------------------------ multi-GPU plumbing (device buffers)
+    BUF_WORDS, BUF_NMASK, BUF_ROW_RID, BUF_ROW_LEN, BUF_ROW_WOFF, BUF_ROW_HASN = 0, 1, 2, 3, 4, 5
+    BUF_LEVEL0, BUF_LEVEL1, BUF_LEVEL2 = 8, 9, 10
+
+    def buffer_elems(self, which):
+        return self.L.pgb_buffer_elems(self.h, which)
+
+    def buffer_copy_out(self, which, dst_device_ptr: int):
+        self._ck(self.L.pgb_buffer_copy_out(self.h, which, C.c_void_p(dst_device_ptr)), "pgb_buffer_copy_out")
+
+    def load_packed_device(self, words_ptr, nmask_ptr, n_words, row_rid_ptr, row_len_ptr, row_woff_ptr, row_hasn_ptr, n_rows):
+        self._ck(self.L.pgb_load_packed_device(self.h, C.c_void_p(words_ptr), C.c_void_p(nmask_ptr), n_words, C.c_void_p(row_rid_ptr),
+                                               C.c_void_p(row_len_ptr), C.c_void_p(row_woff_ptr), C.c_void_p(row_hasn_ptr), n_rows),
+                 "pgb_load_packed_device")
+
+    def set_shimmers_device(self, mm_ptr: int, n: int):
+        self._ck(self.L.pgb_set_shimmers_device(self.h, C.c_void_p(mm_ptr), n), "pgb_set_shimmers_device")
 
     # ------------------------------------------------------------------ stats
     def event_record(self, slot):

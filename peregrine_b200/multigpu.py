@@ -1,0 +1,123 @@
+"""One process per GPU: shard the SHIMMER index by read id and the overlap by SHIMMER-hash chunk, exactly as the reference
+shards its processes (rid % T for shmr_index, src/shmr_index.c:157; (hash % T) for shmr_overlap, src/shmr_utils.c:337,362),
+with T = world size and rank r owning chunk r + 1.
+
+The reference's "exchange" is the shared file system: every shmr_overlap process reads ALL L2 chunk files and mmaps the whole
+.seqdb (src/shmr_overlap.c:359-382,200).  Here it is one collective step over NVLink (torch.distributed / NCCL):
+
+  * all-gather of the 2-bit packed reads + read table (so that any rank can align any pair of reads), and
+  * all-gather of the per-chunk SHIMMER lists in chunk order (= the reference's file concatenation order, which fixes the
+    hash-table insertion order and therefore the output order).
+
+After the exchange no rank needs another rank again (rid_pairs is per chunk in the reference as well).  The functions below
+are device-agnostic torch code so that the layout logic is covered by gloo/CPU tests; the engine calls move bytes between
+libpgb200's buffers and torch tensors.
+"""
+from __future__ import annotations
+
+import torch
+
+READ_KEYS = ("words", "nmask", "row_rid", "row_len", "row_woff", "row_hasn")
+
+
+def all_gather_var(t: torch.Tensor, group=None):
+    """all_gather of 1-D tensors whose length differs per rank (pad to the longest; NCCL needs equal sizes)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    if t.dim() == 1:
+        pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+    else:
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return [o[:s] for o, s in zip(outs, sizes)]
+
+
+def concat_reads(parts):
+    """parts[r] = dict of rank r's buffers (READ_KEYS).  Concatenate in rank order; row_woff is rebased onto the
+    concatenated word array (each rank's block keeps its own guard words, which is harmless)."""
+    out = {}
+    base = 0
+    woffs = []
+    for p in parts:
+        woffs.append(p["row_woff"] + base)
+        base += int(p["words"].shape[0])
+    out["row_woff"] = torch.cat(woffs)
+    for k in ("words", "nmask", "row_rid", "row_len", "row_hasn"):
+        out[k] = torch.cat([p[k] for p in parts])
+    return out
+
+
+def exchange_reads(part, group=None):
+    gathered = {k: all_gather_var(part[k], group) for k in READ_KEYS}
+    world = len(gathered["words"])
+    return concat_reads([{k: gathered[k][r] for k in READ_KEYS} for r in range(world)])
+
+
+def exchange_shimmers(l2: torch.Tensor, group=None):
+    """l2: (n, 2) int64 view of this rank's mm128_t list.  Result: all chunks concatenated in chunk (= rank) order."""
+    return torch.cat(all_gather_var(l2, group))
+
+
+# ------------------------------------------------------------------------------------------------ engine <-> torch
+def export_reads(eng, device):
+    """Copy the engine's packed reads + read table into fresh torch tensors on `device` (a CUDA device)."""
+    E = eng
+    spec = (("words", E.BUF_WORDS, torch.int64), ("nmask", E.BUF_NMASK, torch.int32), ("row_rid", E.BUF_ROW_RID, torch.int32),
+            ("row_len", E.BUF_ROW_LEN, torch.int32), ("row_woff", E.BUF_ROW_WOFF, torch.int64), ("row_hasn", E.BUF_ROW_HASN, torch.int32))
+    out = {}
+    for name, which, dt in spec:
+        t = torch.empty(E.buffer_elems(which), dtype=dt, device=device)
+        E.buffer_copy_out(which, t.data_ptr())
+        out[name] = t
+    return out
+
+
+def export_level(eng, level, device):
+    n = eng.buffer_elems(eng.BUF_LEVEL0 + level)
+    t = torch.empty((n, 2), dtype=torch.int64, device=device)
+    eng.buffer_copy_out(eng.BUF_LEVEL0 + level, t.data_ptr())
+    return t
+
+
+def import_reads(eng, reads):
+    r = {k: v.contiguous() for k, v in reads.items()}
+    eng.load_packed_device(r["words"].data_ptr(), r["nmask"].data_ptr(), r["words"].shape[0], r["row_rid"].data_ptr(), r["row_len"].data_ptr(),
+                           r["row_woff"].data_ptr(), r["row_hasn"].data_ptr(), r["row_rid"].shape[0])
+
+
+def import_shimmers(eng, l2_all):
+    l2_all = l2_all.contiguous()
+    eng.set_shimmers_device(l2_all.data_ptr(), l2_all.shape[0])
+
+
+class ShardedJob:
+    """index (own reads) -> exchange -> overlap (own hash chunk) for one rank.
+
+    idx_eng holds the rank's own reads (index stage); ovl_eng receives the gathered read set (overlap stage).  They may be
+    the same Engine when the raw image does not have to stay resident between steps."""
+
+    def __init__(self, idx_eng, ovl_eng, rank, world, device, group=None):
+        self.idx_eng, self.ovl_eng, self.rank, self.world, self.device, self.group = idx_eng, ovl_eng, rank, world, device, group
+
+    def index_and_exchange(self, w, k, r):
+        self.idx_eng.index(w, k, r, 2, 0)
+        part = export_reads(self.idx_eng, self.device)
+        l2 = export_level(self.idx_eng, 2, self.device)
+        torch.cuda.synchronize(self.device)
+        reads = exchange_reads(part, self.group)
+        l2_all = exchange_shimmers(l2, self.group)
+        torch.cuda.synchronize(self.device)
+        import_reads(self.ovl_eng, reads)
+        import_shimmers(self.ovl_eng, l2_all)
+        return int(reads["words"].shape[0]) * 12 + int(l2_all.shape[0]) * 16  # bytes this rank ends up holding from the exchange
+
+    def overlap(self, bestn=4, mc_lower=2, mc_upper=240, bw=100, ovlp_upper=120, copy=True):
+        return self.ovl_eng.overlap(self.world, self.rank + 1, bestn, mc_lower, mc_upper, bw, ovlp_upper, copy=copy)

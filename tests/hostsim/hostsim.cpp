@@ -243,7 +243,11 @@ static int one_match(const Packed &P, size_t r0, uint32_t start0, int s0, size_t
   SeqView t = make_view(P.w.data(), P.nm.data(), P.woff[r1], rlen1, 0, s1, P.has_n[r1]);
   match_t mine; int err = 0;
   ovlp_match_core(q, qlen, t, tlen, bw, Va.data(), Vb.data(), bw + 8, &mine, &err);
-  int ok = same_match(*ref, mine) && err == 0;
+  match_t flat; int err2 = 0;
+  std::vector<int> Vf(2 * (bw + 8));
+  ovlp_match_flat(q, qlen, t, tlen, bw, Vf.data(), bw + 8, &flat, &err2);
+  int ok = same_match(*ref, mine) && err == 0 && same_match(*ref, flat) && err2 == 0;
+  if (!same_match(*ref, flat) && *bad < 8) fprintf(stderr, "FLAT differs: {%d %d %d %d %d %d %d %d}\n", flat.m_size, flat.dist, flat.q_bgn, flat.q_end, flat.t_bgn, flat.t_end, flat.t_m_end, flat.q_m_end);
   if (!ok) {
     if (*bad < 8)
       fprintf(stderr, "match mismatch rows %zu(+%u,s%d) %zu(s%d) bw=%d err=%d: ref{%d %d %d %d %d %d %d %d} mine{%d %d %d %d %d %d %d %d}\n", r0,
@@ -315,6 +319,12 @@ static match_t do_align(const Packed &P, uint32_t rid0, uint32_t start0, uint32_
   match_t m; int err = 0;
   ovlp_match_core(q, (int)(rlen0 - start0), t, (int)rlen1, bw, Va.data(), Vb.data(), bw + 8, &m, &err);
   if (err) fprintf(stderr, "ovlp_match_core err=%d\n", err);
+  {  // the flattened (SIMT-friendly) form must give the same answer on every alignment the pipeline runs
+    static std::vector<int> Vf; Vf.resize(2 * (bw + 8));
+    match_t f; int e2 = 0;
+    ovlp_match_flat(q, (int)(rlen0 - start0), t, (int)rlen1, bw, Vf.data(), bw + 8, &f, &e2);
+    if (e2 || memcmp(&f, &m, sizeof f)) { fprintf(stderr, "ovlp_match_flat disagrees with ovlp_match_core (rid %u vs %u)\n", rid0, rid1); exit(5); }
+  }
   return m;
 }
 

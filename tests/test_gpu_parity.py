@@ -190,3 +190,44 @@ def test_tiled_sketch_reports_fallbacks(workdir, ref_dir):
     rp = D.ref_index(ref_dir, p, os.path.join(workdir, "adv/ref_T1"), T=1, extra=["-m", "1"])
     assert np.array_equal(eng.level(0), F.read_mmlist(rp + "-L0-01-of-01.dat"))
     eng.close()
+
+
+def test_warp_cooperative_replay_kernel(sim1, workdir, ref_dir, monkeypatch):
+    """PGB_REPLAY=warp selects the warp-cooperative replay kernel (the default is one thread per bucket)."""
+    monkeypatch.setenv("PGB_REPLAY", "warp")
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref1"), T=1)
+    oo = ours_overlap(sim1, rp, 2, os.path.join(workdir, "sim1/our_warp"), T=1)
+    assert_same_ovlp(oo[0], ro[0])
+
+
+def test_sharded_exchange_matches_reference(sim1, workdir, ref_dir):
+    """Multi-GPU data path on one device: three 'ranks' (engines) each sketch the reads of their index chunk, the packed
+    reads and SHIMMER lists are concatenated exactly as the NCCL all-gather of peregrine_b200.multigpu does, and every rank
+    then produces its hash chunk; records must equal the reference's shmr_overlap -t 3 -c {1,2,3} on 3 index chunk files."""
+    import torch
+    from peregrine_b200 import Engine, multigpu as M
+
+    T = 3
+    dev = torch.device("cuda", 0)
+    rid, ln, off = F.read_idx(sim1 + ".idx")
+    seqdb = np.fromfile(sim1 + ".seqdb", dtype=np.uint8)
+    engs = [Engine(0) for _ in range(T)]
+    parts, l2s = [], []
+    for r in range(T):
+        engs[r].load_reads(seqdb, rid, ln, off, T, r + 1)
+        engs[r].index(80, 16, 6, 2)
+        parts.append(M.export_reads(engs[r], dev))
+        l2s.append(M.export_level(engs[r], 2, dev))
+    reads = M.concat_reads(parts)
+    l2_all = torch.cat(l2s)
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref3"), T=T, extra=["-m", "0"])
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref3o"), T=T)
+    for r in range(T):
+        M.import_reads(engs[r], reads)
+        M.import_shimmers(engs[r], l2_all)
+        ov = engs[r].overlap(T, r + 1)
+        want = F.normalise_ovlp(F.read_ovlp(ro[r]))
+        assert len(ov) == len(want) and ov.tobytes() == want.tobytes(), f"chunk {r + 1}"
+    for e in engs:
+        e.close()

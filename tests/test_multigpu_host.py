@@ -1,0 +1,74 @@
+"""CPU tests of the multi-GPU host logic: world_size-2 gloo run of the exchange (variable-size all-gather, concatenation
+order, word-offset rebasing).  The GPU-side equivalent (three ranks simulated on one device, compared with the reference's
+T=3 chunk files) is tests/test_gpu_parity.py::test_sharded_exchange_matches_reference."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from peregrine_b200 import multigpu as M
+
+
+def _part(rank):
+    g = torch.Generator().manual_seed(100 + rank)
+    n_rows = 3 + rank
+    lens = torch.randint(1, 200, (n_rows,), generator=g, dtype=torch.int32)
+    words_per = (lens.to(torch.int64) + 31) // 32
+    woff = torch.cumsum(torch.cat([torch.tensor([2]), words_per[:-1]]), 0)
+    n_words = int(words_per.sum()) + 4
+    return {
+        "words": torch.randint(0, 2**62, (n_words,), generator=g, dtype=torch.int64),
+        "nmask": torch.randint(0, 2**31 - 1, (n_words,), generator=g, dtype=torch.int32),
+        "row_rid": (torch.arange(n_rows, dtype=torch.int32) * 2 + rank),
+        "row_len": lens,
+        "row_woff": woff.to(torch.int64),
+        "row_hasn": torch.zeros(n_rows, dtype=torch.int32),
+    }
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    part = _part(rank)
+    reads = M.exchange_reads(part)
+    l2 = torch.arange(2 * (5 + 3 * rank), dtype=torch.int64).reshape(-1, 2) + 1000 * rank
+    l2_all = M.exchange_shimmers(l2)
+    q.put((rank, {k: v.numpy() for k, v in reads.items()}, l2_all.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_with_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    parts = [_part(0), _part(1)]
+    want = M.concat_reads(parts)
+    for rank, reads, l2_all in got:
+        for k in M.READ_KEYS:
+            assert np.array_equal(reads[k], want[k].numpy()), (rank, k)
+        # every row's words are where row_woff says they are, in the concatenated array
+        base = 0
+        row = 0
+        for p in parts:
+            for i in range(len(p["row_rid"])):
+                nw = (int(p["row_len"][i]) + 31) // 32
+                a = reads["words"][reads["row_woff"][row]: reads["row_woff"][row] + nw]
+                b = p["words"].numpy()[int(p["row_woff"][i]): int(p["row_woff"][i]) + nw]
+                assert np.array_equal(a, b)
+                row += 1
+            base += len(p["words"])
+        assert l2_all.shape == (8 + 5, 2) and l2_all[0, 0] == 0 and l2_all[5, 0] == 1000  # chunk order = rank order

@@ -2,5 +2,5 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
 cat gpurun_out/pytest_gpu.log
-timeout 900 python tools/probe.py 50e6 30 2 > gpurun_out/probe_50mb.log 2>&1
-tail -2 gpurun_out/probe_50mb.log | cut -c1-1800
+PGB_VERBOSE=1 timeout 900 python tools/probe.py 50e6 30 2 > gpurun_out/probe_50mb.log 2>&1
+grep "replay pass" gpurun_out/probe_50mb.log | tail -32 | cut -c1-130; tail -1 gpurun_out/probe_50mb.log | cut -c1-2000
