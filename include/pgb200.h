@@ -63,6 +63,11 @@ void mm_sketch(void *km, const char *str, int len, int w, int k, uint32_t rid, i
 /* replaces src/shmr_reduce.c:53-90; appends to out */
 void mm_reduce(mm128_v *in, mm128_v *out, uint8_t rs);
 
+/* replaces src/shmr_align.c:21-160 (greedy co-linear chaining of shared minimizers); result freed with free_shmr_alns.
+ * direction 1 reads one element past the end of the second list in the reference (UB); that element is skipped here. */
+shmr_aln_v *shmr_aln(mm128_v *mmers0, mm128_v *mmers1, uint8_t direction, uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat);
+void free_shmr_alns(shmr_aln_v *alns);                      /* src/shmr_align.c:162-169 */
+
 /* ------------------------------------------------------------------ (2) command-line tools ---------------- */
 /* replaces main() of src/shmr_index.c:37-245 : -p seqdb_prefix -o out_prefix -t T -c c [-r 6] [-l 2] [-m 1] [-w 80] [-k 16] */
 int pgb_shmr_index_main(int argc, char **argv);

@@ -943,6 +943,87 @@ __global__ void k_table_carry(const uint64_t *__restrict__ eold, uint64_t *enew,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ shmr_aln (co-linear chaining)
+// src/shmr_align.c:21-160.  k_aln_match_count/fill: for every minimizer of list 1 the ascending indices of the minimizers
+// of list 0 with the same hash (the reference's MMIDX hash map, :40-57).  k_aln_chain: the greedy chaining itself is
+// sequential in the hits (every hit extends the best existing chain or opens a new one, :97-147), so one thread walks the
+// hits; it emits (chain id, idx0, idx1) per hit.
+__global__ void k_aln_match_count(const mm128 *__restrict__ a0, uint32_t n0, const mm128 *__restrict__ a1, uint32_t n1, uint32_t *cnt) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n1) return;
+  uint64_t key = a1[s].x >> 8;
+  uint32_t c = 0;
+  for (uint32_t i = 0; i < n0; i++) c += (a0[i].x >> 8) == key;
+  cnt[s] = c;
+}
+__global__ void k_aln_match_fill(const mm128 *__restrict__ a0, uint32_t n0, const mm128 *__restrict__ a1, uint32_t n1,
+                                 const uint32_t *__restrict__ off, uint32_t *midx) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n1) return;
+  uint64_t key = a1[s].x >> 8;
+  uint32_t at = off[s];
+  for (uint32_t i = 0; i < n0; i++)
+    if ((a0[i].x >> 8) == key) midx[at++] = i;
+}
+struct AlnHit { uint32_t chain, i0, i1; };
+__device__ __forceinline__ int64_t aln_abs_u32(uint32_t v) { int32_t x = (int32_t)v; return x < 0 ? -(int64_t)x : (int64_t)x; }  // abs((int)uint32)
+__global__ void k_aln_chain(const mm128 *__restrict__ a0, const mm128 *__restrict__ a1, uint32_t n1, const uint32_t *__restrict__ off,
+                            const uint32_t *__restrict__ midx, uint32_t direction, uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat,
+                            uint32_t *chain_last0, uint32_t *chain_last1, uint32_t *chain_n, AlnHit *hits, uint32_t *n_out /* [0]=hits [1]=chains */) {
+  if (blockIdx.x || threadIdx.x) return;
+  uint32_t n_hits = 0, n_chains = 0, small_aln_count = 0;
+  for (uint32_t ss = 0; ss < n1; ss++) {
+    uint32_t s = ss;
+    if (direction == 1) {         // the reference indexes a[n - ss] here, i.e. one past the end for ss == 0 (UB, SURVEY A-7);
+      if (ss == 0) continue;      // that element is skipped
+      s = n1 - ss;
+    }
+    const uint32_t c = off[s + 1] - off[s];
+    if (c == 0 || c > max_repeat) continue;            // :71-80
+    const mm128 m1 = a1[s];
+    const uint32_t pos1 = (uint32_t)((m1.y & 0xFFFFFFFFULL) >> 1);
+    for (uint32_t q = 0; q < c; q++) {
+      const uint32_t i = midx[off[s] + q];
+      const mm128 m0 = a0[i];
+      const uint32_t pos0 = (uint32_t)((m0.y & 0xFFFFFFFFULL) >> 1);
+      if (direction == 0 && (m0.y & 1) != (m1.y & 1)) continue;   // :86-92
+      if (direction == 1 && (m0.y & 1) == (m1.y & 1)) continue;
+      const int64_t delta0 = direction == 1 ? aln_abs_u32(pos0 + pos1) : aln_abs_u32(pos0 - pos1);
+      uint32_t best = 0xFFFFFFFFu;
+      double min_diff = (double)max_diff;
+      small_aln_count = 0;
+      for (uint32_t ai = 0; ai < n_chains; ai++) {     // :103-132
+        if (chain_n[ai] < 3) small_aln_count++;
+        if (i < chain_last0[ai]) continue;
+        const mm128 l0 = a0[chain_last0[ai]], l1 = a1[chain_last1[ai]];
+        const uint32_t lp0 = (uint32_t)((l0.y & 0xFFFFFFFFULL) >> 1), lp1 = (uint32_t)((l1.y & 0xFFFFFFFFULL) >> 1);
+        const int64_t mm_dist = aln_abs_u32(pos0 - lp0);
+        if (mm_dist >= (int64_t)max_dist) continue;
+        const int64_t delta1 = direction == 1 ? aln_abs_u32(lp0 + lp1) : aln_abs_u32(lp0 - lp1);
+        int32_t dd = (int32_t)delta0 - (int32_t)delta1;
+        const uint32_t diff = (uint32_t)(dd < 0 ? -dd : dd);
+        if (diff < max_diff && (double)diff < min_diff && mm_dist < (int64_t)max_dist) {
+          min_diff = (double)diff;
+          best = ai;
+        }
+      }
+      if (best == 0xFFFFFFFFu) {
+        best = n_chains++;
+        chain_n[best] = 0;
+      }
+      chain_last0[best] = i;
+      chain_last1[best] = s;
+      chain_n[best]++;
+      AlnHit h;
+      h.chain = best; h.i0 = i; h.i1 = s;
+      hits[n_hits++] = h;
+    }
+    if (small_aln_count > 4800) break;                 // MAX_SMALL_ALNS, :19,149
+  }
+  n_out[0] = n_hits;
+  n_out[1] = n_chains;
+}
+
 __global__ void k_table_diff(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, size_t n, unsigned long long *diffs) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -1349,3 +1349,57 @@ extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_
   }
   return rtn;
 }
+
+static void idxv_push(mm_idx_v *v, mm_idx_t x) {
+  if (v->n == v->m) {
+    v->m = v->m ? v->m << 1 : 2;  // kvec growth (kvec.h:78-84)
+    v->a = (mm_idx_t *)realloc(v->a, sizeof(mm_idx_t) * v->m);
+  }
+  v->a[v->n++] = x;
+}
+extern "C" shmr_aln_v *shmr_aln(mm128_v *mmers0, mm128_v *mmers1, uint8_t direction, uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat) {
+  shmr_aln_v *alns = (shmr_aln_v *)calloc(sizeof(shmr_aln_v), 1);
+  const size_t n0 = mmers0 ? mmers0->n : 0, n1 = mmers1 ? mmers1->n : 0;
+  if (!n0 || !n1) return alns;
+  pgb_ctx *c = shared_ctx();
+  try {
+    CU(cudaSetDevice(c->device));
+    mm128 *d0 = c->alloc<mm128>(n0), *d1 = c->alloc<mm128>(n1);
+    uint32_t *cnt = c->alloc<uint32_t>(n1 + 1), *off = c->alloc<uint32_t>(n1 + 1);
+    c->h2d(d0, mmers0->a, n0 * sizeof(mm128));
+    c->h2d(d1, mmers1->a, n1 * sizeof(mm128));
+    CU(cudaMemsetAsync(cnt, 0, (n1 + 1) * 4, c->st));
+    LAUNCH(c, k_aln_match_count, nblk(n1, 128), 128, d0, (uint32_t)n0, d1, (uint32_t)n1, cnt);
+    uint32_t total = scan_u32(c, cnt, off, n1 + 1);
+    uint32_t *midx = c->alloc<uint32_t>(total);
+    LAUNCH(c, k_aln_match_fill, nblk(n1, 128), 128, d0, (uint32_t)n0, d1, (uint32_t)n1, off, midx);
+    uint32_t *cl0 = c->alloc<uint32_t>(total + 1), *cl1 = c->alloc<uint32_t>(total + 1), *cn = c->alloc<uint32_t>(total + 1), *n_out = c->alloc<uint32_t>(2);
+    AlnHit *hits = c->alloc<AlnHit>(total + 1);
+    LAUNCH(c, k_aln_chain, 1, 32, d0, d1, (uint32_t)n1, off, midx, (uint32_t)direction, max_diff, max_dist, max_repeat, cl0, cl1, cn, hits, n_out);
+    uint32_t h_n[2] = {0, 0};
+    c->d2h(h_n, n_out, 8);
+    std::vector<AlnHit> h_hits(h_n[0]);
+    c->d2h(h_hits.data(), hits, (size_t)h_n[0] * sizeof(AlnHit));
+    c->sync();
+    c->scratch_reset();
+    alns->n = alns->m = h_n[1];
+    alns->a = (shmr_aln_t *)calloc(h_n[1] ? h_n[1] : 1, sizeof(shmr_aln_t));
+    for (auto &h : h_hits) {
+      idxv_push(&alns->a[h.chain].idx0, h.i0);
+      idxv_push(&alns->a[h.chain].idx1, h.i1);
+    }
+  } catch (std::exception &e) {
+    fprintf(stderr, "pgb200: shmr_aln failed: %s\n", e.what());
+    exit(1);
+  }
+  return alns;
+}
+extern "C" void free_shmr_alns(shmr_aln_v *alns) {
+  if (!alns) return;
+  for (size_t i = 0; i < alns->n; i++) {
+    free(alns->a[i].idx0.a);
+    free(alns->a[i].idx1.a);
+  }
+  free(alns->a);
+  free(alns);
+}
