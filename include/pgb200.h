@@ -68,6 +68,14 @@ void mm_reduce(mm128_v *in, mm128_v *out, uint8_t rs);
 shmr_aln_v *shmr_aln(mm128_v *mmers0, mm128_v *mmers1, uint8_t direction, uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat);
 void free_shmr_alns(shmr_aln_v *alns);                      /* src/shmr_align.c:162-169 */
 
+/* replaces src/shimmer4py.c:44-196: an in-memory SHIMMER-pair index for Python.  The multiplicity table, the pair buckets and
+ * their khash visiting order live in HBM behind the handle's void* fields; `mmers` is a host copy of the concatenated list. */
+void build_shimmer_map4py(py_mmer_t *py_mmer, char *seqdb_prefix, char *shimmer_prefix, uint32_t mychunk, uint32_t total_chunk,
+                          uint32_t lowerbound, uint32_t upperbound);
+void get_shimmers_for_read(mm128_v *out, py_mmer_t *py_mmer, uint32_t rid);   /* out aliases py_mmer->mmers; do not free */
+uint32_t get_mmer_count(py_mmer_t *py_mmer, uint64_t mhash);
+void get_shimmer_hits(mp256_v *append_to, py_mmer_t *py_mmer, uint64_t mhash0, uint32_t span);
+
 /* ------------------------------------------------------------------ (2) command-line tools ---------------- */
 /* replaces main() of src/shmr_index.c:37-245 : -p seqdb_prefix -o out_prefix -t T -c c [-r 6] [-l 2] [-m 1] [-w 80] [-k 16] */
 int pgb_shmr_index_main(int argc, char **argv);

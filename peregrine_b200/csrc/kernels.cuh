@@ -943,6 +943,30 @@ __global__ void k_table_carry(const uint64_t *__restrict__ eold, uint64_t *enew,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ shimmer4py index handle
+// per read id: index of its first minimizer in the concatenated list and how many it has (get_ridmm, src/shmr_utils.c:415-443)
+__global__ void k_ridmm(const mm128 *__restrict__ mm, size_t n, uint32_t *first, uint32_t *count) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t rid = (uint32_t)(mm[i].y >> 32);
+  atomicMin(&first[rid], (uint32_t)i);
+  atomicAdd(&count[rid], 1u);
+}
+__global__ void k_slot_to_group(const uint32_t *__restrict__ gslot, uint32_t n, uint32_t *slot2j) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) slot2j[gslot[j]] = j;
+}
+__global__ void k_count_one(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t mask, uint64_t mer, uint32_t *out) {
+  uint32_t s = ht_find(keys, mask, mer);
+  *out = s == PGB_NOSLOT ? 0u : vals[s];
+}
+// outer key -> (group id or NOSLOT)
+__global__ void k_outer_lookup(const uint64_t *__restrict__ xkeys, uint32_t xmask, const uint32_t *__restrict__ xfirst, const uint32_t *__restrict__ xid,
+                               uint64_t key, uint32_t *out) {
+  uint32_t s = ht_find(xkeys, xmask, key);
+  *out = (s == PGB_NOSLOT || xfirst[s] == 0xFFFFFFFFu) ? PGB_NOSLOT : xid[s];
+}
+
 // ------------------------------------------------------------------------------------------------ shmr_aln (co-linear chaining)
 // src/shmr_align.c:21-160.  k_aln_match_count/fill: for every minimizer of list 1 the ascending indices of the minimizers
 // of list 0 with the same hash (the reference's MMIDX hash map, :40-57).  k_aln_chain: the greedy chaining itself is

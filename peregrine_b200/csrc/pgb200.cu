@@ -1403,3 +1403,230 @@ extern "C" void free_shmr_alns(shmr_aln_v *alns) {
   free(alns->a);
   free(alns);
 }
+
+// ================================================================================================ shimmer4py index handle
+struct PyMmerHandle {
+  pgb_ctx *c = nullptr;
+  mm128_v mmers = {0, 0, nullptr};
+  std::vector<uint32_t> rid_first, rid_count;
+  // device-resident pair index (persistent allocations of c)
+  uint64_t *xkeys = nullptr; uint32_t xmask = 0; uint32_t *xfirst = nullptr, *xid = nullptr;
+  uint32_t n_buckets = 0, n_outer = 0;
+  uint32_t *goff = nullptr, *ipos = nullptr, *boff = nullptr;  // group offsets, in-group visiting position, record offset per grouped bucket
+  uint64_t *gk1 = nullptr;
+  uint64_t *sy0 = nullptr, *sy1 = nullptr; uint8_t *sdir = nullptr;
+};
+
+extern "C" void build_shimmer_map4py(py_mmer_t *py, char *seqdb_prefix, char *shimmer_prefix, uint32_t mychunk, uint32_t total_chunk,
+                                     uint32_t lower, uint32_t upper) {
+  assert(total_chunk > 0);
+  assert(mychunk > 0 && mychunk <= total_chunk);
+  const char *sp = seqdb_prefix ? seqdb_prefix : "seq_dataset", *lp = shimmer_prefix ? shimmer_prefix : "shimmer-L2";
+  PyMmerHandle *h = new PyMmerHandle();
+  h->c = cli_ctx();
+  pgb_ctx *c = h->c;
+  ReadTable rt;
+  std::string idx = std::string(sp) + ".idx";
+  fprintf(stderr, "using index file: %s\n", idx.c_str());
+  if (!load_read_table(idx.c_str(), &rt)) { fprintf(stderr, "file '%s' open error\n", idx.c_str()); exit(1); }
+  fprintf(stderr, "using seqdb file: %s.seqdb\n", sp);
+  std::vector<mm128> mm;
+  for (auto &fn : glob_sorted(std::string(lp) + "-[0-9]*-of-[0-9]*.dat")) { fprintf(stderr, "using shimmer data file: %s\n", fn.c_str()); read_mmlist_file(fn.c_str(), &mm); }
+  std::vector<mc_rec> mc;
+  for (auto &fn : glob_sorted(std::string(lp) + "-MC-[0-9]*-of-[0-9]*.dat")) { fprintf(stderr, "using shimmer count file: %s\n", fn.c_str()); read_mc_file(fn.c_str(), &mc); }
+  h->mmers.n = h->mmers.m = mm.size();
+  h->mmers.a = (mm128_t *)malloc((mm.size() ? mm.size() : 1) * sizeof(mm128_t));
+  memcpy((void *)h->mmers.a, mm.data(), mm.size() * sizeof(mm128_t));
+  try {
+    CU(cudaSetDevice(c->device));
+    // read lengths by rid (the mirrored coordinates of reverse records need them, src/shmr_utils.c:376-395); no sequence is loaded
+    uint32_t max_rid = 0;
+    for (uint32_t r : rt.rid) max_rid = std::max(max_rid, r);
+    for (auto &m : mm) max_rid = std::max(max_rid, (uint32_t)(m.y >> 32));
+    std::vector<uint32_t> rl((size_t)max_rid + 1, 0);
+    for (size_t i = 0; i < rt.n(); i++) rl[rt.rid[i]] = rt.len[i];
+    c->free_reads();
+    c->max_rid = max_rid;
+    c->d_rlen_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1);
+    c->h2d(c->d_rlen_by_rid, rl.data(), rl.size() * 4);
+    CLI_CHECK(c, pgb_set_shimmers(c, (const mm128_t *)mm.data(), mm.size(), (const mm_count_t *)mc.data(), mc.size()));
+    const size_t n = c->n_shm;
+    // ridmm
+    h->rid_first.assign((size_t)max_rid + 1, 0xFFFFFFFFu);
+    h->rid_count.assign((size_t)max_rid + 1, 0);
+    if (n) {
+      uint32_t *d_first = c->alloc<uint32_t>((size_t)max_rid + 1), *d_count = c->alloc<uint32_t>((size_t)max_rid + 1);
+      CU(cudaMemsetAsync(d_first, 0xFF, ((size_t)max_rid + 1) * 4, c->st));
+      CU(cudaMemsetAsync(d_count, 0, ((size_t)max_rid + 1) * 4, c->st));
+      LAUNCH(c, k_ridmm, nblk(n), 256, c->d_shm, n, d_first, d_count);
+      c->d2h(h->rid_first.data(), d_first, ((size_t)max_rid + 1) * 4);
+      c->d2h(h->rid_count.data(), d_count, ((size_t)max_rid + 1) * 4);
+    }
+    // build_map -> records -> buckets -> groups -> inner order (same kernels as pgb_overlap, every bucket kept)
+    uint32_t nrec = 0;
+    PairSoA R = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (n) {
+      uint32_t *cnt = c->alloc<uint32_t>(n), *flags = c->alloc<uint32_t>(n + 1), *pos = c->alloc<uint32_t>(n + 1);
+      unsigned long long *d_first = c->alloc<unsigned long long>(1);
+      CU(cudaMemsetAsync(d_first, 0xFF, 8, c->st));
+      CU(cudaMemsetAsync(flags, 0, (n + 1) * 4, c->st));
+      LAUNCH(c, k_count_lookup, nblk(n), 256, c->d_shm, n, c->d_mckeys, c->d_mcvals, c->mcmask, cnt, lower, upper, d_first, c->d_err);
+      LAUNCH(c, k_kept_flags, nblk(n), 256, cnt, n, lower, upper, d_first, flags);
+      uint32_t n_kept = scan_u32(c, flags, pos, n + 1);
+      uint32_t *kept = c->alloc<uint32_t>(n_kept);
+      LAUNCH(c, k_compact_idx, nblk(n), 256, flags, pos, n, kept);
+      uint32_t *n_rec = c->alloc<uint32_t>((size_t)n_kept + 1), *rec_off = c->alloc<uint32_t>((size_t)n_kept + 1);
+      CU(cudaMemsetAsync(n_rec, 0, ((size_t)n_kept + 1) * 4, c->st));
+      LAUNCH(c, k_pair_count, nblk(n_kept), 256, c->d_shm, kept, n_kept, total_chunk, mychunk, n_rec);
+      nrec = scan_u32(c, n_rec, rec_off, (size_t)n_kept + 1);
+      R.k0 = c->alloc<uint64_t>(nrec); R.k1 = c->alloc<uint64_t>(nrec); R.y0 = c->alloc<uint64_t>(nrec); R.y1 = c->alloc<uint64_t>(nrec);
+      R.seq = c->alloc<uint32_t>(nrec); R.dir = c->alloc<uint8_t>(nrec);
+      LAUNCH(c, k_pair_write, nblk(n_kept), 256, c->d_shm, kept, n_kept, total_chunk, mychunk, rec_off, c->d_rlen_by_rid, R);
+    }
+    if (nrec) {
+      uint32_t xcap = pow2_at_least(4 * (uint64_t)nrec), bcap = pow2_at_least(2 * (uint64_t)nrec);
+      h->xkeys = c->palloc<uint64_t>(xcap); h->xmask = xcap - 1; h->xfirst = c->palloc<uint32_t>(xcap); h->xid = c->palloc<uint32_t>(xcap);
+      uint64_t *bkeys = c->alloc<uint64_t>(bcap);
+      uint32_t *bcount = c->alloc<uint32_t>(bcap), *bfirst = c->alloc<uint32_t>(bcap), *blast = c->alloc<uint32_t>(bcap), *rec_bucket = c->alloc<uint32_t>(nrec);
+      LAUNCH(c, k_fill_u64, 1184, 256, h->xkeys, PGB_EMPTY, (size_t)xcap);
+      LAUNCH(c, k_fill_u64, 1184, 256, bkeys, PGB_EMPTY, (size_t)bcap);
+      CU(cudaMemsetAsync(bcount, 0, (size_t)bcap * 4, c->st));
+      CU(cudaMemsetAsync(bfirst, 0xFF, (size_t)bcap * 4, c->st));
+      CU(cudaMemsetAsync(blast, 0, (size_t)bcap * 4, c->st));
+      CU(cudaMemsetAsync(h->xfirst, 0xFF, (size_t)xcap * 4, c->st));
+      LAUNCH(c, k_bucket_insert, nblk(nrec), 256, R, nrec, h->xkeys, xcap - 1, bkeys, bcap - 1, bcount, bfirst, blast, h->xfirst, rec_bucket, c->d_err);
+      uint32_t *bflags = c->alloc<uint32_t>((size_t)bcap + 1), *bpos = c->alloc<uint32_t>((size_t)bcap + 1);
+      CU(cudaMemsetAsync(bflags, 0, ((size_t)bcap + 1) * 4, c->st));
+      LAUNCH(c, k_mc_flags, nblk(bcap), 256, bkeys, (size_t)bcap, bflags);
+      uint32_t nb = scan_u32(c, bflags, bpos, (size_t)bcap + 1);
+      h->n_buckets = nb;
+      uint32_t *lslot = c->alloc<uint32_t>(nb), *lkey = c->alloc<uint32_t>(nb), *sslot = c->alloc<uint32_t>(nb), *skey = c->alloc<uint32_t>(nb);
+      LAUNCH(c, k_bucket_list, nblk(bcap), 256, bkeys, bfirst, bpos, (size_t)bcap, lslot, lkey);
+      sort_pairs_u32(c, lkey, skey, lslot, sslot, nb);
+      uint32_t *isfirst = c->alloc<uint32_t>((size_t)nb + 1), *firstpos = c->alloc<uint32_t>((size_t)nb + 1);
+      CU(cudaMemsetAsync(isfirst, 0, ((size_t)nb + 1) * 4, c->st));
+      LAUNCH(c, k_outer_first, nblk(nb), 256, sslot, nb, bkeys, bfirst, h->xfirst, isfirst);
+      h->n_outer = scan_u32(c, isfirst, firstpos, (size_t)nb + 1);
+      LAUNCH(c, k_outer_id_first, nblk(nb), 256, sslot, nb, bkeys, isfirst, firstpos, h->xid);
+      uint32_t *oid = lkey, *idx0 = lslot, *goid_sorted = skey, *gidx = c->alloc<uint32_t>(nb);
+      LAUNCH(c, k_outer_id_all, nblk(nb), 256, sslot, nb, bkeys, h->xid, oid, idx0);
+      sort_pairs_u32(c, oid, goid_sorted, idx0, gidx, nb);
+      GroupedBuckets G;
+      G.slot = c->alloc<uint32_t>(nb); G.first = c->alloc<uint32_t>(nb); G.last = c->alloc<uint32_t>(nb);
+      G.count = c->alloc<uint32_t>((size_t)nb + 1); G.oid = c->alloc<uint32_t>(nb);
+      h->gk1 = c->palloc<uint64_t>(nb); G.k1 = h->gk1;
+      h->goff = c->palloc<uint32_t>((size_t)h->n_outer + 1); h->ipos = c->palloc<uint32_t>(nb); h->boff = c->palloc<uint32_t>((size_t)nb + 1);
+      uint32_t *big_list = c->alloc<uint32_t>((size_t)h->n_outer + 1);
+      uint64_t *okey = c->alloc<uint64_t>((size_t)h->n_outer + 1);
+      unsigned int *d_small = c->alloc<unsigned int>(2);
+      CU(cudaMemsetAsync(d_small, 0, 8, c->st));
+      CU(cudaMemsetAsync(G.count, 0, ((size_t)nb + 1) * 4, c->st));
+      LAUNCH(c, k_group_gather, nblk(nb), 256, gidx, goid_sorted, nb, sslot, bkeys, h->xkeys, bfirst, blast, bcount, G, h->goff, h->n_outer, okey, d_small);
+      LAUNCH(c, k_inner_order, nblk(h->n_outer, 128), 128, h->goff, h->n_outer, G, h->ipos, big_list, d_small + 1);
+      unsigned int h_small[2];
+      c->d2h(h_small, d_small, 8);
+      if (h_small[1]) {  // oversized groups: inner replay on the host
+        std::vector<uint32_t> big(h_small[1]), h_goff((size_t)h->n_outer + 1);
+        c->d2h(big.data(), big_list, (size_t)h_small[1] * 4);
+        c->d2h(h_goff.data(), h->goff, ((size_t)h->n_outer + 1) * 4);
+        KhashEmu inner;
+        for (uint32_t o : big) {
+          uint32_t b = h_goff[o], m = h_goff[o + 1] - b;
+          std::vector<uint64_t> k1(m);
+          std::vector<uint32_t> fi(m), la(m), ps(m);
+          c->d2h(k1.data(), G.k1 + b, (size_t)m * 8); c->d2h(fi.data(), G.first + b, (size_t)m * 4); c->d2h(la.data(), G.last + b, (size_t)m * 4);
+          inner.clear();
+          uint32_t last = 0;
+          for (uint32_t i = 0; i < m; i++) { inner.put_new(k1[i], i); last = std::max(last, la[i]); }
+          if (last > fi[m - 1]) inner.touch_existing();
+          uint32_t r = 0;
+          inner.for_each_in_slot_order([&](uint64_t, uint32_t i) { ps[i] = r++; });
+          c->h2d(h->ipos + b, ps.data(), (size_t)m * 4);
+          c->sync();
+        }
+      }
+      // every bucket's records, grouped order, sorted like mp128_comp + glibc qsort (stable, descending position)
+      uint32_t n_all = scan_u32(c, G.count, h->boff, (size_t)nb + 1);
+      uint32_t *slot2j = c->alloc<uint32_t>(bcap), *fill = c->alloc<uint32_t>(nb), *sseq = c->alloc<uint32_t>(n_all);
+      LAUNCH(c, k_fill_u32, 1184, 256, slot2j, PGB_NOSLOT, (size_t)bcap);
+      LAUNCH(c, k_slot_to_group, nblk(nb), 256, G.slot, nb, slot2j);
+      CU(cudaMemsetAsync(fill, 0, (size_t)nb * 4, c->st));
+      h->sy0 = c->palloc<uint64_t>(n_all); h->sy1 = c->palloc<uint64_t>(n_all); h->sdir = c->palloc<uint8_t>(n_all);
+      LAUNCH(c, k_scatter, nblk(nrec), 256, R, nrec, rec_bucket, slot2j, h->boff, fill, h->sy0, h->sy1, sseq, h->sdir);
+      LAUNCH(c, k_sort_buckets, nblk(nb, 64), 64, nb, h->boff, h->sy0, h->sy1, sseq, h->sdir);
+    }
+    c->sync();
+    if (c->check_err("build_shimmer_map4py")) { fprintf(stderr, "pgb200: %s\n", pgb_last_error(c)); exit(1); }
+    c->scratch_reset();
+  } catch (std::exception &e) {
+    fprintf(stderr, "pgb200: build_shimmer_map4py failed: %s\n", e.what());
+    exit(1);
+  }
+  py->mmers = &h->mmers;
+  py->mmer0_map = h; py->rlmap = h; py->mcmap = h; py->ridmm = h;
+}
+
+extern "C" void get_shimmers_for_read(mm128_v *out, py_mmer_t *py, uint32_t rid) {
+  PyMmerHandle *h = (PyMmerHandle *)py->ridmm;
+  out->n = out->m = 0; out->a = nullptr;
+  if (rid < h->rid_count.size() && h->rid_count[rid]) {
+    out->n = out->m = h->rid_count[rid];
+    out->a = h->mmers.a + h->rid_first[rid];
+  }
+}
+
+extern "C" uint32_t get_mmer_count(py_mmer_t *py, uint64_t mhash) {
+  PyMmerHandle *h = (PyMmerHandle *)py->mcmap;
+  pgb_ctx *c = h->c;
+  uint32_t v = 0;
+  try {
+    CU(cudaSetDevice(c->device));
+    if (!c->d_mckeys) return 0;
+    uint32_t *d = c->alloc<uint32_t>(1);
+    LAUNCH(c, k_count_one, 1, 1, c->d_mckeys, c->d_mcvals, c->mcmask, mhash, d);
+    c->d2h(&v, d, 4);
+    c->scratch_reset();
+  } catch (std::exception &e) { fprintf(stderr, "pgb200: get_mmer_count failed: %s\n", e.what()); exit(1); }
+  return v;
+}
+
+extern "C" void get_shimmer_hits(mp256_v *out, py_mmer_t *py, uint64_t mhash0, uint32_t span) {
+  PyMmerHandle *h = (PyMmerHandle *)py->mmer0_map;
+  pgb_ctx *c = h->c;
+  if (!h->xkeys) return;
+  const uint64_t key = mhash0 << 8 | span;  // src/shimmer4py.c:172-173
+  try {
+    CU(cudaSetDevice(c->device));
+    uint32_t *d = c->alloc<uint32_t>(1), o = PGB_NOSLOT;
+    LAUNCH(c, k_outer_lookup, 1, 1, h->xkeys, h->xmask, h->xfirst, h->xid, key, d);
+    c->d2h(&o, d, 4);
+    c->scratch_reset();
+    if (o == PGB_NOSLOT) return;
+    uint32_t g[2];
+    c->d2h(g, h->goff + o, 8);
+    const uint32_t b = g[0], m = g[1] - g[0];
+    std::vector<uint32_t> ipos(m), boff(m + 1);
+    std::vector<uint64_t> k1(m);
+    c->d2h(ipos.data(), h->ipos + b, (size_t)m * 4);
+    c->d2h(boff.data(), h->boff + b, ((size_t)m + 1) * 4);
+    c->d2h(k1.data(), h->gk1 + b, (size_t)m * 8);
+    std::vector<uint32_t> order(m);
+    for (uint32_t i = 0; i < m; i++) order[ipos[i]] = i;  // inner khash slot order (src/shimmer4py.c:181)
+    const uint32_t r0 = boff[0], nr = boff[m] - boff[0];
+    std::vector<uint64_t> y0(nr), y1(nr);
+    std::vector<uint8_t> dir(nr);
+    c->d2h(y0.data(), h->sy0 + r0, (size_t)nr * 8); c->d2h(y1.data(), h->sy1 + r0, (size_t)nr * 8); c->d2h(dir.data(), h->sdir + r0, nr);
+    for (uint32_t q = 0; q < m; q++) {
+      const uint32_t i = order[q];
+      for (uint32_t t = boff[i] - r0; t < boff[i + 1] - r0; t++) {
+        if (out->n == out->m) {
+          out->m = out->m ? out->m << 1 : 2;
+          out->a = (mp256_t *)realloc(out->a, out->m * sizeof(mp256_t));
+        }
+        mp256_t *e = &out->a[out->n++];
+        memset(e, 0, sizeof *e);
+        e->x0 = key; e->x1 = k1[i]; e->y0 = y0[t]; e->y1 = y1[t]; e->direction = dir[t];
+      }
+    }
+  } catch (std::exception &e) { fprintf(stderr, "pgb200: get_shimmer_hits failed: %s\n", e.what()); exit(1); }
+}
