@@ -147,57 +147,74 @@ inline std::vector<std::string> glob_sorted(const std::string &pattern) {
 // the in-place kick-out rehash.  order() returns the keys' indices (in insertion order numbering) by ascending slot,
 // which is the order `for (i = kh_begin; i != kh_end; ++i) if (kh_exist(i))` visits them.
 struct KhashEmu {
-  uint32_t nb = 0, size = 0, nocc = 0, ub = 0;
-  std::vector<uint64_t> keys;
-  std::vector<uint32_t> tag;   // insertion number of the key stored in the slot
-  std::vector<uint8_t> used;
+  // One 8-byte slot per bucket: the key's 32-bit khash value (placement depends on the key only through it; keys are
+  // distinct by contract, so equality is never tested) and insertion number + 1 with a generation bit on top
+  // (0 = empty).  A rehash flips the generation: slots still carrying the old one are khash's "not yet moved" keys.
+  struct Slot { uint32_t h, t; };
+  uint32_t nb = 0, size = 0, nocc = 0, ub = 0, gen = 0;
+  std::vector<Slot> slots;
   static inline uint32_t H(uint64_t key) { return (uint32_t)(key >> 33 ^ key ^ key << 11); }
   void resize(uint32_t m) {
     --m; m |= m >> 1; m |= m >> 2; m |= m >> 4; m |= m >> 8; m |= m >> 16; ++m;
     if (m < 4) m = 4;
     if (size >= (uint32_t)(m * 0.77 + 0.5)) return;
-    std::vector<uint8_t> nused(m, 0);
-    if (nb < m) { keys.resize(m); tag.resize(m); used.resize(m, 0); }
-    uint32_t nmask = m - 1;
+    if (nb < m) slots.resize(m, Slot{0, 0});
+    const uint32_t nmask = m - 1, ngen = gen ^ 0x80000000u;
     for (uint32_t j = 0; j != nb; ++j) {
-      if (!used[j]) continue;
-      uint64_t key = keys[j];
-      uint32_t tg = tag[j];
-      used[j] = 0;
+      Slot s = slots[j];
+      if (s.t == 0 || (s.t & 0x80000000u) == ngen) continue;
+      slots[j].t = 0;
+      s.t = (s.t & 0x7FFFFFFFu) | ngen;
       for (;;) {
-        uint32_t i = H(key) & nmask, step = 0;
-        while (nused[i]) i = (i + (++step)) & nmask;
-        nused[i] = 1;
-        if (i < nb && used[i]) {
-          std::swap(keys[i], key);
-          std::swap(tag[i], tg);
-          used[i] = 0;
+        uint32_t i = s.h & nmask, step = 0;
+        while (slots[i].t != 0 && (slots[i].t & 0x80000000u) == ngen) i = (i + (++step)) & nmask;
+        if (slots[i].t != 0) {  // an unmoved key lives here: kick it out (khash.h:265-270)
+          Slot k = slots[i];
+          slots[i] = s;
+          s = k;
+          s.t = (s.t & 0x7FFFFFFFu) | ngen;
         } else {
-          keys[i] = key;
-          tag[i] = tg;
+          slots[i] = s;
           break;
         }
       }
     }
-    if (nb > m) { keys.resize(m); tag.resize(m); }
-    used.swap(nused);
+    if (nb > m) slots.resize(m);
+    gen = ngen;
     nb = m;
     nocc = size;
     ub = (uint32_t)(nb * 0.77 + 0.5);
   }
-  // the caller guarantees `key` was not inserted before
+  // the caller guarantees `key` was not inserted before; t < 2^31 - 1
   void put_new(uint64_t key, uint32_t t) {
     if (nocc >= ub) {
       if (nb > (size << 1)) resize(nb - 1);
       else resize(nb + 1);
     }
-    uint32_t mask = nb - 1, i = H(key) & mask, step = 0;
-    while (used[i]) i = (i + (++step)) & mask;
-    keys[i] = key;
-    tag[i] = t;
-    used[i] = 1;
+    const uint32_t mask = nb - 1, h = H(key);
+    uint32_t i = h & mask, step = 0;
+    while (slots[i].t != 0) i = (i + (++step)) & mask;
+    slots[i].h = h;
+    slots[i].t = (t + 1) | gen;
     ++size;
     ++nocc;
+  }
+  // put_new of keys[0..n) with tags 0..n-1, prefetching the home slots ahead (the table outgrows the host caches)
+  void put_all(const uint64_t *keys, uint32_t n) {
+    const uint32_t D = 12;
+    {  // final table size is known: allocate once
+      uint32_t m = 4;
+      while (n >= (uint32_t)(m * 0.77 + 0.5) && m < 0x80000000u) m <<= 1;
+      slots.reserve(m);
+    }
+    for (uint32_t o = 0; o < n; o++) {
+      if (o + D < n && nb) {  // the first probes land in the home slot's cache line and the next one
+        const Slot *hp = &slots[H(keys[o + D]) & (nb - 1)];
+        __builtin_prefetch(hp, 1);
+        __builtin_prefetch(hp + 8, 1);
+      }
+      put_new(keys[o], o);
+    }
   }
   // kh_put of a key that is ALREADY present still runs the load-factor check first (khash.h:289-297), so a put of an
   // existing key that follows the insertion which filled the table to its upper bound rehashes it.  Only the last such
@@ -208,12 +225,13 @@ struct KhashEmu {
       else resize(nb + 1);
     }
   }
+  // f(tag) in ascending slot order = the order `for (i = kh_begin; i != kh_end; ++i) if (kh_exist(i))` visits the keys
   template <class F>
   void for_each_in_slot_order(F &&f) const {
     for (uint32_t i = 0; i < nb; i++)
-      if (used[i]) f(keys[i], tag[i]);
+      if (slots[i].t) f((uint64_t)slots[i].h, (slots[i].t & 0x7FFFFFFFu) - 1);
   }
-  void clear() { nb = size = nocc = ub = 0; keys.clear(); tag.clear(); used.clear(); }
+  void clear() { nb = size = nocc = ub = gen = 0; slots.clear(); }  // keeps the capacity
 };
 
 }  // namespace pgb

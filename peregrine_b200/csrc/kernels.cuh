@@ -110,6 +110,45 @@ __global__ void k_pack_reads(const uint8_t *__restrict__ raw, const uint64_t *__
   if (nmask) atomicOr(&hasn_by_rid[row_rid[row]], 1u);
 }
 
+// Reverse-complement image of the packed reads (same word offsets as the forward image): base p of read r in wrc is
+// 3 - (forward base len-1-p), which is the high nibble of .seqdb byte p (src/shmr_utils.c:44-51).  A reverse-strand
+// alignment operand then reads forward through wrc exactly like a forward-strand operand reads w (ovlp_match_lean).
+// One thread builds one word; bases past the end of the read are zero.
+__global__ void k_make_rc(const uint64_t *__restrict__ w, const uint32_t *__restrict__ row_len, const uint64_t *__restrict__ row_woff,
+                          uint32_t n_rows, uint64_t first_word, uint64_t n_words, uint64_t *__restrict__ wrc) {
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_words) return;
+  uint64_t word = first_word + g;
+  uint32_t lo = 0, hi = n_rows;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (row_woff[mid] <= word) lo = mid; else hi = mid;
+  }
+  const uint64_t base = row_woff[lo];
+  const int64_t len = row_len[lo];
+  const int64_t a = len - (int64_t)(word - base) * 32 - 32;  // forward bases [a, a+32) feed this word, reversed
+  uint64_t out = 0;
+  if (a > -32) {
+    uint64_t v;
+    if (a >= 0) {
+      const uint64_t i = base + (uint64_t)(a >> 5);
+      const int s2 = (int)(a & 31) * 2;
+      v = w[i] >> s2;
+      if (s2) v |= w[i + 1] << (64 - s2);
+      out = ~rev2(v);
+    } else {
+      const int valid = (int)(32 + a);  // forward bases [0, valid)
+      v = w[base] << (2 * (32 - valid));
+      out = ~rev2(v) & ((1ULL << (2 * valid)) - 1ULL);
+    }
+  }
+  wrc[word] = out;
+}
+__global__ void k_count_nonzero_u32(const uint32_t *__restrict__ a, size_t n, unsigned int *out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && a[i]) atomicAdd(out, 1u);
+}
+
 // ------------------------------------------------------------------------------------------------ read-table helpers
 __global__ void k_rows_hasn(const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ hasn_by_rid, uint32_t n, uint32_t *out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -853,18 +892,20 @@ __global__ void k_align_keys(const AlnReq *__restrict__ reqs, uint32_t first, ui
   AlnReq q = reqs[first + i];
   uint32_t a = rlen_by_rid[q.rid0] - q.start0, b = rlen_by_rid[q.rid1];
   uint32_t e = (a < b ? a : b) >> 8;
-  keys[i] = e > 255 ? 255 : e;
+  keys[i] = 255u - (e > 255 ? 255 : e);  // longest first: the tail of the launch is made of short alignments
   idx[i] = i;
 }
 // 1 thread = 1 alignment, flattened state machine (ovlp_match_flat); perm (optional) = processing order
+// only_n: take only the requests that involve a read with N (the rest is done by k_align_lean)
 __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint32_t *__restrict__ perm,
                         const uint64_t *__restrict__ w, const uint32_t *__restrict__ nm, const uint64_t *__restrict__ woff_by_rid,
                         const uint32_t *__restrict__ rlen_by_rid, const uint32_t *__restrict__ hasn_by_rid, int bw, match_t *results,
-                        int *err, unsigned long long *bases_total) {
+                        int *err, unsigned long long *bases_total, int only_n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (perm) i = perm[i];
   AlnReq q = reqs[first + i];
+  if (only_n && !(hasn_by_rid[q.rid0] | hasn_by_rid[q.rid1])) return;
   uint32_t rl0 = rlen_by_rid[q.rid0], rl1 = rlen_by_rid[q.rid1];
   SeqView qv = make_view(w, nm, woff_by_rid[q.rid0], rl0, q.start0, q.strands & 1, (int)hasn_by_rid[q.rid0]);
   SeqView tv = make_view(w, nm, woff_by_rid[q.rid1], rl1, 0, (q.strands >> 1) & 1, (int)hasn_by_rid[q.rid1]);
@@ -875,6 +916,29 @@ __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_
   if (e) atomicOr(err, 128 | (e << 8));
   results[first + i] = m;
   // bases compared along the final path (algorithmic-bytes accounting, SURVEY 8d: (q_end + t_end)/4 per alignment)
+  atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
+}
+
+// 1 thread = 1 alignment between N-free reads, forward views over the forward / reverse-complement images
+// (ovlp_match_lean); requests that involve a read with N are left to k_align(only_n = 1)
+#define PGB_ALIGN_THREADS 64
+__global__ void __launch_bounds__(PGB_ALIGN_THREADS) k_align_lean(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n,
+                                                                  const uint32_t *__restrict__ perm, const uint64_t *__restrict__ w,
+                                                                  const uint64_t *__restrict__ wrc, const uint64_t *__restrict__ woff_by_rid,
+                                                                  const uint32_t *__restrict__ rlen_by_rid, const uint32_t *__restrict__ hasn_by_rid,
+                                                                  int bw, match_t *results, unsigned long long *bases_total) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (perm) i = perm[i];
+  const AlnReq q = reqs[first + i];
+  if (hasn_by_rid[q.rid0] | hasn_by_rid[q.rid1]) return;
+  const uint32_t rl0 = rlen_by_rid[q.rid0], rl1 = rlen_by_rid[q.rid1];
+  const uint64_t *qw = ((q.strands & 1) ? wrc : w) + woff_by_rid[q.rid0];
+  const uint64_t *tw = ((q.strands & 2) ? wrc : w) + woff_by_rid[q.rid1];
+  int V[2 * PGB_MAXV];
+  match_t m;
+  ovlp_match_lean(qw, q.start0, (int)(rl0 - q.start0), tw, 0u, (int)rl1, bw, V, PGB_MAXV, &m);
+  results[first + i] = m;
   atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
 }
 
@@ -928,6 +992,23 @@ __global__ void k_mark_dirty_pairs(const uint64_t *__restrict__ changed, uint32_
 __global__ void k_dirty_from_unknown(const uint8_t *__restrict__ unk_flag, uint32_t n_ranks, uint8_t *dirty) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < n_ranks) dirty[r] = unk_flag[r];
+}
+// Size classes of the buckets that run in a pass: flags[r] = runs && small, flags[n_ranks + r] = runs && big.  Small
+// buckets are replayed one per thread (k_replay), big ones one per warp (k_replay_warp): a thread walking a 120-record
+// bucket alone (7 140 dependent pair-table probes) was the critical path of every pass.  dirty == nullptr: all buckets run.
+__global__ void k_class_flags(const uint32_t *__restrict__ rank_off, uint32_t n_ranks, const uint8_t *__restrict__ dirty, uint32_t big_n,
+                              uint32_t *flags) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_ranks) return;
+  const bool run = dirty ? dirty[r] != 0 : true;
+  const bool big = rank_off[r + 1] - rank_off[r] >= big_n;
+  flags[r] = run && !big;
+  flags[n_ranks + r] = run && big;
+}
+__global__ void k_compact_classes(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos, uint32_t n_ranks, uint32_t *list) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * n_ranks) return;
+  if (flags[i]) list[pos[i]] = i < n_ranks ? i : i - n_ranks;
 }
 __global__ void k_dirty_flags32(const uint8_t *__restrict__ dirty, uint32_t n_ranks, uint32_t *flags) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;

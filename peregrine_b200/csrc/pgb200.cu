@@ -58,6 +58,8 @@ struct pgb_ctx {
   uint64_t sel_bases = 0;
   uint8_t *d_raw = nullptr; size_t raw_bytes = 0;
   uint64_t *d_w = nullptr; uint32_t *d_nm = nullptr;
+  uint64_t *d_wrc = nullptr;   // reverse-complement image of d_w (built on first use by the overlap / ovlp_match paths)
+  uint32_t n_reads_with_n = 0;  // valid once d_wrc exists
   uint32_t *d_rlen_by_rid = nullptr, *d_hasn_by_rid = nullptr; uint64_t *d_woff_by_rid = nullptr;
   uint32_t *d_row_rid = nullptr, *d_row_len = nullptr; uint64_t *d_row_woff = nullptr, *d_row_raw_off = nullptr;
   uint32_t *d_sel_rows = nullptr;  // identity 0..n_rows-1 (rows are already the selected ones)
@@ -73,6 +75,7 @@ struct pgb_ctx {
   // ---- overlap output
   ovlp_rec *d_ovl = nullptr; size_t n_ovl = 0;
   int *d_err = nullptr;
+  KhashEmu outer_emu;  // host replay of the outer khash (visiting order), storage reused between calls
 
   // persistent device memory (reads, index levels, overlap output)
   template <class T> T *palloc(size_t n) {
@@ -165,7 +168,7 @@ struct pgb_ctx {
     return e;
   }
   void free_reads() {
-    release(d_raw); release(d_w); release(d_nm); release(d_rlen_by_rid); release(d_hasn_by_rid); release(d_woff_by_rid);
+    release(d_raw); release(d_w); release(d_nm); release(d_wrc); release(d_rlen_by_rid); release(d_hasn_by_rid); release(d_woff_by_rid);
     release(d_row_rid); release(d_row_len); release(d_row_woff); release(d_row_raw_off); release(d_sel_rows);
     n_rows = 0;
   }
@@ -333,6 +336,24 @@ static void do_pack(pgb_ctx *c) {
            (uint32_t)c->n_rows, (uint64_t)2, body, c->d_w, c->d_nm, c->d_hasn_by_rid);
   c->stats.ms_pack += c->toc();
   c->stats.bases_packed += c->sel_bases;
+}
+
+// reverse-complement image + number of reads with N, built once per loaded read set
+static void ensure_rc(pgb_ctx *c) {
+  if (c->d_wrc || !c->d_w) return;
+  c->tic();
+  c->d_wrc = c->palloc<uint64_t>(c->n_words);
+  CU(cudaMemsetAsync(c->d_wrc, 0, c->n_words * 8, c->st));
+  uint64_t body = c->n_words - 4;
+  if (body && c->n_rows) LAUNCH(c, k_make_rc, nblk(body), 256, c->d_w, c->d_row_len, c->d_row_woff, (uint32_t)c->n_rows, (uint64_t)2, body, c->d_wrc);
+  unsigned int *d_n = c->alloc<unsigned int>(1);
+  CU(cudaMemsetAsync(d_n, 0, 4, c->st));
+  LAUNCH(c, k_count_nonzero_u32, nblk((size_t)c->max_rid + 1), 256, c->d_hasn_by_rid, (size_t)c->max_rid + 1, d_n);
+  unsigned int h = 0;
+  c->d2h(&h, d_n, 4);
+  c->n_reads_with_n = h;
+  c->release(d_n);
+  c->stats.ms_pack += c->toc();
 }
 
 extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_bytes, const uint32_t *rid, const uint32_t *len,
@@ -765,6 +786,7 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   if (bw + 3 > PGB_MAXV) throw std::runtime_error("align bandwidth (-w) above 256 is not supported by this build");
   if (ovlp_upper > 65535) throw std::runtime_error("ovlp_upper (-n) above 65535 is not supported");
   bestn &= 0xFF;  // uint8_t bestn = atoi(), src/shmr_overlap.c:245,286
+  ensure_rc(c);
   c->release(c->d_ovl); c->n_ovl = 0;
   size_t n = c->n_shm;
   if (n == 0) { c->sync(); return 0; }
@@ -867,8 +889,9 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   double t_host0 = now_ms();
   std::vector<uint32_t> orank(n_outer);
   {
-    KhashEmu outer;
-    for (uint32_t o = 0; o < n_outer; o++) outer.put_new(h_okey[o], o);
+    KhashEmu &outer = c->outer_emu;  // kept across calls: its table (8 B per slot) is not re-faulted every step
+    outer.clear();
+    outer.put_all(h_okey.data(), n_outer);
     if (h_small[0] > newest_outer_seq) outer.touch_existing();  // a put of a known outer key followed the last new one
     uint32_t r = 0;
     outer.for_each_in_slot_order([&](uint64_t, uint32_t o) { orank[o] = r++; });
@@ -941,7 +964,7 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
 
   // ---------------- replay / align fix-point (DESIGN.md "ordered greedy as a fix-point")
   ReplayState S;
-  uint32_t ecap = pow2_at_least(8 * (uint64_t)n_elig), acap = pow2_at_least(4 * (uint64_t)n_elig);
+  uint32_t ecap = pow2_at_least(4 * (uint64_t)n_elig), acap = pow2_at_least(4 * (uint64_t)n_elig);
   S.emask = ecap - 1; S.amask = acap - 1; S.req_cap = 2 * n_elig + 1024;
   S.ekeys = c->alloc<uint64_t>(ecap); S.eold = c->alloc<uint64_t>(ecap); S.enew = c->alloc<uint64_t>(ecap);
   S.akeys = c->alloc<uint64_t>(acap); S.aidx = c->alloc<uint32_t>(acap);
@@ -968,7 +991,31 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   uint32_t *rid_sorted = c->alloc<uint32_t>(n_elig), *rank_sorted = c->alloc<uint32_t>(n_elig);
   uint64_t *bloom = c->alloc<uint64_t>(4 * (size_t)n_ranks), *changed = c->alloc<uint64_t>(CHANGED_CAP);
   uint8_t *unk_flag = c->alloc<uint8_t>(n_ranks), *dirty = c->alloc<uint8_t>(n_ranks);
-  uint32_t *dflags = c->alloc<uint32_t>((size_t)n_ranks + 1), *dpos = c->alloc<uint32_t>((size_t)n_ranks + 1), *dlist = c->alloc<uint32_t>(n_ranks);
+  uint32_t *dflags = c->alloc<uint32_t>(2 * (size_t)n_ranks + 1), *dpos = c->alloc<uint32_t>(2 * (size_t)n_ranks + 1), *dlist = c->alloc<uint32_t>(n_ranks);
+  uint32_t *all_list = c->alloc<uint32_t>(n_ranks);
+  const uint32_t BIG_N = getenv("PGB_REPLAY_BIG") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG")) : 20u;  // records; >= BIG_N: one warp per bucket
+  // (small..., big...) run list of a pass; returns the number of small buckets, *n_run = total
+  auto class_lists = [&](const uint8_t *dirty_or_null, uint32_t *list, uint32_t *n_run) -> uint32_t {
+    CU(cudaMemsetAsync(dflags + 2 * (size_t)n_ranks, 0, 4, c->st));
+    LAUNCH(c, k_class_flags, nblk(n_ranks), 256, d_rank_off, n_ranks, dirty_or_null, BIG_N, dflags);
+    *n_run = scan_u32(c, dflags, dpos, 2 * (size_t)n_ranks + 1);
+    uint32_t n_small = 0;
+    c->d2h(&n_small, dpos + n_ranks, 4);
+    LAUNCH(c, k_compact_classes, nblk(2 * (size_t)n_ranks), 256, dflags, dpos, n_ranks, list);
+    return n_small;
+  };
+  uint32_t n_all = 0;
+  const uint32_t n_all_small = class_lists(nullptr, all_list, &n_all);
+  auto launch_replay = [&](const uint32_t *list, uint32_t n_small, uint32_t n_total, int request, int emit, const uint32_t *ooff, ovlp_rec *out) {
+    if (warp_replay) {
+      LAUNCH(c, k_replay_warp, nblk((size_t)n_total * 32, 128), 128, S, n_total, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, d_ctr,
+             unk_flag, list);
+      return;
+    }
+    LAUNCH(c, k_replay, nblk(n_small, 64), 64, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, d_ctr, unk_flag);
+    LAUNCH(c, k_replay_warp, nblk((size_t)(n_total - n_small) * 32, 128), 128, S, n_total - n_small, d_rank_off, sy0, sdir, contained, bestn, request, emit,
+           acc, ooff, out, d_ctr, unk_flag, list + n_small);
+  };
   {
     uint32_t *rr = c->alloc<uint32_t>(n_elig), *rk = c->alloc<uint32_t>(n_elig);
     LAUNCH(c, k_bucket_reads, nblk(n_ranks, 128), 128, n_ranks, d_rank_off, sy0, rr, rk, bloom);
@@ -982,27 +1029,20 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     c->tic();
     CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
     // which buckets run in this pass
-    uint32_t n_run = n_ranks;
-    const uint32_t *run_list = nullptr;
+    uint32_t n_run = n_all, n_run_small = n_all_small;
+    const uint32_t *run_list = all_list;
     const bool partial = incremental && pass > 0 && last_diffs <= CHANGED_CAP;
     if (partial) {
       LAUNCH(c, k_dirty_from_unknown, nblk(n_ranks), 256, unk_flag, n_ranks, dirty);
       if (last_diffs) LAUNCH(c, k_mark_dirty_pairs, nblk(last_diffs), 256, changed, (uint32_t)last_diffs, rid_sorted, rank_sorted, n_elig, bloom, dirty);
-      LAUNCH(c, k_dirty_flags32, nblk(n_ranks), 256, dirty, n_ranks, dflags);
-      n_run = scan_u32(c, dflags, dpos, (size_t)n_ranks + 1);
-      LAUNCH(c, k_compact_idx, nblk(n_ranks), 256, dflags, dpos, (size_t)n_ranks, dlist);
+      n_run_small = class_lists(dirty, dlist, &n_run);
       LAUNCH(c, k_table_carry, 1184, 256, S.eold, S.enew, (size_t)ecap, dirty);
       run_list = dlist;
     } else {
       LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
     }
     c->ktic();
-    if (warp_replay)
-      LAUNCH(c, k_replay_warp, nblk((size_t)n_run * 32, 128), 128, S, n_run, d_rank_off, sy0, sdir, contained, bestn, wet ? 1 : 0, 0, acc,
-             (const uint32_t *)nullptr, (ovlp_rec *)nullptr, d_ctr, unk_flag, run_list);
-    else
-      LAUNCH(c, k_replay, nblk(n_run, 64), 64, S, n_run, run_list, d_rank_off, sy0, sdir, contained, bestn, wet ? 1 : 0, 0, acc,
-             (const uint32_t *)nullptr, (ovlp_rec *)nullptr, d_ctr, unk_flag);
+    launch_replay(run_list, n_run_small, n_run, wet ? 1 : 0, 0, (const uint32_t *)nullptr, (ovlp_rec *)nullptr);
     c->stats.ms_k_replay += c->ktoc(); c->stats.n_k_replay++;
     LAUNCH(c, k_table_diff_list, 1184, 256, S.eold, S.enew, S.ekeys, (size_t)ecap, d_ctr + 1, changed, CHANGED_CAP);
     unsigned long long ctr[2];
@@ -1027,8 +1067,11 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
         c->stats.kernel_launches += 3;
       }
       c->ktic();
-      LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, S.n_done, nn, perm, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
-             (int)bw, S.results, c->d_err, c->d_align_bases);
+      LAUNCH(c, k_align_lean, nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, S.n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid,
+             c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.results, c->d_align_bases);
+      if (c->n_reads_with_n)
+        LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, S.n_done, nn, perm, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
+               (int)bw, S.results, c->d_err, c->d_align_bases, 1);
       c->stats.ms_k_align += c->ktoc(); c->stats.n_k_align++;
       {
         unsigned long long ab = 0;
@@ -1065,12 +1108,7 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   c->d_ovl = c->palloc<ovlp_rec>(n_out); c->n_ovl = n_out;
   LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
   CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
-  if (warp_replay)
-    LAUNCH(c, k_replay_warp, nblk((size_t)n_ranks * 32, 128), 128, S, n_ranks, d_rank_off, sy0, sdir, contained, bestn, 0, 1, acc, out_off, c->d_ovl, d_ctr,
-           unk_flag, (const uint32_t *)nullptr);
-  else
-    LAUNCH(c, k_replay, nblk(n_ranks, 64), 64, S, n_ranks, (const uint32_t *)nullptr, d_rank_off, sy0, sdir, contained, bestn, 0, 1, acc, out_off, c->d_ovl,
-           d_ctr, unk_flag);
+  launch_replay(all_list, n_all_small, n_all, 0, 1, out_off, c->d_ovl);
   c->sync();
   c->stats.ms_emit += c->toc();
   c->stats.n_overlaps += n_out;
@@ -1337,7 +1375,7 @@ extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_
     AlnReq *d_q = c->alloc<AlnReq>(1);
     match_t *d_m = c->alloc<match_t>(1);
     c->h2d(d_q, &q, sizeof q);
-    LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, (const uint32_t *)nullptr, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err, c->d_align_bases);
+    LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, (const uint32_t *)nullptr, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err, c->d_align_bases, 0);
     c->d2h(rtn, d_m, sizeof(match_t));
     c->release(d_q); c->release(d_m);
     c->sync();

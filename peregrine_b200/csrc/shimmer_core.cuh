@@ -376,6 +376,143 @@ PGB_HD void ovlp_match_flat(const SeqView &q, int q_len, const SeqView &t, int t
   *out = r;
 }
 
+// ---------------------------------------------------------------------------------------------- ovlp_match, lean form
+// The production form of the same algorithm (identical results; checked call-for-call against the reference in
+// tests/hostsim and on the GPU).  Differences from ovlp_match_flat, all of them about cost per lane-iteration:
+//  * operands are FORWARD views only: a reverse-strand operand reads the materialised reverse-complement image of the
+//    packed reads (k_make_rc), so the snake needs no bit reversal (BREV/FLO run on the quarter-rate XU pipe) and the
+//    four strand combinations share one instruction stream; reads that contain N take ovlp_match_flat instead;
+//  * the high word of each operand is kept across word-steps of a snake (2 loads per continued step instead of 4), the
+//    shift amounts are per-snake constants, and the mismatch position (count-trailing-zeros) is computed once per
+//    snake, not once per step;
+//  * the previous row of the band is streamed: V[k-1] of a cell is V[k+1] of the cell before it (1 load + 1 store per
+//    cell), and the band trim scans inwards from both ends and stops at the diagonal that holds best_m, which is valid by
+//    definition (0 loads in the common 3-diagonal band), instead of re-reading the whole row;
+//  * cell set-up is folded into the tail of the previous cell, so an iteration is "word-step, then (if the snake ended)
+//    one tail block" - one divergent region instead of three.
+PGB_HD uint32_t funnel_r32(uint32_t lo, uint32_t hi, uint32_t sh) {  // low 32 bits of (hi:lo) >> sh, sh in [0,31]
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+}
+// 32 bases (64 bits) starting s2 bits (even, 0..62) into the 128-bit value B:A
+PGB_HD uint64_t window64(uint64_t A, uint64_t B, uint32_t s2) {
+  const uint32_t a0 = (uint32_t)A, a1 = (uint32_t)(A >> 32), b0 = (uint32_t)B, b1 = (uint32_t)(B >> 32);
+  const bool up = s2 >= 32;
+  const uint32_t w0 = up ? a1 : a0, w1 = up ? b0 : a1, w2 = up ? b1 : b0, sh = s2 & 31;
+  return (uint64_t)funnel_r32(w0, w1, sh) | ((uint64_t)funnel_r32(w1, w2, sh) << 32);
+}
+// qw / tw: first packed word of the read in the image of the operand's strand; qo / to: base offset of logical base 0.
+// V: caller scratch of 2*cap ints, cap >= band_tolerance + 2.
+PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const uint64_t *tw, uint32_t to, int t_len,
+                            int band_tolerance, int *V, int cap, match_t *out) {
+  match_t r;
+  r.m_size = r.dist = r.q_bgn = r.q_end = r.t_bgn = r.t_end = r.t_m_end = r.q_m_end = 0;
+  const int max_d = (int)(0.3 * (double)(q_len + t_len));  // DWmatch.c:96
+  const int band_size = band_tolerance * 2;
+  uint32_t longest_match = 0;
+  bool start = false, matched = false;
+  int best_m = -1, k_best = 0, u_first = 0;
+  int min_k = 0, max_k = 0, d = 0, k = 0, idx = 0, x = 0, x1 = 0;
+  int *Vc = V, *Vp = V + cap;  // row being written / row of d-1
+  int vcarry = 0;  // V[d-1][k+1] read by the previous cell of this row = V[d-1][k-1] of the current cell
+  int poff = 0;    // index of V[d-1][min_k+1] in the previous row's storage
+  const uint64_t *qp = qw + (qo >> 5), *tp = tw + (to >> 5);
+  uint32_t qs = (qo & 31) * 2, ts = (to & 31) * 2;
+  uint64_t qA = 0, qB = 0, tA = 0, tB = 0;
+  bool fresh = true;
+  bool running = max_d > 0;
+  // ONE loop, no continue / break: every iteration is a word-step followed by either "stay in the snake" or the tail of
+  // the cell, and the lanes of a warp reconverge at the end of every iteration (a `continue` makes the compiler build an
+  // inner snake loop at whose exit all lanes wait for the longest snake of the warp).
+  while (running) {
+    const int rem = (q_len - x) < (t_len - (x - k)) ? (q_len - x) : (t_len - (x - k));
+    uint64_t df = 0;
+    if (rem > 0) {  // one 32-base word-step of the snake (DWmatch.c:135-140)
+      if (fresh) { qA = qp[0]; tA = tp[0]; }
+      qB = qp[1];
+      tB = tp[1];
+      df = window64(qA, qB, qs) ^ window64(tA, tB, ts);
+    }
+    if (df == 0 && rem > 32) {  // all 32 bases equal and more to compare: stay in this snake
+      x += 32; qp++; tp++;
+      qA = qB; tA = tB;
+      fresh = false;
+    } else {
+      // ---- the snake of cell (d, k) ended
+      int n = rem > 0 ? rem : 0;
+      if (df) {
+        const uint32_t lo = (uint32_t)df;
+        const int nb = lo ? (ctz32(lo) >> 1) : 16 + (ctz32((uint32_t)(df >> 32)) >> 1);
+        if (nb < n) n = nb;
+      } else if (n > 32) n = 32;
+      x += n;
+      const int y = x - k;
+      if ((x - x1 > 16) && !start) { r.q_bgn = x1; r.t_bgn = x1 - k; start = true; }                                   // DWmatch.c:142-146
+      if ((uint32_t)(x - x1) > longest_match) { longest_match = (uint32_t)(x - x1); r.q_m_end = x; r.t_m_end = y; }  // :148-152
+      Vc[idx] = x;
+      const int u = x + y;
+      if (u > best_m) { best_m = u; k_best = k; }
+      if (idx == 0) u_first = u;
+      if (x >= q_len || y >= t_len) {  // :161-164, :185-194
+        r.q_end = x;
+        r.t_end = y;
+        r.dist = d;
+        r.m_size = (r.q_end - r.q_bgn + r.t_end - r.t_bgn + 2 * d) / 2;
+        matched = true;
+        running = false;
+      } else {
+        if (k < max_k) {
+          k += 2;
+          idx++;
+        } else {
+          // ---- end of edit distance d: trim the band to the hull of { k : x+y >= best_m - band_tolerance } (:168-183).
+          // k_best (this row's first diagonal that reached best_m; every row raises best_m) is in the hull.
+          const int thr = best_m - band_tolerance;
+          int lo_k = min_k, off = 0;
+          if (u_first < thr) {
+            lo_k += 2; off = 1;
+            while (lo_k < k_best && 2 * Vc[off] - lo_k < thr) { lo_k += 2; off++; }
+          }
+          int hi_k = max_k;
+          if (u < thr) {  // u is the row's last cell here
+            int i2 = idx - 1;
+            hi_k -= 2;
+            while (hi_k > k_best && 2 * Vc[i2] - hi_k < thr) { hi_k -= 2; i2--; }
+          }
+          poff = off;
+          min_k = lo_k - 1;
+          max_k = hi_k + 1;
+          int *tmp = Vc; Vc = Vp; Vp = tmp;
+          d++;
+          k = min_k;
+          idx = 0;
+          if (d >= max_d || max_k - min_k > band_size) running = false;  // DWmatch.c:118-122, not matched
+        }
+        // ---- set-up of the next cell (DWmatch.c:125-131); d >= 1 here, so min_k < max_k
+        int vp = 0;
+        if (k != max_k) vp = Vp[poff + idx];  // V[d-1][k+1]
+        if (idx == 0) x = vp;
+        else if (k == max_k) x = vcarry + 1;
+        else x = (vcarry < vp) ? vp : vcarry + 1;
+        vcarry = vp;
+        x1 = x;
+        const uint32_t qb = qo + (uint32_t)x, tb = to + (uint32_t)(x - k);
+        qp = qw + (qb >> 5); qs = (qb & 31) * 2;
+        tp = tw + (tb >> 5); ts = (tb & 31) * 2;
+        fresh = true;
+      }
+    }
+  }
+  if (!matched) {  // DWmatch.c:196-199
+    r.q_bgn = 0;
+    r.t_bgn = 0;
+  }
+  *out = r;
+}
+
 // ---------------------------------------------------------------------------------------------- mm_sketch (exact automaton)
 // One read, forward strand, sequential — a literal restatement of src/mm_sketch.c:84-150 for is_hpc == 0 over the
 // packed representation.  Used (a) for reads the tiled fast kernel flags (N, hash ties, palindrome-dense halos) and

@@ -46,7 +46,7 @@ static void load_ref() {
 
 struct Packed {
   ReadTable rt;
-  std::vector<uint64_t> w;
+  std::vector<uint64_t> w, wrc;  // forward image and reverse-complement image (same word offsets)
   std::vector<uint32_t> nm;
   std::vector<uint64_t> woff;  // per row
   std::vector<uint8_t> has_n;
@@ -80,6 +80,22 @@ static void load_packed(const char *prefix, Packed *P) {
     }
     P->has_n[i] = hn;
   }
+  P->wrc.assign(words, 0);  // what k_make_rc builds on the device: rc base p = 3 - forward base (len-1-p)
+  for (size_t i = 0; i < n; i++) {
+    uint32_t L = P->rt.len[i];
+    for (uint32_t p = 0; p < L; p++) {
+      uint32_t f = L - 1 - p;
+      uint64_t c = 3 - ((P->w[P->woff[i] + f / 32] >> (2 * (f & 31))) & 3);
+      P->wrc[P->woff[i] + p / 32] |= c << (2 * (p & 31));
+    }
+  }
+}
+static bool lean_match(const Packed &P, size_t r0, uint32_t start0, int s0, size_t r1, int s1, int bw, match_t *m) {
+  if (P.has_n[r0] || P.has_n[r1]) return false;  // reads with N take ovlp_match_flat in the product too
+  std::vector<int> V(2 * (bw + 2));
+  ovlp_match_lean((s0 ? P.wrc.data() : P.w.data()) + P.woff[r0], start0, (int)(P.rt.len[r0] - start0),
+                  (s1 ? P.wrc.data() : P.w.data()) + P.woff[r1], 0, (int)P.rt.len[r1], bw, V.data(), bw + 2, m);
+  return true;
 }
 
 static void sim_reduce(const std::vector<mm128> &in, std::vector<mm128> &out, uint32_t rs) {
@@ -247,6 +263,11 @@ static int one_match(const Packed &P, size_t r0, uint32_t start0, int s0, size_t
   std::vector<int> Vf(2 * (bw + 8));
   ovlp_match_flat(q, qlen, t, tlen, bw, Vf.data(), bw + 8, &flat, &err2);
   int ok = same_match(*ref, mine) && err == 0 && same_match(*ref, flat) && err2 == 0;
+  match_t lean;
+  if (lean_match(P, r0, start0, s0, r1, s1, bw, &lean) && !same_match(*ref, lean)) {
+    ok = 0;
+    if (*bad < 8) fprintf(stderr, "LEAN differs: {%d %d %d %d %d %d %d %d}\n", lean.m_size, lean.dist, lean.q_bgn, lean.q_end, lean.t_bgn, lean.t_end, lean.t_m_end, lean.q_m_end);
+  }
   if (!same_match(*ref, flat) && *bad < 8) fprintf(stderr, "FLAT differs: {%d %d %d %d %d %d %d %d}\n", flat.m_size, flat.dist, flat.q_bgn, flat.q_end, flat.t_bgn, flat.t_end, flat.t_m_end, flat.q_m_end);
   if (!ok) {
     if (*bad < 8)
@@ -324,6 +345,10 @@ static match_t do_align(const Packed &P, uint32_t rid0, uint32_t start0, uint32_
     match_t f; int e2 = 0;
     ovlp_match_flat(q, (int)(rlen0 - start0), t, (int)rlen1, bw, Vf.data(), bw + 8, &f, &e2);
     if (e2 || memcmp(&f, &m, sizeof f)) { fprintf(stderr, "ovlp_match_flat disagrees with ovlp_match_core (rid %u vs %u)\n", rid0, rid1); exit(5); }
+    match_t l;
+    if (lean_match(P, r0, start0, (int)s0, r1, (int)s1, bw, &l) && memcmp(&l, &m, sizeof l)) {
+      fprintf(stderr, "ovlp_match_lean disagrees with ovlp_match_core (rid %u vs %u)\n", rid0, rid1); exit(5);
+    }
   }
   return m;
 }
