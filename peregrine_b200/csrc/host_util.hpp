@@ -150,15 +150,33 @@ struct KhashEmu {
   // One 8-byte slot per bucket: the key's 32-bit khash value (placement depends on the key only through it; keys are
   // distinct by contract, so equality is never tested) and insertion number + 1 with a generation bit on top
   // (0 = empty).  A rehash flips the generation: slots still carrying the old one are khash's "not yet moved" keys.
+  //
+  // Probe shortcut.  SHIMMER keys are hash<<8 | span with small hash values (they are minimizers of minimizers), so
+  // khash's hash function maps them onto very few home slots (the low 8 bits of key ^ key<<11 ^ key>>33 are constant):
+  // on the 50 Mb benchmark 195 k outer keys share ~1000 homes and every insertion walks ~100 occupied slots - in the
+  // reference as well.  All keys of one home walk the SAME probe sequence, and between two rehashes slots only fill up,
+  // so the first free probe step of a home never decreases: next[home] remembers where the last search of that home
+  // ended and the next one resumes there.  Same layout, O(1) probes per insertion.
   struct Slot { uint32_t h, t; };
   uint32_t nb = 0, size = 0, nocc = 0, ub = 0, gen = 0;
   std::vector<Slot> slots;
+  std::vector<uint32_t> next;  // per home slot: probe step at which to resume
   static inline uint32_t H(uint64_t key) { return (uint32_t)(key >> 33 ^ key ^ key << 11); }
+  // first slot of `home`'s probe sequence (i += ++step, khash.h:226,315) for which taken(slot) is false
+  template <class Taken>
+  inline uint32_t probe(uint32_t home, uint32_t mask, Taken &&taken) {
+    uint32_t step = next[home];
+    uint32_t i = (uint32_t)((home + (uint64_t)step * (step + 1) / 2) & mask);
+    while (taken(slots[i])) i = (i + (++step)) & mask;
+    next[home] = step;
+    return i;
+  }
   void resize(uint32_t m) {
     --m; m |= m >> 1; m |= m >> 2; m |= m >> 4; m |= m >> 8; m |= m >> 16; ++m;
     if (m < 4) m = 4;
     if (size >= (uint32_t)(m * 0.77 + 0.5)) return;
     if (nb < m) slots.resize(m, Slot{0, 0});
+    next.assign(m, 0);
     const uint32_t nmask = m - 1, ngen = gen ^ 0x80000000u;
     for (uint32_t j = 0; j != nb; ++j) {
       Slot s = slots[j];
@@ -166,8 +184,8 @@ struct KhashEmu {
       slots[j].t = 0;
       s.t = (s.t & 0x7FFFFFFFu) | ngen;
       for (;;) {
-        uint32_t i = s.h & nmask, step = 0;
-        while (slots[i].t != 0 && (slots[i].t & 0x80000000u) == ngen) i = (i + (++step)) & nmask;
+        // khash.h:262-264: skip the slots that already hold a moved key
+        const uint32_t i = probe(s.h & nmask, nmask, [ngen](const Slot &q) { return q.t != 0 && (q.t & 0x80000000u) == ngen; });
         if (slots[i].t != 0) {  // an unmoved key lives here: kick it out (khash.h:265-270)
           Slot k = slots[i];
           slots[i] = s;
@@ -192,29 +210,21 @@ struct KhashEmu {
       else resize(nb + 1);
     }
     const uint32_t mask = nb - 1, h = H(key);
-    uint32_t i = h & mask, step = 0;
-    while (slots[i].t != 0) i = (i + (++step)) & mask;
+    const uint32_t i = probe(h & mask, mask, [](const Slot &q) { return q.t != 0; });
     slots[i].h = h;
     slots[i].t = (t + 1) | gen;
     ++size;
     ++nocc;
   }
-  // put_new of keys[0..n) with tags 0..n-1, prefetching the home slots ahead (the table outgrows the host caches)
+  // put_new of keys[0..n) with tags 0..n-1
   void put_all(const uint64_t *keys, uint32_t n) {
-    const uint32_t D = 12;
     {  // final table size is known: allocate once
       uint32_t m = 4;
       while (n >= (uint32_t)(m * 0.77 + 0.5) && m < 0x80000000u) m <<= 1;
       slots.reserve(m);
+      next.reserve(m);
     }
-    for (uint32_t o = 0; o < n; o++) {
-      if (o + D < n && nb) {  // the first probes land in the home slot's cache line and the next one
-        const Slot *hp = &slots[H(keys[o + D]) & (nb - 1)];
-        __builtin_prefetch(hp, 1);
-        __builtin_prefetch(hp + 8, 1);
-      }
-      put_new(keys[o], o);
-    }
+    for (uint32_t o = 0; o < n; o++) put_new(keys[o], o);
   }
   // kh_put of a key that is ALREADY present still runs the load-factor check first (khash.h:289-297), so a put of an
   // existing key that follows the insertion which filled the table to its upper bound rehashes it.  Only the last such
@@ -231,7 +241,7 @@ struct KhashEmu {
     for (uint32_t i = 0; i < nb; i++)
       if (slots[i].t) f((uint64_t)slots[i].h, (slots[i].t & 0x7FFFFFFFu) - 1);
   }
-  void clear() { nb = size = nocc = ub = gen = 0; slots.clear(); }  // keeps the capacity
+  void clear() { nb = size = nocc = ub = gen = 0; slots.clear(); next.clear(); }  // keeps the capacity
 };
 
 }  // namespace pgb

@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__r
                                                              int wsz, int k, uint32_t *__restrict__ tile_cnt, uint32_t *row_flags,
                                                              mm128 *__restrict__ tmp, uint32_t tile_cap) {
   extern __shared__ __align__(16) unsigned char sk_smem[];
-  SkShared<HT> &sh = *reinterpret_cast<SkShared<HT> *>(sk_smem);
+  SkTile<HT> sh;
+  sk_tile_layout<HT>(sh, sk_smem, wsz);
   const uint32_t tile = blockIdx.x;
   const int tid = threadIdx.x;
   // owning row: last row with tile_off[row] <= tile
@@ -305,51 +306,48 @@ __global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__r
     }
     return;
   }
-  if (tid == 0) { sh.n_pal = 0; sh.n_halo_slots = 0; sh.flags = 0; }
+  if (tid < 4) sh.ctr[tid] = 0;
   __syncthreads();
-  HT hv[SK_G];
-  uint16_t ps[SK_G];
   uint32_t slot_mask, np, hs;
-  sk_phase1<HT>(tid, p, H, hv, ps, &slot_mask, &np, &hs);
-  if (np) atomicAdd(&sh.n_pal, np);
-  if (hs) atomicAdd(&sh.n_halo_slots, hs);
-  uint32_t total = 0;
-  const uint32_t slot_base = block_exscan_256((uint32_t)__popc(slot_mask), sh.scan, &total);
-  if (tid == 0) sh.n_slots = total;
+  {
+    HT hv[SK_G];
+    uint16_t ps[SK_G];
+    sk_phase1<HT>(tid, p, H, hv, ps, &slot_mask, &np, &hs);
+    if (np) atomicAdd(&sh.ctr[SK_N_PAL], np);
+    if (hs) atomicAdd(&sh.ctr[SK_N_HALO], hs);
+    uint32_t total = 0;
+    const uint32_t slot_base = block_exscan_256((uint32_t)__popc(slot_mask), sh.scan, &total);
+    if (tid == 0) sh.ctr[SK_N_SLOTS] = total;
+    sk_phase2_write<HT>(sh, hv, ps, slot_mask, slot_base);
+  }
   __syncthreads();
-  if (sh.n_pal > SK_PALPAD) {
+  if (sh.ctr[SK_N_PAL] > SK_PALPAD) {
     if (tid == 0) { atomicOr(&row_flags[row], (uint32_t)SK_FLAG_PAL); tile_cnt[tile] = 0; }
     return;
   }
-  sk_phase2_write<HT>(sh, hv, ps, slot_mask, slot_base);
+  // one thread per block of ceil(w/2) slots (at most SK_R / 9 + 1 < 2 * SK_THREADS blocks)
+  const int n_blocks = ((int)sh.ctr[SK_N_SLOTS] + sh.B - 1) / sh.B;
+  for (int b = tid; b < n_blocks; b += SK_THREADS) sk_phase3_suffix<HT>(b, sh);
   __syncthreads();
-  sk_phase3_group<HT>(tid, sh);
-  if (tid + SK_THREADS < SK_NG) sk_phase3_group<HT>(tid + SK_THREADS, sh);
+  for (int b = tid; b < n_blocks; b += SK_THREADS) sk_phase3_prefix<HT>(b, sh);
   __syncthreads();
   int s_eval, s_emit, s_first_full;
-  sk_ranges(p, sh.n_halo_slots, &s_eval, &s_emit, &s_first_full);
-  uint32_t tie = sk_phase4_group<HT>(tid, sh, wsz, s_eval);
-  if (tid + SK_THREADS < SK_NG) tie |= sk_phase4_group<HT>(tid + SK_THREADS, sh, wsz, s_eval);
-  if (tie) atomicOr(&sh.flags, (uint32_t)SK_FLAG_TIE);
-  __syncthreads();
-  if (sh.flags) {
-    if (tid == 0) { atomicOr(&row_flags[row], sh.flags); tile_cnt[tile] = 0; }
+  sk_ranges(p, sh.ctr[SK_N_HALO], &s_eval, &s_emit, &s_first_full);
+  uint32_t emit_mask, tie;
+  const uint32_t cnt = sk_phase4<HT>(tid, sh, wsz, s_eval, s_emit, s_first_full, &emit_mask, &tie);
+  if (tie) atomicOr(&sh.ctr[SK_FLAGS], (uint32_t)SK_FLAG_TIE);
+  uint32_t total = 0;
+  const uint32_t pre = block_exscan_256(cnt, sh.scan, &total);  // its barriers also publish the tie flag
+  if (sh.ctr[SK_FLAGS]) {
+    if (tid == 0) { atomicOr(&row_flags[row], sh.ctr[SK_FLAGS]); tile_cnt[tile] = 0; }
     return;
   }
-  // groups tid (first stride) precede groups tid+256 (second stride) in slot order: scan both counts in one packed word
-  const uint32_t cA = sk_phase5_group<HT, false>(tid, sh, p, s_emit, s_first_full, nullptr);
-  const uint32_t cB = (tid + SK_THREADS < SK_NG) ? sk_phase5_group<HT, false>(tid + SK_THREADS, sh, p, s_emit, s_first_full, nullptr) : 0u;
-  uint32_t packed_total = 0;
-  const uint32_t pre = block_exscan_256(cA | (cB << 16), sh.scan, &packed_total);
-  const uint32_t totA = packed_total & 0xFFFFu, totB = packed_total >> 16;
-  if (totA + totB > tile_cap) {
+  if (total > tile_cap) {
     if (tid == 0) { atomicOr(&row_flags[row], (uint32_t)SK_FLAG_OVERFLOW); tile_cnt[tile] = 0; }
     return;
   }
-  mm128 *dst = tmp + (size_t)tile * tile_cap;
-  if (cA) sk_phase5_group<HT, true>(tid, sh, p, s_emit, s_first_full, dst + (pre & 0xFFFFu));
-  if (cB) sk_phase5_group<HT, true>(tid + SK_THREADS, sh, p, s_emit, s_first_full, dst + totA + (pre >> 16));
-  if (tid == 0) tile_cnt[tile] = totA + totB;
+  if (cnt) sk_phase5_write<HT>(tid, sh, p, emit_mask, tmp + (size_t)tile * tile_cap + pre);
+  if (tid == 0) tile_cnt[tile] = total;
 }
 
 // per row: minimizer count from its tiles, or mark it for the exact automaton
@@ -668,70 +666,112 @@ __global__ void k_sort_buckets(uint32_t n_ranks, const uint32_t *__restrict__ ra
 }
 
 // ------------------------------------------------------------------------------------------------ replay + align
-struct AlnReq { uint32_t rid0, start0, rid1, strands; };  // strands: bit0 = strand0, bit1 = strand1
+// Tables of the fix-point.  Both are open addressing with linear probing over a capacity that is not a
+// power of two (slot = mulhi(mix(key), cap)), sized close to what a chunk needs so that they stay largely L2-resident:
+//  * time-stamped rid_pairs E: 16-byte entries {read-id pair, value of iteration 0, value of iteration 1}; value =
+//    rank<<2 | type of the first bucket (in visiting order) that accepted the pair, PGB_VNONE = none.  One 16-byte load
+//    answers "was this pair in rid_pairs when the reference reached my bucket" for both iterations.
+//  * alignment cache: key rank<<32 | i<<16 | j -> match_t stored AT the key's slot (m_size == PGB_ALN_PENDING until
+//    k_align* filled it in); a request carries its slot.
+struct AlnReq { uint32_t rid0, start0, rid1, strands, slot; };  // strands: bit0 = strand0, bit1 = strand1
+struct EEntry { uint64_t key; uint32_t v[2]; };
+#define PGB_VNONE 0xFFFFFFFFu
+#define PGB_ALN_PENDING ((int32_t)0x80000000)
+#define PGB_MAXV 264  // band rows of ovlp_match: supports band_tolerance <= 256
 struct ReplayState {
-  // time-stamped rid_pairs
-  uint64_t *ekeys; uint64_t *eold; uint64_t *enew; uint32_t emask;
-  // alignment cache
-  uint64_t *akeys; uint32_t *aidx; uint32_t amask;
-  AlnReq *reqs; match_t *results; uint32_t req_cap;
-  uint32_t *n_req;      // device counter
-  uint32_t n_done;      // requests [0, n_done) have results
+  EEntry *E; uint32_t ecap; uint32_t cur;  // v[cur] is being built in this pass, v[cur ^ 1] is the previous pass
+  uint64_t *akeys; match_t *ares; uint32_t acap;
+  AlnReq *reqs; uint32_t req_cap;
+  uint32_t *n_req;  // device counter
   const uint32_t *rlen_by_rid;
+  unsigned long long *ctr;  // [0] predicted (unknown) alignments [1] table diffs
   int *err;
 };
+__device__ __forceinline__ uint32_t ht_home(uint64_t key, uint32_t cap) { return __umulhi(ht_mix(key), cap); }
+
 struct DevReplayCtx {
   ReplayState s;
   uint32_t rank;
   bool request_enabled;
   ovlp_rec *out;
   __device__ uint32_t rlen(uint32_t rid) const { return s.rlen_by_rid[rid]; }
-  __device__ uint64_t pair_old(uint64_t p) const {
-    uint32_t sl = ht_find(s.ekeys, s.emask, p);
-    return sl == PGB_NOSLOT ? ~0ULL : s.eold[sl];
-  }
-  __device__ uint64_t pair_new(uint64_t p) const {
-    uint32_t sl = ht_find(s.ekeys, s.emask, p);
-    return sl == PGB_NOSLOT ? ~0ULL : *(volatile uint64_t *)&s.enew[sl];
+  __device__ void pair_get(uint64_t p, uint64_t *vold, uint64_t *vnew) const {
+    *vold = *vnew = ~0ULL;
+    uint32_t h = ht_home(p, s.ecap);
+    for (uint32_t probe = 0; probe < s.ecap; probe++) {
+      const uint4 e = __ldcg((const uint4 *)&s.E[h]);  // L2: entries are updated with atomics by other SMs (and by this thread)
+      const uint64_t k = (uint64_t)e.x | ((uint64_t)e.y << 32);
+      if (k == p) {
+        const uint32_t vo = s.cur ? e.z : e.w, vn = s.cur ? e.w : e.z;
+        if (vo != PGB_VNONE) *vold = vo;
+        if (vn != PGB_VNONE) *vnew = vn;
+        return;
+      }
+      if (k == PGB_EMPTY) return;
+      if (++h == s.ecap) h = 0;
+    }
   }
   __device__ void pair_set(uint64_t p, uint64_t v) {
-    uint32_t sl = ht_insert(s.ekeys, s.emask, p);
-    if (sl == PGB_NOSLOT) { atomicOr(s.err, 32); return; }
-    atomicMin((unsigned long long *)&s.enew[sl], (unsigned long long)v);
+    uint32_t h = ht_home(p, s.ecap);
+    for (uint32_t probe = 0; probe < s.ecap; probe++) {
+      uint64_t k = __ldcg(&s.E[h].key);
+      if (k == PGB_EMPTY) {
+        k = atomicCAS((unsigned long long *)&s.E[h].key, (unsigned long long)PGB_EMPTY, (unsigned long long)p);
+        if (k == PGB_EMPTY) k = p;
+      }
+      if (k == p) {
+        atomicMin(&s.E[h].v[s.cur], (uint32_t)v);
+        return;
+      }
+      if (++h == s.ecap) h = 0;
+    }
+    atomicOr(s.err, 32);
   }
+  __device__ uint32_t aln_slot(uint64_t key, bool insert) const {
+    uint32_t h = ht_home(key, s.acap);
+    for (uint32_t probe = 0; probe < s.acap; probe++) {
+      uint64_t k = __ldcg(&s.akeys[h]);
+      if (k == PGB_EMPTY) {
+        if (!insert) return PGB_NOSLOT;
+        k = atomicCAS((unsigned long long *)&s.akeys[h], (unsigned long long)PGB_EMPTY, (unsigned long long)key);
+        if (k == PGB_EMPTY) k = key;
+      }
+      if (k == key) return h;
+      if (++h == s.acap) h = 0;
+    }
+    return PGB_NOSLOT;
+  }
+  __device__ uint64_t aln_key(uint32_t i, uint32_t j) const { return ((uint64_t)rank << 32) | ((uint64_t)i << 16) | j; }
   __device__ bool aln_get(uint32_t i, uint32_t j, match_t *m) const {
-    uint32_t sl = ht_find(s.akeys, s.amask, ((uint64_t)rank << 32) | ((uint64_t)i << 16) | j);
+    const uint32_t sl = aln_slot(aln_key(i, j), false);
     if (sl == PGB_NOSLOT) return false;
-    uint32_t idx = s.aidx[sl];
-    if (idx >= s.n_done) return false;
-    *m = s.results[idx];
+    const int4 a = __ldcg((const int4 *)&s.ares[sl]), b = __ldcg((const int4 *)&s.ares[sl] + 1);
+    if (a.x == PGB_ALN_PENDING) return false;
+    m->m_size = a.x; m->dist = a.y; m->q_bgn = a.z; m->q_end = a.w; m->t_bgn = b.x; m->t_end = b.y; m->t_m_end = b.z; m->q_m_end = b.w;
     return true;
   }
   __device__ void aln_request(uint32_t i, uint32_t j, uint32_t rid0, uint32_t start0, uint32_t s0, uint32_t rid1, uint32_t s1) {
     if (!request_enabled) return;
-    uint64_t key = ((uint64_t)rank << 32) | ((uint64_t)i << 16) | j;
-    uint32_t sl = ht_find(s.akeys, s.amask, key);
-    if (sl != PGB_NOSLOT) return;  // already requested in this pass (cannot happen: each (i,j) is visited once)
-    uint32_t idx = atomicAdd(s.n_req, 1u);
-    if (idx >= s.req_cap) { atomicOr(s.err, 64); return; }
-    sl = ht_insert(s.akeys, s.amask, key);
+    const uint32_t sl = aln_slot(aln_key(i, j), true);
     if (sl == PGB_NOSLOT) { atomicOr(s.err, 64); return; }
-    s.aidx[sl] = idx;
+    const uint32_t idx = atomicAdd(s.n_req, 1u);
+    if (idx >= s.req_cap) { atomicOr(s.err, 64); return; }
+    s.ares[sl].m_size = PGB_ALN_PENDING;
     AlnReq q;
-    q.rid0 = rid0; q.start0 = start0; q.rid1 = rid1; q.strands = s0 | (s1 << 1);
+    q.rid0 = rid0; q.start0 = start0; q.rid1 = rid1; q.strands = s0 | (s1 << 1); q.slot = sl;
     s.reqs[idx] = q;
   }
   __device__ void emit(uint32_t n, const ovlp_rec &o) { out[n] = o; }
 };
 
-// list != nullptr: only the n_ranks buckets named in list are replayed (incremental passes)
-__global__ void k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ list, const uint32_t *__restrict__ rank_off,
-                         const uint64_t *__restrict__ sy0, const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn,
-                         int request_enabled, int do_emit, uint32_t *acc_count, const uint32_t *__restrict__ out_off, ovlp_rec *out,
-                         unsigned long long *n_unknown_total, uint8_t *unk_flag) {
+// one thread = one bucket; only the n_ranks buckets named in list are replayed
+__global__ void __launch_bounds__(64) k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ list, const uint32_t *__restrict__ rank_off,
+                                               const uint64_t *__restrict__ sy0, const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn,
+                                               int request_enabled, int do_emit, uint32_t *acc_count, const uint32_t *__restrict__ out_off,
+                                               ovlp_rec *out, uint8_t *unk_flag) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_ranks) return;
-  if (list) r = list[r];
+  r = list[r];
   uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
   DevReplayCtx c;
   c.s = st;
@@ -742,7 +782,7 @@ __global__ void k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__res
   uint32_t acc = replay_bucket(c, r, sy0 + b, sdir + b, n, contained + b, bestn, do_emit != 0, &unk);
   acc_count[r] = acc;
   unk_flag[r] = unk != 0;
-  if (unk) atomicAdd(n_unknown_total, (unsigned long long)unk);
+  if (unk) atomicAdd(&st.ctr[0], (unsigned long long)unk);
 }
 
 // Warp-cooperative form of the same scan (one warp = one bucket): the candidates j of a row i are classified by 32 lanes
@@ -751,15 +791,16 @@ __global__ void k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__res
 // earlier lane ended the row (CONTAINED, src/shmr_overlap.c:176); only reached lanes apply side effects (pair_set,
 // contained[], alignment requests, record emission, in lane order).  A lane whose read also occurs in an earlier
 // still-unresolved lane of the same chunk is deferred to the next round so that it sees that lane's pair_set.
+// Kept as an alternative (PGB_REPLAY=warp): with the one-probe pair table the per-thread form is faster on every input tried.
 __global__ void __launch_bounds__(128) k_replay_warp(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ rank_off,
                                                      const uint64_t *__restrict__ sy0, const uint8_t *__restrict__ sdir, uint8_t *contained,
                                                      uint32_t bestn, int request_enabled, int do_emit, uint32_t *acc_count,
-                                                     const uint32_t *__restrict__ out_off, ovlp_rec *out, unsigned long long *n_unknown_total,
-                                                     uint8_t *unk_flag, const uint32_t *__restrict__ list) {
+                                                     const uint32_t *__restrict__ out_off, ovlp_rec *out, uint8_t *unk_flag,
+                                                     const uint32_t *__restrict__ list) {
   uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (r >= n_ranks) return;
-  if (list) r = list[r];
+  r = list[r];
   const uint32_t FULL = 0xffffffffu, lt = (1u << lane) - 1u;
   const uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
   const uint64_t *y0s = sy0 + b;
@@ -799,10 +840,11 @@ __global__ void __launch_bounds__(128) k_replay_warp(ReplayState st, uint32_t n_
         rid1 = (uint32_t)(y1 >> 32);
         if (rid1 != rid0) {
           ridp = rid0 < rid1 ? ((uint64_t)rid0 << 32) | rid1 : ((uint64_t)rid1 << 32) | rid0;
-          uint64_t v = c.pair_old(ridp);
+          uint64_t v, vnew;
+          c.pair_get(ridp, &v, &vnew);
           bool hit = (v != NONE) && ((uint32_t)(v >> 2) < r);
           if (!hit) {
-            v = c.pair_new(ridp);
+            v = vnew;
             hit = (v != NONE) && ((uint32_t)(v >> 2) <= r);
           }
           if (hit) {
@@ -879,10 +921,9 @@ __global__ void __launch_bounds__(128) k_replay_warp(ReplayState st, uint32_t n_
   if (lane == 0) acc_count[r] = n_acc;
   const uint32_t unk_total = __reduce_add_sync(FULL, n_unk);
   if (lane == 0) unk_flag[r] = unk_total != 0;
-  if (lane == 0 && unk_total) atomicAdd(n_unknown_total, (unsigned long long)unk_total);
+  if (lane == 0 && unk_total) atomicAdd(&st.ctr[0], (unsigned long long)unk_total);
 }
 
-#define PGB_MAXV 264  // supports band_tolerance <= 256
 // sort key of an alignment request = predicted overlap length in 256-base units: warps then hold alignments of similar
 // length and finish together
 __global__ void k_align_keys(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint32_t *__restrict__ rlen_by_rid,
@@ -895,8 +936,8 @@ __global__ void k_align_keys(const AlnReq *__restrict__ reqs, uint32_t first, ui
   keys[i] = 255u - (e > 255 ? 255 : e);  // longest first: the tail of the launch is made of short alignments
   idx[i] = i;
 }
-// 1 thread = 1 alignment, flattened state machine (ovlp_match_flat); perm (optional) = processing order
-// only_n: take only the requests that involve a read with N (the rest is done by k_align_lean)
+// 1 thread = 1 alignment, flattened state machine (ovlp_match_flat) over (read, strand) views with N masks; the result goes
+// to results[request.slot].  only_n: take only the requests that involve a read with N (the rest is done by k_align_lean)
 __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint32_t *__restrict__ perm,
                         const uint64_t *__restrict__ w, const uint32_t *__restrict__ nm, const uint64_t *__restrict__ woff_by_rid,
                         const uint32_t *__restrict__ rlen_by_rid, const uint32_t *__restrict__ hasn_by_rid, int bw, match_t *results,
@@ -914,7 +955,7 @@ __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_
   int e = 0;
   ovlp_match_flat(qv, (int)(rl0 - q.start0), tv, (int)rl1, bw, V, PGB_MAXV, &m, &e);
   if (e) atomicOr(err, 128 | (e << 8));
-  results[first + i] = m;
+  results[q.slot] = m;
   // bases compared along the final path (algorithmic-bytes accounting, SURVEY 8d: (q_end + t_end)/4 per alignment)
   atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
 }
@@ -938,8 +979,41 @@ __global__ void __launch_bounds__(PGB_ALIGN_THREADS) k_align_lean(const AlnReq *
   int V[2 * PGB_MAXV];
   match_t m;
   ovlp_match_lean(qw, q.start0, (int)(rl0 - q.start0), tw, 0u, (int)rl1, bw, V, PGB_MAXV, &m);
-  results[first + i] = m;
+  results[q.slot] = m;
   atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
+}
+
+// ---- pair-table maintenance between passes
+__global__ void k_e_init(EEntry *E, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { E[i].key = PGB_EMPTY; E[i].v[0] = PGB_VNONE; E[i].v[1] = PGB_VNONE; }
+}
+__global__ void k_e_fill_new(EEntry *E, size_t n, uint32_t cur) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) E[i].v[cur] = PGB_VNONE;
+}
+// entries whose value changed between the two iterations: count, and list the read-id pairs (up to cap)
+__global__ void k_e_diff_list(const EEntry *__restrict__ E, size_t n, unsigned long long *diffs, uint64_t *changed, uint32_t cap) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint4 e = *(const uint4 *)&E[i];
+    if (e.z != e.w) {
+      unsigned long long at = atomicAdd(diffs, 1ULL);
+      if (at < cap) changed[at] = (uint64_t)e.x | ((uint64_t)e.y << 32);
+    }
+  }
+}
+// incremental pass: entries owned by clean buckets are carried over, entries owned by dirty buckets are rebuilt by their replay
+__global__ void k_e_carry(EEntry *E, size_t n, uint32_t cur, const uint8_t *__restrict__ dirty) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const uint32_t v = E[i].v[cur ^ 1];
+    E[i].v[cur] = (v != PGB_VNONE && !dirty[v >> 2]) ? v : PGB_VNONE;
+  }
 }
 
 // ---- incremental replay (DESIGN.md "dirty buckets"): a bucket has to be replayed again only if it still had predicted
@@ -960,17 +1034,6 @@ __global__ void k_bucket_reads(uint32_t n_ranks, const uint32_t *__restrict__ ra
     if ((bit >> 6) == 0) b0 |= m; else if ((bit >> 6) == 1) b1 |= m; else if ((bit >> 6) == 2) b2 |= m; else b3 |= m;
   }
   bloom[4 * (size_t)r] = b0; bloom[4 * (size_t)r + 1] = b1; bloom[4 * (size_t)r + 2] = b2; bloom[4 * (size_t)r + 3] = b3;
-}
-// table diff that also lists the changed pairs (up to cap)
-__global__ void k_table_diff_list(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, const uint64_t *__restrict__ keys, size_t n,
-                                  unsigned long long *diffs, uint64_t *changed, uint32_t cap) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride)
-    if (a[i] != b[i]) {
-      unsigned long long at = atomicAdd(diffs, 1ULL);
-      if (at < cap) changed[at] = keys[i];
-    }
 }
 // thread per changed pair: every bucket holding read a that may also hold read b becomes dirty
 __global__ void k_mark_dirty_pairs(const uint64_t *__restrict__ changed, uint32_t n_changed, const uint32_t *__restrict__ rid_sorted,
@@ -1009,19 +1072,6 @@ __global__ void k_compact_classes(const uint32_t *__restrict__ flags, const uint
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * n_ranks) return;
   if (flags[i]) list[pos[i]] = i < n_ranks ? i : i - n_ranks;
-}
-__global__ void k_dirty_flags32(const uint8_t *__restrict__ dirty, uint32_t n_ranks, uint32_t *flags) {
-  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_ranks) flags[r] = dirty[r];
-}
-// entries owned by clean buckets are carried over, entries owned by dirty buckets are rebuilt by their replay
-__global__ void k_table_carry(const uint64_t *__restrict__ eold, uint64_t *enew, size_t n, const uint8_t *__restrict__ dirty) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    uint64_t v = eold[i];
-    enew[i] = (v != PGB_EMPTY && !dirty[(uint32_t)(v >> 2)]) ? v : PGB_EMPTY;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------ shimmer4py index handle

@@ -512,7 +512,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
   c->d_level_off[0] = c->palloc<uint64_t>(ns + 1);
   const char *force = getenv("PGB_SKETCH");
-  const bool use_tiled = w >= SK_GS + 1 && !(force && !strcmp(force, "exact")) && ns > 0;
+  const bool use_tiled = w >= SK_MINW && !(force && !strcmp(force, "exact")) && ns > 0;
   if (!use_tiled) {
     // exact automaton for every read (tiny windows, or PGB_SKETCH=exact)
     c->ktic();
@@ -546,7 +546,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     CU(cudaMemsetAsync(exact_flag, 0, (ns + 1) * 4, c->st));
     c->ktic();
     if (k <= 16) {
-      size_t smem = sizeof(SkShared<uint32_t>);
+      size_t smem = sk_smem_bytes<uint32_t>(w);
       CU(cudaFuncSetAttribute(k_sketch_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       if (n_tiles) {
         k_sketch_tiled<uint32_t><<<n_tiles, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
@@ -555,7 +555,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
         CU(cudaGetLastError());
       }
     } else {
-      size_t smem = sizeof(SkShared<uint64_t>);
+      size_t smem = sk_smem_bytes<uint64_t>(w);
       CU(cudaFuncSetAttribute(k_sketch_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       if (n_tiles) {
         k_sketch_tiled<uint64_t><<<n_tiles, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
@@ -893,8 +893,12 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     outer.clear();
     outer.put_all(h_okey.data(), n_outer);
     if (h_small[0] > newest_outer_seq) outer.touch_existing();  // a put of a known outer key followed the last new one
+    const double t_put = now_ms();
     uint32_t r = 0;
     outer.for_each_in_slot_order([&](uint64_t, uint32_t o) { orank[o] = r++; });
+    if (getenv("PGB_VERBOSE"))
+      fprintf(stderr, "pgb200: outer khash replay: %u keys, table %u slots, put %.2f ms, slot order %.2f ms; %u oversized inner groups\n", n_outer, outer.nb,
+              t_put - t_host0, now_ms() - t_put, h_small[1]);
   }
   if (h_small[1]) {
     std::vector<uint32_t> big(h_small[1]), h_goff((size_t)n_outer + 1);
@@ -963,37 +967,30 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   c->stats.ms_buckets += c->toc();
 
   // ---------------- replay / align fix-point (DESIGN.md "ordered greedy as a fix-point")
-  ReplayState S;
-  uint32_t ecap = pow2_at_least(4 * (uint64_t)n_elig), acap = pow2_at_least(4 * (uint64_t)n_elig);
-  S.emask = ecap - 1; S.amask = acap - 1; S.req_cap = 2 * n_elig + 1024;
-  S.ekeys = c->alloc<uint64_t>(ecap); S.eold = c->alloc<uint64_t>(ecap); S.enew = c->alloc<uint64_t>(ecap);
-  S.akeys = c->alloc<uint64_t>(acap); S.aidx = c->alloc<uint32_t>(acap);
-  S.reqs = c->alloc<AlnReq>(S.req_cap); S.results = c->alloc<match_t>(S.req_cap);
-  S.n_req = c->alloc<uint32_t>(1); S.n_done = 0; S.rlen_by_rid = c->d_rlen_by_rid; S.err = c->d_err;
-  uint32_t *acc = c->alloc<uint32_t>((size_t)n_ranks + 1), *out_off = c->alloc<uint32_t>((size_t)n_ranks + 1);
-  unsigned long long *d_ctr = c->alloc<unsigned long long>(2);  // [0] unknown alignments, [1] table diffs
-  LAUNCH(c, k_fill_u64, 1184, 256, S.ekeys, PGB_EMPTY, (size_t)ecap);
-  LAUNCH(c, k_fill_u64, 1184, 256, S.eold, PGB_EMPTY, (size_t)ecap);
-  LAUNCH(c, k_fill_u64, 1184, 256, S.akeys, PGB_EMPTY, (size_t)acap);
-  CU(cudaMemsetAsync(S.n_req, 0, 4, c->st));
-  CU(cudaMemsetAsync(acc, 0, ((size_t)n_ranks + 1) * 4, c->st));
-  auto free_S = [&]() {
-    c->release(S.ekeys); c->release(S.eold); c->release(S.enew); c->release(S.akeys); c->release(S.aidx); c->release(S.reqs);
-    c->release(S.results); c->release(S.n_req); c->release(acc); c->release(out_off); c->release(d_ctr);
-    c->release(sy0); c->release(sy1); c->release(sseq); c->release(sdir); c->release(contained); c->release(d_rank_off);
-  };
-  bool wet = false, converged = false;
+  if (n_ranks >= (1u << 30)) throw std::runtime_error("more than 2^30 eligible buckets in one overlap call");
   const char *rp_env = getenv("PGB_REPLAY");
-  const bool warp_replay = rp_env && !strcmp(rp_env, "warp");  // default: one thread per bucket (the warp form issues ~30x more instructions)
+  const bool warp_replay = rp_env && !strcmp(rp_env, "warp");  // every bucket by a warp (default: one thread per bucket)
   const bool incremental = !(getenv("PGB_REPLAY_FULL"));        // PGB_REPLAY_FULL=1: replay every bucket in every pass
-  // incremental passes: (rid, rank) index of the eligible records sorted by rid + per-bucket Bloom filter of read ids
+  // buckets with >= BIG_N records are replayed by a warp (hybrid; measured slower than all-threads, so off by default)
+  const uint32_t BIG_N = getenv("PGB_REPLAY_BIG") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG")) : 0xFFFFFFFFu;
+  // speculative passes before real alignments are computed: 2 cost ~2 % extra alignments and save two full passes
+  const int MAX_DRY = getenv("PGB_DRY_PASSES") ? atoi(getenv("PGB_DRY_PASSES")) : 2;
+  const bool verbose = getenv("PGB_VERBOSE") != nullptr;
   const uint32_t CHANGED_CAP = 16384;
+  // incremental passes: (rid, rank) index of the eligible records sorted by rid + per-bucket Bloom filter of read ids
   uint32_t *rid_sorted = c->alloc<uint32_t>(n_elig), *rank_sorted = c->alloc<uint32_t>(n_elig);
   uint64_t *bloom = c->alloc<uint64_t>(4 * (size_t)n_ranks), *changed = c->alloc<uint64_t>(CHANGED_CAP);
   uint8_t *unk_flag = c->alloc<uint8_t>(n_ranks), *dirty = c->alloc<uint8_t>(n_ranks);
   uint32_t *dflags = c->alloc<uint32_t>(2 * (size_t)n_ranks + 1), *dpos = c->alloc<uint32_t>(2 * (size_t)n_ranks + 1), *dlist = c->alloc<uint32_t>(n_ranks);
   uint32_t *all_list = c->alloc<uint32_t>(n_ranks);
-  const uint32_t BIG_N = getenv("PGB_REPLAY_BIG") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG")) : 20u;  // records; >= BIG_N: one warp per bucket
+  uint32_t *acc = c->alloc<uint32_t>((size_t)n_ranks + 1), *out_off = c->alloc<uint32_t>((size_t)n_ranks + 1);
+  unsigned long long *d_ctr = c->alloc<unsigned long long>(2);  // [0] unknown alignments [1] table diffs
+  {
+    uint32_t *rr = c->alloc<uint32_t>(n_elig), *rk = c->alloc<uint32_t>(n_elig);
+    LAUNCH(c, k_bucket_reads, nblk(n_ranks, 128), 128, n_ranks, d_rank_off, sy0, rr, rk, bloom);
+    sort_pairs_u32(c, rr, rid_sorted, rk, rank_sorted, n_elig);
+    c->release(rr); c->release(rk);
+  }
   // (small..., big...) run list of a pass; returns the number of small buckets, *n_run = total
   auto class_lists = [&](const uint8_t *dirty_or_null, uint32_t *list, uint32_t *n_run) -> uint32_t {
     CU(cudaMemsetAsync(dflags + 2 * (size_t)n_ranks, 0, 4, c->st));
@@ -1006,113 +1003,152 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   };
   uint32_t n_all = 0;
   const uint32_t n_all_small = class_lists(nullptr, all_list, &n_all);
-  auto launch_replay = [&](const uint32_t *list, uint32_t n_small, uint32_t n_total, int request, int emit, const uint32_t *ooff, ovlp_rec *out) {
-    if (warp_replay) {
-      LAUNCH(c, k_replay_warp, nblk((size_t)n_total * 32, 128), 128, S, n_total, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, d_ctr,
-             unk_flag, list);
-      return;
-    }
-    LAUNCH(c, k_replay, nblk(n_small, 64), 64, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, d_ctr, unk_flag);
-    LAUNCH(c, k_replay_warp, nblk((size_t)(n_total - n_small) * 32, 128), 128, S, n_total - n_small, d_rank_off, sy0, sdir, contained, bestn, request, emit,
-           acc, ooff, out, d_ctr, unk_flag, list + n_small);
+  auto free_common = [&]() {
+    c->release(rid_sorted); c->release(rank_sorted); c->release(bloom); c->release(changed); c->release(unk_flag); c->release(dirty);
+    c->release(dflags); c->release(dpos); c->release(dlist); c->release(all_list); c->release(acc); c->release(out_off); c->release(d_ctr);
+    c->release(sy0); c->release(sy1); c->release(sseq); c->release(sdir); c->release(contained); c->release(d_rank_off);
   };
-  {
-    uint32_t *rr = c->alloc<uint32_t>(n_elig), *rk = c->alloc<uint32_t>(n_elig);
-    LAUNCH(c, k_bucket_reads, nblk(n_ranks, 128), 128, n_ranks, d_rank_off, sy0, rr, rk, bloom);
-    sort_pairs_u32(c, rr, rid_sorted, rk, rank_sorted, n_elig);
+
+  // table capacities: sized for what a chunk normally needs (pairs ever accepted ~ 0.3 n_elig, alignments ~ 0.25 n_elig);
+  // a chunk that needs more raises the overflow flag and the fix-point restarts with doubled tables
+  uint64_t ecap64 = (uint64_t)n_elig + n_elig / 4 + 4096, acap64 = (uint64_t)n_elig / 2 + n_elig / 4 + 4096;
+  bool converged = false;
+  ReplayState S;
+  for (int attempt = 0; !converged; attempt++) {
+    if (attempt > 8 || ecap64 >= (1ull << 32) || acap64 >= (1ull << 32)) { free_common(); throw std::runtime_error("replay tables overflow"); }
+    memset(&S, 0, sizeof S);
+    S.ecap = (uint32_t)ecap64; S.acap = (uint32_t)acap64; S.req_cap = S.acap;
+    S.E = c->alloc<EEntry>(S.ecap);
+    S.akeys = c->alloc<uint64_t>(S.acap); S.ares = c->alloc<match_t>(S.acap);
+    S.reqs = c->alloc<AlnReq>(S.req_cap);
+    S.n_req = c->alloc<uint32_t>(1); S.rlen_by_rid = c->d_rlen_by_rid; S.err = c->d_err;
+    S.ctr = d_ctr;
+    S.cur = 0;
+    auto free_S = [&]() { c->release(S.E); c->release(S.akeys); c->release(S.ares); c->release(S.reqs); c->release(S.n_req); };
+    LAUNCH(c, k_e_init, 1184, 256, S.E, (size_t)S.ecap);
+    LAUNCH(c, k_fill_u64, 1184, 256, S.akeys, PGB_EMPTY, (size_t)S.acap);
+    CU(cudaMemsetAsync(S.n_req, 0, 4, c->st));
+    CU(cudaMemsetAsync(acc, 0, ((size_t)n_ranks + 1) * 4, c->st));
     CU(cudaMemsetAsync(unk_flag, 0, n_ranks, c->st));
-    CU(cudaMemsetAsync(dflags, 0, ((size_t)n_ranks + 1) * 4, c->st));
-  }
-  uint64_t prev_diffs = ~0ULL, last_diffs = ~0ULL;
-  int dry_passes = 0;
-  for (int pass = 0; pass < 400; pass++) {
-    c->tic();
-    CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
-    // which buckets run in this pass
-    uint32_t n_run = n_all, n_run_small = n_all_small;
-    const uint32_t *run_list = all_list;
-    const bool partial = incremental && pass > 0 && last_diffs <= CHANGED_CAP;
-    if (partial) {
-      LAUNCH(c, k_dirty_from_unknown, nblk(n_ranks), 256, unk_flag, n_ranks, dirty);
-      if (last_diffs) LAUNCH(c, k_mark_dirty_pairs, nblk(last_diffs), 256, changed, (uint32_t)last_diffs, rid_sorted, rank_sorted, n_elig, bloom, dirty);
-      n_run_small = class_lists(dirty, dlist, &n_run);
-      LAUNCH(c, k_table_carry, 1184, 256, S.eold, S.enew, (size_t)ecap, dirty);
-      run_list = dlist;
-    } else {
-      LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
-    }
-    c->ktic();
-    launch_replay(run_list, n_run_small, n_run, wet ? 1 : 0, 0, (const uint32_t *)nullptr, (ovlp_rec *)nullptr);
-    c->stats.ms_k_replay += c->ktoc(); c->stats.n_k_replay++;
-    LAUNCH(c, k_table_diff_list, 1184, 256, S.eold, S.enew, S.ekeys, (size_t)ecap, d_ctr + 1, changed, CHANGED_CAP);
-    unsigned long long ctr[2];
-    uint32_t n_req = 0;
-    c->d2h(ctr, d_ctr, 16);
-    c->d2h(&n_req, S.n_req, 4);
-    c->stats.ms_replay += c->toc();
-    c->stats.n_replay_passes++;
-    if (c->check_err("pgb_overlap/replay")) { free_S(); return -1; }
-    if (n_req > S.n_done) {
+    auto launch_replay = [&](const uint32_t *list, uint32_t n_small, uint32_t n_total, int request, int emit, const uint32_t *ooff, ovlp_rec *out) {
+      const uint32_t ns = warp_replay ? 0u : n_small, nb = n_total - ns;
+      LAUNCH(c, k_replay, nblk(ns, 64), 64, S, ns, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag);
+      LAUNCH(c, k_replay_warp, nblk((size_t)nb * 32, 128), 128, S, nb, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag,
+             list + ns);
+    };
+    bool wet = false, overflow = false;
+    uint64_t prev_diffs = ~0ULL, last_diffs = ~0ULL;
+    uint32_t n_done = 0;
+    int dry_passes = 0;
+    for (int pass = 0; pass < 400; pass++) {
       c->tic();
-      uint32_t nn = n_req - S.n_done;
-      uint32_t *perm = nullptr;
-      if (nn > 8192) {  // group alignments of similar predicted length into the same warps
-        uint32_t *keys = c->alloc<uint32_t>(nn), *keys2 = c->alloc<uint32_t>(nn), *idx0 = c->alloc<uint32_t>(nn);
-        perm = c->alloc<uint32_t>(nn);
-        LAUNCH(c, k_align_keys, nblk(nn), 256, S.reqs, S.n_done, nn, c->d_rlen_by_rid, keys, idx0);
-        size_t tmp_bytes = 0;
-        CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
-        uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
-        CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
-        c->stats.kernel_launches += 3;
+      CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
+      // which buckets run in this pass
+      uint32_t n_run = n_all, n_run_small = n_all_small;
+      const uint32_t *run_list = all_list;
+      const bool partial = incremental && pass > 0 && last_diffs <= CHANGED_CAP;
+      if (partial) {
+        LAUNCH(c, k_dirty_from_unknown, nblk(n_ranks), 256, unk_flag, n_ranks, dirty);
+        if (last_diffs) LAUNCH(c, k_mark_dirty_pairs, nblk(last_diffs), 256, changed, (uint32_t)last_diffs, rid_sorted, rank_sorted, n_elig, bloom, dirty);
+        n_run_small = class_lists(dirty, dlist, &n_run);
+        LAUNCH(c, k_e_carry, 1184, 256, S.E, (size_t)S.ecap, S.cur, dirty);
+        run_list = dlist;
+      } else {
+        LAUNCH(c, k_e_fill_new, 1184, 256, S.E, (size_t)S.ecap, S.cur);
       }
       c->ktic();
-      LAUNCH(c, k_align_lean, nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, S.n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid,
-             c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.results, c->d_align_bases);
-      if (c->n_reads_with_n)
-        LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, S.n_done, nn, perm, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
-               (int)bw, S.results, c->d_err, c->d_align_bases, 1);
-      c->stats.ms_k_align += c->ktoc(); c->stats.n_k_align++;
+      launch_replay(run_list, n_run_small, n_run, wet ? 1 : 0, 0, (const uint32_t *)nullptr, (ovlp_rec *)nullptr);
+      const double ms_rp = c->ktoc();
+      c->stats.ms_k_replay += ms_rp; c->stats.n_k_replay++;
+      LAUNCH(c, k_e_diff_list, 1184, 256, S.E, (size_t)S.ecap, d_ctr + 1, changed, CHANGED_CAP);
+      unsigned long long ctr[2];
+      uint32_t n_req = 0;
+      c->d2h(ctr, d_ctr, 16);
+      c->d2h(&n_req, S.n_req, 4);
+      c->stats.ms_replay += c->toc();
+      c->stats.n_replay_passes++;
       {
-        unsigned long long ab = 0;
-        c->d2h(&ab, c->d_align_bases, 8);
-        c->stats.n_align_bases += ab;
-        CU(cudaMemsetAsync(c->d_align_bases, 0, 8, c->st));
+        int e = 0;
+        c->d2h(&e, c->d_err, sizeof e);
+        if (e & (32 | 64)) {  // a table filled up: grow it and start over
+          if (e & 32) ecap64 *= 2;
+          if (e & 64) acap64 *= 2;
+          int z = 0;
+          c->h2d(c->d_err, &z, sizeof z);
+          c->sync();
+          if (verbose) fprintf(stderr, "pgb200: replay tables too small (flags %d): restarting with pair table %llu, alignment table %llu\n", e,
+                               (unsigned long long)ecap64, (unsigned long long)acap64);
+          overflow = true;
+          break;
+        }
       }
-      c->stats.ms_align += c->toc();
-      c->stats.n_alignments += nn;
-      if (c->check_err("pgb_overlap/align")) { free_S(); return -1; }
+      if (c->check_err("pgb_overlap/replay")) { free_S(); free_common(); return -1; }
+      double ms_al = 0;
+      if (n_req > n_done) {
+        c->tic();
+        uint32_t nn = n_req - n_done;
+        uint32_t *perm = nullptr;
+        if (nn > 8192) {  // group alignments of similar predicted length into the same warps
+          uint32_t *keys = c->alloc<uint32_t>(nn), *keys2 = c->alloc<uint32_t>(nn), *idx0 = c->alloc<uint32_t>(nn);
+          perm = c->alloc<uint32_t>(nn);
+          LAUNCH(c, k_align_keys, nblk(nn), 256, S.reqs, n_done, nn, c->d_rlen_by_rid, keys, idx0);
+          size_t tmp_bytes = 0;
+          CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
+          uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+          CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
+          c->stats.kernel_launches += 3;
+        }
+        c->ktic();
+        LAUNCH(c, k_align_lean, nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid,
+               c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
+        if (c->n_reads_with_n)
+          LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, n_done, nn, perm, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
+                 (int)bw, S.ares, c->d_err, c->d_align_bases, 1);
+        ms_al = c->ktoc();
+        c->stats.ms_k_align += ms_al; c->stats.n_k_align++;
+        {
+          unsigned long long ab = 0;
+          c->d2h(&ab, c->d_align_bases, 8);
+          c->stats.n_align_bases += ab;
+          CU(cudaMemsetAsync(c->d_align_bases, 0, 8, c->st));
+        }
+        c->stats.ms_align += c->toc();
+        c->stats.n_alignments += nn;
+        if (c->check_err("pgb_overlap/align")) { free_S(); free_common(); return -1; }
+      }
+      const bool new_requests = n_req > n_done;
+      n_done = n_req;
+      S.cur ^= 1;
+      if (verbose)
+        fprintf(stderr, "pgb200: replay pass %d %s: buckets=%u/%u unknown=%llu table_diffs=%llu requests=%u  k_replay %.3f ms, k_align %.3f ms\n", pass,
+                wet ? "wet" : "dry", n_run, n_ranks, ctr[0], ctr[1], n_req, ms_rp, ms_al);
+      last_diffs = ctr[1];
+      c->stats.n_replay_buckets += n_run;
+      if (wet && !new_requests && ctr[0] == 0 && ctr[1] == 0) { converged = true; break; }
+      if (!wet) {
+        // speculative ("dry") passes settle the time-stamped pair table with predicted alignments only; switch to real
+        // alignments once the table is nearly stable or stops improving
+        dry_passes++;
+        if (ctr[1] <= 16 + ctr[0] / 512 || ctr[1] >= prev_diffs || dry_passes >= MAX_DRY) wet = true;
+        prev_diffs = ctr[1];
+      }
     }
-    bool new_requests = n_req > S.n_done;
-    S.n_done = n_req;
-    std::swap(S.eold, S.enew);
-    if (getenv("PGB_VERBOSE"))
-      fprintf(stderr, "pgb200: replay pass %d %s: buckets=%u/%u unknown=%llu table_diffs=%llu requests=%u\n", pass, wet ? "wet" : "dry", n_run, n_ranks,
-              ctr[0], ctr[1], n_req);
-    last_diffs = ctr[1];
-    c->stats.n_replay_buckets += n_run;
-    if (wet && !new_requests && ctr[0] == 0 && ctr[1] == 0) { converged = true; break; }
-    if (!wet) {
-      // speculative ("dry") passes settle the time-stamped pair table with predicted alignments only; switch to real
-      // alignments once the table is nearly stable or stops improving
-      dry_passes++;
-      if (ctr[1] <= 16 + ctr[0] / 512 || ctr[1] >= prev_diffs || dry_passes >= 12) wet = true;
-      prev_diffs = ctr[1];
-    }
-  }
-  if (!converged) { free_S(); throw std::runtime_error("replay fix-point did not converge in 400 passes"); }
+    if (overflow) { free_S(); continue; }
+    if (!converged) { free_S(); free_common(); throw std::runtime_error("replay fix-point did not converge in 400 passes"); }
 
-  // ---------------- emission pass in visiting order
-  c->tic();
-  uint32_t n_out = scan_u32(c, acc, out_off, (size_t)n_ranks + 1);
-  c->d_ovl = c->palloc<ovlp_rec>(n_out); c->n_ovl = n_out;
-  LAUNCH(c, k_fill_u64, 1184, 256, S.enew, PGB_EMPTY, (size_t)ecap);
-  CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
-  launch_replay(all_list, n_all_small, n_all, 0, 1, out_off, c->d_ovl);
-  c->sync();
-  c->stats.ms_emit += c->toc();
-  c->stats.n_overlaps += n_out;
-  free_S();
+    // ---------------- emission pass in visiting order
+    c->tic();
+    uint32_t n_out = scan_u32(c, acc, out_off, (size_t)n_ranks + 1);
+    c->d_ovl = c->palloc<ovlp_rec>(n_out); c->n_ovl = n_out;
+    LAUNCH(c, k_e_fill_new, 1184, 256, S.E, (size_t)S.ecap, S.cur);
+    CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
+    launch_replay(all_list, n_all_small, n_all, 0, 1, out_off, c->d_ovl);
+    c->sync();
+    c->stats.ms_emit += c->toc();
+    c->stats.n_overlaps += n_out;
+    free_S();
+  }
+  free_common();
   c->sync();
   c->check_err("pgb_overlap/emit");
   API_END(c)
@@ -1371,7 +1407,7 @@ extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_
   uint64_t offs[2] = {0, (uint64_t)q_len};
   CLI_CHECK(c, pgb_load_reads(c, img.data(), img.size(), rids, lens, offs, 2, 1, 1, 0));
   try {
-    AlnReq q; q.rid0 = 0; q.start0 = 0; q.rid1 = 1; q.strands = 0;
+    AlnReq q; q.rid0 = 0; q.start0 = 0; q.rid1 = 1; q.strands = 0; q.slot = 0;
     AlnReq *d_q = c->alloc<AlnReq>(1);
     match_t *d_m = c->alloc<match_t>(1);
     c->h2d(d_q, &q, sizeof q);

@@ -730,8 +730,8 @@ PGB_HD bool pair_far_enough(uint64_t y0, uint64_t y1) {
 //
 // Ctx must provide:
 //   uint32_t rlen(uint32_t rid)
-//   uint64_t pair_old(uint64_t ridp)            value from the previous iteration (NONE = ~0)
-//   uint64_t pair_new(uint64_t ridp)            value being built in this iteration
+//   void     pair_get(uint64_t ridp, uint64_t *vold, uint64_t *vnew)   value from the previous iteration and value being
+//                                               built in this iteration (NONE = ~0), one table probe for both
 //   void     pair_set(uint64_t ridp, uint64_t v)   atomic-min into the table being built
 //   bool     aln_get(uint32_t i, uint32_t j, match_t *m)     true if the alignment of records (i,j) is known
 //   void     aln_request(uint32_t i, uint32_t j, uint32_t rid0, uint32_t start0, uint32_t strand0,
@@ -774,10 +774,11 @@ PGB_HD uint32_t replay_bucket(Ctx &c, uint32_t rank, const uint64_t *y0s, const 
       if (rid0 == rid1) continue;
       const uint64_t ridp = rid0 < rid1 ? ((uint64_t)rid0 << 32) | rid1 : ((uint64_t)rid1 << 32) | rid0;
       {
-        uint64_t v = c.pair_old(ridp);
+        uint64_t v, vnew;
+        c.pair_get(ridp, &v, &vnew);
         bool hit = (v != NONE) && ((uint32_t)(v >> 2) < rank);
         if (!hit) {
-          v = c.pair_new(ridp);
+          v = vnew;
           hit = (v != NONE) && ((uint32_t)(v >> 2) <= rank);
         }
         if (hit) {

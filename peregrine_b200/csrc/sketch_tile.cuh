@@ -1,17 +1,22 @@
 // sketch_tile.cuh — tiled, data-parallel (w,k)-minimizer kernel (the fast path of mm_sketch, src/mm_sketch.c:70-151).
 //
-// One CTA of 256 threads sketches one TILE of one read out of shared memory:
-//   phase 1  each thread hashes 17 consecutive positions (k-mer registers extracted once from the packed words, then
-//            rolled) and notes palindromic k-mers (they occupy no window slot, mm_sketch.c:104-105);
+// One CTA of 256 threads sketches one TILE (SK_R positions incl. a w+16 halo) of one read out of shared memory:
+//   phase 1  each thread hashes SK_G consecutive positions: the k-mer pair is extracted once from the packed words and
+//            then rolled out of one 64-bit register of bases; k-mer and hash arithmetic run in 32 bits when k <= 16 (the
+//            reference's hash64 masks to 2k bits after every step, so it is arithmetic mod 2^2k); palindromic k-mers are
+//            noted (they occupy no window slot, mm_sketch.c:104-105);
 //   phase 2  block scan of slot counts; slots (hash, pos<<1|strand) are written to shared memory in slot order;
-//   phase 3  per 16-slot group: minimum (rightmost on ties, with a "tie seen" bit) and all suffix minima;
-//   phase 4  for every window end s: rightmost arg-min of slots [s-w+1, s] = suffix(left group) + whole groups +
-//            running prefix(own group)  (3 combines per window, no divergence);
-//   phase 5  a slot is emitted when it becomes the window arg-min (first full window, or arg-min changed); block scan
-//            of emit counts; records leave in position order.
+//   phase 3  van Herk / Gil-Werman with blocks of B = ceil(w/2) slots: one thread per block runs the suffix minima
+//            (right to left), then the prefix minima (left to right, in place).  Every minimum carries its arg-min slot
+//            (rightmost on ties) and a "this minimum occurs twice" bit.  Blocks are padded to an odd stride, so the
+//            per-thread sequential walks are free of bank conflicts;
+//   phase 4  each thread evaluates SK_G consecutive window ends: window [e-w+1, e] = suffix(left block) (+ one whole
+//            block) + prefix(right block), i.e. at most two combines; a slot is emitted when it becomes the window
+//            arg-min (first full window, or arg-min changed);
+//   phase 5  block scan of emit counts; records leave in position order.
 // Exactness: on tie-free, N-free windows "rightmost arg-min of every full window" IS the reference's output (SURVEY
 // App. A-5; re-checked against the reference by tests/hostsim, which runs these very functions on the CPU).  Every
-// other case is detected and the whole read is handed to the exact automaton (k_sketch_exact): reads with N, reads
+// other case is detected and the whole read is handed to the exact automaton (k_sketch_exact_seg): reads with N, reads
 // shorter than one window (+ margin), any evaluated window whose minimum occurs twice (hash tie), regions with more
 // than SK_PALPAD palindromic k-mers, tiles that overflow their record budget.
 #pragma once
@@ -19,13 +24,22 @@
 
 namespace pgb {
 
-enum { SK_THREADS = 256, SK_G = 17, SK_R = SK_THREADS * SK_G /* 4352 region positions */, SK_GS = 16, SK_PALPAD = 16,
-       SK_NG = (SK_R + SK_GS - 1) / SK_GS /* 272 slot groups */, SK_CAP = 512 /* records per tile */ };
+#ifndef PGB_SK_G
+#define PGB_SK_G 13
+#endif
+enum { SK_THREADS = 256, SK_G = PGB_SK_G, SK_R = SK_THREADS * SK_G /* region positions */, SK_PALPAD = 16, SK_CAP = 512 /* records per tile */,
+       SK_MINW = 17 /* smallest window the tiled kernel takes */ };
 enum { SK_FLAG_TIE = 1, SK_FLAG_PAL = 2, SK_FLAG_OVERFLOW = 4, SK_FLAG_SHORT = 8, SK_FLAG_N = 16 };
 
 PGB_HD int sk_halo(int wsz) { return wsz + SK_PALPAD; }
 PGB_HD int sk_tile_len(int wsz) { return SK_R - sk_halo(wsz); }
 PGB_HD int sk_min_len(int wsz, int k) { return wsz + k + SK_PALPAD + 1; }  // shorter reads go to the exact automaton
+PGB_HD int sk_block_len(int wsz) { return (wsz + 1) / 2; }
+PGB_HD int sk_block_pad(int B) { return 1 + (B & 1); }  // B + pad is odd
+PGB_HD int sk_padn(int wsz) {                          // padded slot-array length
+  const int B = sk_block_len(wsz);
+  return SK_R + (SK_R / B + 1) * sk_block_pad(B) + 4;
+}
 
 struct SkParams {
   const uint64_t *w;  // packed reads
@@ -37,18 +51,36 @@ struct SkParams {
   int first_tile;
 };
 
+// shared-memory image of a tile (pointers into one dynamic allocation; plain vectors in tests/hostsim)
 template <class HT>
-struct SkShared {
-  HT hv[SK_R];               // hash per slot (all ones = sentinel: k-mer not complete yet)
-  HT sv[SK_R];               // suffix minimum value within the slot's 16-group
-  uint16_t ps[SK_R];         // (region-relative position) << 1 | strand
-  uint16_t sp[SK_R];         // suffix arg-min slot | tie << 15
-  uint16_t amin[SK_R];       // window arg-min slot for the window ending at this slot
-  HT gv[SK_NG];              // group minimum
-  uint16_t gp[SK_NG];        // group arg-min slot | tie << 15
-  uint32_t scan[2 * SK_THREADS + 2];
-  uint32_t n_slots, n_pal, n_halo_slots, flags, n_emit;
+struct SkTile {
+  HT *hv;        // [padn] hash per slot (all ones = sentinel: k-mer not complete yet); prefix minimum after phase 3
+  HT *sv;        // [padn] suffix minimum within the slot's block
+  uint16_t *pp;  // [padn] prefix arg-min slot | tie << 15
+  uint16_t *sp;  // [padn] suffix arg-min slot | tie << 15
+  uint16_t *ps;  // [SK_R] (region-relative position) << 1 | strand, by slot
+  uint32_t *scan;  // [16]
+  uint32_t *ctr;   // [4] n_slots, n_pal, n_halo_slots, flags
+  int B, pad;
 };
+enum { SK_N_SLOTS = 0, SK_N_PAL = 1, SK_N_HALO = 2, SK_FLAGS = 3 };
+template <class HT>
+PGB_HD size_t sk_smem_bytes(int wsz) {
+  return (size_t)sk_padn(wsz) * (2 * sizeof(HT) + 4) + (size_t)SK_R * 2 + 20 * 4 + 16;
+}
+template <class HT>
+PGB_HD void sk_tile_layout(SkTile<HT> &t, unsigned char *base, int wsz) {
+  const size_t n = (size_t)sk_padn(wsz);
+  t.hv = reinterpret_cast<HT *>(base);
+  t.sv = t.hv + n;
+  t.scan = reinterpret_cast<uint32_t *>(t.sv + n);
+  t.ctr = t.scan + 16;
+  t.pp = reinterpret_cast<uint16_t *>(t.ctr + 4);
+  t.sp = t.pp + n;
+  t.ps = t.sp + n;
+  t.B = sk_block_len(wsz);
+  t.pad = sk_block_pad(t.B);
+}
 
 template <class HT>
 struct SkMin {
@@ -73,18 +105,45 @@ PGB_HD int sk_popc(uint32_t v) {
 #endif
 }
 
+// src/mm_sketch.c:23-32 in HT arithmetic: identical to the 64-bit original because every step is masked to 2k <= bits(HT)
+template <class HT>
+PGB_HD HT sk_hash(HT key, HT mask) {
+  key = (HT)(~key + (HT)(key << 21)) & mask;
+  key = key ^ (HT)(key >> 24);
+  key = (HT)((HT)(key + (HT)(key << 3)) + (HT)(key << 8)) & mask;
+  key = key ^ (HT)(key >> 14);
+  key = (HT)((HT)(key + (HT)(key << 2)) + (HT)(key << 4)) & mask;
+  key = key ^ (HT)(key >> 28);
+  key = (HT)(key + (HT)(key << 31)) & mask;
+  return key;
+}
+
 // ---- phase 1: hash the thread's SK_G positions.  slot_mask bit i = position i is a window slot; halo_slots = slots whose
 // region-relative position is below `halo`.
 template <class HT>
 PGB_HD void sk_phase1(int tid, const SkParams &p, int halo, HT *hv_out, uint16_t *ps_out, uint32_t *slot_mask, uint32_t *n_pal,
                       uint32_t *halo_slots) {
   const int k = p.k;
-  const uint64_t mask = (1ULL << 2 * k) - 1, shift1 = 2 * (uint64_t)(k - 1);
+  const HT mask = (HT)(((uint64_t)1 << 2 * k) - 1);
+  const int shift1 = 2 * (k - 1);
   const int q0 = tid * SK_G;
   uint32_t sm = 0, np = 0, hs = 0;
-  uint64_t kmer0 = 0, kmer1 = 0;
-  bool have = false;
+  HT kmer0 = 0, kmer1 = 0;
   const int64_t base0 = (int64_t)p.word_off * 32;
+  // first position of this thread whose k-mer is complete and inside the read
+  int i0 = 0;
+  {
+    const int need = k - 1 - (p.r0 + q0);  // pos >= k-1
+    if (need > i0) i0 = need;
+  }
+  uint64_t bases = 0;  // bases at positions (p.r0 + q0 + i0 + 1 + j), j = 0.., 2 bits each: the rolled-in bases
+  if (i0 < SK_G && p.r0 + q0 + i0 < p.len) {
+    const int pos = p.r0 + q0 + i0;
+    const uint64_t v = fetch_fwd64(p.w, base0 + pos - k + 1) & (((uint64_t)1 << 2 * k) - 1);  // bases pos-k+1 .. pos, earliest in the low bits
+    kmer1 = (HT)((~v) & (((uint64_t)1 << 2 * k) - 1));
+    kmer0 = (HT)(rev2(v) >> (64 - 2 * k));
+    bases = fetch_fwd64(p.w, base0 + pos + 1);
+  }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -93,25 +152,19 @@ PGB_HD void sk_phase1(int tid, const SkParams &p, int halo, HT *hv_out, uint16_t
     hv_out[i] = (HT)~(HT)0;
     ps_out[i] = 0;
     if (pos < 0 || pos >= p.len) continue;  // does not exist
-    if (pos < k - 1) {                     // exists, k-mer incomplete: sentinel slot (l < k)
+    if (i < i0) {                          // exists, k-mer incomplete: sentinel slot (l < k)
       sm |= 1u << i;
       if (q0 + i < halo) hs++;
       continue;
     }
-    if (!have) {
-      uint64_t v = fetch_fwd64(p.w, base0 + pos - k + 1) & mask;  // bases pos-k+1 .. pos, earliest in the low bits
-      kmer1 = (~v) & mask;
-      kmer0 = rev2(v) >> (64 - 2 * k);
-      have = true;
-    } else {
-      const int64_t a = base0 + pos;
-      const uint64_t c = (p.w[a >> 5] >> (2 * (a & 31))) & 3;
-      kmer0 = (kmer0 << 2 | c) & mask;
-      kmer1 = (kmer1 >> 2) | (3ULL ^ c) << shift1;
+    if (i > i0) {
+      const HT c = (HT)((bases >> (2 * (i - i0 - 1))) & 3);
+      kmer0 = (HT)((HT)(kmer0 << 2) | c) & mask;
+      kmer1 = (HT)(kmer1 >> 2) | (HT)((HT)(3 ^ c) << shift1);
     }
     if (kmer0 == kmer1) { np++; continue; }  // palindromic k-mer: no slot
     const int z = kmer0 < kmer1 ? 0 : 1;
-    hv_out[i] = (HT)hash64(z ? kmer1 : kmer0, mask);
+    hv_out[i] = sk_hash<HT>(z ? kmer1 : kmer0, mask);
     ps_out[i] = (uint16_t)(((q0 + i) << 1) | z);
     sm |= 1u << i;
     if (q0 + i < halo) hs++;
@@ -121,119 +174,146 @@ PGB_HD void sk_phase1(int tid, const SkParams &p, int halo, HT *hv_out, uint16_t
   *halo_slots = hs;
 }
 
+// position of a slot in the padded arrays
+struct SkCursor { int s, blk, off, pi; };
+PGB_HD void sk_cursor_init(SkCursor &c, int s, int B, int pad) {
+  c.s = s;
+  c.blk = s / B;
+  c.off = s - c.blk * B;
+  c.pi = s + c.blk * pad;
+}
+PGB_HD void sk_cursor_next(SkCursor &c, int B, int pad) {
+  c.s++;
+  c.pi++;
+  if (++c.off == B) { c.off = 0; c.blk++; c.pi += pad; }
+}
+
 // ---- phase 2: write the thread's slots at their slot index
 template <class HT>
-PGB_HD void sk_phase2_write(SkShared<HT> &sh, const HT *hv, const uint16_t *ps, uint32_t slot_mask, uint32_t slot_base) {
-  uint32_t s = slot_base;
+PGB_HD void sk_phase2_write(SkTile<HT> &sh, const HT *hv, const uint16_t *ps, uint32_t slot_mask, uint32_t slot_base) {
+  SkCursor c;
+  sk_cursor_init(c, (int)slot_base, sh.B, sh.pad);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int i = 0; i < SK_G; i++)
     if (slot_mask >> i & 1) {
-      sh.hv[s] = hv[i];
-      sh.ps[s] = ps[i];
-      s++;
+      sh.hv[c.pi] = hv[i];
+      sh.ps[c.s] = ps[i];
+      sk_cursor_next(c, sh.B, sh.pad);
     }
 }
 
-// ---- phase 3: group minimum + suffix minima of group g
+// ---- phase 3a: suffix minima of block b
 template <class HT>
-PGB_HD void sk_phase3_group(int g, SkShared<HT> &sh) {
-  const uint32_t ns = sh.n_slots;
-  const uint32_t b = (uint32_t)g * SK_GS;
-  if (b >= ns) return;
-  const uint32_t e = b + SK_GS < ns ? b + SK_GS : ns;
+PGB_HD void sk_phase3_suffix(int b, SkTile<HT> &sh) {
+  const int ns = (int)sh.ctr[SK_N_SLOTS], B = sh.B;
+  const int first = b * B;
+  if (first >= ns) return;
+  const int last = (first + B < ns ? first + B : ns) - 1;
+  const int base = b * (B + sh.pad) - first;  // padded index = base + slot
   SkMin<HT> run;
-  run.v = sh.hv[e - 1];
-  run.p = e - 1;
-  sh.sv[e - 1] = run.v;
-  sh.sp[e - 1] = (uint16_t)run.p;
-  for (uint32_t s = e - 1; s-- > b;) {
+  run.v = sh.hv[base + last];
+  run.p = (uint32_t)last;
+  sh.sv[base + last] = run.v;
+  sh.sp[base + last] = (uint16_t)run.p;
+  for (int s = last - 1; s >= first; s--) {
     SkMin<HT> c;
-    c.v = sh.hv[s];
-    c.p = s;
-    run = sk_combine(c, run);  // c is to the LEFT of run
-    sh.sv[s] = run.v;
-    sh.sp[s] = (uint16_t)run.p;
-  }
-  sh.gv[g] = run.v;
-  sh.gp[g] = (uint16_t)run.p;
-}
-
-// ---- phase 4: window arg-min for the window-end slots of group g (windows ending at s >= s_eval); returns tie bit.
-// Requires wsz >= SK_GS + 1 so that the left window edge always lies in an earlier group.
-template <class HT>
-PGB_HD uint32_t sk_phase4_group(int g, SkShared<HT> &sh, int wsz, int s_eval) {
-  const int ns = (int)sh.n_slots;
-  const int b = g * SK_GS;
-  if (b >= ns) return 0;
-  const int e = b + SK_GS < ns ? b + SK_GS : ns;
-  if (e - 1 < s_eval) return 0;
-  int first = b > s_eval ? b : s_eval;          // first evaluated window end in this group
-  const int ga = (first - wsz + 1) / SK_GS;      // group of the left edge for the first evaluated window (>= 0)
-  // whole groups strictly between the left-edge group and this group: Mb = groups ga+2 .. g-1, Ma = ga+1 .. g-1
-  SkMin<HT> Mb, Ma;
-  bool hasMb = false, hasMa = false;
-  Mb.v = 0; Mb.p = 0;
-  for (int gi = ga + 2; gi < g; gi++) {
-    SkMin<HT> c;
-    c.v = sh.gv[gi];
-    c.p = sh.gp[gi];
-    if (!hasMb) { Mb = c; hasMb = true; } else Mb = sk_combine(Mb, c);
-  }
-  Ma = Mb;
-  hasMa = hasMb;
-  if (ga + 1 < g) {
-    SkMin<HT> c;
-    c.v = sh.gv[ga + 1];
-    c.p = sh.gp[ga + 1];
-    if (hasMb) Ma = sk_combine(c, Mb); else { Ma = c; hasMa = true; }
-  }
-  uint32_t tie = 0;
-  SkMin<HT> pre;
-  pre.v = 0; pre.p = 0;
-  for (int s = b; s < e; s++) {
-    SkMin<HT> c;
-    c.v = sh.hv[s];
+    c.v = sh.hv[base + s];
     c.p = (uint32_t)s;
-    if (s == b) pre = c; else pre = sk_combine(pre, c);
-    if (s < s_eval) continue;
-    const int lo = s - wsz + 1;
-    const int gl = lo / SK_GS;
-    SkMin<HT> win;
-    win.v = sh.sv[lo];
-    win.p = sh.sp[lo];
-    if (gl == ga) { if (hasMa) win = sk_combine(win, Ma); }
-    else { if (hasMb) win = sk_combine(win, Mb); }
-    win = sk_combine(win, pre);
-    sh.amin[s] = (uint16_t)(win.p & 0x7FFF);
-    tie |= win.p >> 15;
+    run = sk_combine(c, run);  // c is to the LEFT of run
+    sh.sv[base + s] = run.v;
+    sh.sp[base + s] = (uint16_t)run.p;
   }
-  return tie;
+}
+// ---- phase 3b: prefix minima of block b, in place over hv (run after ALL suffix scans)
+template <class HT>
+PGB_HD void sk_phase3_prefix(int b, SkTile<HT> &sh) {
+  const int ns = (int)sh.ctr[SK_N_SLOTS], B = sh.B;
+  const int first = b * B;
+  if (first >= ns) return;
+  const int last = (first + B < ns ? first + B : ns) - 1;
+  const int base = b * (B + sh.pad) - first;
+  SkMin<HT> run;
+  run.v = sh.hv[base + first];
+  run.p = (uint32_t)first;
+  sh.pp[base + first] = (uint16_t)run.p;
+  for (int s = first + 1; s <= last; s++) {
+    SkMin<HT> c;
+    c.v = sh.hv[base + s];
+    c.p = (uint32_t)s;
+    run = sk_combine(run, c);
+    sh.hv[base + s] = run.v;
+    sh.pp[base + s] = (uint16_t)run.p;
+  }
 }
 
-// ---- phase 5: records emitted by the window ends of group g
-template <class HT, bool WRITE>
-PGB_HD uint32_t sk_phase5_group(int g, const SkShared<HT> &sh, const SkParams &p, int s_emit, int s_first_full, mm128 *out) {
-  const int ns = (int)sh.n_slots;
-  const int b = g * SK_GS;
-  if (b >= ns) return 0;
-  const int e = b + SK_GS < ns ? b + SK_GS : ns;
-  uint32_t n = 0;
-  for (int s = b > s_emit ? b : s_emit; s < e; s++) {
-    const uint32_t a = sh.amin[s];
-    const bool emit = (s == s_first_full) || (a != sh.amin[s - 1]);
-    if (!emit) continue;
-    if (WRITE) {
-      const uint32_t pz = sh.ps[a];
-      mm128 m;
-      m.x = (uint64_t)sh.hv[a] << 8 | (uint64_t)p.k;
-      m.y = (uint64_t)p.rid << 32 | (uint64_t)(uint32_t)(p.r0 + (int)(pz >> 1)) << 1 | (pz & 1);
-      out[n] = m;
-    }
-    n++;
+// minimum of the window [lo.s, e.s] (e.s - lo.s = w - 1): suffix of lo's block, the whole block in between if there is
+// one, prefix of e's block
+template <class HT>
+PGB_HD SkMin<HT> sk_window(const SkTile<HT> &sh, const SkCursor &lo, const SkCursor &e) {
+  SkMin<HT> win, c;
+  win.v = sh.sv[lo.pi];
+  win.p = sh.sp[lo.pi];
+  if (e.blk - lo.blk == 2) {
+    const int mid = (lo.blk + 1) * (sh.B + sh.pad) + sh.B - 1;  // last slot of the block in between = its total
+    c.v = sh.hv[mid];
+    c.p = sh.pp[mid];
+    win = sk_combine(win, c);
   }
+  c.v = sh.hv[e.pi];
+  c.p = sh.pp[e.pi];
+  return sk_combine(win, c);
+}
+
+// ---- phase 4: the thread's SK_G window ends.  Returns the number of records; bit i of *emit_mask = window end
+// SK_G*tid + i emits; *tie = some evaluated window's minimum occurs twice.  Windows ending at e >= s_eval are evaluated
+// (s_eval >= w - 1, so every evaluated window is full), windows ending at e >= s_emit may emit.
+template <class HT>
+PGB_HD uint32_t sk_phase4(int tid, const SkTile<HT> &sh, int wsz, int s_eval, int s_emit, int s_first_full, uint32_t *emit_mask, uint32_t *tie) {
+  const int ns = (int)sh.ctr[SK_N_SLOTS];
+  const int e0 = tid * SK_G, e1 = e0 + SK_G < ns ? e0 + SK_G : ns;
+  *emit_mask = 0;
+  *tie = 0;
+  int e = e0 - 1 > s_eval ? e0 - 1 : s_eval;  // one window before the thread's own: its arg-min is the "previous" one
+  if (e >= e1) return 0;
+  SkCursor ce, cl;
+  sk_cursor_init(ce, e, sh.B, sh.pad);
+  sk_cursor_init(cl, e - wsz + 1, sh.B, sh.pad);
+  uint32_t prev = 0xFFFFFFFFu, n = 0, em = 0, ti = 0;
+  for (; e < e1; e++) {
+    const SkMin<HT> win = sk_window(sh, cl, ce);
+    const uint32_t a = win.p & 0x7FFFu;
+    if (e >= e0) {
+      ti |= win.p >> 15;
+      if (e >= s_emit && (e == s_first_full || a != prev)) { em |= 1u << (e - e0); n++; }
+    }
+    prev = a;
+    sk_cursor_next(ce, sh.B, sh.pad);
+    sk_cursor_next(cl, sh.B, sh.pad);
+  }
+  *emit_mask = em;
+  *tie = ti;
   return n;
+}
+
+// ---- phase 5: write the thread's records
+template <class HT>
+PGB_HD void sk_phase5_write(int tid, const SkTile<HT> &sh, const SkParams &p, uint32_t emit_mask, mm128 *out) {
+  uint32_t n = 0;
+  for (int i = 0; i < SK_G; i++) {
+    if (!(emit_mask >> i & 1)) continue;
+    const int e = tid * SK_G + i;
+    SkCursor ce, cl;
+    sk_cursor_init(ce, e, sh.B, sh.pad);
+    sk_cursor_init(cl, e - p.wsz + 1, sh.B, sh.pad);
+    const SkMin<HT> win = sk_window(sh, cl, ce);
+    const uint32_t pz = sh.ps[win.p & 0x7FFFu];
+    mm128 m;
+    m.x = (uint64_t)win.v << 8 | (uint64_t)p.k;
+    m.y = (uint64_t)p.rid << 32 | (uint64_t)(uint32_t)(p.r0 + (int)(pz >> 1)) << 1 | (pz & 1);
+    out[n++] = m;
+  }
 }
 
 // window bookkeeping of a tile once n_slots / n_halo_slots are known

@@ -128,7 +128,9 @@ static uint32_t sketch_tiled_host(const Packed &P, size_t row, int wsz, int k, s
   if (len < sk_min_len(wsz, k)) return SK_FLAG_SHORT;
   const int H = sk_halo(wsz), TILE = sk_tile_len(wsz);
   const int n_tiles = (len + TILE - 1) / TILE;
-  static SkShared<HT> sh;
+  std::vector<unsigned char> smem(sk_smem_bytes<HT>(wsz) + 16);
+  SkTile<HT> sh;
+  sk_tile_layout<HT>(sh, smem.data(), wsz);
   std::vector<mm128> rec;
   for (int j = 0; j < n_tiles; j++) {
     SkParams p;
@@ -137,30 +139,31 @@ static uint32_t sketch_tiled_host(const Packed &P, size_t row, int wsz, int k, s
     static HT hv[SK_THREADS][SK_G];
     static uint16_t ps[SK_THREADS][SK_G];
     uint32_t mask[SK_THREADS], base[SK_THREADS];
-    sh.n_pal = 0; sh.n_halo_slots = 0; sh.flags = 0;
+    memset(smem.data(), 0xAB, smem.size());  // nothing may depend on stale shared memory
+    for (int q = 0; q < 4; q++) sh.ctr[q] = 0;
     uint32_t tot = 0;
     for (int t = 0; t < SK_THREADS; t++) {
       uint32_t np, hs;
       sk_phase1<HT>(t, p, H, hv[t], ps[t], &mask[t], &np, &hs);
-      sh.n_pal += np; sh.n_halo_slots += hs;
+      sh.ctr[SK_N_PAL] += np; sh.ctr[SK_N_HALO] += hs;
       base[t] = tot; tot += (uint32_t)sk_popc(mask[t]);
     }
-    sh.n_slots = tot;
-    if (sh.n_pal > SK_PALPAD) return SK_FLAG_PAL;
+    sh.ctr[SK_N_SLOTS] = tot;
+    if (sh.ctr[SK_N_PAL] > SK_PALPAD) return SK_FLAG_PAL;
     for (int t = 0; t < SK_THREADS; t++) sk_phase2_write<HT>(sh, hv[t], ps[t], mask[t], base[t]);
-    for (int t = 0; t < SK_THREADS; t++) for (int g = t; g < SK_NG; g += SK_THREADS) sk_phase3_group<HT>(g, sh);
+    const int n_blocks = ((int)tot + sh.B - 1) / sh.B;
+    for (int b = 0; b < n_blocks; b++) sk_phase3_suffix<HT>(b, sh);
+    for (int b = 0; b < n_blocks; b++) sk_phase3_prefix<HT>(b, sh);
     int s_eval, s_emit, s_first_full;
-    sk_ranges(p, sh.n_halo_slots, &s_eval, &s_emit, &s_first_full);
-    uint32_t tie = 0;
-    for (int t = 0; t < SK_THREADS; t++) for (int g = t; g < SK_NG; g += SK_THREADS) tie |= sk_phase4_group<HT>(g, sh, wsz, s_eval);
+    sk_ranges(p, sh.ctr[SK_N_HALO], &s_eval, &s_emit, &s_first_full);
+    uint32_t tie = 0, total = 0, em[SK_THREADS], cn[SK_THREADS];
+    for (int t = 0; t < SK_THREADS; t++) { uint32_t ti; cn[t] = sk_phase4<HT>(t, sh, wsz, s_eval, s_emit, s_first_full, &em[t], &ti); tie |= ti; total += cn[t]; }
     if (tie) return SK_FLAG_TIE;
-    uint32_t total = 0;
-    for (int g = 0; g < SK_NG; g++) total += sk_phase5_group<HT, false>(g, sh, p, s_emit, s_first_full, nullptr);
     if (total > SK_CAP) return SK_FLAG_OVERFLOW;
     size_t at = rec.size();
     rec.resize(at + total);
     uint32_t o = 0;
-    for (int g = 0; g < SK_NG; g++) o += sk_phase5_group<HT, true>(g, sh, p, s_emit, s_first_full, rec.data() + at + o);
+    for (int t = 0; t < SK_THREADS; t++) { if (cn[t]) sk_phase5_write<HT>(t, sh, p, em[t], rec.data() + at + o); o += cn[t]; }
   }
   out.insert(out.end(), rec.begin(), rec.end());
   return 0;
@@ -206,7 +209,7 @@ static int cmd_sketch(int argc, char **argv) {
         }
       }
     }
-    if (w >= SK_GS + 1) {
+    if (w >= SK_MINW) {
       std::vector<mm128> tiled;
       uint32_t fl = (k <= 16) ? sketch_tiled_host<uint32_t>(P, i, w, k, tiled) : sketch_tiled_host<uint64_t>(P, i, w, k, tiled);
       if (fl) { n_fallback++; fallback_flags |= fl; }
@@ -318,6 +321,7 @@ struct HostCtx {
     if (strict && (uint32_t)(it->second >> 2) != rank) return ~0ULL;
     return it->second;
   }
+  void pair_get(uint64_t p, uint64_t *vo, uint64_t *vn) const { *vo = pair_old(p); *vn = pair_new(p); }
   void pair_set(uint64_t p, uint64_t v) { auto it = e_new->find(p); if (it == e_new->end() || v < it->second) (*e_new)[p] = v; }
   bool aln_get(uint32_t i, uint32_t j, match_t *m) const {
     auto it = aln->find(((uint64_t)rank << 32) | (i << 16) | j);
