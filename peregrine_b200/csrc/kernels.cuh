@@ -287,13 +287,17 @@ __global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__r
   sk_tile_layout<HT>(sh, sk_smem, wsz);
   const uint32_t tile = blockIdx.x;
   const int tid = threadIdx.x;
-  // owning row: last row with tile_off[row] <= tile
-  uint32_t lo = 0, hi = n_rows;
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+  if (tid == 0) {  // owning row: last row with tile_off[row] <= tile
+    uint32_t lo = 0, hi = n_rows;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
+    sh.scan[12] = lo;
   }
-  const uint32_t row = lo;
+  if (tid >= 32 && tid < 36) sh.ctr[tid - 32] = 0;
+  __syncthreads();
+  const uint32_t row = sh.scan[12];
   const int j = (int)(tile - tile_off[row]);
   SkParams p;
   p.w = w; p.word_off = row_woff[row]; p.len = (int)row_len[row]; p.rid = row_rid[row]; p.wsz = wsz; p.k = k;
@@ -306,8 +310,6 @@ __global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__r
     }
     return;
   }
-  if (tid < 4) sh.ctr[tid] = 0;
-  __syncthreads();
   uint32_t slot_mask, np, hs;
   {
     HT hv[SK_G];
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__r
     if (tid == 0) { atomicOr(&row_flags[row], (uint32_t)SK_FLAG_PAL); tile_cnt[tile] = 0; }
     return;
   }
-  // one thread per block of ceil(w/2) slots (at most SK_R / 9 + 1 < 2 * SK_THREADS blocks)
+  // one thread per block of B slots (at most SK_R / 9 + 1 < 2 * SK_THREADS blocks)
   const int n_blocks = ((int)sh.ctr[SK_N_SLOTS] + sh.B - 1) / sh.B;
   for (int b = tid; b < n_blocks; b += SK_THREADS) sk_phase3_suffix<HT>(b, sh);
   __syncthreads();

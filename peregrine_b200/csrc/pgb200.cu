@@ -546,7 +546,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     CU(cudaMemsetAsync(exact_flag, 0, (ns + 1) * 4, c->st));
     c->ktic();
     if (k <= 16) {
-      size_t smem = sk_smem_bytes<uint32_t>(w);
+      size_t smem = sk_smem_bytes<uint32_t>();
       CU(cudaFuncSetAttribute(k_sketch_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       if (n_tiles) {
         k_sketch_tiled<uint32_t><<<n_tiles, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
@@ -555,7 +555,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
         CU(cudaGetLastError());
       }
     } else {
-      size_t smem = sk_smem_bytes<uint64_t>(w);
+      size_t smem = sk_smem_bytes<uint64_t>();
       CU(cudaFuncSetAttribute(k_sketch_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       if (n_tiles) {
         k_sketch_tiled<uint64_t><<<n_tiles, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,

@@ -6,10 +6,10 @@
 //            reference's hash64 masks to 2k bits after every step, so it is arithmetic mod 2^2k); palindromic k-mers are
 //            noted (they occupy no window slot, mm_sketch.c:104-105);
 //   phase 2  block scan of slot counts; slots (hash, pos<<1|strand) are written to shared memory in slot order;
-//   phase 3  van Herk / Gil-Werman with blocks of B = ceil(w/2) slots: one thread per block runs the suffix minima
+//   phase 3  van Herk / Gil-Werman with blocks of B = ceil(w/2)|1 slots: one thread per block runs the suffix minima
 //            (right to left), then the prefix minima (left to right, in place).  Every minimum carries its arg-min slot
-//            (rightmost on ties) and a "this minimum occurs twice" bit.  Blocks are padded to an odd stride, so the
-//            per-thread sequential walks are free of bank conflicts;
+//            (rightmost on ties) and a "this minimum occurs twice" bit.  B is odd, so the per-thread sequential walks
+//            (stride B between threads) are free of bank conflicts;
 //   phase 4  each thread evaluates SK_G consecutive window ends: window [e-w+1, e] = suffix(left block) (+ one whole
 //            block) + prefix(right block), i.e. at most two combines; a slot is emitted when it becomes the window
 //            arg-min (first full window, or arg-min changed);
@@ -34,12 +34,11 @@ enum { SK_FLAG_TIE = 1, SK_FLAG_PAL = 2, SK_FLAG_OVERFLOW = 4, SK_FLAG_SHORT = 8
 PGB_HD int sk_halo(int wsz) { return wsz + SK_PALPAD; }
 PGB_HD int sk_tile_len(int wsz) { return SK_R - sk_halo(wsz); }
 PGB_HD int sk_min_len(int wsz, int k) { return wsz + k + SK_PALPAD + 1; }  // shorter reads go to the exact automaton
-PGB_HD int sk_block_len(int wsz) { return (wsz + 1) / 2; }
-PGB_HD int sk_block_pad(int B) { return 1 + (B & 1); }  // B + pad is odd
-PGB_HD int sk_padn(int wsz) {                          // padded slot-array length
-  const int B = sk_block_len(wsz);
-  return SK_R + (SK_R / B + 1) * sk_block_pad(B) + 4;
-}
+PGB_HD int sk_block_len(int wsz) { return ((wsz + 1) / 2) | 1; }  // odd; ceil(w/2) <= B <= w - 1 for w >= SK_MINW
+PGB_HD int sk_padn() { return SK_R + 4; }
+// exact s / B for 0 <= s < 2^13 and 9 <= B <= 129 (s * magic < 2^32; error term s / 2^22 < 1 / B)
+PGB_HD uint32_t sk_div_magic(int B) { return (uint32_t)(((1u << 22) + (uint32_t)B - 1u) / (uint32_t)B); }
+PGB_HD int sk_div(int s, uint32_t magic) { return (int)(((uint32_t)s * magic) >> 22); }
 
 struct SkParams {
   const uint64_t *w;  // packed reads
@@ -61,16 +60,18 @@ struct SkTile {
   uint16_t *ps;  // [SK_R] (region-relative position) << 1 | strand, by slot
   uint32_t *scan;  // [16]
   uint32_t *ctr;   // [4] n_slots, n_pal, n_halo_slots, flags
-  int B, pad;
+  int B;           // block length of the prefix / suffix scans
+  uint32_t magic;  // sk_div_magic(B)
+  int two_blocks;  // a window whose left edge has in-block offset >= two_blocks spans a whole block in between
 };
 enum { SK_N_SLOTS = 0, SK_N_PAL = 1, SK_N_HALO = 2, SK_FLAGS = 3 };
 template <class HT>
-PGB_HD size_t sk_smem_bytes(int wsz) {
-  return (size_t)sk_padn(wsz) * (2 * sizeof(HT) + 4) + (size_t)SK_R * 2 + 20 * 4 + 16;
+PGB_HD size_t sk_smem_bytes() {
+  return (size_t)sk_padn() * (2 * sizeof(HT) + 4) + (size_t)SK_R * 2 + 20 * 4 + 16;
 }
 template <class HT>
 PGB_HD void sk_tile_layout(SkTile<HT> &t, unsigned char *base, int wsz) {
-  const size_t n = (size_t)sk_padn(wsz);
+  const size_t n = (size_t)sk_padn();
   t.hv = reinterpret_cast<HT *>(base);
   t.sv = t.hv + n;
   t.scan = reinterpret_cast<uint32_t *>(t.sv + n);
@@ -79,7 +80,8 @@ PGB_HD void sk_tile_layout(SkTile<HT> &t, unsigned char *base, int wsz) {
   t.sp = t.pp + n;
   t.ps = t.sp + n;
   t.B = sk_block_len(wsz);
-  t.pad = sk_block_pad(t.B);
+  t.magic = sk_div_magic(t.B);
+  t.two_blocks = 2 * t.B - wsz + 1;
 }
 
 template <class HT>
@@ -124,83 +126,88 @@ template <class HT>
 PGB_HD void sk_phase1(int tid, const SkParams &p, int halo, HT *hv_out, uint16_t *ps_out, uint32_t *slot_mask, uint32_t *n_pal,
                       uint32_t *halo_slots) {
   const int k = p.k;
-  const HT mask = (HT)(((uint64_t)1 << 2 * k) - 1);
+  const uint64_t mask64 = ((uint64_t)1 << 2 * k) - 1;
+  const HT mask = (HT)mask64;
   const int shift1 = 2 * (k - 1);
   const int q0 = tid * SK_G;
-  uint32_t sm = 0, np = 0, hs = 0;
-  HT kmer0 = 0, kmer1 = 0;
+  const int pos0 = p.r0 + q0;
   const int64_t base0 = (int64_t)p.word_off * 32;
-  // first position of this thread whose k-mer is complete and inside the read
-  int i0 = 0;
-  {
-    const int need = k - 1 - (p.r0 + q0);  // pos >= k-1
-    if (need > i0) i0 = need;
-  }
-  uint64_t bases = 0;  // bases at positions (p.r0 + q0 + i0 + 1 + j), j = 0.., 2 bits each: the rolled-in bases
-  if (i0 < SK_G && p.r0 + q0 + i0 < p.len) {
-    const int pos = p.r0 + q0 + i0;
-    const uint64_t v = fetch_fwd64(p.w, base0 + pos - k + 1) & (((uint64_t)1 << 2 * k) - 1);  // bases pos-k+1 .. pos, earliest in the low bits
-    kmer1 = (HT)((~v) & (((uint64_t)1 << 2 * k) - 1));
+  uint32_t sm = 0, np = 0;
+  HT kmer0 = 0, kmer1 = 0;
+  if (pos0 >= k - 1 && pos0 + SK_G <= p.len) {
+    // interior thread (all but the few at the ends of the read): every position has a complete k-mer
+    const uint64_t v = fetch_fwd64(p.w, base0 + pos0 - k + 1) & mask64;  // bases pos-k+1 .. pos, earliest in the low bits
+    kmer1 = (HT)((~v) & mask64);
     kmer0 = (HT)(rev2(v) >> (64 - 2 * k));
-    bases = fetch_fwd64(p.w, base0 + pos + 1);
-  }
+    const uint64_t bases = fetch_fwd64(p.w, base0 + pos0 + 1);  // the bases rolled in at i = 1 ..
+    uint32_t pal = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int i = 0; i < SK_G; i++) {
-    const int pos = p.r0 + q0 + i;
-    hv_out[i] = (HT)~(HT)0;
-    ps_out[i] = 0;
-    if (pos < 0 || pos >= p.len) continue;  // does not exist
-    if (i < i0) {                          // exists, k-mer incomplete: sentinel slot (l < k)
+    for (int i = 0; i < SK_G; i++) {
+      if (i > 0) {
+        const HT c = (HT)((bases >> (2 * (i - 1))) & 3);
+        kmer0 = (HT)((HT)(kmer0 << 2) | c) & mask;
+        kmer1 = (HT)(kmer1 >> 2) | (HT)((HT)(3 ^ c) << shift1);
+      }
+      const bool z = !(kmer0 < kmer1);
+      pal |= (uint32_t)(kmer0 == kmer1) << i;  // palindromic k-mer: no slot
+      hv_out[i] = sk_hash<HT>(z ? kmer1 : kmer0, mask);
+      ps_out[i] = (uint16_t)(((q0 + i) << 1) | (int)z);
+    }
+    np = (uint32_t)sk_popc(pal);
+    sm = ~pal & ((1u << SK_G) - 1u);
+  } else {
+    // first position of this thread whose k-mer is complete
+    int i0 = k - 1 - pos0;
+    if (i0 < 0) i0 = 0;
+    uint64_t bases = 0;
+    if (i0 < SK_G && pos0 + i0 < p.len) {
+      const int pos = pos0 + i0;
+      const uint64_t v = fetch_fwd64(p.w, base0 + pos - k + 1) & mask64;
+      kmer1 = (HT)((~v) & mask64);
+      kmer0 = (HT)(rev2(v) >> (64 - 2 * k));
+      bases = fetch_fwd64(p.w, base0 + pos + 1);
+    }
+    for (int i = 0; i < SK_G; i++) {
+      const int pos = pos0 + i;
+      hv_out[i] = (HT)~(HT)0;
+      ps_out[i] = 0;
+      if (pos < 0 || pos >= p.len) continue;  // does not exist
+      if (i < i0) {                          // exists, k-mer incomplete: sentinel slot (l < k)
+        sm |= 1u << i;
+        continue;
+      }
+      if (i > i0) {
+        const HT c = (HT)((bases >> (2 * (i - i0 - 1))) & 3);
+        kmer0 = (HT)((HT)(kmer0 << 2) | c) & mask;
+        kmer1 = (HT)(kmer1 >> 2) | (HT)((HT)(3 ^ c) << shift1);
+      }
+      if (kmer0 == kmer1) { np++; continue; }
+      const int z = kmer0 < kmer1 ? 0 : 1;
+      hv_out[i] = sk_hash<HT>(z ? kmer1 : kmer0, mask);
+      ps_out[i] = (uint16_t)(((q0 + i) << 1) | z);
       sm |= 1u << i;
-      if (q0 + i < halo) hs++;
-      continue;
     }
-    if (i > i0) {
-      const HT c = (HT)((bases >> (2 * (i - i0 - 1))) & 3);
-      kmer0 = (HT)((HT)(kmer0 << 2) | c) & mask;
-      kmer1 = (HT)(kmer1 >> 2) | (HT)((HT)(3 ^ c) << shift1);
-    }
-    if (kmer0 == kmer1) { np++; continue; }  // palindromic k-mer: no slot
-    const int z = kmer0 < kmer1 ? 0 : 1;
-    hv_out[i] = sk_hash<HT>(z ? kmer1 : kmer0, mask);
-    ps_out[i] = (uint16_t)(((q0 + i) << 1) | z);
-    sm |= 1u << i;
-    if (q0 + i < halo) hs++;
   }
   *slot_mask = sm;
   *n_pal = np;
-  *halo_slots = hs;
-}
-
-// position of a slot in the padded arrays
-struct SkCursor { int s, blk, off, pi; };
-PGB_HD void sk_cursor_init(SkCursor &c, int s, int B, int pad) {
-  c.s = s;
-  c.blk = s / B;
-  c.off = s - c.blk * B;
-  c.pi = s + c.blk * pad;
-}
-PGB_HD void sk_cursor_next(SkCursor &c, int B, int pad) {
-  c.s++;
-  c.pi++;
-  if (++c.off == B) { c.off = 0; c.blk++; c.pi += pad; }
+  const int nh = halo - q0;  // positions of this thread inside the halo
+  *halo_slots = nh <= 0 ? 0u : (uint32_t)sk_popc(nh >= SK_G ? sm : (sm & ((1u << nh) - 1u)));
 }
 
 // ---- phase 2: write the thread's slots at their slot index
 template <class HT>
 PGB_HD void sk_phase2_write(SkTile<HT> &sh, const HT *hv, const uint16_t *ps, uint32_t slot_mask, uint32_t slot_base) {
-  SkCursor c;
-  sk_cursor_init(c, (int)slot_base, sh.B, sh.pad);
+  uint32_t s = slot_base;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int i = 0; i < SK_G; i++)
     if (slot_mask >> i & 1) {
-      sh.hv[c.pi] = hv[i];
-      sh.ps[c.s] = ps[i];
-      sk_cursor_next(c, sh.B, sh.pad);
+      sh.hv[s] = hv[i];
+      sh.ps[s] = ps[i];
+      s++;
     }
 }
 
@@ -211,19 +218,18 @@ PGB_HD void sk_phase3_suffix(int b, SkTile<HT> &sh) {
   const int first = b * B;
   if (first >= ns) return;
   const int last = (first + B < ns ? first + B : ns) - 1;
-  const int base = b * (B + sh.pad) - first;  // padded index = base + slot
   SkMin<HT> run;
-  run.v = sh.hv[base + last];
+  run.v = sh.hv[last];
   run.p = (uint32_t)last;
-  sh.sv[base + last] = run.v;
-  sh.sp[base + last] = (uint16_t)run.p;
+  sh.sv[last] = run.v;
+  sh.sp[last] = (uint16_t)run.p;
   for (int s = last - 1; s >= first; s--) {
     SkMin<HT> c;
-    c.v = sh.hv[base + s];
+    c.v = sh.hv[s];
     c.p = (uint32_t)s;
     run = sk_combine(c, run);  // c is to the LEFT of run
-    sh.sv[base + s] = run.v;
-    sh.sp[base + s] = (uint16_t)run.p;
+    sh.sv[s] = run.v;
+    sh.sp[s] = (uint16_t)run.p;
   }
 }
 // ---- phase 3b: prefix minima of block b, in place over hv (run after ALL suffix scans)
@@ -233,36 +239,35 @@ PGB_HD void sk_phase3_prefix(int b, SkTile<HT> &sh) {
   const int first = b * B;
   if (first >= ns) return;
   const int last = (first + B < ns ? first + B : ns) - 1;
-  const int base = b * (B + sh.pad) - first;
   SkMin<HT> run;
-  run.v = sh.hv[base + first];
+  run.v = sh.hv[first];
   run.p = (uint32_t)first;
-  sh.pp[base + first] = (uint16_t)run.p;
+  sh.pp[first] = (uint16_t)run.p;
   for (int s = first + 1; s <= last; s++) {
     SkMin<HT> c;
-    c.v = sh.hv[base + s];
+    c.v = sh.hv[s];
     c.p = (uint32_t)s;
     run = sk_combine(run, c);
-    sh.hv[base + s] = run.v;
-    sh.pp[base + s] = (uint16_t)run.p;
+    sh.hv[s] = run.v;
+    sh.pp[s] = (uint16_t)run.p;
   }
 }
 
-// minimum of the window [lo.s, e.s] (e.s - lo.s = w - 1): suffix of lo's block, the whole block in between if there is
-// one, prefix of e's block
+// minimum of the window [lo, e], e - lo = w - 1, lo_off = offset of lo in its block: suffix of lo's block, the whole block
+// in between if there is one (its total = prefix at its last slot), prefix of e's block
 template <class HT>
-PGB_HD SkMin<HT> sk_window(const SkTile<HT> &sh, const SkCursor &lo, const SkCursor &e) {
+PGB_HD SkMin<HT> sk_window(const SkTile<HT> &sh, int lo, int lo_off, int e) {
   SkMin<HT> win, c;
-  win.v = sh.sv[lo.pi];
-  win.p = sh.sp[lo.pi];
-  if (e.blk - lo.blk == 2) {
-    const int mid = (lo.blk + 1) * (sh.B + sh.pad) + sh.B - 1;  // last slot of the block in between = its total
+  win.v = sh.sv[lo];
+  win.p = sh.sp[lo];
+  if (lo_off >= sh.two_blocks) {
+    const int mid = lo - lo_off + 2 * sh.B - 1;
     c.v = sh.hv[mid];
     c.p = sh.pp[mid];
     win = sk_combine(win, c);
   }
-  c.v = sh.hv[e.pi];
-  c.p = sh.pp[e.pi];
+  c.v = sh.hv[e];
+  c.p = sh.pp[e];
   return sk_combine(win, c);
 }
 
@@ -277,20 +282,19 @@ PGB_HD uint32_t sk_phase4(int tid, const SkTile<HT> &sh, int wsz, int s_eval, in
   *tie = 0;
   int e = e0 - 1 > s_eval ? e0 - 1 : s_eval;  // one window before the thread's own: its arg-min is the "previous" one
   if (e >= e1) return 0;
-  SkCursor ce, cl;
-  sk_cursor_init(ce, e, sh.B, sh.pad);
-  sk_cursor_init(cl, e - wsz + 1, sh.B, sh.pad);
+  int lo = e - wsz + 1;
+  int lo_off = lo - sk_div(lo, sh.magic) * sh.B;
   uint32_t prev = 0xFFFFFFFFu, n = 0, em = 0, ti = 0;
   for (; e < e1; e++) {
-    const SkMin<HT> win = sk_window(sh, cl, ce);
+    const SkMin<HT> win = sk_window(sh, lo, lo_off, e);
     const uint32_t a = win.p & 0x7FFFu;
     if (e >= e0) {
       ti |= win.p >> 15;
       if (e >= s_emit && (e == s_first_full || a != prev)) { em |= 1u << (e - e0); n++; }
     }
     prev = a;
-    sk_cursor_next(ce, sh.B, sh.pad);
-    sk_cursor_next(cl, sh.B, sh.pad);
+    lo++;
+    lo_off = lo_off + 1 == sh.B ? 0 : lo_off + 1;
   }
   *emit_mask = em;
   *tie = ti;
@@ -301,13 +305,11 @@ PGB_HD uint32_t sk_phase4(int tid, const SkTile<HT> &sh, int wsz, int s_eval, in
 template <class HT>
 PGB_HD void sk_phase5_write(int tid, const SkTile<HT> &sh, const SkParams &p, uint32_t emit_mask, mm128 *out) {
   uint32_t n = 0;
-  for (int i = 0; i < SK_G; i++) {
-    if (!(emit_mask >> i & 1)) continue;
-    const int e = tid * SK_G + i;
-    SkCursor ce, cl;
-    sk_cursor_init(ce, e, sh.B, sh.pad);
-    sk_cursor_init(cl, e - p.wsz + 1, sh.B, sh.pad);
-    const SkMin<HT> win = sk_window(sh, cl, ce);
+  while (emit_mask) {
+    const int i = ctz32(emit_mask);
+    emit_mask &= emit_mask - 1;
+    const int e = tid * SK_G + i, lo = e - p.wsz + 1;
+    const SkMin<HT> win = sk_window(sh, lo, lo - sk_div(lo, sh.magic) * sh.B, e);
     const uint32_t pz = sh.ps[win.p & 0x7FFFu];
     mm128 m;
     m.x = (uint64_t)win.v << 8 | (uint64_t)p.k;

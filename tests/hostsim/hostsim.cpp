@@ -128,7 +128,7 @@ static uint32_t sketch_tiled_host(const Packed &P, size_t row, int wsz, int k, s
   if (len < sk_min_len(wsz, k)) return SK_FLAG_SHORT;
   const int H = sk_halo(wsz), TILE = sk_tile_len(wsz);
   const int n_tiles = (len + TILE - 1) / TILE;
-  std::vector<unsigned char> smem(sk_smem_bytes<HT>(wsz) + 16);
+  std::vector<unsigned char> smem(sk_smem_bytes<HT>() + 16);
   SkTile<HT> sh;
   sk_tile_layout<HT>(sh, smem.data(), wsz);
   std::vector<mm128> rec;
@@ -171,6 +171,10 @@ static uint32_t sketch_tiled_host(const Packed &P, size_t row, int wsz, int k, s
 
 static int cmd_sketch(int argc, char **argv) {
   if (argc < 5) return 1;
+  for (int B = 9; B <= 129; B++)
+    for (int q = 0; q < 8192; q++)
+      if (sk_div(q, sk_div_magic(B)) != q / B) { fprintf(stderr, "sk_div(%d, %d) is wrong\n", q, B); return 4; }
+  static_assert(SK_R <= 8192, "sk_div is exact below 2^13 only");
   Packed P; load_packed(argv[2], &P);
   int w = atoi(argv[3]), k = atoi(argv[4]);
   int rs = argc > 5 ? atoi(argv[5]) : 6;
