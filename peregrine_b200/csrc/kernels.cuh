@@ -787,143 +787,171 @@ __global__ void __launch_bounds__(64) k_replay(ReplayState st, uint32_t n_ranks,
   if (unk) atomicAdd(&st.ctr[0], (unsigned long long)unk);
 }
 
-// Warp-cooperative form of the same scan (one warp = one bucket): the candidates j of a row i are classified by 32 lanes
-// in parallel (pair-table lookups, alignment-cache lookups, acceptance test), then the row's sequential semantics are
-// restored with ballots: a lane is "reached" iff overlap_count (prefix over earlier lanes) is still below bestn and no
-// earlier lane ended the row (CONTAINED, src/shmr_overlap.c:176); only reached lanes apply side effects (pair_set,
-// contained[], alignment requests, record emission, in lane order).  A lane whose read also occurs in an earlier
-// still-unresolved lane of the same chunk is deferred to the next round so that it sees that lane's pair_set.
-// Kept as an alternative (PGB_REPLAY=warp): with the one-probe pair table the per-thread form is faster on every input tried.
-__global__ void __launch_bounds__(128) k_replay_warp(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ rank_off,
-                                                     const uint64_t *__restrict__ sy0, const uint8_t *__restrict__ sdir, uint8_t *contained,
-                                                     uint32_t bestn, int request_enabled, int do_emit, uint32_t *acc_count,
-                                                     const uint32_t *__restrict__ out_off, ovlp_rec *out, uint8_t *unk_flag,
-                                                     const uint32_t *__restrict__ list) {
-  uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t lane = threadIdx.x & 31;
-  if (r >= n_ranks) return;
-  r = list[r];
-  const uint32_t FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+// Block-cooperative form of the same scan for BIG buckets (one CTA of 128 threads = one bucket of up to PGB_RB_MAXN records).
+// A thread walking a 120-record bucket alone performs hundreds of DEPENDENT table probes (~0.5-1 ms), which is the critical
+// path of every pass, however few buckets run.  Here the probes of all n(n-1)/2 candidate pairs are issued in parallel:
+//   phase 1  (all threads) every candidate (i, j): pair-table probe; if the pair is not in rid_pairs, alignment-cache probe
+//            and acceptance test -> one code byte in shared memory (nothing is written to global memory);
+//   phase 2  (thread 0) the reference's sequential scan (rows n-2..0, bestn, contained[], CONTAINED ends the row) over the
+//            code bytes: shared-memory speed, produces the list of events (accepted / predicted candidates) in order;
+//   phase 3  (all threads) the events' side effects: pair_set, alignment requests, records.
+// Phase 1 sees rid_pairs as it was when the bucket started, so a read PAIR that occurs twice inside the bucket (possible
+// only if some read has two records in it) would miss its own bucket's entry: such buckets, and buckets whose event list
+// overflows, are scanned by thread 0 with the generic replay_bucket instead.
+#define PGB_RB_THREADS 128
+#define PGB_RB_MAXN 128
+#define PGB_RB_MAXEV 1536
+__global__ void __launch_bounds__(PGB_RB_THREADS) k_replay_block(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ list,
+                                                                 const uint32_t *__restrict__ rank_off, const uint64_t *__restrict__ sy0,
+                                                                 const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn,
+                                                                 int request_enabled, int do_emit, uint32_t *acc_count,
+                                                                 const uint32_t *__restrict__ out_off, ovlp_rec *out, uint8_t *unk_flag) {
+  __shared__ uint8_t code[PGB_RB_MAXN * PGB_RB_MAXN];  // [i * n + j], j > i: kind | type << 2 | accepted << 4
+  __shared__ uint64_t s_y0[PGB_RB_MAXN];
+  __shared__ uint32_t s_rlen[PGB_RB_MAXN];
+  __shared__ uint8_t s_dir[PGB_RB_MAXN], s_cont[PGB_RB_MAXN];
+  __shared__ uint32_t s_ev[PGB_RB_MAXEV];  // i | j << 8 | type << 16 | accepted << 18 | known << 19
+  __shared__ uint32_t s_nev, s_generic;
+  if (blockIdx.x >= n_ranks) return;
+  const uint32_t r = list[blockIdx.x];
+  const uint32_t tid = threadIdx.x;
   const uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
-  const uint64_t *y0s = sy0 + b;
-  const uint8_t *dirs = sdir + b;
-  uint8_t *cont = contained + b;
   DevReplayCtx c;
   c.s = st;
   c.rank = r;
   c.request_enabled = request_enabled != 0;
   c.out = do_emit ? out + out_off[r] : nullptr;
-  for (uint32_t t = lane; t < n; t += 32) cont[t] = 0;
-  __syncwarp();
-  uint32_t n_acc = 0, n_unk = 0;
   const uint64_t NONE = ~0ULL;
-  for (uint32_t k0 = n - 1; k0 > 0; k0--) {
-    const uint32_t i = k0 - 1;
-    if (cont[i]) continue;  // warp-uniform
-    const uint64_t y0 = y0s[i];
-    const uint32_t rid0 = (uint32_t)(y0 >> 32);
-    const uint32_t pos0 = (uint32_t)((y0 & 0xFFFFFFFFULL) >> 1) + 1;
-    const uint32_t rlen0 = c.rlen(rid0);
-    const uint32_t strand0 = dirs[i];
-    uint32_t oc = 0;
-    bool row_done = false;
-    uint32_t j0 = i + 1;
-    while (j0 < n && !row_done) {
-      const uint32_t j = j0 + lane;
-      // ---- phase A: classify (no side effects)
-      int kind = 0;  // 0 skip, 1 pair-table hit, 2 evaluate alignment
-      uint32_t type = 0, rid1 = 0, rlen1 = 0, strand1 = 0, start0 = 0;
-      uint64_t y1 = 0, ridp = 0;
-      bool accepted = false, known = true;
-      match_t m;
-      m.m_size = m.dist = m.q_bgn = m.q_end = m.t_bgn = m.t_end = m.t_m_end = m.q_m_end = 0;
-      if (j < n && !cont[j]) {
-        y1 = y0s[j];
-        rid1 = (uint32_t)(y1 >> 32);
-        if (rid1 != rid0) {
-          ridp = rid0 < rid1 ? ((uint64_t)rid0 << 32) | rid1 : ((uint64_t)rid1 << 32) | rid0;
-          uint64_t v, vnew;
-          c.pair_get(ridp, &v, &vnew);
-          bool hit = (v != NONE) && ((uint32_t)(v >> 2) < r);
-          if (!hit) {
-            v = vnew;
-            hit = (v != NONE) && ((uint32_t)(v >> 2) <= r);
-          }
-          if (hit) {
-            kind = 1;
-            type = (uint32_t)(v & 3);
-          } else {
-            kind = 2;
-            const uint32_t pos1 = (uint32_t)((y1 & 0xFFFFFFFFULL) >> 1) + 1;
-            rlen1 = c.rlen(rid1);
-            strand1 = dirs[j];
-            start0 = pos0 - pos1;
-            const uint32_t slen0 = rlen0 - pos0 + pos1, slen1 = rlen1;
-            known = c.aln_get(i, j, &m);
-            if (!known) predict_match(rlen0, rlen1, start0, &m);
-            const int64_t q_bgn = m.q_bgn, q_end = m.q_end, t_bgn = m.t_bgn, t_end = m.t_end;
-            int64_t dq = (int64_t)slen0 - q_end, dt = (int64_t)slen1 - t_end;
-            if (dq < 0) dq = -dq;
-            if (dt < 0) dt = -dt;
-            if (q_bgn < READ_END_FUZZINESS && t_bgn < READ_END_FUZZINESS && (dq < READ_END_FUZZINESS || dt < READ_END_FUZZINESS) &&
-                q_end > 500 && t_end > 500) {
-              accepted = true;
-              int64_t c0 = (int64_t)rlen0 - (q_end - q_bgn), c1 = (int64_t)rlen1 - (t_end - t_bgn);
-              if (c0 < 0) c0 = -c0;
-              if (c1 < 0) c1 = -c1;
-              if (c0 < READ_END_FUZZINESS * 2 || c1 < READ_END_FUZZINESS * 2) type = rlen0 >= rlen1 ? OVL_CONTAINS : OVL_CONTAINED;
-              else type = OVL_OVERLAP;
-            }
-          }
+  if (tid == 0) { s_nev = 0; s_generic = n > PGB_RB_MAXN ? 1u : 0u; }
+  for (uint32_t t = tid; t < n && t < PGB_RB_MAXN; t += PGB_RB_THREADS) {
+    const uint64_t y = sy0[b + t];
+    s_y0[t] = y;
+    s_rlen[t] = st.rlen_by_rid[(uint32_t)(y >> 32)];
+    s_dir[t] = sdir[b + t];
+    s_cont[t] = 0;
+  }
+  __syncthreads();
+  if (!s_generic) {
+    // ---- phase 1
+    for (uint32_t cell = tid; cell < n * n; cell += PGB_RB_THREADS) {
+      const uint32_t i = cell / n, j = cell - i * n;
+      if (j <= i) continue;
+      const uint64_t y0 = s_y0[i], y1 = s_y0[j];
+      const uint32_t rid0 = (uint32_t)(y0 >> 32), rid1 = (uint32_t)(y1 >> 32);
+      uint32_t cd = 0;
+      if (rid0 == rid1) {
+        s_generic = 1;  // a read with two records in this bucket (benign race: every writer stores 1)
+      } else {
+        const uint64_t ridp = rid0 < rid1 ? ((uint64_t)rid0 << 32) | rid1 : ((uint64_t)rid1 << 32) | rid0;
+        uint64_t v, vnew;
+        c.pair_get(ridp, &v, &vnew);
+        bool hit = (v != NONE) && ((uint32_t)(v >> 2) < r);
+        if (!hit) {
+          v = vnew;
+          hit = (v != NONE) && ((uint32_t)(v >> 2) <= r);
+        }
+        if (hit) {
+          cd = 1u | ((uint32_t)(v & 3) << 2);
+        } else {
+          const uint32_t pos0 = (uint32_t)((y0 & 0xFFFFFFFFULL) >> 1) + 1, pos1 = (uint32_t)((y1 & 0xFFFFFFFFULL) >> 1) + 1;
+          const uint32_t rlen0 = s_rlen[i], rlen1 = s_rlen[j], start0 = pos0 - pos1;
+          match_t m;
+          const bool known = c.aln_get(i, j, &m);
+          if (!known) predict_match(rlen0, rlen1, start0, &m);
+          uint32_t type = 0;
+          const bool accepted = classify_match(m, rlen0, rlen1, rlen0 - pos0 + pos1, rlen1, &type);
+          cd = (known ? 2u : 3u) | (type << 2) | ((uint32_t)accepted << 4);
         }
       }
-      // ---- a lane that repeats the read of an earlier evaluate-lane must wait for that lane's pair_set
-      const uint32_t k2mask = __ballot_sync(FULL, kind == 2);
-      const uint32_t peers = __match_any_sync(FULL, kind ? rid1 : (0xF0000000u | lane));  // skip lanes never match each other
-      const bool dependent = kind != 0 && ((peers & lt & k2mask) != 0);
-      const uint32_t depmask = __ballot_sync(FULL, dependent);
-      const uint32_t live = depmask ? ((1u << (__ffs(depmask) - 1)) - 1u) : FULL;  // lanes handled this round
-      const bool mine = (live >> lane) & 1u;
-      // ---- phase B: sequential semantics
-      const bool inc = mine && ((kind == 1 && type == OVL_OVERLAP) || (kind == 2 && accepted && type == OVL_OVERLAP));
-      const bool stop = mine && kind == 2 && accepted && type == OVL_CONTAINED;
-      const uint32_t incmask = __ballot_sync(FULL, inc), stopmask = __ballot_sync(FULL, stop);
-      const bool reached = mine && (oc + __popc(incmask & lt) < bestn) && ((stopmask & lt) == 0);
-      const uint32_t reachmask = __ballot_sync(FULL, reached);
-      const bool acc = reached && kind == 2 && accepted;
-      const uint32_t accmask = __ballot_sync(FULL, acc);
-      if (reached && kind == 2) {
-        if (!known) {
-          n_unk++;
-          c.aln_request(i, j, rid0, start0, strand0, rid1, strand1);
-        }
-        if (accepted) {
-          if (type == OVL_CONTAINS) cont[j] = 1;
-          else if (type == OVL_CONTAINED) cont[i] = 1;
-          c.pair_set(ridp, ((uint64_t)r << 2) | type);
-          if (do_emit) {
-            ovlp_rec o;
-            o.y0 = y0; o.y1 = y1; o.rl0 = rlen0; o.rl1 = rlen1;
-            o.strand0 = (uint8_t)strand0; o.strand1 = (uint8_t)strand1; o.ovlp_type = (uint8_t)type; o.pad0 = 0;
-            o.match = m; o.pad1 = 0;
-            c.out[n_acc + __popc(accmask & lt)] = o;
-          }
-        }
-      }
-      __threadfence_block();
-      __syncwarp();
-      n_acc += __popc(accmask);
-      oc += __popc(incmask & reachmask);
-      const uint32_t handled = depmask ? (uint32_t)(__ffs(depmask) - 1) : 32u;
-      // the row ends when bestn overlaps were counted, a CONTAINED record was reached, or a handled lane was not reached
-      if (oc >= bestn || (stopmask & reachmask) != 0) row_done = true;
-      j0 += handled;
+      code[cell] = (uint8_t)cd;
     }
   }
-  if (lane == 0) acc_count[r] = n_acc;
-  const uint32_t unk_total = __reduce_add_sync(FULL, n_unk);
-  if (lane == 0) unk_flag[r] = unk_total != 0;
-  if (lane == 0 && unk_total) atomicAdd(&st.ctr[0], (unsigned long long)unk_total);
+  __syncthreads();
+  // ---- phase 2
+  if (tid == 0) {
+    uint32_t n_acc = 0, n_unk = 0, n_ev = 0;
+    bool generic = s_generic != 0;
+    if (!generic) {
+      for (uint32_t k0 = n - 1; k0 > 0 && !generic; k0--) {
+        const uint32_t i = k0 - 1;
+        if (s_cont[i]) continue;
+        uint32_t oc = 0;
+        for (uint32_t j = i + 1; j < n && oc < bestn; j++) {
+          if (s_cont[j]) continue;
+          const uint32_t cd = code[i * n + j], kind = cd & 3u, type = (cd >> 2) & 3u;
+          if (kind == 0) continue;
+          if (kind == 1) {
+            if (type == OVL_OVERLAP) oc++;
+            continue;
+          }
+          const bool accepted = (cd >> 4) & 1u, known = kind == 2;
+          if (!known) n_unk++;
+          if (accepted || !known) {
+            if (n_ev >= PGB_RB_MAXEV) { generic = true; break; }
+            s_ev[n_ev++] = i | (j << 8) | (type << 16) | ((uint32_t)accepted << 18) | ((uint32_t)known << 19);
+          }
+          if (accepted) {
+            if (type == OVL_CONTAINS) s_cont[j] = 1;
+            else if (type == OVL_CONTAINED) s_cont[i] = 1;
+            else oc++;
+            n_acc++;
+          }
+          if (s_cont[i]) break;
+        }
+      }
+    }
+    if (generic) {  // exact sequential path (duplicate reads in the bucket, oversized bucket or event list)
+      uint32_t unk = 0;
+      n_acc = replay_bucket(c, r, sy0 + b, sdir + b, n, contained + b, bestn, do_emit != 0, &unk);
+      n_unk = unk;
+      n_ev = 0;
+    }
+    s_nev = n_ev;
+    acc_count[r] = n_acc;
+    unk_flag[r] = n_unk != 0;
+    if (n_unk) atomicAdd(&st.ctr[0], (unsigned long long)n_unk);
+  }
+  __syncthreads();
+  // ---- phase 3: side effects of the events, in parallel; the record index of an accepted event = accepted events before it
+  __shared__ uint32_t s_wtot[PGB_RB_THREADS / 32];
+  const uint32_t n_ev = s_nev;
+  uint32_t base = 0;
+  for (uint32_t e0 = 0; e0 < n_ev; e0 += PGB_RB_THREADS) {
+    const uint32_t e = e0 + tid;
+    uint32_t ev = 0;
+    bool accepted = false;
+    if (e < n_ev) { ev = s_ev[e]; accepted = (ev >> 18) & 1u; }
+    const uint32_t bal = __ballot_sync(0xffffffffu, accepted);
+    if ((tid & 31) == 0) s_wtot[tid >> 5] = __popc(bal);
+    __syncthreads();
+    uint32_t before = __popc(bal & ((1u << (tid & 31)) - 1u)), chunk_total = 0;
+    for (uint32_t wv = 0; wv < PGB_RB_THREADS / 32; wv++) {
+      if (wv < (tid >> 5)) before += s_wtot[wv];
+      chunk_total += s_wtot[wv];
+    }
+    if (e < n_ev) {
+      const uint32_t i = ev & 0xFF, j = (ev >> 8) & 0xFF, type = (ev >> 16) & 3u;
+      const bool known = (ev >> 19) & 1u;
+      const uint64_t y0 = s_y0[i], y1 = s_y0[j];
+      const uint32_t rid0 = (uint32_t)(y0 >> 32), rid1 = (uint32_t)(y1 >> 32);
+      const uint32_t pos0 = (uint32_t)((y0 & 0xFFFFFFFFULL) >> 1) + 1, pos1 = (uint32_t)((y1 & 0xFFFFFFFFULL) >> 1) + 1;
+      if (!known) c.aln_request(i, j, rid0, pos0 - pos1, s_dir[i], rid1, s_dir[j]);
+      if (accepted) {
+        const uint64_t ridp = rid0 < rid1 ? ((uint64_t)rid0 << 32) | rid1 : ((uint64_t)rid1 << 32) | rid0;
+        c.pair_set(ridp, ((uint64_t)r << 2) | type);
+        if (do_emit) {
+          ovlp_rec o;
+          o.y0 = y0; o.y1 = y1; o.rl0 = s_rlen[i]; o.rl1 = s_rlen[j];
+          o.strand0 = s_dir[i]; o.strand1 = s_dir[j]; o.ovlp_type = (uint8_t)type; o.pad0 = 0;
+          if (!c.aln_get(i, j, &o.match)) atomicOr(st.err, 64);  // emission runs after convergence: every alignment is known
+          o.pad1 = 0;
+          c.out[base + before] = o;
+        }
+      }
+    }
+    __syncthreads();  // s_wtot is rewritten by the next chunk
+    base += chunk_total;
+  }
 }
 
 // sort key of an alignment request = predicted overlap length in 256-base units: warps then hold alignments of similar
@@ -965,7 +993,10 @@ __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_
 // 1 thread = 1 alignment between N-free reads, forward views over the forward / reverse-complement images
 // (ovlp_match_lean); requests that involve a read with N are left to k_align(only_n = 1)
 #define PGB_ALIGN_THREADS 64
-__global__ void __launch_bounds__(PGB_ALIGN_THREADS) k_align_lean(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n,
+#ifndef PGB_ALIGN_MINBLOCKS
+#define PGB_ALIGN_MINBLOCKS 16
+#endif
+__global__ void __launch_bounds__(PGB_ALIGN_THREADS, PGB_ALIGN_MINBLOCKS) k_align_lean(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n,
                                                                   const uint32_t *__restrict__ perm, const uint64_t *__restrict__ w,
                                                                   const uint64_t *__restrict__ wrc, const uint64_t *__restrict__ woff_by_rid,
                                                                   const uint32_t *__restrict__ rlen_by_rid, const uint32_t *__restrict__ hasn_by_rid,
@@ -983,6 +1014,114 @@ __global__ void __launch_bounds__(PGB_ALIGN_THREADS) k_align_lean(const AlnReq *
   ovlp_match_lean(qw, q.start0, (int)(rl0 - q.start0), tw, 0u, (int)rl1, bw, V, PGB_MAXV, &m);
   results[q.slot] = m;
   atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
+}
+
+// Low-latency form for the small alignment batches of the fix-point's tail passes: 1 warp = 1 alignment.  Same algorithm
+// (the structure of ovlp_match_core: rows d, diagonals k, snake), every lane carries the same scalar state; only the snake
+// is parallel: lane l compares bases [32 l, 32 l + 32) past the snake's start, a ballot finds the first mismatch, so a
+// snake of up to 1024 bases costs one round of loads instead of 32 dependent word-steps.  The band rows live in shared
+// memory.  A single-thread alignment takes ~1 ms of dependent loads; a batch of a few hundred is latency-bound, and
+// this form finishes it in ~0.1 ms.  Reads with N are left to k_align(only_n = 1), as in k_align_lean.
+#define PGB_AW_WARPS 4
+__global__ void __launch_bounds__(PGB_AW_WARPS * 32) k_align_warp(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n,
+                                                                  const uint64_t *__restrict__ w, const uint64_t *__restrict__ wrc,
+                                                                  const uint64_t *__restrict__ woff_by_rid, const uint32_t *__restrict__ rlen_by_rid,
+                                                                  const uint32_t *__restrict__ hasn_by_rid, int bw, match_t *results,
+                                                                  unsigned long long *bases_total) {
+  __shared__ int sV[PGB_AW_WARPS][2 * PGB_MAXV];
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * PGB_AW_WARPS + wid;
+  if (i >= n) return;
+  const AlnReq q = reqs[first + i];
+  if (hasn_by_rid[q.rid0] | hasn_by_rid[q.rid1]) return;
+  const uint32_t rl0 = rlen_by_rid[q.rid0], rl1 = rlen_by_rid[q.rid1];
+  const uint64_t *qw = ((q.strands & 1) ? wrc : w) + woff_by_rid[q.rid0];
+  const uint64_t *tw = ((q.strands & 2) ? wrc : w) + woff_by_rid[q.rid1];
+  const uint32_t qo = q.start0, to = 0;
+  const int q_len = (int)(rl0 - q.start0), t_len = (int)rl1;
+  match_t r;
+  r.m_size = r.dist = r.q_bgn = r.q_end = r.t_bgn = r.t_end = r.t_m_end = r.q_m_end = 0;
+  const int max_d = (int)(0.3 * (double)(q_len + t_len));  // DWmatch.c:96
+  const int band_size = bw * 2;
+  uint32_t longest_match = 0;
+  bool start = false, matched = false;
+  int best_m = -1, min_k = 0, max_k = 0, pbase = 0, x = 0, y = 0, d;
+  int *Vp = sV[wid], *Vc = sV[wid] + PGB_MAXV;
+  for (d = 0; d < max_d; d++) {
+    if (max_k - min_k > band_size) break;  // DWmatch.c:120-122
+    int idx = 0;
+    for (int k = min_k; k <= max_k; k += 2, idx++) {
+      if (d == 0) {
+        x = 0;
+      } else if (k == min_k) {  // DWmatch.c:125-130
+        x = Vp[(k + 1 - pbase) >> 1];
+      } else if (k == max_k) {
+        x = Vp[(k - 1 - pbase) >> 1] + 1;
+      } else {
+        const int vm = Vp[(k - 1 - pbase) >> 1], vp = Vp[(k + 1 - pbase) >> 1];
+        x = (vm < vp) ? vp : vm + 1;
+      }
+      y = x - k;
+      const int x1 = x, y1 = y;
+      for (;;) {  // snake, DWmatch.c:135-140, 1024 bases per round
+        int rem = q_len - x;
+        if (t_len - y < rem) rem = t_len - y;
+        if (rem <= 0) break;
+        int n_l = 32;
+        if ((int)(32 * lane) < rem) {
+          const uint32_t qb = qo + (uint32_t)x + 32 * lane, tb = to + (uint32_t)y + 32 * lane;
+          const uint64_t *qp = qw + (qb >> 5), *tp = tw + (tb >> 5);
+          const uint64_t df = window64(qp[0], qp[1], (qb & 31) * 2) ^ window64(tp[0], tp[1], (tb & 31) * 2);
+          if (df) n_l = ctz64(df) >> 1;
+        }
+        const uint32_t bal = __ballot_sync(FULL, n_l < 32);
+        int nn = 1024;
+        if (bal) {
+          const int L = __ffs((int)bal) - 1;
+          nn = 32 * L + __shfl_sync(FULL, n_l, L);
+        }
+        if (nn > rem) nn = rem;
+        x += nn;
+        y += nn;
+        if (nn < 1024) break;
+      }
+      if ((x - x1 > 16) && !start) { r.q_bgn = x1; r.t_bgn = y1; start = true; }                                        // DWmatch.c:142-146
+      if ((uint32_t)(x - x1) > longest_match) { longest_match = (uint32_t)(x - x1); r.q_m_end = x; r.t_m_end = y; }  // :148-152
+      if (lane == 0) Vc[idx] = x;
+      if (x + y > best_m) best_m = x + y;
+      if (x >= q_len || y >= t_len) {  // :161-164
+        matched = true;
+        break;
+      }
+    }
+    if (matched) {  // :185-194
+      r.q_end = x;
+      r.t_end = y;
+      r.dist = d;
+      r.m_size = (r.q_end - r.q_bgn + r.t_end - r.t_bgn + 2 * d) / 2;
+      break;
+    }
+    __syncwarp();
+    int new_min_k = max_k, new_max_k = min_k;  // band trimming, :168-183
+    idx = 0;
+    for (int k2 = min_k; k2 <= max_k; k2 += 2, idx++) {
+      if (2 * Vc[idx] - k2 >= best_m - bw) {
+        if (k2 < new_min_k) new_min_k = k2;
+        if (k2 > new_max_k) new_max_k = k2;
+      }
+    }
+    pbase = min_k;
+    max_k = new_max_k + 1;
+    min_k = new_min_k - 1;
+    int *tmp = Vp; Vp = Vc; Vc = tmp;
+    __syncwarp();
+  }
+  if (!matched) { r.q_bgn = 0; r.t_bgn = 0; }  // :196-199
+  if (lane == 0) {
+    results[q.slot] = r;
+    atomicAdd(bases_total, (unsigned long long)(r.q_end + r.t_end));
+  }
 }
 
 // ---- pair-table maintenance between passes
@@ -1059,8 +1198,7 @@ __global__ void k_dirty_from_unknown(const uint8_t *__restrict__ unk_flag, uint3
   if (r < n_ranks) dirty[r] = unk_flag[r];
 }
 // Size classes of the buckets that run in a pass: flags[r] = runs && small, flags[n_ranks + r] = runs && big.  Small
-// buckets are replayed one per thread (k_replay), big ones one per warp (k_replay_warp): a thread walking a 120-record
-// bucket alone (7 140 dependent pair-table probes) was the critical path of every pass.  dirty == nullptr: all buckets run.
+// buckets are replayed one per thread (k_replay), big ones one per CTA (k_replay_block).  dirty == nullptr: all buckets run.
 __global__ void k_class_flags(const uint32_t *__restrict__ rank_off, uint32_t n_ranks, const uint8_t *__restrict__ dirty, uint32_t big_n,
                               uint32_t *flags) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -569,7 +569,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     uint32_t n_exact = scan_u32(c, exact_flag, exact_pos, ns + 1);
     uint32_t *exact_list = nullptr, *seg_row = nullptr, *seg_lo = nullptr, *seg_first = nullptr, *list_first = nullptr, *seg_cnt = nullptr, *seg_pos = nullptr;
     uint32_t n_seg = 0;
-    const int SEG = 1024;
+    const int SEG = 256;  // positions per thread of the exact automaton (plus its warm-up): short segments keep the few flagged reads off the critical path
     if (n_exact) {
       exact_list = c->alloc<uint32_t>(n_exact);
       LAUNCH(c, k_compact_idx, nblk(ns), 256, exact_flag, exact_pos, ns, exact_list);
@@ -968,13 +968,15 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
 
   // ---------------- replay / align fix-point (DESIGN.md "ordered greedy as a fix-point")
   if (n_ranks >= (1u << 30)) throw std::runtime_error("more than 2^30 eligible buckets in one overlap call");
-  const char *rp_env = getenv("PGB_REPLAY");
-  const bool warp_replay = rp_env && !strcmp(rp_env, "warp");  // every bucket by a warp (default: one thread per bucket)
-  const bool incremental = !(getenv("PGB_REPLAY_FULL"));        // PGB_REPLAY_FULL=1: replay every bucket in every pass
-  // buckets with >= BIG_N records are replayed by a warp (hybrid; measured slower than all-threads, so off by default)
-  const uint32_t BIG_N = getenv("PGB_REPLAY_BIG") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG")) : 0xFFFFFFFFu;
+  const bool incremental = !(getenv("PGB_REPLAY_FULL"));  // PGB_REPLAY_FULL=1: replay every bucket in every pass
+  // buckets with >= BIG_N records are replayed by a CTA (k_replay_block), smaller ones by a thread (k_replay);
+  // BIG_TAIL is the threshold of the incremental passes, where only the critical path of the biggest bucket matters
+  const uint32_t BIG_N = getenv("PGB_REPLAY_BIG") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG")) : 32u;
+  const uint32_t BIG_TAIL = getenv("PGB_REPLAY_BIG_TAIL") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG_TAIL")) : 8u;
   // speculative passes before real alignments are computed: 2 cost ~2 % extra alignments and save two full passes
   const int MAX_DRY = getenv("PGB_DRY_PASSES") ? atoi(getenv("PGB_DRY_PASSES")) : 2;
+  // alignment batches up to this size go to the warp-per-alignment kernel (k_align_warp), larger ones to k_align_lean
+  const uint32_t ALIGN_WARP_MAX = getenv("PGB_ALIGN_WARP_MAX") ? (uint32_t)strtoul(getenv("PGB_ALIGN_WARP_MAX"), 0, 10) : 16384u;
   const bool verbose = getenv("PGB_VERBOSE") != nullptr;
   const uint32_t CHANGED_CAP = 16384;
   // incremental passes: (rid, rank) index of the eligible records sorted by rid + per-bucket Bloom filter of read ids
@@ -991,10 +993,11 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     sort_pairs_u32(c, rr, rid_sorted, rk, rank_sorted, n_elig);
     c->release(rr); c->release(rk);
   }
+  bool tail_mode = false;  // few buckets left to replay: latency of the biggest one is all that matters
   // (small..., big...) run list of a pass; returns the number of small buckets, *n_run = total
   auto class_lists = [&](const uint8_t *dirty_or_null, uint32_t *list, uint32_t *n_run) -> uint32_t {
     CU(cudaMemsetAsync(dflags + 2 * (size_t)n_ranks, 0, 4, c->st));
-    LAUNCH(c, k_class_flags, nblk(n_ranks), 256, d_rank_off, n_ranks, dirty_or_null, BIG_N, dflags);
+    LAUNCH(c, k_class_flags, nblk(n_ranks), 256, d_rank_off, n_ranks, dirty_or_null, (dirty_or_null && tail_mode) ? std::min(BIG_N, BIG_TAIL) : BIG_N, dflags);
     *n_run = scan_u32(c, dflags, dpos, 2 * (size_t)n_ranks + 1);
     uint32_t n_small = 0;
     c->d2h(&n_small, dpos + n_ranks, 4);
@@ -1031,12 +1034,12 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
     CU(cudaMemsetAsync(acc, 0, ((size_t)n_ranks + 1) * 4, c->st));
     CU(cudaMemsetAsync(unk_flag, 0, n_ranks, c->st));
     auto launch_replay = [&](const uint32_t *list, uint32_t n_small, uint32_t n_total, int request, int emit, const uint32_t *ooff, ovlp_rec *out) {
-      const uint32_t ns = warp_replay ? 0u : n_small, nb = n_total - ns;
-      LAUNCH(c, k_replay, nblk(ns, 64), 64, S, ns, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag);
-      LAUNCH(c, k_replay_warp, nblk((size_t)nb * 32, 128), 128, S, nb, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag,
-             list + ns);
+      const uint32_t nb = n_total - n_small;
+      LAUNCH(c, k_replay, nblk(n_small, 64), 64, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag);
+      LAUNCH(c, k_replay_block, nb, PGB_RB_THREADS, S, nb, list + n_small, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag);
     };
     bool wet = false, overflow = false;
+    tail_mode = false;
     uint64_t prev_diffs = ~0ULL, last_diffs = ~0ULL;
     uint32_t n_done = 0;
     int dry_passes = 0;
@@ -1088,7 +1091,7 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
         c->tic();
         uint32_t nn = n_req - n_done;
         uint32_t *perm = nullptr;
-        if (nn > 8192) {  // group alignments of similar predicted length into the same warps
+        if (nn > 8192 && nn > ALIGN_WARP_MAX) {  // group alignments of similar predicted length into the same warps
           uint32_t *keys = c->alloc<uint32_t>(nn), *keys2 = c->alloc<uint32_t>(nn), *idx0 = c->alloc<uint32_t>(nn);
           perm = c->alloc<uint32_t>(nn);
           LAUNCH(c, k_align_keys, nblk(nn), 256, S.reqs, n_done, nn, c->d_rlen_by_rid, keys, idx0);
@@ -1099,8 +1102,12 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
           c->stats.kernel_launches += 3;
         }
         c->ktic();
-        LAUNCH(c, k_align_lean, nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid,
-               c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
+        if (nn <= ALIGN_WARP_MAX)  // small batch: latency-bound, one warp per alignment
+          LAUNCH(c, k_align_warp, nblk(nn, PGB_AW_WARPS), PGB_AW_WARPS * 32, S.reqs, n_done, nn, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid,
+                 c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
+        else
+          LAUNCH(c, k_align_lean, nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid,
+                 c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
         if (c->n_reads_with_n)
           LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, n_done, nn, perm, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
                  (int)bw, S.ares, c->d_err, c->d_align_bases, 1);
@@ -1123,6 +1130,7 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
         fprintf(stderr, "pgb200: replay pass %d %s: buckets=%u/%u unknown=%llu table_diffs=%llu requests=%u  k_replay %.3f ms, k_align %.3f ms\n", pass,
                 wet ? "wet" : "dry", n_run, n_ranks, ctr[0], ctr[1], n_req, ms_rp, ms_al);
       last_diffs = ctr[1];
+      tail_mode = n_run < 40000;
       c->stats.n_replay_buckets += n_run;
       if (wet && !new_requests && ctr[0] == 0 && ctr[1] == 0) { converged = true; break; }
       if (!wet) {

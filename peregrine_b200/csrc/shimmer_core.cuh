@@ -752,6 +752,24 @@ PGB_HD void predict_match(uint32_t rlen0, uint32_t rlen1, uint32_t start0, match
   m->t_m_end = (int32_t)e;
 }
 
+// Acceptance test and overlap type of src/shmr_overlap.c:134-160 for the alignment m of records (i, j): slen0 / slen1 are
+// the operand lengths handed to ovlp_match.  Returns false when the alignment is rejected.
+PGB_HD bool classify_match(const match_t &m, uint32_t rlen0, uint32_t rlen1, uint32_t slen0, uint32_t slen1, uint32_t *type) {
+  const int64_t q_bgn = m.q_bgn, q_end = m.q_end, t_bgn = m.t_bgn, t_end = m.t_end;
+  int64_t dq = (int64_t)slen0 - q_end, dt = (int64_t)slen1 - t_end;  // abs() on int in the reference, operands fit easily
+  if (dq < 0) dq = -dq;
+  if (dt < 0) dt = -dt;
+  if (!(q_bgn < READ_END_FUZZINESS && t_bgn < READ_END_FUZZINESS && (dq < READ_END_FUZZINESS || dt < READ_END_FUZZINESS) && q_end > 500 &&
+        t_end > 500))
+    return false;
+  int64_t c0 = (int64_t)rlen0 - (q_end - q_bgn), c1 = (int64_t)rlen1 - (t_end - t_bgn);
+  if (c0 < 0) c0 = -c0;
+  if (c1 < 0) c1 = -c1;
+  if (c0 < READ_END_FUZZINESS * 2 || c1 < READ_END_FUZZINESS * 2) *type = rlen0 >= rlen1 ? OVL_CONTAINS : OVL_CONTAINED;  // :142-154
+  else *type = OVL_OVERLAP;
+  return true;
+}
+
 template <class Ctx>
 PGB_HD uint32_t replay_bucket(Ctx &c, uint32_t rank, const uint64_t *y0s, const uint8_t *dirs, uint32_t n,
                               uint8_t *contained, uint32_t bestn, bool do_emit, uint32_t *n_unknown) {
@@ -798,29 +816,11 @@ PGB_HD uint32_t replay_bucket(Ctx &c, uint32_t rank, const uint64_t *y0s, const 
         c.aln_request(i, j, rid0, start0, strand0, rid1, strand1);
         predict_match(rlen0, rlen1, start0, &m);
       }
-      const int64_t q_bgn = m.q_bgn, q_end = m.q_end, t_bgn = m.t_bgn, t_end = m.t_end;
-      // src/shmr_overlap.c:134-137 (abs() on int, operands fit easily)
-      int64_t dq = (int64_t)slen0 - q_end, dt = (int64_t)slen1 - t_end;
-      if (dq < 0) dq = -dq;
-      if (dt < 0) dt = -dt;
-      if (q_bgn < READ_END_FUZZINESS && t_bgn < READ_END_FUZZINESS &&
-          (dq < READ_END_FUZZINESS || dt < READ_END_FUZZINESS) && q_end > 500 && t_end > 500) {
-        int64_t c0 = (int64_t)rlen0 - (q_end - q_bgn), c1 = (int64_t)rlen1 - (t_end - t_bgn);
-        if (c0 < 0) c0 = -c0;
-        if (c1 < 0) c1 = -c1;
-        uint32_t type;
-        if (c0 < READ_END_FUZZINESS * 2 || c1 < READ_END_FUZZINESS * 2) {  // :142-154
-          if (rlen0 >= rlen1) {
-            type = OVL_CONTAINS;
-            contained[j] = 1;
-          } else {
-            type = OVL_CONTAINED;
-            contained[i] = 1;
-          }
-        } else {
-          overlap_count++;
-          type = OVL_OVERLAP;
-        }
+      uint32_t type;
+      if (classify_match(m, rlen0, rlen1, slen0, slen1, &type)) {  // src/shmr_overlap.c:134-160
+        if (type == OVL_CONTAINS) contained[j] = 1;
+        else if (type == OVL_CONTAINED) contained[i] = 1;
+        else overlap_count++;
         c.pair_set(ridp, ((uint64_t)rank << 2) | type);
         if (do_emit) {
           ovlp_rec o;

@@ -192,12 +192,24 @@ def test_tiled_sketch_reports_fallbacks(workdir, ref_dir):
     eng.close()
 
 
-def test_warp_cooperative_replay_kernel(sim1, workdir, ref_dir, monkeypatch):
-    """PGB_REPLAY=warp selects the warp-cooperative replay kernel (the default is one thread per bucket)."""
-    monkeypatch.setenv("PGB_REPLAY", "warp")
+@pytest.mark.parametrize("big", ["3", "1000000"])
+def test_replay_kernel_forms(sim1, workdir, ref_dir, monkeypatch, big):
+    """PGB_REPLAY_BIG=3 sends every bucket through the block-cooperative replay kernel, a huge value through the
+    one-thread-per-bucket kernel (the default mixes them by bucket size); both must reproduce the reference stream."""
+    monkeypatch.setenv("PGB_REPLAY_BIG", big)
+    monkeypatch.setenv("PGB_REPLAY_BIG_TAIL", big)
     rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
     ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref1"), T=1)
-    oo = ours_overlap(sim1, rp, 2, os.path.join(workdir, "sim1/our_warp"), T=1)
+    oo = ours_overlap(sim1, rp, 2, os.path.join(workdir, f"sim1/our_rb{big}"), T=1)
+    assert_same_ovlp(oo[0], ro[0])
+
+
+def test_warp_per_alignment_kernel_on_every_alignment(sim1, workdir, ref_dir, monkeypatch):
+    """PGB_ALIGN_WARP_MAX=huge routes every alignment batch (not only the small tail batches) through k_align_warp."""
+    monkeypatch.setenv("PGB_ALIGN_WARP_MAX", "4000000000")
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref1"), T=1)
+    oo = ours_overlap(sim1, rp, 2, os.path.join(workdir, "sim1/our_aw"), T=1)
     assert_same_ovlp(oo[0], ro[0])
 
 

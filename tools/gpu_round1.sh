@@ -8,11 +8,9 @@ run() { # name, env...
   echo "== $name"; grep -v "replay pass\|outer khash" gpurun_out/probe_$name.log | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline())
-print({k:d[k] for k in ('wall_index_s','wall_overlap_s','overlaps','ms_pack','ms_sketch','ms_k_sketch_tiled','ms_reduce','ms_pairs','ms_buckets','ms_host_order','ms_replay','ms_align','ms_emit','ms_k_align','ms_k_replay','n_alignments','n_replay_passes','kernel_launches')})"
+print({k:d[k] for k in ('wall_index_s','wall_overlap_s','overlaps','ms_sketch','ms_replay','ms_align','ms_emit','ms_k_align','ms_k_replay','n_alignments','n_replay_passes','kernel_launches')})"
 }
 run default A=1
-run g9 PGB200_LIB=build/libpgb200_g9.so
-run g17 PGB200_LIB=build/libpgb200_g17.so
-ncu --set full --clock-control none --import-source on -k regex:'k_align_lean|k_sketch_tiled' -c 2 -o gpurun_out/prof_r1e \
-    python tools/probe.py 20e6 30 1 > gpurun_out/ncu_full.log 2>&1
-tail -2 gpurun_out/ncu_full.log | cut -c1-200
+run aw2k PGB_ALIGN_WARP_MAX=2000
+run aw64k PGB_ALIGN_WARP_MAX=65536
+grep -E "replay pass" gpurun_out/probe_default.log | tail -13 | cut -c1-170
