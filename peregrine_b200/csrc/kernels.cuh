@@ -94,6 +94,31 @@ __global__ void k_pack_reads(const uint8_t *__restrict__ raw, const uint64_t *__
   uint32_t cnt = (len - p0) < 32 ? (uint32_t)(len - p0) : 32u;
   uint64_t bits = 0;
   uint32_t nmask = 0;
+  if (cnt == 32) {
+    // full word: 32 bytes as 8 (unaligned) u32, 4 bases at a time with byte-parallel arithmetic
+    const uintptr_t a = (uintptr_t)s;
+    const uint32_t *p = (const uint32_t *)(a & ~(uintptr_t)3);  // raw has 64 bytes of slack behind the last read
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t prev = p[0];
+#pragma unroll
+    for (uint32_t q = 0; q < 8; q++) {
+      const uint32_t nx = p[q + 1];
+      const uint32_t x = __funnelshift_r(prev, nx, sh) & 0x0F0F0F0Fu;  // low nibbles = forward bases
+      prev = nx;
+      uint32_t pc = (x & 0x05050505u) + ((x >> 1) & 0x05050505u);       // per-byte popcount of the nibble
+      pc = (pc & 0x03030303u) + ((pc >> 2) & 0x03030303u);
+      const uint32_t z = pc ^ 0x01010101u;                                // non-zero byte <=> not exactly one bit <=> 'N'
+      const uint32_t nz = (((z + 0x7F7F7F7Fu) | z) & 0x80808080u) >> 7;   // 1 per 'N' byte
+      uint32_t code = ((x >> 1) & 0x07070707u) - ((x >> 3) & 0x01010101u);  // 1 2 4 8 -> 0 1 2 3
+      code &= ~(nz * 0xFFu);
+      bits |= (uint64_t)((code * 0x01041040u) >> 24) << (8 * q);          // gather the four 2-bit codes
+      nmask |= ((nz * 0x01020408u) >> 24) << (4 * q);                     // gather the four N bits
+    }
+    w[word] = bits;
+    nm[word] = nmask;
+    if (nmask) atomicOr(&hasn_by_rid[row_rid[row]], 1u);
+    return;
+  }
 #pragma unroll 8
   for (uint32_t j = 0; j < 32; j++) {
     if (j < cnt) {

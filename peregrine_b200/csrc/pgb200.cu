@@ -971,8 +971,9 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   const bool incremental = !(getenv("PGB_REPLAY_FULL"));  // PGB_REPLAY_FULL=1: replay every bucket in every pass
   // buckets with >= BIG_N records are replayed by a CTA (k_replay_block), smaller ones by a thread (k_replay);
   // BIG_TAIL is the threshold of the incremental passes, where only the critical path of the biggest bucket matters
-  const uint32_t BIG_N = getenv("PGB_REPLAY_BIG") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG")) : 32u;
+  const uint32_t BIG_N = getenv("PGB_REPLAY_BIG") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG")) : 48u;
   const uint32_t BIG_TAIL = getenv("PGB_REPLAY_BIG_TAIL") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG_TAIL")) : 8u;
+  const uint32_t TAIL_RUN = getenv("PGB_TAIL_RUN") ? (uint32_t)strtoul(getenv("PGB_TAIL_RUN"), 0, 10) : 40000u;
   // speculative passes before real alignments are computed: 2 cost ~2 % extra alignments and save two full passes
   const int MAX_DRY = getenv("PGB_DRY_PASSES") ? atoi(getenv("PGB_DRY_PASSES")) : 2;
   // alignment batches up to this size go to the warp-per-alignment kernel (k_align_warp), larger ones to k_align_lean
@@ -1130,7 +1131,7 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
         fprintf(stderr, "pgb200: replay pass %d %s: buckets=%u/%u unknown=%llu table_diffs=%llu requests=%u  k_replay %.3f ms, k_align %.3f ms\n", pass,
                 wet ? "wet" : "dry", n_run, n_ranks, ctr[0], ctr[1], n_req, ms_rp, ms_al);
       last_diffs = ctr[1];
-      tail_mode = n_run < 40000;
+      tail_mode = n_run < TAIL_RUN;
       c->stats.n_replay_buckets += n_run;
       if (wet && !new_requests && ctr[0] == 0 && ctr[1] == 0) { converged = true; break; }
       if (!wet) {

@@ -8,9 +8,11 @@ run() { # name, env...
   echo "== $name"; grep -v "replay pass\|outer khash" gpurun_out/probe_$name.log | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline())
-print({k:d[k] for k in ('wall_index_s','wall_overlap_s','overlaps','ms_sketch','ms_replay','ms_align','ms_emit','ms_k_align','ms_k_replay','n_alignments','n_replay_passes','kernel_launches')})"
+print({k:d[k] for k in ('wall_index_s','wall_overlap_s','overlaps','ms_pack','ms_sketch','ms_replay','ms_align','ms_emit','ms_k_align','ms_k_replay','n_alignments','n_replay_passes','kernel_launches')})"
 }
 run default A=1
-run aw2k PGB_ALIGN_WARP_MAX=2000
-run aw64k PGB_ALIGN_WARP_MAX=65536
-grep -E "replay pass" gpurun_out/probe_default.log | tail -13 | cut -c1-170
+run tr_all8 PGB_TAIL_RUN=4000000000
+run tr_all16 PGB_TAIL_RUN=4000000000 PGB_REPLAY_BIG_TAIL=16
+run tr_all24 PGB_TAIL_RUN=4000000000 PGB_REPLAY_BIG_TAIL=24
+run big24 PGB_REPLAY_BIG=24
+run big48 PGB_REPLAY_BIG=48
