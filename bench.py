@@ -226,8 +226,8 @@ def run_ours(args):
             return eng.overlap(1, 1, P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy=copy)
 
         def e2e_step():  # host buffers in, host records out
-            eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False)
-            return len(compute(copy=True))
+            eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False, defer=True)  # H2D overlapped with pack + sketch inside index()
+            return len(compute(copy="view"))  # records land in the engine's page-locked host buffer
 
         def dev_prepare():
             eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=True)
@@ -243,9 +243,9 @@ def run_ours(args):
         job = M.ShardedJob(idx_eng, ovl_eng, rank, world, torch.device("cuda", local))
 
         def e2e_step():  # this rank's share of the .seqdb from pinned host memory, its chunk's records back to the host
-            idx_eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False)
+            idx_eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False, defer=True)
             job.index_and_exchange(P["w"], P["k"], P["r"])
-            return len(job.overlap(P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy=True))
+            return len(job.overlap(P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy="view"))
 
         def dev_prepare():
             idx_eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=True)

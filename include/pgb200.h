@@ -92,8 +92,13 @@ const char *pgb_last_error(pgb_ctx *);            /* "" when the last call succe
 
 /* Read set = .seqdb image + .idx table (src/shmr_mkseqdb.c:108-118).  Rows with rid % total_chunk == mychunk % total_chunk
  * (src/shmr_index.c:157) are copied to the device and 2-bit packed; total_chunk = 1 selects everything.
- * seqdb may be pageable or pinned host memory.  keep_raw != 0 keeps the 1-byte/base image in HBM so that
- * pgb_repack() can redo the packing without another host copy (bench.py's device-resident timing). */
+ * seqdb may be pageable or pinned host memory.  keep_raw is a bit set: PGB_LOAD_KEEP_RAW keeps the 1-byte/base image in
+ * HBM so that pgb_repack() can redo the packing without another host copy (bench.py's device-resident timing);
+ * PGB_LOAD_DEFER leaves the bulk of the image on the host and lets the next pgb_index() overlap its host->device copy
+ * with packing and sketching, chunk by chunk (any other call that needs the reads completes the copy first) - the
+ * caller must keep seqdb alive and unchanged until then; it only pays off for page-locked memory. */
+#define PGB_LOAD_KEEP_RAW 1
+#define PGB_LOAD_DEFER 2
 int pgb_load_reads(pgb_ctx *, const uint8_t *seqdb, size_t seqdb_bytes, const uint32_t *rid, const uint32_t *len,
                    const uint64_t *offset, size_t n_reads, uint32_t total_chunk, uint32_t mychunk, int keep_raw);
 int pgb_repack(pgb_ctx *);
@@ -121,6 +126,9 @@ int pgb_overlap(pgb_ctx *, uint32_t total_chunk, uint32_t mychunk, uint32_t best
                 uint32_t align_bandwidth, uint32_t ovlp_upper);
 size_t pgb_overlap_size(pgb_ctx *);
 int pgb_overlap_copy(pgb_ctx *, ovlp_t *out);
+/* Same records through a page-locked host buffer owned by the context (a device-to-host copy into pageable memory runs at
+ * a fraction of the PCIe rate).  *out stays valid until the next pgb_overlap / pgb_destroy on this context. */
+int pgb_overlap_host(pgb_ctx *, const ovlp_t **out, size_t *n);
 
 /* ---- multi-GPU plumbing (one process per GPU; the collective itself is the caller's, e.g. torch.distributed / NCCL) ----
  * A rank sketches the reads of ITS index chunk, then the ranks all-gather (a) the packed reads + read table so that any rank

@@ -306,11 +306,11 @@ __global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__r
                                                              const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ row_len,
                                                              const uint64_t *__restrict__ row_woff, const uint32_t *__restrict__ hasn_by_rid,
                                                              int wsz, int k, uint32_t *__restrict__ tile_cnt, uint32_t *row_flags,
-                                                             mm128 *__restrict__ tmp, uint32_t tile_cap) {
+                                                             mm128 *__restrict__ tmp, uint32_t tile_cap, uint32_t tile_base) {
   extern __shared__ __align__(16) unsigned char sk_smem[];
   SkTile<HT> sh;
   sk_tile_layout<HT>(sh, sk_smem, wsz);
-  const uint32_t tile = blockIdx.x;
+  const uint32_t tile = tile_base + blockIdx.x;
   const int tid = threadIdx.x;
   if (tid == 0) {  // owning row: last row with tile_off[row] <= tile
     uint32_t lo = 0, hi = n_rows;

@@ -58,6 +58,11 @@ struct pgb_ctx {
   uint64_t sel_bases = 0;
   uint8_t *d_raw = nullptr; size_t raw_bytes = 0;
   uint64_t *d_w = nullptr; uint32_t *d_nm = nullptr;
+  // deferred bulk copy (pgb_load_reads with PGB_LOAD_DEFER): pgb_index overlaps the host->device copy of the .seqdb image
+  // with packing and sketching, chunk by chunk; any other consumer of the reads completes the load first (ensure_loaded)
+  struct { const uint8_t *src = nullptr; bool active = false, keep_raw = false; } pend;
+  cudaStream_t st_copy = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
   uint64_t *d_wrc = nullptr;   // reverse-complement image of d_w (built on first use by the overlap / ovlp_match paths)
   uint32_t n_reads_with_n = 0;  // valid once d_wrc exists
   uint32_t *d_rlen_by_rid = nullptr, *d_hasn_by_rid = nullptr; uint64_t *d_woff_by_rid = nullptr;
@@ -74,6 +79,7 @@ struct pgb_ctx {
   uint64_t *d_mckeys = nullptr; uint32_t *d_mcvals = nullptr; uint32_t mcmask = 0;
   // ---- overlap output
   ovlp_rec *d_ovl = nullptr; size_t n_ovl = 0;
+  void *h_ovl = nullptr; size_t h_ovl_cap = 0;  // page-locked staging of the records (pgb_overlap_host)
   int *d_err = nullptr;
   KhashEmu outer_emu;  // host replay of the outer khash (visiting order), storage reused between calls
 
@@ -168,6 +174,7 @@ struct pgb_ctx {
     return e;
   }
   void free_reads() {
+    pend.active = false;
     release(d_raw); release(d_w); release(d_nm); release(d_wrc); release(d_rlen_by_rid); release(d_hasn_by_rid); release(d_woff_by_rid);
     release(d_row_rid); release(d_row_len); release(d_row_woff); release(d_row_raw_off); release(d_sel_rows);
     n_rows = 0;
@@ -251,6 +258,7 @@ extern "C" pgb_ctx *pgb_create(int device) {
     c->device = device;
     memset(&c->stats, 0, sizeof c->stats);
     CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     CU(cudaEventCreate(&c->evk0));
@@ -278,6 +286,7 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   c->free_index();
   c->free_reads();
   c->release(c->d_ovl);
+  if (c->h_ovl) cudaFreeHost(c->h_ovl);
   c->release(c->d_err);
   c->release(c->d_align_bases);
   cudaStreamSynchronize(c->st);
@@ -287,6 +296,8 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   cudaEventDestroy(c->evk0);
   cudaEventDestroy(c->evk1);
   for (int i = 0; i < 8; i++) cudaEventDestroy(c->user_ev[i]);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(c->st_copy);
   cudaStreamDestroy(c->st);
   delete c;
 }
@@ -339,7 +350,9 @@ static void do_pack(pgb_ctx *c) {
 }
 
 // reverse-complement image + number of reads with N, built once per loaded read set
+static void ensure_loaded(pgb_ctx *c);
 static void ensure_rc(pgb_ctx *c) {
+  ensure_loaded(c);
   if (c->d_wrc || !c->d_w) return;
   c->tic();
   c->d_wrc = c->palloc<uint64_t>(c->n_words);
@@ -356,11 +369,24 @@ static void ensure_rc(pgb_ctx *c) {
   c->stats.ms_pack += c->toc();
 }
 
+// completes a deferred bulk copy (no overlap with compute): whoever needs the packed reads before pgb_index ran
+static void ensure_loaded(pgb_ctx *c) {
+  if (!c->pend.active) return;
+  const size_t CH = (size_t)256 << 20;
+  for (size_t o = 0; o < c->raw_bytes; o += CH) c->h2d(c->d_raw + o, c->pend.src + o, std::min(CH, c->raw_bytes - o));
+  do_pack(c);
+  c->sync();
+  c->pend.active = false;
+  if (!c->pend.keep_raw) c->release(c->d_raw);
+}
+
 extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_bytes, const uint32_t *rid, const uint32_t *len,
                               const uint64_t *offset, size_t n_reads, uint32_t T, uint32_t mychunk, int keep_raw) {
   API_BEGIN(c)
   if (T == 0 || mychunk == 0 || mychunk > T) throw std::runtime_error("bad chunk spec");
   c->free_reads();
+  const bool defer = (keep_raw & PGB_LOAD_DEFER) != 0;
+  keep_raw &= 1;
   // the by-rid tables cover every read (lengths are needed for any rid an index file mentions)
   uint32_t max_rid = 0;
   for (size_t i = 0; i < n_reads; i++) if (rid[i] > max_rid) max_rid = rid[i];
@@ -403,7 +429,13 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
   c->h2d(c->d_sel_rows, ident.data(), nsel * 4);
   // raw bytes of the selected reads
   if (nsel) {
-    if (contiguous) {
+    if (contiguous && defer) {
+      c->pend.src = seqdb + offset[rows[0]];
+      c->pend.active = true;
+      c->pend.keep_raw = keep_raw != 0;
+      c->sync();
+      return 0;  // (API_END's bookkeeping is not needed: nothing was taken from the scratch arena)
+    } else if (contiguous) {
       const uint8_t *src = seqdb + offset[rows[0]];
       const size_t CH = (size_t)256 << 20;
       for (size_t o = 0; o < raw; o += CH) c->h2d(c->d_raw + o, src + o, std::min(CH, raw - o));
@@ -440,6 +472,7 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
 
 extern "C" int pgb_repack(pgb_ctx *c) {
   API_BEGIN(c)
+  ensure_loaded(c);
   if (!c->d_raw) throw std::runtime_error("pgb_repack: raw image was not kept (keep_raw = 0)");
   do_pack(c);
   c->sync();
@@ -515,6 +548,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   const bool use_tiled = w >= SK_MINW && !(force && !strcmp(force, "exact")) && ns > 0;
   if (!use_tiled) {
     // exact automaton for every read (tiny windows, or PGB_SKETCH=exact)
+    ensure_loaded(c);
     c->ktic();
     LAUNCH(c, k_sketch_exact<false>, nblk(ns, 64), 64, c->d_w, c->d_nm, c->d_sel_rows, (uint32_t)ns, c->d_row_rid, c->d_row_len,
            c->d_row_woff, c->d_hasn_by_rid, w, k, counts, (const uint64_t *)nullptr, (mm128 *)nullptr);
@@ -544,25 +578,54 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     c->h2d(tile_off, h_tile_off.data(), (ns + 1) * 4);
     CU(cudaMemsetAsync(row_flags, 0, ns * 4, c->st));
     CU(cudaMemsetAsync(exact_flag, 0, (ns + 1) * 4, c->st));
+    const bool k32 = k <= 16;
+    const size_t smem = k32 ? sk_smem_bytes<uint32_t>() : sk_smem_bytes<uint64_t>();
+    if (k32) CU(cudaFuncSetAttribute(k_sketch_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(cudaFuncSetAttribute(k_sketch_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto launch_tiles = [&](uint32_t t0, uint32_t t1) {  // tiles [t0, t1)
+      if (t1 <= t0) return;
+      if (k32)
+        k_sketch_tiled<uint32_t><<<t1 - t0, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
+                                                                        c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap, t0);
+      else
+        k_sketch_tiled<uint64_t><<<t1 - t0, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
+                                                                        c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap, t0);
+      c->stats.kernel_launches++;
+      CU(cudaGetLastError());
+    };
     c->ktic();
-    if (k <= 16) {
-      size_t smem = sk_smem_bytes<uint32_t>();
-      CU(cudaFuncSetAttribute(k_sketch_tiled<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      if (n_tiles) {
-        k_sketch_tiled<uint32_t><<<n_tiles, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
-                                                                       c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap);
-        c->stats.kernel_launches++;
-        CU(cudaGetLastError());
+    if (c->pend.active) {
+      // Deferred load: the .seqdb image is still on the host.  Chunks of whole reads travel on the copy stream; the compute
+      // stream packs and sketches chunk i while chunk i+1 is on the wire (reads are independent up to the L0 gather).
+      CU(cudaMemsetAsync(c->d_w, 0, c->n_words * 8, c->st));
+      CU(cudaMemsetAsync(c->d_nm, 0, c->n_words * 4, c->st));
+      CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
+      const uint64_t CH = getenv("PGB_LOAD_CHUNK_MB") ? strtoull(getenv("PGB_LOAD_CHUNK_MB"), 0, 10) << 20 : (uint64_t)96 << 20;
+      uint64_t raw_o = 0, word_o = 2;
+      size_t r0 = 0, n_ev = 0;
+      while (r0 < ns) {
+        size_t r1 = r0;
+        uint64_t bytes = 0, wcount = 0;
+        while (r1 < ns && bytes < CH) { bytes += c->h_row_len[r1]; wcount += ((uint64_t)c->h_row_len[r1] + 31) / 32; r1++; }
+        if (n_ev == c->ev_pool.size()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_pool.push_back(e); }
+        if (bytes) {
+          CU(cudaMemcpyAsync(c->d_raw + raw_o, c->pend.src + raw_o, bytes, cudaMemcpyHostToDevice, c->st_copy));
+          c->stats.h2d_bytes += bytes;
+        }
+        CU(cudaEventRecord(c->ev_pool[n_ev], c->st_copy));
+        CU(cudaStreamWaitEvent(c->st, c->ev_pool[n_ev], 0));
+        n_ev++;
+        if (wcount)
+          LAUNCH(c, k_pack_reads, nblk(wcount), 256, c->d_raw, c->d_row_raw_off, c->d_row_len, c->d_row_woff, c->d_row_rid, (uint32_t)c->n_rows, word_o,
+                 wcount, c->d_w, c->d_nm, c->d_hasn_by_rid);
+        launch_tiles(h_tile_off[r0], h_tile_off[r1]);
+        raw_o += bytes; word_o += wcount; r0 = r1;
       }
+      c->pend.active = false;
+      c->stats.bases_packed += c->sel_bases;
+      if (!c->pend.keep_raw) c->release(c->d_raw);
     } else {
-      size_t smem = sk_smem_bytes<uint64_t>();
-      CU(cudaFuncSetAttribute(k_sketch_tiled<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      if (n_tiles) {
-        k_sketch_tiled<uint64_t><<<n_tiles, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
-                                                                       c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap);
-        c->stats.kernel_launches++;
-        CU(cudaGetLastError());
-      }
+      launch_tiles(0, n_tiles);
     }
     c->stats.ms_k_sketch_tiled += c->ktoc(); c->stats.n_k_sketch_tiled++;
     LAUNCH(c, k_row_counts, nblk(ns), 256, tile_off, tile_cnt, row_flags, (uint32_t)ns, counts, exact_flag);
@@ -702,6 +765,7 @@ extern "C" size_t pgb_buffer_elems(pgb_ctx *c, int which) {
 }
 extern "C" int pgb_buffer_copy_out(pgb_ctx *c, int which, void *dst) {
   API_BEGIN(c)
+  ensure_loaded(c);
   size_t n = pgb_buffer_elems(c, which);
   const void *src = nullptr;
   size_t esz = 0;
@@ -1169,6 +1233,21 @@ extern "C" int pgb_overlap_copy(pgb_ctx *c, ovlp_t *out) {
   c->d2h(out, c->d_ovl, c->n_ovl * sizeof(ovlp_rec));
   API_END(c)
 }
+extern "C" int pgb_overlap_host(pgb_ctx *c, const ovlp_t **out, size_t *n) {
+  API_BEGIN(c)
+  const size_t bytes = c->n_ovl * sizeof(ovlp_rec);
+  if (bytes > c->h_ovl_cap) {
+    if (c->h_ovl) cudaFreeHost(c->h_ovl);
+    c->h_ovl = nullptr; c->h_ovl_cap = 0;
+    const size_t cap = bytes + bytes / 4 + (1 << 20);
+    CU(cudaMallocHost((void **)&c->h_ovl, cap));
+    c->h_ovl_cap = cap;
+  }
+  c->d2h(c->h_ovl, c->d_ovl, bytes);
+  *out = (const ovlp_t *)c->h_ovl;
+  *n = c->n_ovl;
+  API_END(c)
+}
 
 // ================================================================================================ command-line tools
 static pgb_ctx *cli_ctx() {
@@ -1299,9 +1378,10 @@ extern "C" int pgb_shmr_overlap_main(int argc, char **argv) {
   CLI_CHECK(c, pgb_load_reads_from_files(c, seqdb_prefix, 1, 1, 0));
   CLI_CHECK(c, pgb_set_shimmers(c, (const mm128_t *)mmers.data(), mmers.size(), (const mm_count_t *)mc.data(), mc.size()));
   CLI_CHECK(c, pgb_overlap(c, total_chunk, mychunk, bestn, mc_lower, mc_upper, align_bandwidth, ovlp_upper));
-  std::vector<ovlp_t> recs(pgb_overlap_size(c));
-  CLI_CHECK(c, pgb_overlap_copy(c, recs.data()));
-  if (!recs.empty()) fwrite(recs.data(), sizeof(ovlp_t), recs.size(), out);
+  const ovlp_t *recs_p = nullptr;
+  size_t recs_n = 0;
+  CLI_CHECK(c, pgb_overlap_host(c, &recs_p, &recs_n));
+  if (recs_n) fwrite(recs_p, sizeof(ovlp_t), recs_n, out);
   fclose(out);
   pgb_destroy(c);
   return 0;

@@ -82,6 +82,7 @@ def load_library():
     L.pgb_overlap_size.restype = C.c_size_t
     L.pgb_overlap_size.argtypes = [vp]
     L.pgb_overlap_copy.argtypes = [vp, vp]
+    L.pgb_overlap_host.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.pgb_buffer_elems.restype = C.c_size_t
     L.pgb_buffer_elems.argtypes = [vp, C.c_int]
     L.pgb_buffer_copy_out.argtypes = [vp, C.c_int, vp]
@@ -128,14 +129,17 @@ class Engine:
             raise RuntimeError(f"{what} failed: {self.L.pgb_last_error(self.h).decode()}")
 
     # ------------------------------------------------------------------ reads
-    def load_reads(self, seqdb, rid, length, offset, total_chunk=1, mychunk=1, keep_raw=False):
-        """seqdb: uint8 array (numpy, may wrap pinned memory); rid/length/offset as parsed from .idx."""
+    def load_reads(self, seqdb, rid, length, offset, total_chunk=1, mychunk=1, keep_raw=False, defer=False):
+        """seqdb: uint8 array (numpy, may wrap pinned memory); rid/length/offset as parsed from .idx.
+        defer=True (PGB_LOAD_DEFER): the bulk copy is overlapped with the next index() call; seqdb must stay alive and
+        unchanged until that call returns."""
+        self._seqdb_ref = seqdb if defer else None
         seqdb = np.ascontiguousarray(seqdb, dtype=np.uint8) if not isinstance(seqdb, np.ndarray) else seqdb
         rid = np.ascontiguousarray(rid, dtype=np.uint32)
         length = np.ascontiguousarray(length, dtype=np.uint32)
         offset = np.ascontiguousarray(offset, dtype=np.uint64)
         self._ck(self.L.pgb_load_reads(self.h, _ptr(seqdb), seqdb.size, _ptr(rid), _ptr(length), _ptr(offset), len(rid),
-                                       total_chunk, mychunk, int(keep_raw)), "pgb_load_reads")
+                                       total_chunk, mychunk, int(bool(keep_raw)) | (2 if defer else 0)), "pgb_load_reads")
 
     def load_reads_ptr(self, seqdb_ptr: int, seqdb_bytes: int, rid, length, offset, total_chunk=1, mychunk=1, keep_raw=False):
         """Same, from a raw host address (e.g. a pinned torch tensor's data_ptr())."""
@@ -184,18 +188,24 @@ class Engine:
 
     def overlap(self, total_chunk=1, mychunk=1, bestn=4, mc_lower=2, mc_upper=240, align_bandwidth=100, ovlp_upper=120,
                 copy=True):
+        """copy=True: records as an independent numpy array; copy="view": zero-copy view of the page-locked staging buffer
+        (valid until the next overlap()); copy=False: leave the records on the device, return their number."""
         self._ck(self.L.pgb_overlap(self.h, total_chunk, mychunk, bestn, mc_lower, mc_upper, align_bandwidth, ovlp_upper),
                  "pgb_overlap")
-        if not copy:
+        if copy is False:
             return self.L.pgb_overlap_size(self.h)
-        return self.overlap_records()
+        return self.overlap_records(view=(copy == "view"))
 
-    def overlap_records(self):
-        n = self.L.pgb_overlap_size(self.h)
-        out = np.empty(n, dtype=formats.OVLP)
-        if n:
-            self._ck(self.L.pgb_overlap_copy(self.h, _ptr(out)), "pgb_overlap_copy")
-        return out
+    def overlap_records(self, view=False):
+        """The chunk's ovlp_t records on the host.  view=True: zero-copy numpy view of the context's page-locked staging
+        buffer (valid until the next overlap() / close() of this engine); default: an independent array."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.pgb_overlap_host(self.h, C.byref(p), C.byref(n)), "pgb_overlap_host")
+        if n.value == 0:
+            return np.empty(0, dtype=formats.OVLP)
+        buf = (C.c_uint8 * (n.value * formats.OVLP.itemsize)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=formats.OVLP, count=n.value)
+        return a if view else a.copy()
 
     # ------------------------------------------------------------------ multi-GPU plumbing (device buffers)
     BUF_WORDS, BUF_NMASK, BUF_ROW_RID, BUF_ROW_LEN, BUF_ROW_WOFF, BUF_ROW_HASN = 0, 1, 2, 3, 4, 5

@@ -155,6 +155,33 @@ def test_engine_api_matches_cli(sim1, workdir, ref_dir):
     eng.close()
 
 
+def test_deferred_load_overlaps_copy_with_sketch(sim1, workdir, ref_dir, monkeypatch):
+    """PGB_LOAD_DEFER: index() copies, packs and sketches chunk by chunk (tiny chunks here, so that several are in flight);
+    a consumer other than index() completes the copy first.  Same L0/L2 and same records as the plain load."""
+    from peregrine_b200 import Engine
+
+    monkeypatch.setenv("PGB_LOAD_CHUNK_MB", "1")
+    rid, ln, off = F.read_idx(sim1 + ".idx")
+    seqdb = np.fromfile(sim1 + ".seqdb", dtype=np.uint8)
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref1"), T=1)
+    ref = F.normalise_ovlp(F.read_ovlp(ro[0]))
+    eng = Engine(0)
+    eng.load_reads(seqdb, rid, ln, off, defer=True)
+    eng.index(80, 16, 6, 2)
+    assert np.array_equal(eng.level(0), F.read_mmlist(rp + "-L0-01-of-01.dat"))
+    assert np.array_equal(eng.level(2), F.read_mmlist(rp + "-L2-01-of-01.dat"))
+    eng.set_shimmers_from_index(2)
+    ov = eng.overlap(1, 1, copy="view")
+    assert len(ov) == len(ref) and ov.tobytes() == ref.tobytes()
+    # deferred load consumed by overlap() directly (shimmers from the reference's files)
+    eng.load_reads(seqdb, rid, ln, off, defer=True)
+    eng.set_shimmers(F.read_mmlist(rp + "-L2-01-of-01.dat"), F.read_mc(rp + "-L2-MC-01-of-01.dat"))
+    ov = eng.overlap(1, 1)
+    assert len(ov) == len(ref) and ov.tobytes() == ref.tobytes()
+    eng.close()
+
+
 def test_empty_and_tiny_inputs(workdir, ref_dir):
     """Chunks with no reads, reads with no minimizer, and an index with no eligible bucket."""
     recs = [("t/000000/0_5", "ACGTA"), ("t/000001/0_40", "ACGTTGCAAGGCTTAACCGGTTAACCGGATATCGCGATAT" )]
