@@ -242,9 +242,15 @@ def run_ours(args):
         engines = [idx_eng, ovl_eng]
         job = M.ShardedJob(idx_eng, ovl_eng, rank, world, torch.device("cuda", local))
 
+        def exchange():
+            if args.exchange == "routed":  # SHIMMER-pair records travel: one NCCL all-to-all (north_star / SURVEY 8e)
+                job.index_and_route(P["w"], P["k"], P["r"], P["mc_lower"], P["mc_upper"])
+            else:  # every rank gathers all SHIMMER lists and rescans them
+                job.index_and_exchange(P["w"], P["k"], P["r"])
+
         def e2e_step():  # this rank's share of the .seqdb from pinned host memory, its chunk's records back to the host
             idx_eng.load_reads(seqdb, rid, ln, off, 1, 1, keep_raw=False, defer=True)
-            job.index_and_exchange(P["w"], P["k"], P["r"])
+            exchange()
             return len(job.overlap(P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy="view"))
 
         def dev_prepare():
@@ -252,7 +258,7 @@ def run_ours(args):
 
         def dev_step():
             idx_eng.repack()
-            job.index_and_exchange(P["w"], P["k"], P["r"])
+            exchange()
             return job.overlap(P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy=False)
 
     def all_stats():
@@ -327,7 +333,9 @@ def run_ours(args):
         "config": {"workload": f"synthetic {args.genome_mb * world:g} Mb genome, {args.cov:g}x 15 kb reads @99.5%, k=16 w=80 r=6 l=2, T={T}",
                    "reads_per_rank": int(len(rid)), "bases": bases, "overlaps_per_step": int(n_ovl), "l2_flush": "inputs (1.5 GB image) exceed the 126 MB L2",
                    "wall_ms_per_step_device_resident": dev_wall * 1e3,
-                   "sharding": "reads by rid % N for the index, SHIMMER-hash chunk c of T=N for the overlap; NCCL all-gather of packed reads + L2 lists" if world > 1 else "single GPU"},
+                   "sharding": ("reads by rid % N for the index, SHIMMER-hash chunk c of T=N for the overlap; " +
+                                ("NCCL all-to-all of SHIMMER-pair records to the owning chunk + all-gather of packed reads and partial count tables" if args.exchange == "routed"
+                                 else "NCCL all-gather of packed reads + L2 lists")) if world > 1 else "single GPU"},
         "e2e": {"value": n_ovl / e2e_s, "unit": "overlaps/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"] // K, "d2h_bytes_per_step": st_e2e["d2h_bytes"] // K,
                 "ms_per_step": e2e_s * 1e3, "read_bases_per_s": bases / e2e_s},
         "gpu_launches": int(st["kernel_launches"]),
@@ -355,6 +363,7 @@ def main():
     ap.add_argument("--cov", type=float, default=30.0)
     ap.add_argument("--ref-genome-mb", type=float, default=4.0, help="reference arm: genome size of each per-core sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="routed", choices=["routed", "gathered"], help="multi-GPU exchange step (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

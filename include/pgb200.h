@@ -141,7 +141,9 @@ enum pgb_buffer {
   PGB_BUF_ROW_LEN = 3,  /* uint32[rows]                                                                                */
   PGB_BUF_ROW_WOFF = 4, /* uint64[rows]: word offset of each row inside PGB_BUF_WORDS                                  */
   PGB_BUF_ROW_HASN = 5, /* uint32[rows]: 1 if the read contains a non-ACGT base                                        */
-  PGB_BUF_LEVEL0 = 8, PGB_BUF_LEVEL1 = 9, PGB_BUF_LEVEL2 = 10 /* mm128_t[n] of the index level                        */
+  PGB_BUF_LEVEL0 = 8, PGB_BUF_LEVEL1 = 9, PGB_BUF_LEVEL2 = 10, /* mm128_t[n] of the index level                       */
+  PGB_BUF_COUNTS = 11,  /* mm_count_t[n]: the multiplicity table dumped by pgb_counts_dump                             */
+  PGB_BUF_ROUTE = 12    /* mp256_t-like 40-byte records {x0,x1,y0,y1,direction(u64)} grouped by owner chunk 1..T       */
 };
 size_t pgb_buffer_elems(pgb_ctx *, int which);                       /* element count of a buffer                      */
 int pgb_buffer_copy_out(pgb_ctx *, int which, void *dst_device);     /* device -> caller's device buffer               */
@@ -152,6 +154,26 @@ int pgb_load_packed_device(pgb_ctx *, const uint64_t *words, const uint32_t *nma
 /* Overlap input from a DEVICE array of mm128_t (all chunks concatenated in chunk order); the multiplicity table is rebuilt
  * from it, which equals summing the per-chunk -MC- files (src/shmr_utils.c:162-176). */
 int pgb_set_shimmers_device(pgb_ctx *, const mm128_t *mmers_device, size_t n);
+
+/* ---- routed exchange: the SHIMMER-pair records travel, not the lists (one all-to-all) --------------------------
+ * Each rank keeps the shimmers of its own reads (pgb_set_shimmers_from_index).  build_map (src/shmr_utils.c:295-404) is a
+ * single scan over the concatenation of all chunk lists; because a read never straddles two index chunks the scan splits
+ * by rank, except for (a) the multiplicities, which are global, and (b) the asymmetric bound of the very first kept element
+ * (:318 `< upper` vs :327 `<= upper`), which only the first rank that has such an element applies.
+ *   pgb_counts_dump        compact the context's multiplicity table into PGB_BUF_COUNTS (this rank's partial counts)
+ *   pgb_counts_set_device  replace the table by the SUM of the given entries (all ranks' partials concatenated; duplicates
+ *                          add up, as aggregate_mm_count does over the -MC- files, src/shmr_utils.c:162-176)
+ *   pgb_route_scan         global-count lookup of every local shimmer; *has_first = 1 if one has lower <= count < upper
+ *   pgb_route_build        first_found_before = 1 if a LOWER rank reported has_first.  Emits the forward and the reverse record
+ *                          of every kept pair into PGB_BUF_ROUTE, grouped by owner chunk (chunk c owns (x>>8) % T == c % T,
+ *                          src/shmr_utils.c:337,362), scan order kept inside a group; n_per_chunk[c-1] = size of group c
+ *   pgb_overlap_routed     process_overlaps over the records an owner received: source ranks concatenated in rank order.
+ *                          Needs all reads loaded (pgb_load_packed_device); the result is read like pgb_overlap's. */
+int pgb_counts_dump(pgb_ctx *, size_t *n_entries);
+int pgb_counts_set_device(pgb_ctx *, const mm_count_t *entries_device, size_t n);
+int pgb_route_scan(pgb_ctx *, uint32_t mc_lower, uint32_t mc_upper, int *has_first);
+int pgb_route_build(pgb_ctx *, uint32_t total_chunk, uint32_t mc_lower, uint32_t mc_upper, int first_found_before, uint64_t *n_per_chunk);
+int pgb_overlap_routed(pgb_ctx *, const void *records_device, size_t n, uint32_t bestn, uint32_t align_bandwidth, uint32_t ovlp_upper);
 
 /* counters for bench.py / profiles */
 typedef struct {

@@ -528,6 +528,59 @@ __global__ void k_pair_write(const mm128 *__restrict__ mm, const uint32_t *__res
   }
 }
 
+// ---- routed form (multi-GPU): a rank scans only ITS OWN shimmer list and emits the records of EVERY hash chunk, each tagged
+// with the chunk that owns it (src/shmr_utils.c:337,362: chunk c of T owns hashes with (x>>8) % T == c % T, so residue v
+// belongs to chunk v, residue 0 to chunk T).  Wire format: 40 bytes {x0, x1, y0, y1, direction} = mp256_t (shimmer.h:123-126).
+struct route_rec { uint64_t k0, k1, y0, y1, dir; };
+__device__ __forceinline__ uint32_t route_dest(uint64_t x, uint32_t T) {  // 0-based owner chunk index (chunk id - 1)
+  uint32_t v = (uint32_t)((x >> 8) % T);
+  return v ? v - 1 : T - 1;
+}
+// kept flags when the global first element (src/shmr_utils.c:311-321) lies in an EARLIER rank's list: every element uses
+// the non-strict bound
+__global__ void k_kept_flags_nonfirst(const uint32_t *__restrict__ cnt, size_t n, uint32_t lower, uint32_t upper, uint32_t *flags) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t c = cnt[i];
+  flags[i] = !(c < lower || c > upper);
+}
+__global__ void k_pair_count_all(const mm128 *__restrict__ mm, const uint32_t *__restrict__ kept, uint32_t n_kept, uint32_t *n_rec) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t + 1 >= n_kept) { if (t < n_kept) n_rec[t] = 0; return; }
+  mm128 m0 = mm[kept[t]], m1 = mm[kept[t + 1]];
+  n_rec[t] = ((m0.y >> 32) == (m1.y >> 32) && pair_far_enough(m0.y, m1.y)) ? 2u : 0u;
+}
+__global__ void k_pair_write_all(const mm128 *__restrict__ mm, const uint32_t *__restrict__ kept, uint32_t n_kept, uint32_t T,
+                                 const uint32_t *__restrict__ rec_off, const uint32_t *__restrict__ rlen_by_rid, route_rec *out,
+                                 uint32_t *dest, uint32_t *idx, uint32_t *per_dest) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t + 1 >= n_kept) return;
+  mm128 m0 = mm[kept[t]], m1 = mm[kept[t + 1]];
+  if ((m0.y >> 32) != (m1.y >> 32) || !pair_far_enough(m0.y, m1.y)) return;
+  uint32_t at = rec_off[t];
+  uint32_t rl = rlen_by_rid[(uint32_t)(m0.y >> 32)];
+  route_rec f, r;
+  f.k0 = m0.x; f.k1 = m1.x; f.y0 = m0.y; f.y1 = m1.y; f.dir = 0;
+  r.k0 = m1.x; r.k1 = m0.x; r.y0 = rev_y(m1.y, m1.x, rl); r.y1 = rev_y(m0.y, m0.x, rl); r.dir = 1;
+  out[at] = f; out[at + 1] = r;
+  uint32_t d0 = route_dest(m0.x, T), d1 = route_dest(m1.x, T);
+  dest[at] = d0; dest[at + 1] = d1;
+  idx[at] = at; idx[at + 1] = at + 1;
+  atomicAdd(&per_dest[d0], 1u);
+  atomicAdd(&per_dest[d1], 1u);
+}
+__global__ void k_route_gather(const route_rec *__restrict__ in, const uint32_t *__restrict__ perm, uint32_t n, route_rec *out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[perm[i]];
+}
+// received records (source ranks concatenated in rank order = insertion order of the owning chunk) -> the SoA build_map form
+__global__ void k_route_unpack(const route_rec *__restrict__ in, uint32_t n, PairSoA o) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  route_rec r = in[i];
+  o.k0[i] = r.k0; o.k1[i] = r.k1; o.y0[i] = r.y0; o.y1[i] = r.y1; o.seq[i] = i; o.dir[i] = (uint8_t)r.dir;
+}
+
 // ------------------------------------------------------------------------------------------------ bucket tables
 // X table: distinct full x values -> slot (a dense id).  B table: (slot(x0)<<32 | slot(x1)) -> bucket.
 __global__ void k_bucket_insert(PairSoA r, uint32_t n_rec, uint64_t *xkeys, uint32_t xmask, uint64_t *bkeys, uint32_t bmask,

@@ -77,18 +77,65 @@ struct pgb_ctx {
   // ---- overlap inputs
   mm128 *d_shm = nullptr; size_t n_shm = 0; bool shm_owned = false;
   uint64_t *d_mckeys = nullptr; uint32_t *d_mcvals = nullptr; uint32_t mcmask = 0;
+  // ---- routed exchange (multi-GPU): dumped partial count table, per-mmer counts of the scan, records grouped by owner chunk
+  mc_entry *d_mc_dump = nullptr; size_t n_mc_dump = 0;
+  uint32_t *d_route_cnt = nullptr; unsigned long long route_first = ~0ULL;
+  void *d_route = nullptr; size_t n_route = 0;
   // ---- overlap output
   ovlp_rec *d_ovl = nullptr; size_t n_ovl = 0;
   void *h_ovl = nullptr; size_t h_ovl_cap = 0;  // page-locked staging of the records (pgb_overlap_host)
   int *d_err = nullptr;
   KhashEmu outer_emu;  // host replay of the outer khash (visiting order), storage reused between calls
 
-  // persistent device memory (reads, index levels, overlap output)
-  template <class T> T *palloc(size_t n) {
-    void *p = nullptr;
-    CU(cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st));
-    return (T *)p;
+  // persistent device memory (reads, index levels, overlap output).  Blocks are recycled through a per-context cache: a
+  // steady-state job asks for the same sizes every step, so after the first step no call reaches the driver's allocator
+  // (the stream-ordered pool re-maps memory when its free list fragments, which showed up as 0.4-0.8 s host stalls).
+  // Every user of a block runs on `st` (or, for d_raw, on st_copy fenced by events that `st` waits on) and every API call
+  // ends with a synchronize of `st`, so handing a released block to the next palloc is safe.
+  struct Blk { void *p; size_t bytes; };
+  std::vector<Blk> blk_cache;
+  std::unordered_map<void *, size_t> blk_live;
+  size_t blk_cached_bytes = 0;
+  void blk_flush() {
+    if (blk_cache.empty()) return;
+    cudaStreamSynchronize(st);
+    for (auto &b : blk_cache) cudaFree(b.p);
+    blk_cache.clear();
+    blk_cached_bytes = 0;
   }
+  void *blk_alloc(size_t bytes) {
+    bytes = (bytes + 511) & ~(size_t)511;
+    int best = -1;
+    for (int i = 0; i < (int)blk_cache.size(); i++)
+      if (blk_cache[i].bytes >= bytes && blk_cache[i].bytes <= bytes + bytes / 4 + (1 << 20) && (best < 0 || blk_cache[i].bytes < blk_cache[best].bytes))
+        best = i;
+    void *p = nullptr;
+    if (best >= 0) {
+      p = blk_cache[best].p;
+      bytes = blk_cache[best].bytes;
+      blk_cached_bytes -= bytes;
+      blk_cache[best] = blk_cache.back();
+      blk_cache.pop_back();
+    } else {
+      // a miss means the job changed shape: stale blocks would only pile up
+      if (blk_cached_bytes > ((size_t)8 << 30) || blk_cache.size() > 256) blk_flush();
+      if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        blk_flush();
+        CU(cudaMalloc(&p, bytes));
+      }
+    }
+    blk_live[p] = bytes;
+    return p;
+  }
+  void blk_release(void *p) {
+    auto it = blk_live.find(p);
+    if (it == blk_live.end()) { cudaFreeAsync(p, st); return; }
+    blk_cache.push_back(Blk{p, it->second});
+    blk_cached_bytes += it->second;
+    blk_live.erase(it);
+  }
+  template <class T> T *palloc(size_t n) { return (T *)blk_alloc((n ? n : 1) * sizeof(T)); }
   // stage temporaries: bump allocation out of slabs that are kept for the lifetime of the context, reset at the end of every
   // API call (no per-step cudaMalloc/cudaFree traffic once the slabs have reached their steady-state size)
   struct Slab { char *base; size_t cap, used; };
@@ -128,7 +175,7 @@ struct pgb_ctx {
     slabs.clear();
   }
   template <class T> void release(T *&p) {
-    if (p && !in_scratch((const void *)p)) cudaFreeAsync((void *)p, st);
+    if (p && !in_scratch((const void *)p)) blk_release((void *)p);
     p = nullptr;
   }
   void sync() { CU(cudaStreamSynchronize(st)); }
@@ -189,6 +236,9 @@ struct pgb_ctx {
     if (shm_owned) release(d_shm);
     d_shm = nullptr; n_shm = 0; shm_owned = false;
     release(d_mckeys); release(d_mcvals);
+    release(d_mc_dump); n_mc_dump = 0;
+    release(d_route_cnt);
+    release(d_route); n_route = 0;
   }
 };
 
@@ -290,6 +340,7 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   c->release(c->d_err);
   c->release(c->d_align_bases);
   cudaStreamSynchronize(c->st);
+  c->blk_flush();
   c->scratch_free();
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
@@ -760,6 +811,8 @@ extern "C" size_t pgb_buffer_elems(pgb_ctx *c, int which) {
     case PGB_BUF_WORDS: case PGB_BUF_NMASK: return c->d_w ? (size_t)c->n_words : 0;
     case PGB_BUF_ROW_RID: case PGB_BUF_ROW_LEN: case PGB_BUF_ROW_WOFF: case PGB_BUF_ROW_HASN: return c->n_rows;
     case PGB_BUF_LEVEL0: case PGB_BUF_LEVEL1: case PGB_BUF_LEVEL2: return c->level_n[which - PGB_BUF_LEVEL0];
+    case PGB_BUF_COUNTS: return c->n_mc_dump;
+    case PGB_BUF_ROUTE: return c->n_route;
     default: return 0;
   }
 }
@@ -781,6 +834,8 @@ extern "C" int pgb_buffer_copy_out(pgb_ctx *c, int which, void *dst) {
       LAUNCH(c, k_rows_hasn, nblk(n), 256, c->d_row_rid, c->d_hasn_by_rid, (uint32_t)n, tmp);
       src = tmp; esz = 4; break;
     case PGB_BUF_LEVEL0: case PGB_BUF_LEVEL1: case PGB_BUF_LEVEL2: src = c->d_level[which - PGB_BUF_LEVEL0]; esz = 16; break;
+    case PGB_BUF_COUNTS: src = c->d_mc_dump; esz = 16; break;
+    case PGB_BUF_ROUTE: src = c->d_route; esz = 40; break;
     default: throw std::runtime_error("unknown buffer id");
   }
   if (n) CU(cudaMemcpyAsync(dst, src, n * esz, cudaMemcpyDeviceToDevice, c->st));
@@ -841,22 +896,10 @@ extern "C" int pgb_set_shimmers_device(pgb_ctx *c, const mm128_t *mmers, size_t 
 }
 
 // ================================================================================================ overlap
-extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t bestn, uint32_t mc_lower, uint32_t mc_upper,
-                           uint32_t bw, uint32_t ovlp_upper) {
-  API_BEGIN(c)
-  if (T == 0 || mychunk == 0 || mychunk > T) throw std::runtime_error("bad chunk spec");
-  if (!c->d_w) throw std::runtime_error("no reads loaded");
-  if (!c->d_shm && c->n_shm) throw std::runtime_error("no shimmers set");
-  if (bw + 3 > PGB_MAXV) throw std::runtime_error("align bandwidth (-w) above 256 is not supported by this build");
-  if (ovlp_upper > 65535) throw std::runtime_error("ovlp_upper (-n) above 65535 is not supported");
-  bestn &= 0xFF;  // uint8_t bestn = atoi(), src/shmr_overlap.c:245,286
-  ensure_rc(c);
-  c->release(c->d_ovl); c->n_ovl = 0;
+// build_map's record stream for hash chunk `mychunk` of T from the context's shimmer list + multiplicity table
+// (src/shmr_utils.c:295-404).  Returns the number of records; R is allocated from the scratch arena.
+static uint32_t build_pair_records(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t mc_lower, uint32_t mc_upper, PairSoA &R) {
   size_t n = c->n_shm;
-  if (n == 0) { c->sync(); return 0; }
-  if (n >= (1ull << 31)) throw std::runtime_error("more than 2^31 shimmers in one overlap call");
-
-  // ---------------- build_map: kept set, adjacent pairs, records
   c->tic();
   uint32_t *cnt = c->alloc<uint32_t>(n);
   uint32_t *flags = c->alloc<uint32_t>(n + 1), *pos = c->alloc<uint32_t>(n + 1);
@@ -873,13 +916,22 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   CU(cudaMemsetAsync(n_rec, 0, ((size_t)n_kept + 1) * 4, c->st));
   LAUNCH(c, k_pair_count, nblk(n_kept), 256, c->d_shm, kept, n_kept, T, mychunk, n_rec);
   uint32_t nrec = scan_u32(c, n_rec, rec_off, (size_t)n_kept + 1);
-  PairSoA R;
   R.k0 = c->alloc<uint64_t>(nrec); R.k1 = c->alloc<uint64_t>(nrec); R.y0 = c->alloc<uint64_t>(nrec); R.y1 = c->alloc<uint64_t>(nrec);
   R.seq = c->alloc<uint32_t>(nrec); R.dir = c->alloc<uint8_t>(nrec);
   LAUNCH(c, k_pair_write, nblk(n_kept), 256, c->d_shm, kept, n_kept, T, mychunk, rec_off, c->d_rlen_by_rid, R);
   c->release(kept); c->release(n_rec); c->release(rec_off);
   c->stats.ms_pairs += c->toc();
   c->stats.n_pair_records += nrec;
+  return nrec;
+}
+
+// process_overlaps (src/shmr_overlap.c:182-231) over a chunk's record stream (records in insertion order, seq ascending).
+// Consumes R.  Returns 0, or -1 with c->err set; throws on resource errors.
+static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, uint32_t bw, uint32_t ovlp_upper) {
+  if (bw + 3 > PGB_MAXV) throw std::runtime_error("align bandwidth (-w) above 256 is not supported by this build");
+  if (ovlp_upper > 65535) throw std::runtime_error("ovlp_upper (-n) above 65535 is not supported");
+  bestn &= 0xFF;  // uint8_t bestn = atoi(), src/shmr_overlap.c:245,286
+  ensure_rc(c);
   auto free_R = [&]() { c->release(R.k0); c->release(R.k1); c->release(R.y0); c->release(R.y1); c->release(R.seq); c->release(R.dir); };
   if (nrec == 0) { free_R(); c->sync(); c->check_err("pgb_overlap/build_map"); return c->err.empty() ? 0 : -1; }
 
@@ -1224,6 +1276,136 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   free_common();
   c->sync();
   c->check_err("pgb_overlap/emit");
+  return c->err.empty() ? 0 : -1;
+}
+
+extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t bestn, uint32_t mc_lower, uint32_t mc_upper,
+                           uint32_t bw, uint32_t ovlp_upper) {
+  API_BEGIN(c)
+  if (T == 0 || mychunk == 0 || mychunk > T) throw std::runtime_error("bad chunk spec");
+  if (!c->d_w) throw std::runtime_error("no reads loaded");
+  if (!c->d_shm && c->n_shm) throw std::runtime_error("no shimmers set");
+  c->release(c->d_ovl); c->n_ovl = 0;
+  if (c->n_shm == 0) { c->sync(); return 0; }
+  if (c->n_shm >= (1ull << 31)) throw std::runtime_error("more than 2^31 shimmers in one overlap call");
+  ensure_loaded(c);
+  PairSoA R;
+  uint32_t nrec = build_pair_records(c, T, mychunk, mc_lower, mc_upper, R);
+  if (overlap_core(c, R, nrec, bestn, bw, ovlp_upper) != 0) return -1;
+  API_END(c)
+}
+
+// ================================================================================================ routed exchange (multi-GPU)
+// Rank r holds the shimmers of ITS reads only.  (1) pgb_counts_dump: its partial multiplicity table as (mer,count) entries;
+// the ranks all-gather them and pgb_counts_set_device sums them (aggregate_mm_count over the -MC- files, src/shmr_utils.c:162-176).
+// (2) pgb_route_scan / pgb_route_build: build_map over the rank's own list, emitting the records of EVERY hash chunk grouped by
+// owner chunk; one all-to-all moves each group to its owner.  (3) pgb_overlap_routed: the owner's records, source ranks
+// concatenated in rank order (= the insertion order of the reference's single scan over the concatenated chunk files).
+extern "C" int pgb_counts_dump(pgb_ctx *c, size_t *n_out) {
+  API_BEGIN(c)
+  if (!c->d_mckeys) throw std::runtime_error("no shimmers set");
+  c->release(c->d_mc_dump); c->n_mc_dump = 0;
+  size_t cap = (size_t)c->mcmask + 1;
+  uint32_t *flags = c->alloc<uint32_t>(cap + 1), *pos = c->alloc<uint32_t>(cap + 1);
+  CU(cudaMemsetAsync(flags, 0, (cap + 1) * 4, c->st));
+  LAUNCH(c, k_mc_flags, nblk(cap), 256, c->d_mckeys, cap, flags);
+  uint32_t distinct = scan_u32(c, flags, pos, cap + 1);
+  c->d_mc_dump = c->palloc<mc_entry>(distinct);
+  LAUNCH(c, k_mc_dump, nblk(cap), 256, c->d_mckeys, c->d_mcvals, pos, cap, c->d_mc_dump);
+  c->n_mc_dump = distinct;
+  if (n_out) *n_out = distinct;
+  API_END(c)
+}
+extern "C" int pgb_counts_set_device(pgb_ctx *c, const mm_count_t *entries_device, size_t n) {
+  API_BEGIN(c)
+  c->tic();
+  build_mc_table(c, (const mc_entry *)entries_device, n);
+  c->stats.ms_count += c->toc();
+  c->check_err("pgb_counts_set_device");
+  API_END(c)
+}
+extern "C" int pgb_route_scan(pgb_ctx *c, uint32_t mc_lower, uint32_t mc_upper, int *has_first) {
+  API_BEGIN(c)
+  if (!c->d_mckeys) throw std::runtime_error("no multiplicity table set");
+  c->release(c->d_route_cnt);
+  size_t n = c->n_shm;
+  c->tic();
+  c->d_route_cnt = c->palloc<uint32_t>(n);
+  unsigned long long *d_first = c->alloc<unsigned long long>(1);
+  CU(cudaMemsetAsync(d_first, 0xFF, 8, c->st));
+  LAUNCH(c, k_count_lookup, nblk(n), 256, c->d_shm, n, c->d_mckeys, c->d_mcvals, c->mcmask, c->d_route_cnt, mc_lower, mc_upper, d_first, c->d_err);
+  c->d2h(&c->route_first, d_first, 8);
+  c->stats.ms_pairs += c->toc();
+  if (has_first) *has_first = c->route_first != ~0ULL;
+  c->check_err("pgb_route_scan");
+  API_END(c)
+}
+extern "C" int pgb_route_build(pgb_ctx *c, uint32_t T, uint32_t mc_lower, uint32_t mc_upper, int first_found_before, uint64_t *n_per_chunk) {
+  API_BEGIN(c)
+  if (T == 0 || T > 4096) throw std::runtime_error("bad chunk count");
+  if (!c->d_route_cnt && c->n_shm) throw std::runtime_error("pgb_route_scan has not run");
+  if (!c->d_rlen_by_rid) throw std::runtime_error("no reads loaded");
+  c->release(c->d_route); c->n_route = 0;
+  for (uint32_t t = 0; t < T; t++) n_per_chunk[t] = 0;
+  size_t n = c->n_shm;
+  if (n == 0) { c->sync(); return 0; }
+  c->tic();
+  uint32_t *flags = c->alloc<uint32_t>(n + 1), *pos = c->alloc<uint32_t>(n + 1);
+  CU(cudaMemsetAsync(flags, 0, (n + 1) * 4, c->st));
+  if (first_found_before) {
+    LAUNCH(c, k_kept_flags_nonfirst, nblk(n), 256, c->d_route_cnt, n, mc_lower, mc_upper, flags);
+  } else {
+    unsigned long long *d_first = c->alloc<unsigned long long>(1);
+    c->h2d(d_first, &c->route_first, 8);
+    LAUNCH(c, k_kept_flags, nblk(n), 256, c->d_route_cnt, n, mc_lower, mc_upper, d_first, flags);
+  }
+  uint32_t n_kept = scan_u32(c, flags, pos, n + 1);
+  uint32_t *kept = c->alloc<uint32_t>(n_kept);
+  LAUNCH(c, k_compact_idx, nblk(n), 256, flags, pos, n, kept);
+  uint32_t *n_rec = c->alloc<uint32_t>((size_t)n_kept + 1), *rec_off = c->alloc<uint32_t>((size_t)n_kept + 1);
+  CU(cudaMemsetAsync(n_rec, 0, ((size_t)n_kept + 1) * 4, c->st));
+  LAUNCH(c, k_pair_count_all, nblk(n_kept), 256, c->d_shm, kept, n_kept, n_rec);
+  uint32_t nrec = scan_u32(c, n_rec, rec_off, (size_t)n_kept + 1);
+  route_rec *raw = c->alloc<route_rec>(nrec);
+  uint32_t *dest = c->alloc<uint32_t>(nrec), *dest2 = c->alloc<uint32_t>(nrec), *idx = c->alloc<uint32_t>(nrec), *perm = c->alloc<uint32_t>(nrec);
+  uint32_t *per_dest = c->alloc<uint32_t>(T);
+  CU(cudaMemsetAsync(per_dest, 0, (size_t)T * 4, c->st));
+  LAUNCH(c, k_pair_write_all, nblk(n_kept), 256, c->d_shm, kept, n_kept, T, rec_off, c->d_rlen_by_rid, raw, dest, idx, per_dest);
+  c->d_route = c->palloc<route_rec>(nrec);
+  if (nrec) {
+    int bits = 1;
+    while ((1u << bits) < T) bits++;
+    size_t tmp_bytes = 0;  // stable: records of one destination keep their scan (= insertion) order
+    CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, dest, dest2, idx, perm, (int)nrec, 0, bits, c->st));
+    uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+    CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, dest, dest2, idx, perm, (int)nrec, 0, bits, c->st));
+    c->stats.kernel_launches += 3;
+    LAUNCH(c, k_route_gather, nblk(nrec), 256, raw, perm, nrec, (route_rec *)c->d_route);
+  }
+  std::vector<uint32_t> h(T);
+  c->d2h(h.data(), per_dest, (size_t)T * 4);
+  for (uint32_t t = 0; t < T; t++) n_per_chunk[t] = h[t];
+  c->n_route = nrec;
+  c->release(c->d_route_cnt);
+  c->stats.ms_pairs += c->toc();
+  c->stats.n_pair_records += nrec;
+  c->check_err("pgb_route_build");
+  API_END(c)
+}
+extern "C" int pgb_overlap_routed(pgb_ctx *c, const void *records_device, size_t n, uint32_t bestn, uint32_t bw, uint32_t ovlp_upper) {
+  API_BEGIN(c)
+  if (!c->d_w) throw std::runtime_error("no reads loaded");
+  if (n >= (1ull << 32)) throw std::runtime_error("more than 2^32 pair records in one overlap call");
+  c->release(c->d_ovl); c->n_ovl = 0;
+  ensure_loaded(c);
+  uint32_t nrec = (uint32_t)n;
+  PairSoA R;
+  c->tic();
+  R.k0 = c->alloc<uint64_t>(nrec); R.k1 = c->alloc<uint64_t>(nrec); R.y0 = c->alloc<uint64_t>(nrec); R.y1 = c->alloc<uint64_t>(nrec);
+  R.seq = c->alloc<uint32_t>(nrec); R.dir = c->alloc<uint8_t>(nrec);
+  LAUNCH(c, k_route_unpack, nblk(nrec), 256, (const route_rec *)records_device, nrec, R);
+  c->stats.ms_pairs += c->toc();
+  if (overlap_core(c, R, nrec, bestn, bw, ovlp_upper) != 0) return -1;
   API_END(c)
 }
 

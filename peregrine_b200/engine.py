@@ -88,6 +88,11 @@ def load_library():
     L.pgb_buffer_copy_out.argtypes = [vp, C.c_int, vp]
     L.pgb_load_packed_device.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp, vp, C.c_size_t]
     L.pgb_set_shimmers_device.argtypes = [vp, vp, C.c_size_t]
+    L.pgb_counts_dump.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.pgb_counts_set_device.argtypes = [vp, vp, C.c_size_t]
+    L.pgb_route_scan.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
+    L.pgb_route_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u64p]
+    L.pgb_overlap_routed.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32]
     L.pgb_stats_reset.argtypes = [vp]
     L.pgb_stats_get.argtypes = [vp, C.POINTER(_Stats)]
     L.pgb_event_record.argtypes = [vp, C.c_int]
@@ -224,6 +229,33 @@ class Engine:
 
     def set_shimmers_device(self, mm_ptr: int, n: int):
         self._ck(self.L.pgb_set_shimmers_device(self.h, C.c_void_p(mm_ptr), n), "pgb_set_shimmers_device")
+
+    # ------------------------------------------------------------------ routed exchange (pair records travel)
+    BUF_COUNTS, BUF_ROUTE = 11, 12
+
+    def counts_dump(self) -> int:
+        n = C.c_size_t()
+        self._ck(self.L.pgb_counts_dump(self.h, C.byref(n)), "pgb_counts_dump")
+        return n.value
+
+    def counts_set_device(self, entries_ptr: int, n: int):
+        self._ck(self.L.pgb_counts_set_device(self.h, C.c_void_p(entries_ptr), n), "pgb_counts_set_device")
+
+    def route_scan(self, mc_lower=2, mc_upper=240) -> bool:
+        f = C.c_int()
+        self._ck(self.L.pgb_route_scan(self.h, mc_lower, mc_upper, C.byref(f)), "pgb_route_scan")
+        return bool(f.value)
+
+    def route_build(self, total_chunk, mc_lower=2, mc_upper=240, first_found_before=False):
+        out = (C.c_uint64 * total_chunk)()
+        self._ck(self.L.pgb_route_build(self.h, total_chunk, mc_lower, mc_upper, int(first_found_before), out), "pgb_route_build")
+        return [int(x) for x in out]
+
+    def overlap_routed(self, records_ptr: int, n: int, bestn=4, align_bandwidth=100, ovlp_upper=120, copy=True):
+        self._ck(self.L.pgb_overlap_routed(self.h, C.c_void_p(records_ptr), n, bestn, align_bandwidth, ovlp_upper), "pgb_overlap_routed")
+        if copy is False:
+            return self.L.pgb_overlap_size(self.h)
+        return self.overlap_records(view=(copy == "view"))
 
     # ------------------------------------------------------------------ stats
     def event_record(self, slot):

@@ -3,11 +3,17 @@ shards its processes (rid % T for shmr_index, src/shmr_index.c:157; (hash % T) f
 with T = world size and rank r owning chunk r + 1.
 
 The reference's "exchange" is the shared file system: every shmr_overlap process reads ALL L2 chunk files and mmaps the whole
-.seqdb (src/shmr_overlap.c:359-382,200).  Here it is one collective step over NVLink (torch.distributed / NCCL):
+.seqdb (src/shmr_overlap.c:359-382,200).  Here it is one collective step over NVLink (torch.distributed / NCCL), in two forms:
 
-  * all-gather of the 2-bit packed reads + read table (so that any rank can align any pair of reads), and
-  * all-gather of the per-chunk SHIMMER lists in chunk order (= the reference's file concatenation order, which fixes the
-    hash-table insertion order and therefore the output order).
+  routed (ShardedJob.index_and_route, the default of bench.py; BASELINE.json north_star / SURVEY 8e):
+  * all-gather + sum of the per-rank partial multiplicity tables (aggregate_mm_count over the -MC- files, shmr_utils.c:162-176),
+  * every rank runs build_map over the shimmers of ITS reads and emits the SHIMMER-pair records of every hash chunk; ONE
+    all-to-all sends each 40-byte record to the rank that owns its chunk; records received from ranks 0..N-1 in rank order
+    are exactly the insertion order of the reference's scan over the concatenated chunk files,
+  * all-gather of the 2-bit packed reads + read table (so that the owner can align any pair of reads).
+
+  gathered (ShardedJob.index_and_exchange): all-gather of the packed reads and of the per-chunk SHIMMER lists in chunk order;
+  every rank then scans the whole list and keeps the records of its chunk (closest to what the reference processes do).
 
 After the exchange no rank needs another rank again (rid_pairs is per chunk in the reference as well).  The functions below
 are device-agnostic torch code so that the layout logic is covered by gloo/CPU tests; the engine calls move bytes between
@@ -66,6 +72,34 @@ def exchange_shimmers(l2: torch.Tensor, group=None):
     return torch.cat(all_gather_var(l2, group))
 
 
+def all_to_all_var(send: torch.Tensor, split_sizes, group=None):
+    """send: (n, ...) rows grouped by destination rank, split_sizes[d] rows for rank d.  One all-to-all of the counts, one of
+    the rows.  Returns (received rows, concatenated in source-rank order; list of per-source row counts)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    assert len(split_sizes) == world and sum(split_sizes) == send.shape[0]
+    n_out = torch.tensor(list(split_sizes), dtype=torch.int64, device=send.device)
+    n_in = torch.empty_like(n_out)
+    dist.all_to_all_single(n_in, n_out, group=group)
+    in_sizes = [int(x) for x in n_in.tolist()]
+    recv = torch.empty((sum(in_sizes),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=in_sizes, input_split_sizes=list(split_sizes), group=group)
+    return recv, in_sizes
+
+
+def first_found_before(has_first: bool, device, group=None) -> bool:
+    """build_map treats the FIRST kept element of the concatenated list specially (src/shmr_utils.c:311-321); with the list
+    split by rank, a rank needs to know whether a lower rank already holds that element."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    f = torch.tensor([1 if has_first else 0], dtype=torch.int64, device=device)
+    fs = [torch.zeros_like(f) for _ in range(world)]
+    dist.all_gather(fs, f, group=group)
+    return any(int(x.item()) for x in fs[:rank])
+
+
 # ------------------------------------------------------------------------------------------------ engine <-> torch
 def export_reads(eng, device):
     """Copy the engine's packed reads + read table into fresh torch tensors on `device` (a CUDA device)."""
@@ -84,6 +118,22 @@ def export_level(eng, level, device):
     n = eng.buffer_elems(eng.BUF_LEVEL0 + level)
     t = torch.empty((n, 2), dtype=torch.int64, device=device)
     eng.buffer_copy_out(eng.BUF_LEVEL0 + level, t.data_ptr())
+    return t
+
+
+def export_counts(eng, device):
+    """This rank's partial multiplicity table as an (n, 2) int64 tensor of (mer, count) rows (mm_count_t, 16 bytes)."""
+    n = eng.counts_dump()
+    t = torch.empty((n, 2), dtype=torch.int64, device=device)
+    eng.buffer_copy_out(eng.BUF_COUNTS, t.data_ptr())
+    return t
+
+
+def export_route(eng, device):
+    """The routed SHIMMER-pair records of pgb_route_build: (n, 5) int64 rows {x0, x1, y0, y1, direction}, grouped by owner."""
+    n = eng.buffer_elems(eng.BUF_ROUTE)
+    t = torch.empty((n, 5), dtype=torch.int64, device=device)
+    eng.buffer_copy_out(eng.BUF_ROUTE, t.data_ptr())
     return t
 
 
@@ -106,8 +156,10 @@ class ShardedJob:
 
     def __init__(self, idx_eng, ovl_eng, rank, world, device, group=None):
         self.idx_eng, self.ovl_eng, self.rank, self.world, self.device, self.group = idx_eng, ovl_eng, rank, world, device, group
+        self.routed = None  # set by index_and_route: the records this rank owns
 
     def index_and_exchange(self, w, k, r):
+        self.routed = None
         self.idx_eng.index(w, k, r, 2, 0)
         part = export_reads(self.idx_eng, self.device)
         l2 = export_level(self.idx_eng, 2, self.device)
@@ -120,4 +172,30 @@ class ShardedJob:
         return int(reads["words"].shape[0]) * 12 + int(l2_all.shape[0]) * 16  # bytes this rank ends up holding from the exchange
 
     def overlap(self, bestn=4, mc_lower=2, mc_upper=240, bw=100, ovlp_upper=120, copy=True):
+        if self.routed is not None:
+            return self.ovl_eng.overlap_routed(self.routed.data_ptr(), int(self.routed.shape[0]), bestn, bw, ovlp_upper, copy=copy)
         return self.ovl_eng.overlap(self.world, self.rank + 1, bestn, mc_lower, mc_upper, bw, ovlp_upper, copy=copy)
+
+    def index_and_route(self, w, k, r, mc_lower=2, mc_upper=240):
+        """north_star's exchange: the SHIMMER-pair records travel.  Every rank runs build_map over its own reads' shimmers
+        with GLOBAL multiplicities (all-gather + sum of the partial count tables, as aggregate_mm_count does over the -MC-
+        files) and sends each record to the rank that owns its hash chunk with ONE all-to-all; the packed reads are
+        all-gathered so that the owner can align any pair.  Returns the bytes this rank received."""
+        E = self.idx_eng
+        E.index(w, k, r, 2, 0)
+        E.set_shimmers_from_index(2)
+        part = export_reads(E, self.device)
+        counts = export_counts(E, self.device)
+        torch.cuda.synchronize(self.device)
+        all_counts = torch.cat(all_gather_var(counts, self.group)).contiguous()
+        E.counts_set_device(all_counts.data_ptr(), int(all_counts.shape[0]))
+        has_first = E.route_scan(mc_lower, mc_upper)
+        before = first_found_before(has_first, self.device, self.group)
+        per_chunk = E.route_build(self.world, mc_lower, mc_upper, before)
+        send = export_route(E, self.device)
+        torch.cuda.synchronize(self.device)
+        self.routed, _ = all_to_all_var(send, per_chunk, self.group)  # chunk c is owned by rank c-1
+        reads = exchange_reads(part, self.group)
+        torch.cuda.synchronize(self.device)
+        import_reads(self.ovl_eng, reads)
+        return int(reads["words"].shape[0]) * 12 + int(self.routed.shape[0]) * 40 + int(all_counts.shape[0]) * 16

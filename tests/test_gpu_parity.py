@@ -270,3 +270,49 @@ def test_sharded_exchange_matches_reference(sim1, workdir, ref_dir):
         assert len(ov) == len(want) and ov.tobytes() == want.tobytes(), f"chunk {r + 1}"
     for e in engs:
         e.close()
+
+
+def test_routed_exchange_matches_reference(sim1, workdir, ref_dir):
+    """north_star's exchange on one device: three 'ranks' each scan only their own reads' shimmers with the summed
+    multiplicity tables, emit the pair records of every hash chunk grouped by owner (pgb_route_build), the groups are moved
+    as the all-to-all of peregrine_b200.multigpu does (source ranks concatenated in rank order), and every owner runs
+    pgb_overlap_routed; records must equal the reference's shmr_overlap -t 3 -c {1,2,3} over 3 index chunk files."""
+    import torch
+    from peregrine_b200 import Engine, multigpu as M
+
+    T = 3
+    dev = torch.device("cuda", 0)
+    rid, ln, off = F.read_idx(sim1 + ".idx")
+    seqdb = np.fromfile(sim1 + ".seqdb", dtype=np.uint8)
+    engs = [Engine(0) for _ in range(T)]
+    parts, counts = [], []
+    for r in range(T):
+        engs[r].load_reads(seqdb, rid, ln, off, T, r + 1)
+        engs[r].index(80, 16, 6, 2)
+        engs[r].set_shimmers_from_index(2)
+        parts.append(M.export_reads(engs[r], dev))
+        counts.append(M.export_counts(engs[r], dev))
+    all_counts = torch.cat(counts).contiguous()
+    has_first, sends, splits = [], [], []
+    for r in range(T):
+        engs[r].counts_set_device(all_counts.data_ptr(), int(all_counts.shape[0]))
+        has_first.append(engs[r].route_scan(2, 240))
+    for r in range(T):
+        per_chunk = engs[r].route_build(T, 2, 240, any(has_first[:r]))
+        send = M.export_route(engs[r], dev)
+        assert sum(per_chunk) == send.shape[0]
+        sends.append(send)
+        splits.append(np.concatenate([[0], np.cumsum(per_chunk)]))
+    reads = M.concat_reads(parts)
+    rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref3"), T=T, extra=["-m", "0"])
+    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref3o"), T=T)
+    ovl = Engine(0)
+    M.import_reads(ovl, reads)
+    for d in range(T):  # owner of chunk d + 1
+        recv = torch.cat([sends[src][int(splits[src][d]): int(splits[src][d + 1])] for src in range(T)]).contiguous()
+        ov = ovl.overlap_routed(recv.data_ptr(), int(recv.shape[0]))
+        want = F.normalise_ovlp(F.read_ovlp(ro[d]))
+        assert len(ov) == len(want) and ov.tobytes() == want.tobytes(), f"chunk {d + 1}"
+    ovl.close()
+    for e in engs:
+        e.close()

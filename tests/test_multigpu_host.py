@@ -36,7 +36,12 @@ def _worker(rank, world, port, q):
     reads = M.exchange_reads(part)
     l2 = torch.arange(2 * (5 + 3 * rank), dtype=torch.int64).reshape(-1, 2) + 1000 * rank
     l2_all = M.exchange_shimmers(l2)
-    q.put((rank, {k: v.numpy() for k, v in reads.items()}, l2_all.numpy()))
+    # routed exchange: rank r sends (r + 1) * (d + 2) rows to rank d, rows tagged (source, destination, running number)
+    sizes = [(rank + 1) * (d + 2) for d in range(world)]
+    send = torch.tensor([[rank, d, i, 0, 0] for d in range(world) for i in range(sizes[d])], dtype=torch.int64).reshape(-1, 5)
+    recv, in_sizes = M.all_to_all_var(send, sizes)
+    before = M.first_found_before(rank == 1, torch.device("cpu"))
+    q.put((rank, {k: v.numpy() for k, v in reads.items()}, l2_all.numpy(), recv.numpy(), in_sizes, before))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,7 +62,12 @@ def test_exchange_with_gloo_world2():
         assert p.exitcode == 0
     parts = [_part(0), _part(1)]
     want = M.concat_reads(parts)
-    for rank, reads, l2_all in got:
+    for rank, _, _, recv, in_sizes, before in got:
+        assert in_sizes == [(src + 1) * (rank + 2) for src in range(2)]
+        want_rows = [[src, rank, i, 0, 0] for src in range(2) for i in range((src + 1) * (rank + 2))]  # source-rank order, scan order inside
+        assert recv.tolist() == want_rows
+        assert before is False  # only rank 1 holds a "first" element, and no rank lies after it
+    for rank, reads, l2_all, *_ in got:
         for k in M.READ_KEYS:
             assert np.array_equal(reads[k], want[k].numpy()), (rank, k)
         # every row's words are where row_woff says they are, in the concatenated array
