@@ -175,6 +175,20 @@ int pgb_route_scan(pgb_ctx *, uint32_t mc_lower, uint32_t mc_upper, int *has_fir
 int pgb_route_build(pgb_ctx *, uint32_t total_chunk, uint32_t mc_lower, uint32_t mc_upper, int first_found_before, uint64_t *n_per_chunk);
 int pgb_overlap_routed(pgb_ctx *, const void *records_device, size_t n, uint32_t bestn, uint32_t align_bandwidth, uint32_t ovlp_upper);
 
+/* ---- shmr_dedup: raw ovlp_t stream -> preads.ovl text ------------------------------------------------------
+ * replaces main() of src/shmr_dedup.c:19-101: keeps the FIRST record of every unordered read pair in stream order (the
+ * concatenation of the chunk files, `cat ovlp-*.dat | shmr_dedup`, py/scripts/pg_run.py:352) and prints
+ * "%09d %09d %d %0.1f %u %d %d %u %u %d %d %u %s\n" per kept record, byte-identical to the reference (incl. its unsigned
+ * coordinate arithmetic and "%0.1f" rounding).  An EMPTY stream yields no output (the reference prints one line from an
+ * uninitialised struct).  pgb_shmr_dedup_main: stdin -> stdout, no options. */
+int pgb_shmr_dedup_main(int argc, char **argv);
+int pgb_dedup(pgb_ctx *, const ovlp_t *records, size_t n);               /* host stream                                   */
+int pgb_dedup_device(pgb_ctx *, const ovlp_t *records_device, size_t n); /* stream already in HBM                         */
+int pgb_dedup_overlaps(pgb_ctx *);                                       /* the records of the last pgb_overlap, in place */
+size_t pgb_dedup_kept(pgb_ctx *);
+size_t pgb_dedup_text_bytes(pgb_ctx *);
+int pgb_dedup_text_copy(pgb_ctx *, char *out);                           /* device -> host, pgb_dedup_text_bytes bytes     */
+
 /* counters for bench.py / profiles */
 typedef struct {
   uint64_t kernel_launches;      /* launches of this library's kernels since pgb_stats_reset */
@@ -189,6 +203,8 @@ typedef struct {
   double ms_k_sketch_tiled;
   uint64_t n_k_sketch_tiled, n_sketch_fallback_reads;
   uint64_t n_replay_buckets;     /* buckets replayed, summed over passes (incremental passes replay only dirty buckets) */
+  double ms_dedup;               /* shmr_dedup stage */
+  uint64_t n_dedup_in, n_dedup_kept;
 } pgb_stats;
 void pgb_stats_reset(pgb_ctx *);
 /* CUDA events on the context's stream (the stream every kernel of this library is launched on): record slot 0..7, then

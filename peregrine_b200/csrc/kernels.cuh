@@ -298,13 +298,26 @@ __device__ __forceinline__ uint32_t block_exscan_256(uint32_t v, uint32_t *scrat
   return base + x - v;
 }
 
-// One CTA = one tile of one read.  tile_off[row] = first tile of the row (exclusive prefix, n_rows+1 entries).
+// Per-tile descriptor, written once per pgb_index call by k_tile_desc (one thread per row): the sketch CTAs find their read
+// with ONE broadcast load instead of a 17-step binary search by thread 0 behind a barrier (31 % of the kernel's warp time
+// was spent waiting at that barrier, profiles/r1g_ncu.md).
+struct TileDesc { uint64_t word_off; uint32_t len, rid, j, row; };
+__global__ void k_tile_desc(const uint32_t *__restrict__ tile_off, uint32_t n_rows, const uint32_t *__restrict__ row_rid,
+                            const uint32_t *__restrict__ row_len, const uint64_t *__restrict__ row_woff, TileDesc *desc) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  TileDesc d;
+  d.word_off = row_woff[row]; d.len = row_len[row]; d.rid = row_rid[row]; d.row = row;
+  const uint32_t t0 = tile_off[row], t1 = tile_off[row + 1];
+  for (uint32_t t = t0; t < t1; t++) { d.j = t - t0; desc[t] = d; }
+}
+
+// One CTA = one tile of one read.
 // Output: tile_cnt[tile] records in tmp[tile * SK_CAP ...] (position order); row_flags[row] |= reason when the read must be
 // redone by the exact automaton (the tile then reports 0 records).
 template <class HT>
-__global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__restrict__ w, const uint32_t *__restrict__ tile_off, uint32_t n_rows,
-                                                             const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ row_len,
-                                                             const uint64_t *__restrict__ row_woff, const uint32_t *__restrict__ hasn_by_rid,
+__global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__restrict__ w, const TileDesc *__restrict__ desc,
+                                                             const uint32_t *__restrict__ hasn_by_rid,
                                                              int wsz, int k, uint32_t *__restrict__ tile_cnt, uint32_t *row_flags,
                                                              mm128 *__restrict__ tmp, uint32_t tile_cap, uint32_t tile_base) {
   extern __shared__ __align__(16) unsigned char sk_smem[];
@@ -312,20 +325,13 @@ __global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__r
   sk_tile_layout<HT>(sh, sk_smem, wsz);
   const uint32_t tile = tile_base + blockIdx.x;
   const int tid = threadIdx.x;
-  if (tid == 0) {  // owning row: last row with tile_off[row] <= tile
-    uint32_t lo = 0, hi = n_rows;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (tile_off[mid] <= tile) lo = mid; else hi = mid;
-    }
-    sh.scan[12] = lo;
-  }
+  const TileDesc td = desc[tile];  // same address for the whole CTA: one broadcast transaction
   if (tid >= 32 && tid < 36) sh.ctr[tid - 32] = 0;
   __syncthreads();
-  const uint32_t row = sh.scan[12];
-  const int j = (int)(tile - tile_off[row]);
+  const uint32_t row = td.row;
+  const int j = (int)td.j;
   SkParams p;
-  p.w = w; p.word_off = row_woff[row]; p.len = (int)row_len[row]; p.rid = row_rid[row]; p.wsz = wsz; p.k = k;
+  p.w = w; p.word_off = td.word_off; p.len = (int)td.len; p.rid = td.rid; p.wsz = wsz; p.k = k;
   const int H = sk_halo(wsz), TILE = sk_tile_len(wsz);
   p.r0 = j * TILE - H; p.first_tile = j == 0;
   if (hasn_by_rid[p.rid] || p.len < sk_min_len(wsz, k)) {  // block-uniform
@@ -1292,6 +1298,15 @@ __global__ void k_compact_classes(const uint32_t *__restrict__ flags, const uint
   if (flags[i]) list[pos[i]] = i < n_ranks ? i : i - n_ranks;
 }
 
+// sort key of a bucket in a replay run list: larger buckets first, so that the 32 buckets a warp of k_replay walks have
+// similar sizes (one thread = one bucket; the lanes of a warp wait for the largest bucket among them)
+__global__ void k_size_keys(const uint32_t *__restrict__ list, uint32_t n, const uint32_t *__restrict__ rank_off, uint32_t max_n, uint32_t *keys) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = list[i], sz = rank_off[r + 1] - rank_off[r];
+  keys[i] = max_n - (sz < max_n ? sz : max_n);
+}
+
 // ------------------------------------------------------------------------------------------------ shimmer4py index handle
 // per read id: index of its first minimizer in the concatenated list and how many it has (get_ridmm, src/shmr_utils.c:415-443)
 __global__ void k_ridmm(const mm128 *__restrict__ mm, size_t n, uint32_t *first, uint32_t *count) {
@@ -1406,3 +1421,5 @@ __global__ void k_table_diff(const uint64_t *__restrict__ a, const uint64_t *__r
 }
 
 }  // namespace pgb
+
+#include "dedup.cuh"

@@ -81,6 +81,8 @@ struct pgb_ctx {
   mc_entry *d_mc_dump = nullptr; size_t n_mc_dump = 0;
   uint32_t *d_route_cnt = nullptr; unsigned long long route_first = ~0ULL;
   void *d_route = nullptr; size_t n_route = 0;
+  // ---- dedup output (preads.ovl text)
+  char *d_dedup_text = nullptr; size_t dedup_bytes = 0, dedup_kept = 0;
   // ---- overlap output
   ovlp_rec *d_ovl = nullptr; size_t n_ovl = 0;
   void *h_ovl = nullptr; size_t h_ovl_cap = 0;  // page-locked staging of the records (pgb_overlap_host)
@@ -212,7 +214,7 @@ struct pgb_ctx {
     if (e) {
       char buf[256];
       snprintf(buf, sizeof buf, "device error flag 0x%x in %s (4=count table full, 8=mer missing from count table, 16=bucket table full, "
-               "32=pair table full, 64=alignment queue full, 128=ovlp_match band state)", e, where);
+               "32=pair table full, 64=alignment queue full, 128=ovlp_match band state, 256=dedup pair table)", e, where);
       err = buf;
       int z = 0;
       h2d(d_err, &z, sizeof z);
@@ -336,6 +338,7 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   c->free_index();
   c->free_reads();
   c->release(c->d_ovl);
+  c->release(c->d_dedup_text);
   if (c->h_ovl) cudaFreeHost(c->h_ovl);
   c->release(c->d_err);
   c->release(c->d_align_bases);
@@ -627,6 +630,8 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     if (tile_cap > SK_CAP) tile_cap = SK_CAP;
     mm128 *tmp = c->alloc<mm128>((size_t)n_tiles * tile_cap);
     c->h2d(tile_off, h_tile_off.data(), (ns + 1) * 4);
+    TileDesc *tile_desc = c->alloc<TileDesc>(n_tiles);
+    LAUNCH(c, k_tile_desc, nblk(ns), 256, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff, tile_desc);
     CU(cudaMemsetAsync(row_flags, 0, ns * 4, c->st));
     CU(cudaMemsetAsync(exact_flag, 0, (ns + 1) * 4, c->st));
     const bool k32 = k <= 16;
@@ -636,11 +641,9 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     auto launch_tiles = [&](uint32_t t0, uint32_t t1) {  // tiles [t0, t1)
       if (t1 <= t0) return;
       if (k32)
-        k_sketch_tiled<uint32_t><<<t1 - t0, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
-                                                                        c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap, t0);
+        k_sketch_tiled<uint32_t><<<t1 - t0, SK_THREADS, smem, c->st>>>(c->d_w, tile_desc, c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap, t0);
       else
-        k_sketch_tiled<uint64_t><<<t1 - t0, SK_THREADS, smem, c->st>>>(c->d_w, tile_off, (uint32_t)ns, c->d_row_rid, c->d_row_len, c->d_row_woff,
-                                                                        c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap, t0);
+        k_sketch_tiled<uint64_t><<<t1 - t0, SK_THREADS, smem, c->st>>>(c->d_w, tile_desc, c->d_hasn_by_rid, w, k, tile_cnt, row_flags, tmp, tile_cap, t0);
       c->stats.kernel_launches++;
       CU(cudaGetLastError());
     };
@@ -720,6 +723,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
       c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
       c->release(exact_list); c->release(seg_row); c->release(seg_lo); c->release(seg_first); c->release(list_first); c->release(seg_cnt); c->release(seg_pos);
     }
+    c->release(tile_desc);
     c->release(tile_off); c->release(tile_cnt); c->release(row_flags); c->release(exact_flag); c->release(exact_pos); c->release(tmp);
   }
   c->stats.ms_sketch += c->toc();
@@ -1123,6 +1127,19 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   };
   uint32_t n_all = 0;
   const uint32_t n_all_small = class_lists(nullptr, all_list, &n_all);
+  if (n_all_small > 64 && !getenv("PGB_REPLAY_UNSORTED")) {  // group buckets of similar size into the same warps (stable: rank order inside a size)
+    uint32_t *keys = c->alloc<uint32_t>(n_all_small), *keys2 = c->alloc<uint32_t>(n_all_small), *list2 = c->alloc<uint32_t>(n_all_small);
+    int bits = 1;
+    while ((1u << bits) <= BIG_N && bits < 31) bits++;
+    LAUNCH(c, k_size_keys, nblk(n_all_small), 256, all_list, n_all_small, d_rank_off, BIG_N, keys);
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, keys, keys2, all_list, list2, (int)n_all_small, 0, bits, c->st));
+    uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+    CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, keys2, all_list, list2, (int)n_all_small, 0, bits, c->st));
+    c->stats.kernel_launches += 3;
+    CU(cudaMemcpyAsync(all_list, list2, (size_t)n_all_small * 4, cudaMemcpyDeviceToDevice, c->st));
+    c->release(keys); c->release(keys2); c->release(list2); c->release(tmp);
+  }
   auto free_common = [&]() {
     c->release(rid_sorted); c->release(rank_sorted); c->release(bloom); c->release(changed); c->release(unk_flag); c->release(dirty);
     c->release(dflags); c->release(dpos); c->release(dlist); c->release(all_list); c->release(acc); c->release(out_off); c->release(d_ctr);
@@ -1431,6 +1448,59 @@ extern "C" int pgb_overlap_host(pgb_ctx *c, const ovlp_t **out, size_t *n) {
   API_END(c)
 }
 
+// ================================================================================================ shmr_dedup
+// first record of every unordered read pair, in stream order, as preads.ovl text (src/shmr_dedup.c:19-101)
+static void dedup_core(pgb_ctx *c, const ovlp_rec *d_recs, size_t n) {
+  c->release(c->d_dedup_text); c->dedup_bytes = 0; c->dedup_kept = 0;
+  if (n == 0) return;
+  if (n >= (1ull << 31)) throw std::runtime_error("more than 2^31 records in one dedup call");
+  c->tic();
+  const uint32_t cap = pow2_at_least(2 * (uint64_t)n + 16);
+  uint64_t *keys = c->alloc<uint64_t>(cap);
+  unsigned long long *first = c->alloc<unsigned long long>(cap), *d_kept = c->alloc<unsigned long long>(1);
+  uint32_t *slot_of = c->alloc<uint32_t>(n), *len = c->alloc<uint32_t>(n + 1);
+  uint64_t *off = c->alloc<uint64_t>(n + 1);
+  LAUNCH(c, k_fill_u64, 1184, 256, keys, PGB_EMPTY, (size_t)cap);
+  CU(cudaMemsetAsync(first, 0xFF, (size_t)cap * 8, c->st));
+  CU(cudaMemsetAsync(d_kept, 0, 8, c->st));
+  CU(cudaMemsetAsync(len + n, 0, 4, c->st));
+  LAUNCH(c, k_dedup_insert, nblk(n), 256, d_recs, n, keys, cap - 1, first, slot_of, c->d_err);
+  LAUNCH(c, k_dedup_len, nblk(n), 256, d_recs, n, first, slot_of, len, d_kept);
+  const uint64_t bytes = scan_u32_to_u64(c, len, off, n + 1);
+  c->d_dedup_text = c->palloc<char>(bytes);
+  LAUNCH(c, k_dedup_write, nblk(n), 256, d_recs, n, len, off, c->d_dedup_text);
+  unsigned long long kept = 0;
+  c->d2h(&kept, d_kept, 8);
+  c->dedup_bytes = bytes; c->dedup_kept = kept;
+  c->stats.ms_dedup += c->toc();
+  c->stats.n_dedup_in += n; c->stats.n_dedup_kept += kept;
+  c->check_err("pgb_dedup");
+}
+extern "C" int pgb_dedup(pgb_ctx *c, const ovlp_t *records, size_t n) {
+  API_BEGIN(c)
+  ovlp_rec *d = c->alloc<ovlp_rec>(n);
+  c->h2d(d, records, n * sizeof(ovlp_rec));
+  dedup_core(c, d, n);
+  API_END(c)
+}
+extern "C" int pgb_dedup_device(pgb_ctx *c, const ovlp_t *records_device, size_t n) {
+  API_BEGIN(c)
+  dedup_core(c, (const ovlp_rec *)records_device, n);
+  API_END(c)
+}
+extern "C" int pgb_dedup_overlaps(pgb_ctx *c) {
+  API_BEGIN(c)
+  dedup_core(c, c->d_ovl, c->n_ovl);
+  API_END(c)
+}
+extern "C" size_t pgb_dedup_kept(pgb_ctx *c) { return c ? c->dedup_kept : 0; }
+extern "C" size_t pgb_dedup_text_bytes(pgb_ctx *c) { return c ? c->dedup_bytes : 0; }
+extern "C" int pgb_dedup_text_copy(pgb_ctx *c, char *out) {
+  API_BEGIN(c)
+  c->d2h(out, c->d_dedup_text, c->dedup_bytes);
+  API_END(c)
+}
+
 // ================================================================================================ command-line tools
 static pgb_ctx *cli_ctx() {
   int dev = 0;
@@ -1565,6 +1635,36 @@ extern "C" int pgb_shmr_overlap_main(int argc, char **argv) {
   CLI_CHECK(c, pgb_overlap_host(c, &recs_p, &recs_n));
   if (recs_n) fwrite(recs_p, sizeof(ovlp_t), recs_n, out);
   fclose(out);
+  pgb_destroy(c);
+  return 0;
+}
+
+// shmr_dedup: raw ovlp_t stream on stdin -> preads.ovl text on stdout (src/shmr_dedup.c:19-101; no options)
+extern "C" int pgb_shmr_dedup_main(int argc, char **argv) {
+  (void)argc; (void)argv;
+  std::vector<char> in;
+  {
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof buf, stdin)) > 0) in.insert(in.end(), buf, buf + got);
+  }
+  const size_t n = in.size() / sizeof(ovlp_t);  // a truncated trailing record is ignored
+  if (n == 0) return 0;
+  pgb_ctx *c = cli_ctx();
+  if (!c) return 1;
+  if (pgb_dedup(c, (const ovlp_t *)in.data(), n) != 0) {
+    fprintf(stderr, "shmr_dedup: %s\n", pgb_last_error(c));
+    pgb_destroy(c);
+    return 1;
+  }
+  std::vector<char> text(pgb_dedup_text_bytes(c));
+  if (pgb_dedup_text_copy(c, text.data()) != 0) {
+    fprintf(stderr, "shmr_dedup: %s\n", pgb_last_error(c));
+    pgb_destroy(c);
+    return 1;
+  }
+  fwrite(text.data(), 1, text.size(), stdout);
+  fflush(stdout);
   pgb_destroy(c);
   return 0;
 }

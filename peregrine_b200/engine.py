@@ -43,7 +43,7 @@ class _Stats(C.Structure):
         + [(n, C.c_double) for n in ("ms_k_sketch_count", "ms_k_sketch_write", "ms_k_align", "ms_k_replay")]
         + [(n, C.c_uint64) for n in ("n_k_sketch_count", "n_k_sketch_write", "n_k_align", "n_k_replay")]
         + [("ms_k_sketch_tiled", C.c_double), ("n_k_sketch_tiled", C.c_uint64), ("n_sketch_fallback_reads", C.c_uint64),
-           ("n_replay_buckets", C.c_uint64)]
+           ("n_replay_buckets", C.c_uint64), ("ms_dedup", C.c_double), ("n_dedup_in", C.c_uint64), ("n_dedup_kept", C.c_uint64)]
     )
 
 
@@ -93,6 +93,15 @@ def load_library():
     L.pgb_route_scan.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
     L.pgb_route_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u64p]
     L.pgb_overlap_routed.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.pgb_dedup.argtypes = [vp, vp, C.c_size_t]
+    L.pgb_dedup_device.argtypes = [vp, vp, C.c_size_t]
+    L.pgb_dedup_overlaps.argtypes = [vp]
+    L.pgb_dedup_kept.restype = C.c_size_t
+    L.pgb_dedup_kept.argtypes = [vp]
+    L.pgb_dedup_text_bytes.restype = C.c_size_t
+    L.pgb_dedup_text_bytes.argtypes = [vp]
+    L.pgb_dedup_text_copy.argtypes = [vp, vp]
+    L.pgb_shmr_dedup_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     L.pgb_stats_reset.argtypes = [vp]
     L.pgb_stats_get.argtypes = [vp, C.POINTER(_Stats)]
     L.pgb_event_record.argtypes = [vp, C.c_int]
@@ -256,6 +265,26 @@ class Engine:
         if copy is False:
             return self.L.pgb_overlap_size(self.h)
         return self.overlap_records(view=(copy == "view"))
+
+    # ------------------------------------------------------------------ shmr_dedup
+    def dedup(self, records=None, device_ptr=None, n=None, text=True):
+        """First record of every read pair in stream order -> preads.ovl text (bytes).  records: numpy array of ovlp_t on the
+        host; device_ptr/n: a stream already in HBM; neither: the records of this engine's last overlap(), in place.
+        text=False leaves the text on the device and returns (kept, bytes)."""
+        if records is not None:
+            records = np.ascontiguousarray(records)
+            self._ck(self.L.pgb_dedup(self.h, _ptr(records), len(records)), "pgb_dedup")
+        elif device_ptr is not None:
+            self._ck(self.L.pgb_dedup_device(self.h, C.c_void_p(device_ptr), n), "pgb_dedup_device")
+        else:
+            self._ck(self.L.pgb_dedup_overlaps(self.h), "pgb_dedup_overlaps")
+        nb = self.L.pgb_dedup_text_bytes(self.h)
+        if not text:
+            return self.L.pgb_dedup_kept(self.h), nb
+        out = np.empty(nb, dtype=np.uint8)
+        if nb:
+            self._ck(self.L.pgb_dedup_text_copy(self.h, _ptr(out)), "pgb_dedup_text_copy")
+        return out.tobytes()
 
     # ------------------------------------------------------------------ stats
     def event_record(self, slot):

@@ -8,6 +8,7 @@
 //   hostsim sketch  <seqdb_prefix> <w> <k>            every read: sketch_exact vs reference mm_sketch, reduce x2
 //   hostsim match   <seqdb_prefix> <n_pairs> <bw>     random + adversarial operand pairs vs reference ovlp_match
 //   hostsim overlap <seqdb_prefix> <l2_prefix> <T> <c> <ref_ovlp_file> [jacobi]
+//   hostsim dedup   < ovlp stream > text                the product's dedup_pair_key / dedup_format, first-seen per pair
 #include <dlfcn.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -20,6 +21,8 @@
 #include "../../peregrine_b200/csrc/host_util.hpp"
 #include "../../peregrine_b200/csrc/sketch_tile.cuh"
 #include "../../peregrine_b200/csrc/khash_small.cuh"
+#include "../../peregrine_b200/csrc/dedup.cuh"
+#include <unordered_set>
 
 using namespace pgb;
 
@@ -531,8 +534,23 @@ static int cmd_overlap(int argc, char **argv) {
   return (nb || out.size() != ref.size()) ? 3 : 0;
 }
 
+static int cmd_dedup() {
+  std::vector<ovlp_rec> recs;
+  ovlp_rec r;
+  while (fread(&r, sizeof r, 1, stdin) == 1) recs.push_back(r);
+  std::unordered_set<uint64_t> seen;
+  char buf[192];
+  for (const ovlp_rec &o : recs) {
+    if (!seen.insert(dedup_pair_key(o)).second) continue;
+    int n = dedup_format(o, buf);
+    fwrite(buf, 1, (size_t)n, stdout);
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
-  if (argc < 2) { fprintf(stderr, "usage: hostsim sketch|match|overlap ...\n"); return 1; }
+  if (argc < 2) { fprintf(stderr, "usage: hostsim sketch|match|overlap|dedup ...\n"); return 1; }
+  if (!strcmp(argv[1], "dedup")) return cmd_dedup();
   load_ref();
   if (!strcmp(argv[1], "sketch")) return cmd_sketch(argc, argv);
   if (!strcmp(argv[1], "match")) return cmd_match(argc, argv);
