@@ -189,6 +189,14 @@ size_t pgb_dedup_kept(pgb_ctx *);
 size_t pgb_dedup_text_bytes(pgb_ctx *);
 int pgb_dedup_text_copy(pgb_ctx *, char *out);                           /* device -> host, pgb_dedup_text_bytes bytes     */
 
+/* ---- shmr_mkseqdb: FASTA/FASTQ(.gz) -> <prefix>.idx + <prefix>.seqdb -------------------------------------------
+ * pgb_shmr_mkseqdb_main replaces main() of src/shmr_mkseqdb.c:15-132 (-d file list, -p output prefix; same defaults and
+ * messages).  pgb_encode_biseq replaces encode_biseq (src/shmr_utils.c:44-51) for a batch: read i is
+ * ascii[offset[i] .. offset[i] + len[i]); its .seqdb bytes are written to seqdb_out at the same offsets (host buffers). */
+int pgb_shmr_mkseqdb_main(int argc, char **argv);
+int pgb_encode_biseq(pgb_ctx *, const char *ascii, size_t total_bytes, const uint64_t *offset, const uint32_t *len, size_t n_reads,
+                     uint8_t *seqdb_out);
+
 /* counters for bench.py / profiles */
 typedef struct {
   uint64_t kernel_launches;      /* launches of this library's kernels since pgb_stats_reset */
@@ -205,6 +213,8 @@ typedef struct {
   uint64_t n_replay_buckets;     /* buckets replayed, summed over passes (incremental passes replay only dirty buckets) */
   double ms_dedup;               /* shmr_dedup stage */
   uint64_t n_dedup_in, n_dedup_kept;
+  double ms_encode, ms_k_encode; /* pgb_encode_biseq: whole call incl. copies / kernel only */
+  uint64_t n_k_encode, bases_encoded;
 } pgb_stats;
 void pgb_stats_reset(pgb_ctx *);
 /* CUDA events on the context's stream (the stream every kernel of this library is launched on): record slot 0..7, then

@@ -139,7 +139,30 @@ PGB_HD uint64_t dedup_pair_key(const ovlp_rec &ov) {  // :37-40
   return rid0 < rid1 ? ((uint64_t)rid0 << 32) | rid1 : ((uint64_t)rid1 << 32) | rid0;
 }
 
+// ---------------------------------------------------------------------------------------------- shmr_mkseqdb: encode_biseq
+// .seqdb byte p of a read = fourbit_map_f[seq[p]] | fourbit_map_r[seq[len-1-p]] << 4 (src/shmr_utils.c:18-51): A/a 1, C/c 2,
+// G/g 4, T/t 8 in the low nibble, the complement of the mirrored base in the high nibble, every other byte 0.
+PGB_HD uint32_t biseq_f(uint32_t ch) {
+  const uint32_t u = ch & 0xDFu;  // 'a'..'t' -> 'A'..'T'; no other byte folds onto A, C, G or T
+  return u == 'A' ? 1u : u == 'C' ? 2u : u == 'G' ? 4u : u == 'T' ? 8u : 0u;
+}
+PGB_HD uint32_t biseq_r(uint32_t ch) {
+  const uint32_t u = ch & 0xDFu;
+  return u == 'A' ? 8u : u == 'C' ? 4u : u == 'G' ? 2u : u == 'T' ? 1u : 0u;
+}
+struct EncTile { uint64_t off; uint32_t len, p0; };  // bytes [p0, p0 + ENC_TILE) of the read at ascii[off .. off + len)
+enum { ENC_TILE = 8192 };
+
 #if defined(__CUDACC__)
+// 1 CTA = one tile of one read; forward bytes are read ascending, mirrored bytes descending, both coalesced
+__global__ void k_encode_biseq(const uint8_t *__restrict__ ascii, const EncTile *__restrict__ tiles, uint8_t *__restrict__ out) {
+  const EncTile t = tiles[blockIdx.x];
+  const uint8_t *s = ascii + t.off;
+  uint8_t *o = out + t.off;
+  const uint32_t p1 = t.p0 + ENC_TILE < t.len ? t.p0 + ENC_TILE : t.len;
+  for (uint32_t p = t.p0 + threadIdx.x; p < p1; p += blockDim.x) o[p] = (uint8_t)(biseq_f(s[p]) | (biseq_r(s[t.len - 1 - p]) << 4));
+}
+
 __global__ void k_dedup_insert(const ovlp_rec *__restrict__ recs, size_t n, uint64_t *keys, uint32_t mask, unsigned long long *first,
                                uint32_t *slot_of, int *err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

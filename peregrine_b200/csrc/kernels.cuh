@@ -1298,15 +1298,6 @@ __global__ void k_compact_classes(const uint32_t *__restrict__ flags, const uint
   if (flags[i]) list[pos[i]] = i < n_ranks ? i : i - n_ranks;
 }
 
-// sort key of a bucket in a replay run list: larger buckets first, so that the 32 buckets a warp of k_replay walks have
-// similar sizes (one thread = one bucket; the lanes of a warp wait for the largest bucket among them)
-__global__ void k_size_keys(const uint32_t *__restrict__ list, uint32_t n, const uint32_t *__restrict__ rank_off, uint32_t max_n, uint32_t *keys) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t r = list[i], sz = rank_off[r + 1] - rank_off[r];
-  keys[i] = max_n - (sz < max_n ? sz : max_n);
-}
-
 // ------------------------------------------------------------------------------------------------ shimmer4py index handle
 // per read id: index of its first minimizer in the concatenated list and how many it has (get_ridmm, src/shmr_utils.c:415-443)
 __global__ void k_ridmm(const mm128 *__restrict__ mm, size_t n, uint32_t *first, uint32_t *count) {

@@ -14,6 +14,7 @@
 #include <unordered_map>
 #include "../../include/pgb200.h"
 #include "host_util.hpp"
+#include "fasta_reader.hpp"
 #include "kernels.cuh"
 
 using namespace pgb;
@@ -1127,19 +1128,6 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   };
   uint32_t n_all = 0;
   const uint32_t n_all_small = class_lists(nullptr, all_list, &n_all);
-  if (n_all_small > 64 && !getenv("PGB_REPLAY_UNSORTED")) {  // group buckets of similar size into the same warps (stable: rank order inside a size)
-    uint32_t *keys = c->alloc<uint32_t>(n_all_small), *keys2 = c->alloc<uint32_t>(n_all_small), *list2 = c->alloc<uint32_t>(n_all_small);
-    int bits = 1;
-    while ((1u << bits) <= BIG_N && bits < 31) bits++;
-    LAUNCH(c, k_size_keys, nblk(n_all_small), 256, all_list, n_all_small, d_rank_off, BIG_N, keys);
-    size_t tmp_bytes = 0;
-    CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, keys, keys2, all_list, list2, (int)n_all_small, 0, bits, c->st));
-    uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
-    CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, keys2, all_list, list2, (int)n_all_small, 0, bits, c->st));
-    c->stats.kernel_launches += 3;
-    CU(cudaMemcpyAsync(all_list, list2, (size_t)n_all_small * 4, cudaMemcpyDeviceToDevice, c->st));
-    c->release(keys); c->release(keys2); c->release(list2); c->release(tmp);
-  }
   auto free_common = [&]() {
     c->release(rid_sorted); c->release(rank_sorted); c->release(bloom); c->release(changed); c->release(unk_flag); c->release(dirty);
     c->release(dflags); c->release(dpos); c->release(dlist); c->release(all_list); c->release(acc); c->release(out_off); c->release(d_ctr);
@@ -1501,6 +1489,32 @@ extern "C" int pgb_dedup_text_copy(pgb_ctx *c, char *out) {
   API_END(c)
 }
 
+// ================================================================================================ shmr_mkseqdb
+// encode_biseq over a batch of reads (src/shmr_utils.c:44-51): ascii -> .seqdb bytes at the same offsets
+extern "C" int pgb_encode_biseq(pgb_ctx *c, const char *ascii, size_t total_bytes, const uint64_t *offset, const uint32_t *len, size_t n_reads,
+                                uint8_t *seqdb_out) {
+  API_BEGIN(c)
+  std::vector<EncTile> tiles;
+  for (size_t i = 0; i < n_reads; i++) {
+    if (offset[i] + len[i] > total_bytes) throw std::runtime_error("read extends past the end of the ascii buffer");
+    for (uint32_t p0 = 0; p0 < len[i]; p0 += ENC_TILE) tiles.push_back(EncTile{offset[i], len[i], p0});
+  }
+  if (tiles.size() >= (1ull << 31)) throw std::runtime_error("too many tiles in one pgb_encode_biseq call");
+  c->tic();
+  uint8_t *d_in = c->alloc<uint8_t>(total_bytes), *d_out = c->alloc<uint8_t>(total_bytes);
+  EncTile *d_tiles = c->alloc<EncTile>(tiles.size());
+  c->h2d(d_in, ascii, total_bytes);
+  c->h2d(d_tiles, tiles.data(), tiles.size() * sizeof(EncTile));
+  CU(cudaMemsetAsync(d_out, 0, total_bytes, c->st));  // bytes between reads (none when the reads are contiguous)
+  c->ktic();
+  LAUNCH(c, k_encode_biseq, (unsigned)tiles.size(), 256, d_in, d_tiles, d_out);
+  c->stats.ms_k_encode += c->ktoc(); c->stats.n_k_encode++;
+  c->d2h(seqdb_out, d_out, total_bytes);
+  c->stats.ms_encode += c->toc();
+  c->stats.bases_encoded += total_bytes;
+  API_END(c)
+}
+
 // ================================================================================================ command-line tools
 static pgb_ctx *cli_ctx() {
   int dev = 0;
@@ -1667,6 +1681,100 @@ extern "C" int pgb_shmr_dedup_main(int argc, char **argv) {
   fflush(stdout);
   pgb_destroy(c);
   return 0;
+}
+
+// shmr_mkseqdb -d seq_dataset.lst -p seq_dataset_prefix (src/shmr_mkseqdb.c:15-132): same options, defaults, messages and
+// output files (<p>.idx text "%09d %s %u %lu", <p>.seqdb bytes); the FASTA/FASTQ(.gz) grammar is fasta_reader.hpp's
+// restatement of kseq, the base encoding runs on the GPU in batches through page-locked staging buffers.
+extern "C" int pgb_shmr_mkseqdb_main(int argc, char **argv) {
+  const char *seq_dataset_path = nullptr, *seqdb_prefix = nullptr;
+  int ch;
+  opterr = 0;
+  optind = 1;
+  while ((ch = getopt(argc, argv, "d:p:")) != -1) {
+    switch (ch) {
+      case 'd': seq_dataset_path = optarg; break;
+      case 'p': seqdb_prefix = optarg; break;
+      case '?':
+        if (optopt == 'd') fprintf(stderr, "Option -%c not specified, using 'seq_dataset.lst' as the input file\n", optopt);
+        else if (optopt == 'p') fprintf(stderr, "Option -%c not specified, using 'seq_dataset' as the output prefix\n", optopt);
+        else fprintf(stderr, "Usage: shmr_mkseqdb -d seq_dataset.lst -p seq_dataset_prefix\n");
+        return 1;
+      default: abort();
+    }
+  }
+  if (!seq_dataset_path) seq_dataset_path = "seq_dataset.lst";
+  if (!seqdb_prefix) seqdb_prefix = "seq_dataset";
+  FILE *lst = fopen(seq_dataset_path, "r");
+  printf("input sequence dataset file list: '%s'\n", seq_dataset_path);
+  if (!lst) { fprintf(stderr, "file '%s' open error: %s\n", seq_dataset_path, strerror(errno)); exit(1); }
+  std::string index_fn = std::string(seqdb_prefix) + ".idx", seqdb_fn = std::string(seqdb_prefix) + ".seqdb";
+  printf("output index file: %s\n", index_fn.c_str());
+  FILE *index_file = fopen(index_fn.c_str(), "w");
+  if (!index_file) { fprintf(stderr, "file '%s' open error: %s\n", index_fn.c_str(), strerror(errno)); exit(1); }
+  printf("output seqdb file: %s\n", index_fn.c_str());  // (sic) the reference prints the index name here, src/shmr_mkseqdb.c:92
+  FILE *seqdb_file = fopen(seqdb_fn.c_str(), "wb");
+  if (!seqdb_file) { fprintf(stderr, "file '%s' open error: %s\n", seqdb_fn.c_str(), strerror(errno)); exit(1); }
+  pgb_ctx *c = cli_ctx();
+  if (!c) return 1;
+  // batch of reads staged in page-locked memory
+  size_t cap = (size_t)256 << 20;
+  char *stage_in = nullptr; uint8_t *stage_out = nullptr;
+  if (cudaMallocHost((void **)&stage_in, cap) != cudaSuccess || cudaMallocHost((void **)&stage_out, cap) != cudaSuccess) {
+    fprintf(stderr, "shmr_mkseqdb: cannot allocate staging buffers\n");
+    return 1;
+  }
+  std::vector<uint64_t> b_off;
+  std::vector<uint32_t> b_len;
+  size_t fill = 0;
+  auto flush = [&]() -> bool {
+    if (b_len.empty()) return true;
+    if (fill && pgb_encode_biseq(c, stage_in, fill, b_off.data(), b_len.data(), b_len.size(), stage_out) != 0) {
+      fprintf(stderr, "shmr_mkseqdb: %s\n", pgb_last_error(c));
+      return false;
+    }
+    fwrite(stage_out, 1, fill, seqdb_file);
+    b_off.clear(); b_len.clear(); fill = 0;
+    return true;
+  };
+  char fn[8192];
+  uint32_t rid = 0;
+  size_t offset = 0;
+  std::vector<char> text;
+  int rc = 0;
+  while (rc == 0 && fscanf(lst, "%8191s", fn) != EOF) {
+    if (!slurp_gz(fn, text)) { fprintf(stderr, "file '%s' open error: %s\n", fn, strerror(errno)); exit(1); }
+    FastaScanner sc(text.data(), text.size());
+    FastaRecord r;
+    while (sc.next(r)) {
+      const size_t l = r.seq.size();
+      if (l >= (1ull << 32)) { fprintf(stderr, "shmr_mkseqdb: sequence %s is longer than 2^32\n", r.name.c_str()); rc = 1; break; }
+      if (fill + l > cap) {
+        if (!flush()) { rc = 1; break; }
+        if (l > cap) {  // one sequence larger than the staging buffers (a chromosome-sized contig)
+          cudaFreeHost(stage_in); cudaFreeHost(stage_out);
+          cap = l + (l >> 3);
+          if (cudaMallocHost((void **)&stage_in, cap) != cudaSuccess || cudaMallocHost((void **)&stage_out, cap) != cudaSuccess) {
+            fprintf(stderr, "shmr_mkseqdb: cannot allocate staging buffers\n");
+            return 1;
+          }
+        }
+      }
+      memcpy(stage_in + fill, r.seq.data(), l);
+      b_off.push_back(fill); b_len.push_back((uint32_t)l);
+      fill += l;
+      fprintf(index_file, "%09d %s %u %lu\n", rid, r.name.c_str(), (unsigned)l, offset);
+      rid += 1;
+      offset += l;
+    }
+  }
+  if (rc == 0 && !flush()) rc = 1;
+  fclose(lst);
+  fclose(index_file);
+  fclose(seqdb_file);
+  cudaFreeHost(stage_in); cudaFreeHost(stage_out);
+  pgb_destroy(c);
+  return rc;
 }
 
 // ================================================================================================ reference cffi surface

@@ -43,7 +43,8 @@ class _Stats(C.Structure):
         + [(n, C.c_double) for n in ("ms_k_sketch_count", "ms_k_sketch_write", "ms_k_align", "ms_k_replay")]
         + [(n, C.c_uint64) for n in ("n_k_sketch_count", "n_k_sketch_write", "n_k_align", "n_k_replay")]
         + [("ms_k_sketch_tiled", C.c_double), ("n_k_sketch_tiled", C.c_uint64), ("n_sketch_fallback_reads", C.c_uint64),
-           ("n_replay_buckets", C.c_uint64), ("ms_dedup", C.c_double), ("n_dedup_in", C.c_uint64), ("n_dedup_kept", C.c_uint64)]
+           ("n_replay_buckets", C.c_uint64), ("ms_dedup", C.c_double), ("n_dedup_in", C.c_uint64), ("n_dedup_kept", C.c_uint64),
+           ("ms_encode", C.c_double), ("ms_k_encode", C.c_double), ("n_k_encode", C.c_uint64), ("bases_encoded", C.c_uint64)]
     )
 
 
@@ -102,6 +103,8 @@ def load_library():
     L.pgb_dedup_text_bytes.argtypes = [vp]
     L.pgb_dedup_text_copy.argtypes = [vp, vp]
     L.pgb_shmr_dedup_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.pgb_shmr_mkseqdb_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.pgb_encode_biseq.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_size_t, vp]
     L.pgb_stats_reset.argtypes = [vp]
     L.pgb_stats_get.argtypes = [vp, C.POINTER(_Stats)]
     L.pgb_event_record.argtypes = [vp, C.c_int]
@@ -285,6 +288,16 @@ class Engine:
         if nb:
             self._ck(self.L.pgb_dedup_text_copy(self.h, _ptr(out)), "pgb_dedup_text_copy")
         return out.tobytes()
+
+    # ------------------------------------------------------------------ shmr_mkseqdb
+    def encode_biseq(self, ascii_bytes, offset, length):
+        """encode_biseq of a batch of reads: ascii_bytes (uint8 array), read i at offset[i] with length[i] -> .seqdb bytes."""
+        a = np.ascontiguousarray(ascii_bytes, dtype=np.uint8)
+        off = np.ascontiguousarray(offset, dtype=np.uint64)
+        ln = np.ascontiguousarray(length, dtype=np.uint32)
+        out = np.empty(a.size, dtype=np.uint8)
+        self._ck(self.L.pgb_encode_biseq(self.h, _ptr(a), a.size, _ptr(off), _ptr(ln), len(ln), _ptr(out)), "pgb_encode_biseq")
+        return out
 
     # ------------------------------------------------------------------ stats
     def event_record(self, slot):

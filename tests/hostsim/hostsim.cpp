@@ -8,6 +8,7 @@
 //   hostsim sketch  <seqdb_prefix> <w> <k>            every read: sketch_exact vs reference mm_sketch, reduce x2
 //   hostsim match   <seqdb_prefix> <n_pairs> <bw>     random + adversarial operand pairs vs reference ovlp_match
 //   hostsim overlap <seqdb_prefix> <l2_prefix> <T> <c> <ref_ovlp_file> [jacobi]
+//   hostsim fastaidx <file list>                       the product's FASTA/FASTQ scanner: prints the .idx lines shmr_mkseqdb would
 //   hostsim dedup   < ovlp stream > text                the product's dedup_pair_key / dedup_format, first-seen per pair
 #include <dlfcn.h>
 #include <sys/mman.h>
@@ -22,6 +23,7 @@
 #include "../../peregrine_b200/csrc/sketch_tile.cuh"
 #include "../../peregrine_b200/csrc/khash_small.cuh"
 #include "../../peregrine_b200/csrc/dedup.cuh"
+#include "../../peregrine_b200/csrc/fasta_reader.hpp"
 #include <unordered_set>
 
 using namespace pgb;
@@ -548,9 +550,31 @@ static int cmd_dedup() {
   return 0;
 }
 
+static int cmd_fastaidx(const char *lst) {
+  FILE *f = fopen(lst, "r");
+  if (!f) return 1;
+  char fn[8192];
+  uint32_t rid = 0;
+  size_t offset = 0;
+  std::vector<char> buf;
+  while (fscanf(f, "%8191s", fn) != EOF) {
+    if (!slurp_gz(fn, buf)) return 1;
+    FastaScanner sc(buf.data(), buf.size());
+    FastaRecord r;
+    while (sc.next(r)) {
+      printf("%09d %s %u %lu\n", rid, r.name.c_str(), (unsigned)r.seq.size(), offset);
+      rid++;
+      offset += r.seq.size();
+    }
+  }
+  fclose(f);
+  return 0;
+}
+
 int main(int argc, char **argv) {
-  if (argc < 2) { fprintf(stderr, "usage: hostsim sketch|match|overlap|dedup ...\n"); return 1; }
+  if (argc < 2) { fprintf(stderr, "usage: hostsim sketch|match|overlap|dedup|fastaidx ...\n"); return 1; }
   if (!strcmp(argv[1], "dedup")) return cmd_dedup();
+  if (!strcmp(argv[1], "fastaidx") && argc > 2) return cmd_fastaidx(argv[2]);
   load_ref();
   if (!strcmp(argv[1], "sketch")) return cmd_sketch(argc, argv);
   if (!strcmp(argv[1], "match")) return cmd_match(argc, argv);
