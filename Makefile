@@ -7,9 +7,9 @@ NVFLAGS = -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --ext
 CSRC = peregrine_b200/csrc
 LIB = peregrine_b200/libpgb200.so
 
-all: $(LIB) bin/shmr_index bin/shmr_overlap bin/shmr_dedup bin/shmr_mkseqdb build/simreads
+all: $(LIB) bin/shmr_index bin/shmr_overlap bin/shmr_dedup bin/shmr_mkseqdb bin/shmr_map build/simreads
 
-$(LIB): $(CSRC)/pgb200.cu $(CSRC)/kernels.cuh $(CSRC)/shimmer_core.cuh $(CSRC)/sketch_tile.cuh $(CSRC)/khash_small.cuh $(CSRC)/dedup.cuh $(CSRC)/fasta_reader.hpp $(CSRC)/host_util.hpp include/pgb200.h
+$(LIB): $(CSRC)/pgb200.cu $(CSRC)/kernels.cuh $(CSRC)/shimmer_core.cuh $(CSRC)/sketch_tile.cuh $(CSRC)/khash_small.cuh $(CSRC)/dedup.cuh $(CSRC)/map.cuh $(CSRC)/fasta_reader.hpp $(CSRC)/host_util.hpp include/pgb200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/pgb200.cu -lz
 
 bin/shmr_index: cli/shmr_index.c $(LIB)
@@ -26,6 +26,10 @@ bin/shmr_dedup: cli/shmr_dedup.c $(LIB)
 bin/shmr_mkseqdb: cli/shmr_mkseqdb.c $(LIB)
 	mkdir -p bin
 	gcc -O2 -o $@ cli/shmr_mkseqdb.c -Lperegrine_b200 -lpgb200 -Wl,-rpath,'$$ORIGIN/../peregrine_b200'
+
+bin/shmr_map: cli/shmr_map.c $(LIB)
+	mkdir -p bin
+	gcc -O2 -o $@ cli/shmr_map.c -Lperegrine_b200 -lpgb200 -Wl,-rpath,'$$ORIGIN/../peregrine_b200'
 
 build/simreads: tools/simreads.c
 	mkdir -p build

@@ -197,6 +197,19 @@ int pgb_shmr_mkseqdb_main(int argc, char **argv);
 int pgb_encode_biseq(pgb_ctx *, const char *ascii, size_t total_bytes, const uint64_t *offset, const uint32_t *len, size_t n_reads,
                      uint8_t *seqdb_out);
 
+/* ---- shmr_map: contig shimmers against the reads' SHIMMER-pair index, no alignment ------------------------------
+ * pgb_shmr_map_main replaces main() of src/shmr_map.c:168-380 (-r -m -p -l -M -n -t -c; hits on stdout as
+ * "%u %u %u %u %u %u %d %u %u\n" = ref_id ref_bgn ref_end read_id read_bgn read_end direction mcount0 mcount1).
+ * pgb_map replaces build_map + process_map (src/shmr_map.c:48-166) for the context's shimmers (pgb_set_shimmers: the reads'
+ * lists + count files) and read lengths (pgb_set_read_lengths, or any pgb_load_reads*); ref_mmers = the contigs' lists
+ * concatenated in file order. */
+int pgb_shmr_map_main(int argc, char **argv);
+int pgb_set_read_lengths(pgb_ctx *, const uint32_t *rid, const uint32_t *len, size_t n_reads);
+int pgb_map(pgb_ctx *, const mm128_t *ref_mmers, size_t n_ref, uint32_t total_chunk, uint32_t mychunk, uint32_t mc_lower, uint32_t mc_upper);
+size_t pgb_map_hits(pgb_ctx *);
+size_t pgb_map_text_bytes(pgb_ctx *);
+int pgb_map_text_copy(pgb_ctx *, char *out);
+
 /* counters for bench.py / profiles */
 typedef struct {
   uint64_t kernel_launches;      /* launches of this library's kernels since pgb_stats_reset */
@@ -215,6 +228,8 @@ typedef struct {
   uint64_t n_dedup_in, n_dedup_kept;
   double ms_encode, ms_k_encode; /* pgb_encode_biseq: whole call incl. copies / kernel only */
   uint64_t n_k_encode, bases_encoded;
+  double ms_map;                 /* pgb_map after the pair records are built */
+  uint64_t n_map_hits;
 } pgb_stats;
 void pgb_stats_reset(pgb_ctx *);
 /* CUDA events on the context's stream (the stream every kernel of this library is launched on): record slot 0..7, then

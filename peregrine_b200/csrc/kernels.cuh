@@ -1414,3 +1414,4 @@ __global__ void k_table_diff(const uint64_t *__restrict__ a, const uint64_t *__r
 }  // namespace pgb
 
 #include "dedup.cuh"
+#include "map.cuh"

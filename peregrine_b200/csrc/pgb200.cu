@@ -82,6 +82,8 @@ struct pgb_ctx {
   mc_entry *d_mc_dump = nullptr; size_t n_mc_dump = 0;
   uint32_t *d_route_cnt = nullptr; unsigned long long route_first = ~0ULL;
   void *d_route = nullptr; size_t n_route = 0;
+  // ---- map output (shmr_map text)
+  char *d_map_text = nullptr; size_t map_bytes = 0, map_hits = 0;
   // ---- dedup output (preads.ovl text)
   char *d_dedup_text = nullptr; size_t dedup_bytes = 0, dedup_kept = 0;
   // ---- overlap output
@@ -340,6 +342,7 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   c->free_reads();
   c->release(c->d_ovl);
   c->release(c->d_dedup_text);
+  c->release(c->d_map_text);
   if (c->h_ovl) cudaFreeHost(c->h_ovl);
   c->release(c->d_err);
   c->release(c->d_align_bases);
@@ -1489,6 +1492,96 @@ extern "C" int pgb_dedup_text_copy(pgb_ctx *c, char *out) {
   API_END(c)
 }
 
+// ================================================================================================ shmr_map
+// read lengths only (build_map mirrors the coordinates of reverse records, src/shmr_utils.c:376-395); no sequence is loaded
+extern "C" int pgb_set_read_lengths(pgb_ctx *c, const uint32_t *rid, const uint32_t *len, size_t n_reads) {
+  API_BEGIN(c)
+  c->free_reads();
+  uint32_t max_rid = 0;
+  for (size_t i = 0; i < n_reads; i++) if (rid[i] > max_rid) max_rid = rid[i];
+  if (n_reads && (uint64_t)max_rid > 8 * (uint64_t)n_reads + (1u << 20)) throw std::runtime_error("read ids too sparse");
+  std::vector<uint32_t> by_rid((size_t)max_rid + 1, 0);
+  for (size_t i = 0; i < n_reads; i++) by_rid[rid[i]] = len[i];
+  c->max_rid = max_rid;
+  c->d_rlen_by_rid = c->palloc<uint32_t>(by_rid.size());
+  c->h2d(c->d_rlen_by_rid, by_rid.data(), by_rid.size() * 4);
+  API_END(c)
+}
+// process_map (src/shmr_map.c:48-166): contig shimmers against the pair index of the context's shimmers
+extern "C" int pgb_map(pgb_ctx *c, const mm128_t *ref_mmers, size_t n_ref, uint32_t T, uint32_t mychunk, uint32_t mc_lower, uint32_t mc_upper) {
+  API_BEGIN(c)
+  if (T == 0 || mychunk == 0 || mychunk > T) throw std::runtime_error("bad chunk spec");
+  if (!c->d_rlen_by_rid) throw std::runtime_error("no read lengths loaded");
+  if (!c->d_shm && c->n_shm) throw std::runtime_error("no shimmers set");
+  if (c->n_shm >= (1ull << 31) || n_ref >= (1ull << 31)) throw std::runtime_error("more than 2^31 shimmers in one map call");
+  c->release(c->d_map_text); c->map_bytes = 0; c->map_hits = 0;
+  if (n_ref == 0 || c->n_shm == 0) { c->sync(); return 0; }
+  // ---- pair index of the reads: records, X / B tables, records grouped by bucket in insertion order
+  PairSoA R;
+  const uint32_t nrec = build_pair_records(c, T, mychunk, mc_lower, mc_upper, R);
+  c->tic();
+  if (nrec) {
+    const uint32_t xcap = pow2_at_least(4 * (uint64_t)nrec), bcap = pow2_at_least(2 * (uint64_t)nrec);
+    uint64_t *xkeys = c->alloc<uint64_t>(xcap), *bkeys = c->alloc<uint64_t>(bcap);
+    uint32_t *bcount = c->alloc<uint32_t>((size_t)bcap + 1), *bfirst = c->alloc<uint32_t>(bcap), *blast = c->alloc<uint32_t>(bcap);
+    uint32_t *rec_bucket = c->alloc<uint32_t>(nrec), *xfirst = c->alloc<uint32_t>(xcap), *bstart = c->alloc<uint32_t>((size_t)bcap + 1);
+    LAUNCH(c, k_fill_u64, 1184, 256, xkeys, PGB_EMPTY, (size_t)xcap);
+    LAUNCH(c, k_fill_u64, 1184, 256, bkeys, PGB_EMPTY, (size_t)bcap);
+    CU(cudaMemsetAsync(bcount, 0, ((size_t)bcap + 1) * 4, c->st));
+    CU(cudaMemsetAsync(bfirst, 0xFF, (size_t)bcap * 4, c->st));
+    CU(cudaMemsetAsync(blast, 0, (size_t)bcap * 4, c->st));
+    CU(cudaMemsetAsync(xfirst, 0xFF, (size_t)xcap * 4, c->st));
+    LAUNCH(c, k_bucket_insert, nblk(nrec), 256, R, nrec, xkeys, xcap - 1, bkeys, bcap - 1, bcount, bfirst, blast, xfirst, rec_bucket, c->d_err);
+    scan_u32(c, bcount, bstart, (size_t)bcap + 1);
+    uint32_t *iota = c->alloc<uint32_t>(nrec), *bk_sorted = c->alloc<uint32_t>(nrec), *by_bucket = c->alloc<uint32_t>(nrec);
+    LAUNCH(c, k_iota_u32, nblk(nrec), 256, iota, nrec);
+    sort_pairs_u32(c, rec_bucket, bk_sorted, iota, by_bucket, nrec);  // stable: records of a bucket stay in insertion order
+    if (c->check_err("pgb_map/buckets")) return -1;
+    // ---- contig walk
+    mm128 *d_ref = c->alloc<mm128>(n_ref);
+    c->h2d(d_ref, ref_mmers, n_ref * sizeof(mm128));
+    uint32_t *cnt = c->alloc<uint32_t>(n_ref), *flags = c->alloc<uint32_t>(n_ref + 1), *pos = c->alloc<uint32_t>(n_ref + 1);
+    unsigned long long *d_first = c->alloc<unsigned long long>(1);
+    CU(cudaMemsetAsync(d_first, 0xFF, 8, c->st));
+    CU(cudaMemsetAsync(flags, 0, (n_ref + 1) * 4, c->st));
+    LAUNCH(c, k_map_ref_flags, nblk(n_ref), 256, d_ref, n_ref, c->d_mckeys, c->d_mcvals, c->mcmask, xkeys, xcap - 1, xfirst, cnt, d_first);
+    LAUNCH(c, k_map_kept, nblk(n_ref), 256, cnt, n_ref, mc_lower, mc_upper, d_first, flags);
+    const uint32_t n_kept = scan_u32(c, flags, pos, n_ref + 1);
+    if (n_kept > 1) {
+      uint32_t *kept = c->alloc<uint32_t>(n_kept), *n_hits = c->alloc<uint32_t>((size_t)n_kept + 1), *pair_bucket = c->alloc<uint32_t>(n_kept);
+      uint64_t *hit_off = c->alloc<uint64_t>((size_t)n_kept + 1);
+      LAUNCH(c, k_compact_idx, nblk(n_ref), 256, flags, pos, n_ref, kept);
+      CU(cudaMemsetAsync(n_hits + n_kept, 0, 4, c->st));
+      LAUNCH(c, k_map_pair_count, nblk(n_kept), 256, d_ref, kept, n_kept, xkeys, xcap - 1, bkeys, bcap - 1, bcount, n_hits, pair_bucket);
+      const uint64_t nh = scan_u32_to_u64(c, n_hits, hit_off, (size_t)n_kept + 1);
+      if (nh >= (1ull << 31)) throw std::runtime_error("more than 2^31 map hits in one call");
+      if (nh) {
+        map_hit *hits = c->alloc<map_hit>(nh);
+        LAUNCH(c, k_map_emit, nblk(n_kept), 256, d_ref, kept, n_kept, cnt, pair_bucket, n_hits, hit_off, bstart, by_bucket, R, hits);
+        uint32_t *len = c->alloc<uint32_t>(nh + 1);
+        uint64_t *off = c->alloc<uint64_t>(nh + 1);
+        CU(cudaMemsetAsync(len + nh, 0, 4, c->st));
+        LAUNCH(c, k_map_len, nblk(nh), 256, hits, (size_t)nh, len);
+        const uint64_t bytes = scan_u32_to_u64(c, len, off, nh + 1);
+        c->d_map_text = c->palloc<char>(bytes);
+        LAUNCH(c, k_map_write, nblk(nh), 256, hits, (size_t)nh, off, c->d_map_text);
+        c->map_bytes = bytes; c->map_hits = nh;
+      }
+    }
+  }
+  c->stats.ms_map += c->toc();
+  c->stats.n_map_hits += c->map_hits;
+  c->check_err("pgb_map");
+  API_END(c)
+}
+extern "C" size_t pgb_map_hits(pgb_ctx *c) { return c ? c->map_hits : 0; }
+extern "C" size_t pgb_map_text_bytes(pgb_ctx *c) { return c ? c->map_bytes : 0; }
+extern "C" int pgb_map_text_copy(pgb_ctx *c, char *out) {
+  API_BEGIN(c)
+  c->d2h(out, c->d_map_text, c->map_bytes);
+  API_END(c)
+}
+
 // ================================================================================================ shmr_mkseqdb
 // encode_biseq over a batch of reads (src/shmr_utils.c:44-51): ascii -> .seqdb bytes at the same offsets
 extern "C" int pgb_encode_biseq(pgb_ctx *c, const char *ascii, size_t total_bytes, const uint64_t *offset, const uint32_t *len, size_t n_reads,
@@ -1775,6 +1868,73 @@ extern "C" int pgb_shmr_mkseqdb_main(int argc, char **argv) {
   cudaFreeHost(stage_in); cudaFreeHost(stage_out);
   pgb_destroy(c);
   return rc;
+}
+
+// shmr_map -r ref_prefix -m ref_shimmer_prefix -p seqdb_prefix -l shimmer_prefix [-M 240] [-n 1] [-t 1] [-c 1]
+// (src/shmr_map.c:168-380): same options, defaults, messages; hits on stdout
+extern "C" int pgb_shmr_map_main(int argc, char **argv) {
+  const char *refdb_prefix = "ref", *ref_shimmer_prefix = "ref-L2", *seqdb_prefix = "seq_dataset", *shimmer_prefix = "shimmer-L2";
+  uint32_t total_chunk = 1, mychunk = 1, mc_upper = 240, mc_lower = 1;
+  int ch;
+  opterr = 0; optind = 1;
+  while ((ch = getopt(argc, argv, "r:m:p:l:M:n:t:c:b:")) != -1) {
+    switch (ch) {
+      case 'r': refdb_prefix = optarg; break;
+      case 'm': ref_shimmer_prefix = optarg; break;
+      case 'p': seqdb_prefix = optarg; break;
+      case 'l': shimmer_prefix = optarg; break;
+      case 'M': mc_upper = atoi(optarg); break;
+      case 'n': mc_lower = atoi(optarg); break;
+      case 't': total_chunk = atoi(optarg); break;
+      case 'c': mychunk = atoi(optarg); break;
+      case 'b': abort();  // accepted by the reference's getopt string but has no case: falls to default -> abort()
+      case '?':
+        if (optopt == 'r') fprintf(stderr, "Option -%c not specified, using 'ref' as the ref sequence db prefix\n", optopt);
+        if (optopt == 'p') fprintf(stderr, "Option -%c not specified, using 'seq_dataset' as the sequence db prefix\n", optopt);
+        if (optopt == 'l') fprintf(stderr, "Option -%c not specified, using 'shimmer-L2' as the L2 index prefix\n", optopt);
+        return 1;
+      default: abort();
+    }
+  }
+  assert(total_chunk > 0);
+  assert(mychunk > 0 && mychunk <= total_chunk);
+  std::string ref_idx = std::string(refdb_prefix) + ".idx", seq_idx = std::string(seqdb_prefix) + ".idx";
+  fprintf(stderr, "using ref index file: %s\n", ref_idx.c_str());
+  ReadTable ref_rt, rt;
+  if (!load_read_table(ref_idx.c_str(), &ref_rt)) { fprintf(stderr, "file '%s' open error: %s\n", ref_idx.c_str(), strerror(errno)); exit(1); }
+  fprintf(stderr, "using ref seqdb file: %s.seqdb\n", refdb_prefix);
+  std::vector<mm128> ref_mmers, mmers;
+  for (auto &fn : glob_sorted(std::string(ref_shimmer_prefix) + "-[0-9]*-of-[0-9]*.dat")) {
+    fprintf(stderr, "using ref shimmer data file: %s\n", fn.c_str());
+    const size_t before = ref_mmers.size();
+    read_mmlist_file(fn.c_str(), &ref_mmers);
+    fprintf(stderr, "number of shimmers load: %lu\n", ref_mmers.size() - before);
+  }
+  fprintf(stderr, "using index file: %s\n", seq_idx.c_str());
+  if (!load_read_table(seq_idx.c_str(), &rt)) { fprintf(stderr, "file '%s' open error: %s\n", seq_idx.c_str(), strerror(errno)); exit(1); }
+  fprintf(stderr, "using seqdb file: %s.seqdb\n", seqdb_prefix);
+  for (auto &fn : glob_sorted(std::string(shimmer_prefix) + "-[0-9]*-of-[0-9]*.dat")) {
+    fprintf(stderr, "using shimmer data file: %s\n", fn.c_str());
+    const size_t before = mmers.size();
+    read_mmlist_file(fn.c_str(), &mmers);
+    fprintf(stderr, "number of shimmers load: %lu\n", mmers.size() - before);
+  }
+  std::vector<mc_rec> mc;
+  for (auto &fn : glob_sorted(std::string(shimmer_prefix) + "-MC-[0-9]*-of-[0-9]*.dat")) {
+    fprintf(stderr, "using shimmer count file: %s\n", fn.c_str());
+    read_mc_file(fn.c_str(), &mc);
+  }
+  assert(ref_mmers.size() > 0);  // src/shmr_map.c:84
+  pgb_ctx *c = cli_ctx();
+  CLI_CHECK(c, pgb_set_read_lengths(c, rt.rid.data(), rt.len.data(), rt.n()));
+  CLI_CHECK(c, pgb_set_shimmers(c, (const mm128_t *)mmers.data(), mmers.size(), (const mm_count_t *)mc.data(), mc.size()));
+  CLI_CHECK(c, pgb_map(c, (const mm128_t *)ref_mmers.data(), ref_mmers.size(), total_chunk, mychunk, mc_lower, mc_upper));
+  std::vector<char> text(pgb_map_text_bytes(c));
+  CLI_CHECK(c, pgb_map_text_copy(c, text.data()));
+  fwrite(text.data(), 1, text.size(), stdout);
+  fflush(stdout);
+  pgb_destroy(c);
+  return 0;
 }
 
 // ================================================================================================ reference cffi surface

@@ -44,7 +44,8 @@ class _Stats(C.Structure):
         + [(n, C.c_uint64) for n in ("n_k_sketch_count", "n_k_sketch_write", "n_k_align", "n_k_replay")]
         + [("ms_k_sketch_tiled", C.c_double), ("n_k_sketch_tiled", C.c_uint64), ("n_sketch_fallback_reads", C.c_uint64),
            ("n_replay_buckets", C.c_uint64), ("ms_dedup", C.c_double), ("n_dedup_in", C.c_uint64), ("n_dedup_kept", C.c_uint64),
-           ("ms_encode", C.c_double), ("ms_k_encode", C.c_double), ("n_k_encode", C.c_uint64), ("bases_encoded", C.c_uint64)]
+           ("ms_encode", C.c_double), ("ms_k_encode", C.c_double), ("n_k_encode", C.c_uint64), ("bases_encoded", C.c_uint64),
+           ("ms_map", C.c_double), ("n_map_hits", C.c_uint64)]
     )
 
 
@@ -104,6 +105,14 @@ def load_library():
     L.pgb_dedup_text_copy.argtypes = [vp, vp]
     L.pgb_shmr_dedup_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     L.pgb_shmr_mkseqdb_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.pgb_shmr_map_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    L.pgb_set_read_lengths.argtypes = [vp, vp, vp, C.c_size_t]
+    L.pgb_map.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.pgb_map_hits.restype = C.c_size_t
+    L.pgb_map_hits.argtypes = [vp]
+    L.pgb_map_text_bytes.restype = C.c_size_t
+    L.pgb_map_text_bytes.argtypes = [vp]
+    L.pgb_map_text_copy.argtypes = [vp, vp]
     L.pgb_encode_biseq.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_size_t, vp]
     L.pgb_stats_reset.argtypes = [vp]
     L.pgb_stats_get.argtypes = [vp, C.POINTER(_Stats)]
@@ -298,6 +307,21 @@ class Engine:
         out = np.empty(a.size, dtype=np.uint8)
         self._ck(self.L.pgb_encode_biseq(self.h, _ptr(a), a.size, _ptr(off), _ptr(ln), len(ln), _ptr(out)), "pgb_encode_biseq")
         return out
+
+    # ------------------------------------------------------------------ shmr_map
+    def set_read_lengths(self, rid, length):
+        rid = np.ascontiguousarray(rid, dtype=np.uint32)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        self._ck(self.L.pgb_set_read_lengths(self.h, _ptr(rid), _ptr(length), len(rid)), "pgb_set_read_lengths")
+
+    def map(self, ref_mmers, total_chunk=1, mychunk=1, mc_lower=1, mc_upper=240) -> bytes:
+        """shmr_map's hit lines for the contig shimmer list ref_mmers against this engine's shimmers (set_shimmers)."""
+        ref_mmers = np.ascontiguousarray(ref_mmers)
+        self._ck(self.L.pgb_map(self.h, _ptr(ref_mmers), len(ref_mmers), total_chunk, mychunk, mc_lower, mc_upper), "pgb_map")
+        out = np.empty(self.L.pgb_map_text_bytes(self.h), dtype=np.uint8)
+        if out.size:
+            self._ck(self.L.pgb_map_text_copy(self.h, _ptr(out)), "pgb_map_text_copy")
+        return out.tobytes()
 
     # ------------------------------------------------------------------ stats
     def event_record(self, slot):
