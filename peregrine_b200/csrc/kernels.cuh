@@ -1080,7 +1080,8 @@ __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_
 #ifndef PGB_ALIGN_MINBLOCKS
 #define PGB_ALIGN_MINBLOCKS 16
 #endif
-__global__ void __launch_bounds__(PGB_ALIGN_THREADS, PGB_ALIGN_MINBLOCKS) k_align_lean(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n,
+template <bool PRE, bool TRIMREG, int MINBLOCKS>
+__global__ void __launch_bounds__(PGB_ALIGN_THREADS, MINBLOCKS) k_align_lean(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n,
                                                                   const uint32_t *__restrict__ perm, const uint64_t *__restrict__ w,
                                                                   const uint64_t *__restrict__ wrc, const uint64_t *__restrict__ woff_by_rid,
                                                                   const uint32_t *__restrict__ rlen_by_rid, const uint32_t *__restrict__ hasn_by_rid,
@@ -1095,7 +1096,7 @@ __global__ void __launch_bounds__(PGB_ALIGN_THREADS, PGB_ALIGN_MINBLOCKS) k_alig
   const uint64_t *tw = ((q.strands & 2) ? wrc : w) + woff_by_rid[q.rid1];
   int V[2 * PGB_MAXV];
   match_t m;
-  ovlp_match_lean(qw, q.start0, (int)(rl0 - q.start0), tw, 0u, (int)rl1, bw, V, PGB_MAXV, &m);
+  ovlp_match_lean_t<PRE, TRIMREG>(qw, q.start0, (int)(rl0 - q.start0), tw, 0u, (int)rl1, bw, V, PGB_MAXV, &m);
   results[q.slot] = m;
   atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
 }

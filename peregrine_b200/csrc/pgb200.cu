@@ -690,7 +690,9 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     uint32_t n_exact = scan_u32(c, exact_flag, exact_pos, ns + 1);
     uint32_t *exact_list = nullptr, *seg_row = nullptr, *seg_lo = nullptr, *seg_first = nullptr, *list_first = nullptr, *seg_cnt = nullptr, *seg_pos = nullptr;
     uint32_t n_seg = 0;
-    const int SEG = 256;  // positions per thread of the exact automaton (plus its warm-up): short segments keep the few flagged reads off the critical path
+    // positions per thread of the exact automaton (plus its warm-up of ~w+k and w trailing slots): the few flagged reads are a
+    // pure latency term (far fewer threads than the GPU holds), so short segments keep them off the critical path
+    const int SEG = getenv("PGB_EXACT_SEG") ? std::max(16, atoi(getenv("PGB_EXACT_SEG"))) : 256;
     if (n_exact) {
       exact_list = c->alloc<uint32_t>(n_exact);
       LAUNCH(c, k_compact_idx, nblk(ns), 256, exact_flag, exact_pos, ns, exact_list);
@@ -1103,6 +1105,7 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   // alignment batches up to this size go to the warp-per-alignment kernel (k_align_warp), larger ones to k_align_lean
   const uint32_t ALIGN_WARP_MAX = getenv("PGB_ALIGN_WARP_MAX") ? (uint32_t)strtoul(getenv("PGB_ALIGN_WARP_MAX"), 0, 10) : 16384u;
   const bool verbose = getenv("PGB_VERBOSE") != nullptr;
+  const int ALIGN_VARIANT = getenv("PGB_ALIGN_VARIANT") ? atoi(getenv("PGB_ALIGN_VARIANT")) : 7;
   const uint32_t CHANGED_CAP = 16384;
   // incremental passes: (rid, rank) index of the eligible records sorted by rid + per-bucket Bloom filter of read ids
   uint32_t *rid_sorted = c->alloc<uint32_t>(n_elig), *rank_sorted = c->alloc<uint32_t>(n_elig);
@@ -1230,9 +1233,17 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         if (nn <= ALIGN_WARP_MAX)  // small batch: latency-bound, one warp per alignment
           LAUNCH(c, k_align_warp, nblk(nn, PGB_AW_WARPS), PGB_AW_WARPS * 32, S.reqs, n_done, nn, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid,
                  c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
-        else
-          LAUNCH(c, k_align_lean, nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid,
-                 c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
+        else {
+#define PGB_LEAN(P, T, MB)                                                                                                             \
+  LAUNCH(c, (k_align_lean<P, T, MB>), nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, \
+         c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases)
+          // production form: band-row prefetch + register-cached band trim at 12 CTAs/SM (75 registers, no spills): 20.3 ms per
+          // step against 26.2 ms for the plain form at 16 CTAs/SM, whose 64-register cap forces spills (profiles/r1g_ncu.md);
+          // PGB_ALIGN_VARIANT=0 selects the plain form (kept as the A/B baseline of the parity tests)
+          if (ALIGN_VARIANT == 0) PGB_LEAN(false, false, 16);
+          else PGB_LEAN(true, true, 12);
+#undef PGB_LEAN
+        }
         if (c->n_reads_with_n)
           LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, n_done, nn, perm, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
                  (int)bw, S.ares, c->d_err, c->d_align_bases, 1);

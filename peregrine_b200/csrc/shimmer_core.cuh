@@ -406,8 +406,10 @@ PGB_HD uint64_t window64(uint64_t A, uint64_t B, uint32_t s2) {
 }
 // qw / tw: first packed word of the read in the image of the operand's strand; qo / to: base offset of logical base 0.
 // V: caller scratch of 2*cap ints, cap >= band_tolerance + 2.
-PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const uint64_t *tw, uint32_t to, int t_len,
-                            int band_tolerance, int *V, int cap, match_t *out) {
+// PRE: load V[d-1][k+3] one cell ahead; TRIMREG: serve the first two trim steps per side from registers
+template <bool PRE, bool TRIMREG>
+PGB_HD void ovlp_match_lean_t(const uint64_t *qw, uint32_t qo, int q_len, const uint64_t *tw, uint32_t to, int t_len,
+                              int band_tolerance, int *V, int cap, match_t *out) {
   match_t r;
   r.m_size = r.dist = r.q_bgn = r.q_end = r.t_bgn = r.t_end = r.t_m_end = r.q_m_end = 0;
   const int max_d = (int)(0.3 * (double)(q_len + t_len));  // DWmatch.c:96
@@ -418,7 +420,10 @@ PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const ui
   int min_k = 0, max_k = 0, d = 0, k = 0, idx = 0, x = 0, x1 = 0;
   int *Vc = V, *Vp = V + cap;  // row being written / row of d-1
   int vcarry = 0;  // V[d-1][k+1] read by the previous cell of this row = V[d-1][k-1] of the current cell
+  int vpre = 0;    // V[d-1][k+3], loaded one cell ahead: the band-row load of a cell is off its critical path
   int poff = 0;    // index of V[d-1][min_k+1] in the previous row's storage
+  int u1 = 0, u2 = 0;             // x+y of the row's 2nd and 3rd cell   } the band trim normally inspects one or two cells per
+  int ul0 = 0, ul1 = 0, ul2 = 0;  // x+y of the last three cells so far  } side: served from registers, not from the row array
   const uint64_t *qp = qw + (qo >> 5), *tp = tw + (to >> 5);
   uint32_t qs = (qo & 31) * 2, ts = (to & 31) * 2;
   uint64_t qA = 0, qB = 0, tA = 0, tB = 0;
@@ -456,6 +461,11 @@ PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const ui
       const int u = x + y;
       if (u > best_m) { best_m = u; k_best = k; }
       if (idx == 0) u_first = u;
+      if (TRIMREG) {
+        if (idx == 1) u1 = u;
+        else if (idx == 2) u2 = u;
+        ul2 = ul1; ul1 = ul0; ul0 = u;
+      }
       if (x >= q_len || y >= t_len) {  // :161-164, :185-194
         r.q_end = x;
         r.t_end = y;
@@ -472,15 +482,39 @@ PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const ui
           // k_best (this row's first diagonal that reached best_m; every row raises best_m) is in the hull.
           const int thr = best_m - band_tolerance;
           int lo_k = min_k, off = 0;
-          if (u_first < thr) {
+          // (a cell between the row's end and k_best exists in this row, so u1 / u2 / ul1 / ul2 are this row's when they are read)
+          if (!TRIMREG) {
+            if (u_first < thr) {
+              lo_k += 2; off = 1;
+              while (lo_k < k_best && 2 * Vc[off] - lo_k < thr) { lo_k += 2; off++; }
+            }
+          } else if (u_first < thr) {
             lo_k += 2; off = 1;
-            while (lo_k < k_best && 2 * Vc[off] - lo_k < thr) { lo_k += 2; off++; }
+            if (lo_k < k_best && u1 < thr) {
+              lo_k += 2; off = 2;
+              if (lo_k < k_best && u2 < thr) {
+                lo_k += 2; off = 3;
+                while (lo_k < k_best && 2 * Vc[off] - lo_k < thr) { lo_k += 2; off++; }
+              }
+            }
           }
           int hi_k = max_k;
-          if (u < thr) {  // u is the row's last cell here
-            int i2 = idx - 1;
+          if (!TRIMREG) {
+            if (u < thr) {  // u is the row's last cell here
+              int i2 = idx - 1;
+              hi_k -= 2;
+              while (hi_k > k_best && 2 * Vc[i2] - hi_k < thr) { hi_k -= 2; i2--; }
+            }
+          } else if (u < thr) {
             hi_k -= 2;
-            while (hi_k > k_best && 2 * Vc[i2] - hi_k < thr) { hi_k -= 2; i2--; }
+            if (hi_k > k_best && ul1 < thr) {
+              hi_k -= 2;
+              if (hi_k > k_best && ul2 < thr) {
+                int i2 = idx - 3;
+                hi_k -= 2;
+                while (hi_k > k_best && 2 * Vc[i2] - hi_k < thr) { hi_k -= 2; i2--; }
+              }
+            }
           }
           poff = off;
           min_k = lo_k - 1;
@@ -493,7 +527,13 @@ PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const ui
         }
         // ---- set-up of the next cell (DWmatch.c:125-131); d >= 1 here, so min_k < max_k
         int vp = 0;
-        if (k != max_k) vp = Vp[poff + idx];  // V[d-1][k+1]
+        if (PRE) {
+          vp = vpre;  // V[d-1][k+1] (0 for the row's last cell, which does not use it)
+          if (idx == 0) vp = Vp[poff];  // first cell of a row (min_k < max_k always): the only exposed band-row load
+          vpre = (k + 2 < max_k) ? Vp[poff + idx + 1] : 0;  // for the next cell of this row
+        } else if (k != max_k) {
+          vp = Vp[poff + idx];  // V[d-1][k+1]
+        }
         if (idx == 0) x = vp;
         else if (k == max_k) x = vcarry + 1;
         else x = (vcarry < vp) ? vp : vcarry + 1;
@@ -511,6 +551,10 @@ PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const ui
     r.t_bgn = 0;
   }
   *out = r;
+}
+PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const uint64_t *tw, uint32_t to, int t_len,
+                            int band_tolerance, int *V, int cap, match_t *out) {
+  ovlp_match_lean_t<true, true>(qw, qo, q_len, tw, to, t_len, band_tolerance, V, cap, out);
 }
 
 // ---------------------------------------------------------------------------------------------- mm_sketch (exact automaton)

@@ -240,6 +240,21 @@ def test_warp_per_alignment_kernel_on_every_alignment(sim1, workdir, ref_dir, mo
     assert_same_ovlp(oo[0], ro[0])
 
 
+@pytest.mark.parametrize("variant", ["7", "0"])
+def test_thread_per_alignment_kernel_on_every_alignment(workdir, ref_dir, monkeypatch, variant):
+    """PGB_ALIGN_WARP_MAX=0 routes every alignment batch through k_align_lean (variant 7: band-row prefetch + register-cached
+    band trim, the production form; variant 0: the plain form), on clean and on 3 %-error reads (wide bands, deep trims)."""
+    monkeypatch.setenv("PGB_ALIGN_WARP_MAX", "0")
+    monkeypatch.setenv("PGB_ALIGN_VARIANT", variant)
+    for name, kw in (("lean_a", dict(genome=400_000, cov=20)), ("lean_b", dict(genome=150_000, cov=15, err=0.03))):
+        p = D.make_sim(workdir, name, **kw)
+        rp = D.ref_index(ref_dir, p, os.path.join(workdir, name, "ref"), T=1, extra=["-m", "0"])
+        for extra in ([], ["-w", "30"]):
+            ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, name, "ref" + "".join(extra)), T=1, extra=extra)
+            oo = ours_overlap(p, rp, 2, os.path.join(workdir, name, f"our{variant}" + "".join(extra)), T=1, extra=extra)
+            assert_same_ovlp(oo[0], ro[0])
+
+
 def test_sharded_exchange_matches_reference(sim1, workdir, ref_dir):
     """Multi-GPU data path on one device: three 'ranks' (engines) each sketch the reads of their index chunk, the packed
     reads and SHIMMER lists are concatenated exactly as the NCCL all-gather of peregrine_b200.multigpu does, and every rank
