@@ -163,6 +163,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; stdout carries the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     genome = int(args.genome_mb * 1e6) * world
