@@ -36,10 +36,10 @@ def work_dir():
     return d
 
 
-def make_dataset(name, genome, cov, seed=42, err=0.005):
+def make_dataset(name, genome, cov, seed=42, err=0.005, mod=1, res=0):
     import datasets as D
 
-    return D.make_sim(work_dir(), name, genome=genome, cov=cov, err=err, seed=seed)
+    return D.make_sim(work_dir(), name, genome=genome, cov=cov, err=err, seed=seed, mod=mod, res=res)
 
 
 class ClockSampler:
@@ -168,32 +168,25 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     genome = int(args.genome_mb * 1e6) * world
-    if rank == 0:
-        prefix = make_dataset(f"g{genome}", genome, args.cov)
     if world > 1:
-        dist.barrier()
-    prefix = os.path.join(work_dir(), f"g{genome}", "seq")
+        import faulthandler
+
+        faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)  # a stuck rank shows where it is stuck
+    # Every rank generates ITS share of the read set (rid % N == (rank+1) % N, src/shmr_index.c:157) straight from the
+    # counter-based simulator: read i depends on (seed, i) only, so the shares are exactly the selection of the full set,
+    # and no rank ever writes or scans the whole 1.5 GB x N image.
+    prefix = make_dataset(f"g{genome}" if world == 1 else f"g{genome}_c{rank + 1}of{world}", genome, args.cov, mod=world, res=(rank + 1) % world)
     rid, ln, off = F.read_idx(prefix + ".idx")
+    nbytes = os.path.getsize(prefix + ".seqdb")
+    pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    seqdb = pinned.numpy()
+    with open(prefix + ".seqdb", "rb") as f:
+        f.readinto(memoryview(seqdb))
     bases = int(ln.sum())
-    if world == 1:
-        nbytes = os.path.getsize(prefix + ".seqdb")
-        pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-        seqdb = pinned.numpy()
-        with open(prefix + ".seqdb", "rb") as f:
-            f.readinto(memoryview(seqdb))
-    else:
-        # this rank's share of the read set (rid % N == (rank+1) % N, src/shmr_index.c:157) as its own pinned host image
-        mm = np.memmap(prefix + ".seqdb", dtype=np.uint8, mode="r")
-        sel = np.nonzero(rid % world == (rank + 1) % world)[0]
-        rid, ln_all, off_all = rid[sel], ln[sel], off[sel]
-        ln = ln_all
-        new_off = np.concatenate([[0], np.cumsum(ln.astype(np.uint64))[:-1]]).astype(np.uint64)
-        pinned = torch.empty(int(ln.astype(np.uint64).sum()), dtype=torch.uint8, pin_memory=True)
-        seqdb = pinned.numpy()
-        for i in range(len(sel)):
-            seqdb[int(new_off[i]): int(new_off[i]) + int(ln[i])] = mm[int(off_all[i]): int(off_all[i]) + int(ln[i])]
-        off = new_off
-        del mm
+    if world > 1:
+        t = torch.tensor([bases], dtype=torch.int64, device=f"cuda:{local}")
+        dist.all_reduce(t)
+        bases = int(t.item())
     P = PARAMS
     T = world
     c = rank + 1
@@ -324,7 +317,14 @@ def run_ours(args):
     ms_tot, n_l, bytes_per_launch = kern[top]
     avg_ms = ms_tot / max(n_l, 1)
     achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:  # DRAM bytes of that kernel from the committed ncu capture, per launch like `achieved`
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if top in tj and n_l:
+            traffic = tj[top]["dram_bytes_per_step"] / (n_l / K)
+    except (OSError, ValueError, KeyError):
+        pass
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_l / K,
                 "kernel_ms_per_step": {k_: v[0] / K for k_, v in kern.items()}}
     cpu = cpu_baseline_single_core() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None

@@ -18,12 +18,15 @@ def ensure_simreads():
     return SIMREADS
 
 
-def make_sim(workdir, name, genome, cov=20, err=0.005, seed=42, mean=15000, sd=1500):
+def make_sim(workdir, name, genome, cov=20, err=0.005, seed=42, mean=15000, sd=1500, mod=1, res=0):
+    """mod/res: only the reads with rid % mod == res (one rank's share of a sharded job; rids stay global)."""
     d = os.path.join(workdir, name)
     prefix = os.path.join(d, "seq")
-    if not os.path.exists(prefix + ".seqdb"):
+    if not os.path.exists(prefix + ".seqdb") or not os.path.exists(prefix + ".done"):
         os.makedirs(d, exist_ok=True)
-        run([ensure_simreads(), "-g", str(genome), "-c", str(cov), "-e", str(err), "-S", str(seed), "-l", str(mean), "-s", str(sd), "-p", prefix])
+        run([ensure_simreads(), "-g", str(genome), "-c", str(cov), "-e", str(err), "-S", str(seed), "-l", str(mean), "-s", str(sd),
+             "-m", str(mod), "-r", str(res), "-p", prefix])
+        open(prefix + ".done", "w").close()
     return prefix
 
 

@@ -19,7 +19,10 @@
  *   <prefix>.bed   : truth "name start end strand"
  *   optional -f    : also the FASTA (single file <prefix>.fa) so tests can push it through the real shmr_mkseqdb.
  *
- * usage: simreads -g GENOME_BP -c COVERAGE [-l 15000] [-s 1500] [-e 0.005] [-S 42] [-n NREADS] [-f] -p PREFIX
+ *   -m MOD -r RES  : emit only the reads with rid % MOD == RES (rids stay global, offsets are local to the output): one
+ *                    rank's share of a sharded job without ever writing the whole set (read i depends on (seed, i) only).
+ *
+ * usage: simreads -g GENOME_BP -c COVERAGE [-l 15000] [-s 1500] [-e 0.005] [-S 42] [-n NREADS] [-m MOD -r RES] [-f] -p PREFIX
  */
 #include <math.h>
 #include <stdint.h>
@@ -82,11 +85,11 @@ static void make_read(const uint8_t *genome, uint64_t G, uint64_t seed, uint64_t
 }
 
 int main(int argc, char **argv) {
-  uint64_t G = 0, seed = 42, nreads = 0;
+  uint64_t G = 0, seed = 42, nreads = 0, mod = 1, res = 0;
   double cov = 30, mean = 15000, sd = 1500, perr = 0.005;
   const char *prefix = NULL;
   int fasta = 0, c;
-  while ((c = getopt(argc, argv, "g:c:l:s:e:S:n:p:f")) != -1) {
+  while ((c = getopt(argc, argv, "g:c:l:s:e:S:n:p:fm:r:")) != -1) {
     switch (c) {
       case 'g': G = strtoull(optarg, 0, 10); break;
       case 'c': cov = atof(optarg); break;
@@ -97,6 +100,8 @@ int main(int argc, char **argv) {
       case 'n': nreads = strtoull(optarg, 0, 10); break;
       case 'p': prefix = optarg; break;
       case 'f': fasta = 1; break;
+      case 'm': mod = strtoull(optarg, 0, 10); break;
+      case 'r': res = strtoull(optarg, 0, 10); break;
       default: fprintf(stderr, "bad option\n"); return 1;
     }
   }
@@ -105,6 +110,7 @@ int main(int argc, char **argv) {
     return 1;
   }
   if (!nreads) nreads = (uint64_t)(cov * (double)G / mean);
+  if (mod == 0 || res >= mod) { fprintf(stderr, "need 0 <= RES < MOD\n"); return 1; }
   uint8_t *genome = (uint8_t *)malloc(G);
   {
     uint64_t s = seed ^ 0xA5A5A5A5DEADBEEFULL;
@@ -127,13 +133,15 @@ int main(int argc, char **argv) {
   uint8_t *enc = (uint8_t *)malloc(80000);
   char *asc = (char *)malloc(80000);
   uint64_t per_file = (nreads + 7) / 8, offset = 0, total = 0;
-  for (uint64_t b0 = 0; b0 < nreads; b0 += BATCH) {
-    uint64_t nb = nreads - b0 < BATCH ? nreads - b0 : BATCH;
+  /* the selected rids are res, res + mod, ...; slot q of the selection is rid res + q * mod */
+  const uint64_t nsel = nreads > res ? (nreads - res + mod - 1) / mod : 0;
+  for (uint64_t b0 = 0; b0 < nsel; b0 += BATCH) {
+    uint64_t nb = nsel - b0 < BATCH ? nsel - b0 : BATCH;
 #pragma omp parallel for schedule(dynamic, 16)
-    for (uint64_t j = 0; j < nb; j++) make_read(genome, G, seed, b0 + j, mean, sd, perr, &batch[j]);
+    for (uint64_t j = 0; j < nb; j++) make_read(genome, G, seed, res + (b0 + j) * mod, mean, sd, perr, &batch[j]);
     for (uint64_t j = 0; j < nb; j++) {
       read_t *r = &batch[j];
-      uint64_t rid = b0 + j;
+      uint64_t rid = res + (b0 + j) * mod;
       char name[64];
       snprintf(name, sizeof name, "%02d/%06d/0_%u", (int)(rid / per_file), (int)(rid % per_file), r->len);
       for (uint32_t p = 0; p < r->len; p++) enc[p] = (uint8_t)(FWD[r->b[p]] | (REV[r->b[r->len - 1 - p]] << 4));
@@ -151,6 +159,6 @@ int main(int argc, char **argv) {
   }
   fclose(fdb); fclose(fidx); fclose(fbed); if (ffa) fclose(ffa);
   fprintf(stderr, "simreads: genome=%lu reads=%lu bases=%lu err=%g seed=%lu -> %s.{seqdb,idx,bed}\n", (unsigned long)G,
-          (unsigned long)nreads, (unsigned long)total, perr, (unsigned long)seed, prefix);
+          (unsigned long)nsel, (unsigned long)total, perr, (unsigned long)seed, prefix);
   return 0;
 }
