@@ -43,45 +43,88 @@ def make_dataset(name, genome, cov, seed=42, err=0.005, mod=1, res=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled every ~10 ms through NVML while the timed region runs (a timed region of a few
+    steps lasts ~0.2 s, too short for `nvidia-smi -lms`); falls back to one `nvidia-smi` query loop if pynvml is unusable."""
 
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device, self.rows, self.p = device, [], None
+        self.device, self.sm, self.mx, self.reasons, self.stop_flag, self.t, self.p, self.rows = device, [], 0, set(), False, None, None, []
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; NVML wants the physical one
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device
+            if vis:
+                toks = [t.strip() for t in vis.split(",") if t.strip()]
+                if device < len(toks) and toks[device].isdigit():
+                    idx = int(toks[device])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.h))
+                for bit, name in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
 
     def start(self):
+        self.stop_flag = False
+        if self.nvml:
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
             self.p = None
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def stop(self):
-        if self.p:
+        self.stop_flag = True
+        if self.nvml:
+            if self.t:
+                self.t.join(timeout=1)
+        elif self.p:
             self.p.terminate()
             try:
                 self.p.wait(timeout=2)
             except Exception:
                 self.p.kill()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx = max(mx, float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+            for r in self.rows:
+                try:
+                    self.sm.append(float(r[1]))
+                    self.mx = max(self.mx, float(r[2]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+                except (ValueError, IndexError):
+                    pass
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx or None, "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def measured_peaks():
