@@ -206,8 +206,11 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; stdout carries the one JSON line
+        # NCCL prints its version banner on STDOUT when the first communicator is created; stdout carries the one JSON
+        # line, so native writes to fd 1 go to stderr until the result is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     genome = int(args.genome_mb * 1e6) * world
@@ -319,6 +322,7 @@ def run_ours(args):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     st_e2e = all_stats()
     n_ovl = int(sum_over_ranks(n_mine))
+    h2d_all, d2h_all = int(sum_over_ranks(st_e2e["h2d_bytes"])), int(sum_over_ranks(st_e2e["d2h_bytes"]))  # whole job
 
     # ---- device-resident; CUDA events on the library's stream (+ wall clock, which includes the NCCL exchange at N > 1)
     dev_prepare()
@@ -381,7 +385,7 @@ def run_ours(args):
                    "sharding": ("reads by rid % N for the index, SHIMMER-hash chunk c of T=N for the overlap; " +
                                 ("NCCL all-to-all of SHIMMER-pair records to the owning chunk + all-gather of packed reads and partial count tables" if args.exchange == "routed"
                                  else "NCCL all-gather of packed reads + L2 lists")) if world > 1 else "single GPU"},
-        "e2e": {"value": n_ovl / e2e_s, "unit": "overlaps/s", "h2d_bytes_per_step": st_e2e["h2d_bytes"] // K, "d2h_bytes_per_step": st_e2e["d2h_bytes"] // K,
+        "e2e": {"value": n_ovl / e2e_s, "unit": "overlaps/s", "h2d_bytes_per_step": h2d_all // K, "d2h_bytes_per_step": d2h_all // K,
                 "ms_per_step": e2e_s * 1e3, "read_bases_per_s": bases / e2e_s},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
@@ -392,7 +396,10 @@ def run_ours(args):
     }
     if cpu:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out))
+    if world > 1:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
