@@ -774,6 +774,11 @@ struct ReplayState {
   int *err;
 };
 __device__ __forceinline__ uint32_t ht_home(uint64_t key, uint32_t cap) { return __umulhi(ht_mix(key), cap); }
+// Longest probe sequence of the pair table and of the alignment cache.  An insert that does not find a slot within this
+// many steps reports the table as full (the host grows it and restarts the fix-point); lookups stop there too, since no
+// key can live further from its home.  Without the bound a FULL table turns every operation into a scan of the whole
+// table (millions of steps per thread: the N = 4 / N = 8 bench runs of round 1g never came back from their first wet pass).
+#define PGB_MAX_PROBE 512u
 
 struct DevReplayCtx {
   ReplayState s;
@@ -784,7 +789,8 @@ struct DevReplayCtx {
   __device__ void pair_get(uint64_t p, uint64_t *vold, uint64_t *vnew) const {
     *vold = *vnew = ~0ULL;
     uint32_t h = ht_home(p, s.ecap);
-    for (uint32_t probe = 0; probe < s.ecap; probe++) {
+    const uint32_t lim = s.ecap < PGB_MAX_PROBE ? s.ecap : PGB_MAX_PROBE;
+    for (uint32_t probe = 0; probe < lim; probe++) {
       const uint4 e = __ldcg((const uint4 *)&s.E[h]);  // L2: entries are updated with atomics by other SMs (and by this thread)
       const uint64_t k = (uint64_t)e.x | ((uint64_t)e.y << 32);
       if (k == p) {
@@ -799,7 +805,8 @@ struct DevReplayCtx {
   }
   __device__ void pair_set(uint64_t p, uint64_t v) {
     uint32_t h = ht_home(p, s.ecap);
-    for (uint32_t probe = 0; probe < s.ecap; probe++) {
+    const uint32_t lim = s.ecap < PGB_MAX_PROBE ? s.ecap : PGB_MAX_PROBE;
+    for (uint32_t probe = 0; probe < lim; probe++) {
       uint64_t k = __ldcg(&s.E[h].key);
       if (k == PGB_EMPTY) {
         k = atomicCAS((unsigned long long *)&s.E[h].key, (unsigned long long)PGB_EMPTY, (unsigned long long)p);
@@ -815,7 +822,8 @@ struct DevReplayCtx {
   }
   __device__ uint32_t aln_slot(uint64_t key, bool insert) const {
     uint32_t h = ht_home(key, s.acap);
-    for (uint32_t probe = 0; probe < s.acap; probe++) {
+    const uint32_t lim = s.acap < PGB_MAX_PROBE ? s.acap : PGB_MAX_PROBE;
+    for (uint32_t probe = 0; probe < lim; probe++) {
       uint64_t k = __ldcg(&s.akeys[h]);
       if (k == PGB_EMPTY) {
         if (!insert) return PGB_NOSLOT;
@@ -857,6 +865,7 @@ __global__ void __launch_bounds__(64) k_replay(ReplayState st, uint32_t n_ranks,
                                                ovlp_rec *out, uint8_t *unk_flag) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_ranks) return;
+  if (*(volatile int *)st.err & (32 | 64)) return;  // a table filled up: this pass is void, the host restarts with larger tables
   r = list[r];
   uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
   DevReplayCtx c;
@@ -897,8 +906,12 @@ __global__ void __launch_bounds__(PGB_RB_THREADS) k_replay_block(ReplayState st,
   __shared__ uint32_t s_ev[PGB_RB_MAXEV];  // i | j << 8 | type << 16 | accepted << 18 | known << 19
   __shared__ uint32_t s_nev, s_generic;
   if (blockIdx.x >= n_ranks) return;
-  const uint32_t r = list[blockIdx.x];
   const uint32_t tid = threadIdx.x;
+  __shared__ int s_abort;  // a table filled up: this pass is void (the host restarts with larger tables), finish quickly
+  if (tid == 0) s_abort = *(volatile int *)st.err & (32 | 64);
+  __syncthreads();
+  if (s_abort) return;
+  const uint32_t r = list[blockIdx.x];
   const uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
   DevReplayCtx c;
   c.s = st;

@@ -86,6 +86,8 @@ struct pgb_ctx {
   char *d_map_text = nullptr; size_t map_bytes = 0, map_hits = 0;
   // ---- dedup output (preads.ovl text)
   char *d_dedup_text = nullptr; size_t dedup_bytes = 0, dedup_kept = 0;
+  // ---- replay table sizing relative to the eligible record count (learned: doubled whenever a table overflowed)
+  double ecap_ratio = 1.25, acap_ratio = 0.75;
   // ---- overlap output
   ovlp_rec *d_ovl = nullptr; size_t n_ovl = 0;
   void *h_ovl = nullptr; size_t h_ovl_cap = 0;  // page-locked staging of the records (pgb_overlap_host)
@@ -1142,7 +1144,13 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
 
   // table capacities: sized for what a chunk normally needs (pairs ever accepted ~ 0.3 n_elig, alignments ~ 0.25 n_elig);
   // a chunk that needs more raises the overflow flag and the fix-point restarts with doubled tables
-  uint64_t ecap64 = (uint64_t)n_elig + n_elig / 4 + 4096, acap64 = (uint64_t)n_elig / 2 + n_elig / 4 + 4096;
+  // The ratios are remembered by the context (a later call on a similar job starts with tables that fit) and grow with the
+  // chunk count: rid_pairs is per chunk, so at T chunks a read pair is aligned in up to T of them (x4.5 at T=8).
+  // PGB_TABLE_SCALE (tests): scale the initial capacities down to force the overflow / restart path on small inputs.
+  const char *ts_env = getenv("PGB_TABLE_SCALE");
+  const double tscale = ts_env ? atof(ts_env) : 1.0;
+  uint64_t ecap64 = (uint64_t)(c->ecap_ratio * tscale * n_elig) + (ts_env ? 64 : 4096);
+  uint64_t acap64 = (uint64_t)(c->acap_ratio * tscale * n_elig) + (ts_env ? 64 : 4096);
   bool converged = false;
   ReplayState S;
   for (int attempt = 0; !converged; attempt++) {
@@ -1202,8 +1210,8 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         int e = 0;
         c->d2h(&e, c->d_err, sizeof e);
         if (e & (32 | 64)) {  // a table filled up: grow it and start over
-          if (e & 32) ecap64 *= 2;
-          if (e & 64) acap64 *= 2;
+          if (e & 32) { ecap64 *= 2; if (!ts_env) c->ecap_ratio *= 2; }
+          if (e & 64) { acap64 *= 2; if (!ts_env) c->acap_ratio *= 2; }
           int z = 0;
           c->h2d(c->d_err, &z, sizeof z);
           c->sync();

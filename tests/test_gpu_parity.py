@@ -255,6 +255,23 @@ def test_thread_per_alignment_kernel_on_every_alignment(workdir, ref_dir, monkey
             assert_same_ovlp(oo[0], ro[0])
 
 
+@pytest.mark.parametrize("scale", ["0.02", "0.3"])
+def test_replay_tables_overflow_and_restart(workdir, ref_dir, monkeypatch, scale):
+    """PGB_TABLE_SCALE shrinks the initial pair table / alignment cache so that they fill up: probes are bounded
+    (PGB_MAX_PROBE), the pass is abandoned, the host doubles the table and restarts the fix-point, and the records are
+    still the reference's.  (At T >= 4 chunks of a big job the default sizing overflows for real: rid_pairs is per chunk,
+    so a read pair is aligned in several chunks.)"""
+    monkeypatch.setenv("PGB_TABLE_SCALE", scale)
+    monkeypatch.setenv("PGB_VERBOSE", "1")
+    p = D.make_sim(workdir, "ovf", genome=300_000, cov=20)
+    rp = D.ref_index(ref_dir, p, os.path.join(workdir, "ovf/ref"), T=1, extra=["-m", "0"])
+    for T in (1, 4):
+        ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, f"ovf/ref{T}"), T=T)
+        oo = ours_overlap(p, rp, 2, os.path.join(workdir, f"ovf/our{T}_{scale}"), T=T)
+        for a, b in zip(oo, ro):
+            assert_same_ovlp(a, b)
+
+
 def test_sharded_exchange_matches_reference(sim1, workdir, ref_dir):
     """Multi-GPU data path on one device: three 'ranks' (engines) each sketch the reads of their index chunk, the packed
     reads and SHIMMER lists are concatenated exactly as the NCCL all-gather of peregrine_b200.multigpu does, and every rank
