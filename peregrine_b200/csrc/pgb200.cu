@@ -1154,7 +1154,7 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   bool converged = false;
   ReplayState S;
   for (int attempt = 0; !converged; attempt++) {
-    if (attempt > 8 || ecap64 >= (1ull << 32) || acap64 >= (1ull << 32)) { free_common(); throw std::runtime_error("replay tables overflow"); }
+    if (attempt > 24 || ecap64 >= (1ull << 32) || acap64 >= (1ull << 32)) { free_common(); throw std::runtime_error("replay tables overflow"); }
     memset(&S, 0, sizeof S);
     S.ecap = (uint32_t)ecap64; S.acap = (uint32_t)acap64; S.req_cap = S.acap;
     S.E = c->alloc<EEntry>(S.ecap);
@@ -1211,7 +1211,11 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         c->d2h(&e, c->d_err, sizeof e);
         if (e & (32 | 64)) {  // a table filled up: grow it and start over
           if (e & 32) { ecap64 *= 2; if (!ts_env) c->ecap_ratio *= 2; }
-          if (e & 64) { acap64 *= 2; if (!ts_env) c->acap_ratio *= 2; }
+          if (e & 64) {  // n_req counted every request of the pass, also those that no longer fitted: size for them at once
+            const uint64_t want = std::max(2 * acap64, (uint64_t)n_req + n_req / 2);
+            if (!ts_env) c->acap_ratio *= (double)want / (double)acap64;
+            acap64 = want;
+          }
           int z = 0;
           c->h2d(c->d_err, &z, sizeof z);
           c->sync();
