@@ -99,6 +99,26 @@ def test_index_parameter_sweep(sim1, workdir, ref_dir, k, w, r, l):
     compare_index(rp, op, 1, levels=("L0", f"L{l}"))
 
 
+def test_config5_grid(workdir, ref_dir):
+    """BASELINE.json configs[4]: every (k, w) of {14,16,18} x {60,80,120} through index AND overlap with aln_bw of 50/100/200,
+    on a small noisy set (1 % error: wider bands than the clean sets)."""
+    p = D.make_sim(workdir, "c5", genome=250_000, cov=15, err=0.01)
+    bws = ("50", "100", "200")
+    n = 0
+    for k in (14, 16, 18):
+        for w in (60, 80, 120):
+            tag = f"k{k}w{w}"
+            ex = ["-k", str(k), "-w", str(w), "-m", "0"]
+            rp = D.ref_index(ref_dir, p, os.path.join(workdir, f"c5/ref_{tag}"), T=1, extra=ex)
+            op = ours_index(p, os.path.join(workdir, f"c5/our_{tag}"), T=1, extra=ex)
+            compare_index(rp, op, 1, levels=("L2",))
+            bw = bws[n % 3]
+            n += 1
+            ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, f"c5/refo_{tag}"), T=1, extra=["-w", bw])
+            oo = ours_overlap(p, op, 2, os.path.join(workdir, f"c5/ouro_{tag}"), T=1, extra=["-w", bw])
+            assert_same_ovlp(oo[0], ro[0])
+
+
 @pytest.mark.parametrize("extra", [["-w", "50"], ["-w", "200"], ["-b", "2", "-n", "40"], ["-m", "3", "-M", "60"], ["-b", "8", "-n", "500", "-M", "1000"]])
 def test_overlap_parameter_sweep(sim1, workdir, ref_dir, extra):
     tag = "_".join(x.strip("-") for x in extra)
