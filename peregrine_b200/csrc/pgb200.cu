@@ -44,7 +44,7 @@ static inline double now_ms() {
 }
 
 struct pgb_ctx {
-  int device = 0;
+  int device = 0, sm_count = 148;
   cudaStream_t st = nullptr;
   std::string err;
   pgb_stats stats;
@@ -313,6 +313,7 @@ extern "C" pgb_ctx *pgb_create(int device) {
     CU(cudaSetDevice(device));
     pgb_ctx *c = new pgb_ctx();
     c->device = device;
+    if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count <= 0) c->sm_count = 148;
     memset(&c->stats, 0, sizeof c->stats);
     CU(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
@@ -1253,7 +1254,20 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
           // step against 26.2 ms for the plain form at 16 CTAs/SM, whose 64-register cap forces spills (profiles/r1g_ncu.md);
           // PGB_ALIGN_VARIANT=0 selects the plain form (kept as the A/B baseline of the parity tests)
           if (ALIGN_VARIANT == 0) PGB_LEAN(false, false, 16);
-          else PGB_LEAN(true, true, 12);
+          else if (ALIGN_VARIANT == 12)  // experiment for the next GPU session: + L2 prefetch of the next operand line (unmeasured)
+            LAUNCH(c, (k_align_lean<true, true, 12, true>), nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc,
+                   c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
+          else if (ALIGN_VARIANT == 13 || ALIGN_VARIANT == 14) {  // experiment: persistent lanes with a global request queue (unmeasured)
+            unsigned int *qhead = c->alloc<unsigned int>(1);
+            CU(cudaMemsetAsync(qhead, 0, 4, c->st));
+            const unsigned grid = std::min(nblk(nn, PGB_ALIGN_THREADS), (unsigned)(c->sm_count * 12));
+            if (ALIGN_VARIANT == 13)
+              LAUNCH(c, k_align_stream<false>, grid, PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid,
+                     c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases, qhead);
+            else
+              LAUNCH(c, k_align_stream<true>, grid, PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid,
+                     c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases, qhead);
+          } else PGB_LEAN(true, true, 12);
 #undef PGB_LEAN
         }
         if (c->n_reads_with_n)

@@ -407,7 +407,16 @@ PGB_HD uint64_t window64(uint64_t A, uint64_t B, uint32_t s2) {
 // qw / tw: first packed word of the read in the image of the operand's strand; qo / to: base offset of logical base 0.
 // V: caller scratch of 2*cap ints, cap >= band_tolerance + 2.
 // PRE: load V[d-1][k+3] one cell ahead; TRIMREG: serve the first two trim steps per side from registers
-template <bool PRE, bool TRIMREG>
+// PF: when a continued snake enters a new 128-byte line of an operand, ask L2 for the line after it (a hint only; the
+// walk is sequential, so the DRAM latency of the next line overlaps the 16 word-steps spent in the current one)
+PGB_HD void prefetch_l2(const void *p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+template <bool PRE, bool TRIMREG, bool PF = false>
 PGB_HD void ovlp_match_lean_t(const uint64_t *qw, uint32_t qo, int q_len, const uint64_t *tw, uint32_t to, int t_len,
                               int band_tolerance, int *V, int cap, match_t *out) {
   match_t r;
@@ -433,118 +442,7 @@ PGB_HD void ovlp_match_lean_t(const uint64_t *qw, uint32_t qo, int q_len, const 
   // the cell, and the lanes of a warp reconverge at the end of every iteration (a `continue` makes the compiler build an
   // inner snake loop at whose exit all lanes wait for the longest snake of the warp).
   while (running) {
-    const int rem = (q_len - x) < (t_len - (x - k)) ? (q_len - x) : (t_len - (x - k));
-    uint64_t df = 0;
-    if (rem > 0) {  // one 32-base word-step of the snake (DWmatch.c:135-140)
-      if (fresh) { qA = qp[0]; tA = tp[0]; }
-      qB = qp[1];
-      tB = tp[1];
-      df = window64(qA, qB, qs) ^ window64(tA, tB, ts);
-    }
-    if (df == 0 && rem > 32) {  // all 32 bases equal and more to compare: stay in this snake
-      x += 32; qp++; tp++;
-      qA = qB; tA = tB;
-      fresh = false;
-    } else {
-      // ---- the snake of cell (d, k) ended
-      int n = rem > 0 ? rem : 0;
-      if (df) {
-        const uint32_t lo = (uint32_t)df;
-        const int nb = lo ? (ctz32(lo) >> 1) : 16 + (ctz32((uint32_t)(df >> 32)) >> 1);
-        if (nb < n) n = nb;
-      } else if (n > 32) n = 32;
-      x += n;
-      const int y = x - k;
-      if ((x - x1 > 16) && !start) { r.q_bgn = x1; r.t_bgn = x1 - k; start = true; }                                   // DWmatch.c:142-146
-      if ((uint32_t)(x - x1) > longest_match) { longest_match = (uint32_t)(x - x1); r.q_m_end = x; r.t_m_end = y; }  // :148-152
-      Vc[idx] = x;
-      const int u = x + y;
-      if (u > best_m) { best_m = u; k_best = k; }
-      if (idx == 0) u_first = u;
-      if (TRIMREG) {
-        if (idx == 1) u1 = u;
-        else if (idx == 2) u2 = u;
-        ul2 = ul1; ul1 = ul0; ul0 = u;
-      }
-      if (x >= q_len || y >= t_len) {  // :161-164, :185-194
-        r.q_end = x;
-        r.t_end = y;
-        r.dist = d;
-        r.m_size = (r.q_end - r.q_bgn + r.t_end - r.t_bgn + 2 * d) / 2;
-        matched = true;
-        running = false;
-      } else {
-        if (k < max_k) {
-          k += 2;
-          idx++;
-        } else {
-          // ---- end of edit distance d: trim the band to the hull of { k : x+y >= best_m - band_tolerance } (:168-183).
-          // k_best (this row's first diagonal that reached best_m; every row raises best_m) is in the hull.
-          const int thr = best_m - band_tolerance;
-          int lo_k = min_k, off = 0;
-          // (a cell between the row's end and k_best exists in this row, so u1 / u2 / ul1 / ul2 are this row's when they are read)
-          if (!TRIMREG) {
-            if (u_first < thr) {
-              lo_k += 2; off = 1;
-              while (lo_k < k_best && 2 * Vc[off] - lo_k < thr) { lo_k += 2; off++; }
-            }
-          } else if (u_first < thr) {
-            lo_k += 2; off = 1;
-            if (lo_k < k_best && u1 < thr) {
-              lo_k += 2; off = 2;
-              if (lo_k < k_best && u2 < thr) {
-                lo_k += 2; off = 3;
-                while (lo_k < k_best && 2 * Vc[off] - lo_k < thr) { lo_k += 2; off++; }
-              }
-            }
-          }
-          int hi_k = max_k;
-          if (!TRIMREG) {
-            if (u < thr) {  // u is the row's last cell here
-              int i2 = idx - 1;
-              hi_k -= 2;
-              while (hi_k > k_best && 2 * Vc[i2] - hi_k < thr) { hi_k -= 2; i2--; }
-            }
-          } else if (u < thr) {
-            hi_k -= 2;
-            if (hi_k > k_best && ul1 < thr) {
-              hi_k -= 2;
-              if (hi_k > k_best && ul2 < thr) {
-                int i2 = idx - 3;
-                hi_k -= 2;
-                while (hi_k > k_best && 2 * Vc[i2] - hi_k < thr) { hi_k -= 2; i2--; }
-              }
-            }
-          }
-          poff = off;
-          min_k = lo_k - 1;
-          max_k = hi_k + 1;
-          int *tmp = Vc; Vc = Vp; Vp = tmp;
-          d++;
-          k = min_k;
-          idx = 0;
-          if (d >= max_d || max_k - min_k > band_size) running = false;  // DWmatch.c:118-122, not matched
-        }
-        // ---- set-up of the next cell (DWmatch.c:125-131); d >= 1 here, so min_k < max_k
-        int vp = 0;
-        if (PRE) {
-          vp = vpre;  // V[d-1][k+1] (0 for the row's last cell, which does not use it)
-          if (idx == 0) vp = Vp[poff];  // first cell of a row (min_k < max_k always): the only exposed band-row load
-          vpre = (k + 2 < max_k) ? Vp[poff + idx + 1] : 0;  // for the next cell of this row
-        } else if (k != max_k) {
-          vp = Vp[poff + idx];  // V[d-1][k+1]
-        }
-        if (idx == 0) x = vp;
-        else if (k == max_k) x = vcarry + 1;
-        else x = (vcarry < vp) ? vp : vcarry + 1;
-        vcarry = vp;
-        x1 = x;
-        const uint32_t qb = qo + (uint32_t)x, tb = to + (uint32_t)(x - k);
-        qp = qw + (qb >> 5); qs = (qb & 31) * 2;
-        tp = tw + (tb >> 5); ts = (tb & 31) * 2;
-        fresh = true;
-      }
-    }
+#include "ovlp_match_lean_body.inc"
   }
   if (!matched) {  // DWmatch.c:196-199
     r.q_bgn = 0;
@@ -555,6 +453,59 @@ PGB_HD void ovlp_match_lean_t(const uint64_t *qw, uint32_t qo, int q_len, const 
 PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const uint64_t *tw, uint32_t to, int t_len,
                             int band_tolerance, int *V, int cap, match_t *out) {
   ovlp_match_lean_t<true, true>(qw, qo, q_len, tw, to, t_len, band_tolerance, V, cap, out);
+}
+
+// Streaming form: one lane works through a queue of alignments.  fetch(qw, qo, q_len, tw, to, t_len) -> false when the queue
+// is empty; store(result) is called once per fetched alignment.  When an alignment ends the lane fetches the next one
+// inside the same loop, so the lanes of a warp stay busy until the queue is drained (in ovlp_match_lean_t a lane that
+// finished early idles until the longest alignment of its warp ends: 6 of 32 lanes on average, profiles/r1g_ncu.md).
+// Same results as ovlp_match_lean_t call by call (tests/hostsim `match`).
+template <bool PRE, bool TRIMREG, bool PF, class Fetch, class Store>
+PGB_HD void ovlp_match_lean_stream(Fetch &&fetch, Store &&store, int band_tolerance, int *V, int cap) {
+  const uint64_t *qw = nullptr, *tw = nullptr;
+  uint32_t qo = 0, to = 0;
+  int q_len = 0, t_len = 0;
+  match_t r;
+  int max_d = 0;
+  const int band_size = band_tolerance * 2;
+  uint32_t longest_match = 0;
+  bool start = false, matched = false;
+  int best_m = -1, k_best = 0, u_first = 0;
+  int min_k = 0, max_k = 0, d = 0, k = 0, idx = 0, x = 0, x1 = 0;
+  int *Vc = V, *Vp = V + cap;
+  int vcarry = 0, vpre = 0, poff = 0;
+  int u1 = 0, u2 = 0, ul0 = 0, ul1 = 0, ul2 = 0;
+  const uint64_t *qp = nullptr, *tp = nullptr;
+  uint32_t qs = 0, ts = 0;
+  uint64_t qA = 0, qB = 0, tA = 0, tB = 0;
+  bool fresh = true, running = false, active = true;
+  auto begin = [&]() -> bool {
+    if (!fetch(qw, qo, q_len, tw, to, t_len)) return false;
+    r.m_size = r.dist = r.q_bgn = r.q_end = r.t_bgn = r.t_end = r.t_m_end = r.q_m_end = 0;
+    max_d = (int)(0.3 * (double)(q_len + t_len));  // DWmatch.c:96
+    longest_match = 0;
+    start = false; matched = false;
+    best_m = -1; k_best = 0; u_first = 0;
+    min_k = 0; max_k = 0; d = 0; k = 0; idx = 0; x = 0; x1 = 0;
+    Vc = V; Vp = V + cap;
+    vcarry = 0; vpre = 0; poff = 0;
+    qp = qw + (qo >> 5); tp = tw + (to >> 5);
+    qs = (qo & 31) * 2; ts = (to & 31) * 2;
+    fresh = true;
+    running = max_d > 0;
+    return true;
+  };
+  active = begin();
+  while (active) {
+    if (running) {
+#include "ovlp_match_lean_body.inc"
+    }
+    if (!running) {  // the alignment ended in this iteration (or never started: max_d == 0)
+      if (!matched) { r.q_bgn = 0; r.t_bgn = 0; }  // DWmatch.c:196-199
+      store(r);
+      active = begin();
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- mm_sketch (exact automaton)

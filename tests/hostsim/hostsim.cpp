@@ -95,6 +95,8 @@ static void load_packed(const char *prefix, Packed *P) {
     }
   }
 }
+struct LeanCase { size_t r0; uint32_t start0; int s0; size_t r1; int s1; match_t want; };
+static std::vector<LeanCase> g_lean_cases;  // replayed through ovlp_match_lean_stream at the end of `match`
 static bool lean_match(const Packed &P, size_t r0, uint32_t start0, int s0, size_t r1, int s1, int bw, match_t *m) {
   if (P.has_n[r0] || P.has_n[r1]) return false;  // reads with N take ovlp_match_flat in the product too
   std::vector<int> V(2 * (bw + 2));
@@ -276,7 +278,9 @@ static int one_match(const Packed &P, size_t r0, uint32_t start0, int s0, size_t
   ovlp_match_flat(q, qlen, t, tlen, bw, Vf.data(), bw + 8, &flat, &err2);
   int ok = same_match(*ref, mine) && err == 0 && same_match(*ref, flat) && err2 == 0;
   match_t lean;
-  if (lean_match(P, r0, start0, s0, r1, s1, bw, &lean) && !same_match(*ref, lean)) {
+  const bool has_lean = lean_match(P, r0, start0, s0, r1, s1, bw, &lean);
+  if (has_lean) g_lean_cases.push_back(LeanCase{r0, start0, s0, r1, s1, *ref});
+  if (has_lean && !same_match(*ref, lean)) {
     ok = 0;
     if (*bad < 8) fprintf(stderr, "LEAN differs: {%d %d %d %d %d %d %d %d}\n", lean.m_size, lean.dist, lean.q_bgn, lean.q_end, lean.t_bgn, lean.t_end, lean.t_m_end, lean.q_m_end);
   }
@@ -305,8 +309,27 @@ static int cmd_match(int argc, char **argv) {
     if (it % 4 == 1) st = 0;
     one_match(P, r0, st, (int)(rnd() & 1), r1, (int)(rnd() & 1), bw, &bad);
   }
-  printf("match: pairs=%zu mismatches=%zu\n", npairs, bad);
-  return bad ? 3 : 0;
+  // the streaming form: a few "lanes" work through the recorded pairs as queues; every result must equal the per-call one
+  size_t stream_bad = 0, stream_n = 0;
+  for (int lanes : {1, 3}) {
+    for (int lane = 0; lane < lanes; lane++) {
+      std::vector<int> V(2 * (bw + 2));
+      size_t next = (size_t)lane, cur = 0;
+      auto fetch = [&](const uint64_t *&qw, uint32_t &qo, int &q_len, const uint64_t *&tw, uint32_t &to, int &t_len) -> bool {
+        if (next >= g_lean_cases.size()) return false;
+        cur = next; next += (size_t)lanes;
+        const LeanCase &c = g_lean_cases[cur];
+        qw = (c.s0 ? P.wrc.data() : P.w.data()) + P.woff[c.r0]; qo = c.start0; q_len = (int)(P.rt.len[c.r0] - c.start0);
+        tw = (c.s1 ? P.wrc.data() : P.w.data()) + P.woff[c.r1]; to = 0; t_len = (int)P.rt.len[c.r1];
+        return true;
+      };
+      auto store = [&](const match_t &m) { stream_n++; if (!same_match(m, g_lean_cases[cur].want)) stream_bad++; };
+      ovlp_match_lean_stream<true, true, false>(fetch, store, bw, V.data(), bw + 2);
+    }
+  }
+  if (stream_n != 2 * g_lean_cases.size()) stream_bad++;
+  printf("match: pairs=%zu mismatches=%zu stream_results=%zu stream_mismatches=%zu\n", npairs, bad, stream_n, stream_bad);
+  return (bad || stream_bad) ? 3 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------------------ overlap
