@@ -143,7 +143,8 @@ enum pgb_buffer {
   PGB_BUF_ROW_HASN = 5, /* uint32[rows]: 1 if the read contains a non-ACGT base                                        */
   PGB_BUF_LEVEL0 = 8, PGB_BUF_LEVEL1 = 9, PGB_BUF_LEVEL2 = 10, /* mm128_t[n] of the index level                       */
   PGB_BUF_COUNTS = 11,  /* mm_count_t[n]: the multiplicity table dumped by pgb_counts_dump                             */
-  PGB_BUF_ROUTE = 12    /* mp256_t-like 40-byte records {x0,x1,y0,y1,direction(u64)} grouped by owner chunk 1..T       */
+  PGB_BUF_ROUTE = 12,   /* mp256_t-like 40-byte records {x0,x1,y0,y1,direction(u64)} grouped by owner chunk 1..T       */
+  PGB_BUF_OVLP = 13     /* ovlp_t[n]: the records of the last pgb_overlap / pgb_overlap_routed (for a cross-rank shmr_dedup) */
 };
 size_t pgb_buffer_elems(pgb_ctx *, int which);                       /* element count of a buffer                      */
 int pgb_buffer_copy_out(pgb_ctx *, int which, void *dst_device);     /* device -> caller's device buffer               */

@@ -826,6 +826,7 @@ extern "C" size_t pgb_buffer_elems(pgb_ctx *c, int which) {
     case PGB_BUF_LEVEL0: case PGB_BUF_LEVEL1: case PGB_BUF_LEVEL2: return c->level_n[which - PGB_BUF_LEVEL0];
     case PGB_BUF_COUNTS: return c->n_mc_dump;
     case PGB_BUF_ROUTE: return c->n_route;
+    case PGB_BUF_OVLP: return c->n_ovl;
     default: return 0;
   }
 }
@@ -849,6 +850,7 @@ extern "C" int pgb_buffer_copy_out(pgb_ctx *c, int which, void *dst) {
     case PGB_BUF_LEVEL0: case PGB_BUF_LEVEL1: case PGB_BUF_LEVEL2: src = c->d_level[which - PGB_BUF_LEVEL0]; esz = 16; break;
     case PGB_BUF_COUNTS: src = c->d_mc_dump; esz = 16; break;
     case PGB_BUF_ROUTE: src = c->d_route; esz = 40; break;
+    case PGB_BUF_OVLP: src = c->d_ovl; esz = sizeof(ovlp_rec); break;
     default: throw std::runtime_error("unknown buffer id");
   }
   if (n) CU(cudaMemcpyAsync(dst, src, n * esz, cudaMemcpyDeviceToDevice, c->st));

@@ -252,7 +252,7 @@ class Engine:
         self._ck(self.L.pgb_set_shimmers_device(self.h, C.c_void_p(mm_ptr), n), "pgb_set_shimmers_device")
 
     # ------------------------------------------------------------------ routed exchange (pair records travel)
-    BUF_COUNTS, BUF_ROUTE = 11, 12
+    BUF_COUNTS, BUF_ROUTE, BUF_OVLP = 11, 12, 13
 
     def counts_dump(self) -> int:
         n = C.c_size_t()

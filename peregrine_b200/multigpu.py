@@ -100,6 +100,12 @@ def first_found_before(has_first: bool, device, group=None) -> bool:
     return any(int(x.item()) for x in fs[:rank])
 
 
+def gather_records(mine: torch.Tensor, group=None):
+    """`cat ovlp-01.dat ovlp-02.dat ...` across ranks: every rank's ovlp_t records (an (n, 8) int64 view of the 64-byte records)
+    concatenated in chunk (= rank) order, which is the stream order shmr_dedup sees (py/scripts/pg_run.py:352)."""
+    return torch.cat(all_gather_var(mine, group))
+
+
 # ------------------------------------------------------------------------------------------------ engine <-> torch
 def export_reads(eng, device):
     """Copy the engine's packed reads + read table into fresh torch tensors on `device` (a CUDA device)."""
@@ -175,6 +181,21 @@ class ShardedJob:
         if self.routed is not None:
             return self.ovl_eng.overlap_routed(self.routed.data_ptr(), int(self.routed.shape[0]), bestn, bw, ovlp_upper, copy=copy)
         return self.ovl_eng.overlap(self.world, self.rank + 1, bestn, mc_lower, mc_upper, bw, ovlp_upper, copy=copy)
+
+    def dedup_all(self, dedup_eng=None):
+        """`cat ovlp-*.dat | shmr_dedup` for the whole job: the ranks' record streams are gathered in chunk order and rank 0
+        runs the dedup kernels over the concatenation (first-seen per read pair ACROSS chunks).  Returns the preads.ovl text
+        on rank 0, None elsewhere.  Call after overlap(copy=False)."""
+        E = self.ovl_eng
+        n = E.L.pgb_overlap_size(E.h)
+        mine = torch.empty((n, 8), dtype=torch.int64, device=self.device)
+        if n:
+            E.buffer_copy_out(E.BUF_OVLP, mine.data_ptr())
+        torch.cuda.synchronize(self.device)
+        stream = gather_records(mine, self.group).contiguous()
+        if self.rank != 0:
+            return None
+        return (dedup_eng or E).dedup(device_ptr=stream.data_ptr(), n=int(stream.shape[0]))
 
     def index_and_route(self, w, k, r, mc_lower=2, mc_upper=240):
         """north_star's exchange: the SHIMMER-pair records travel.  Every rank runs build_map over its own reads' shimmers

@@ -41,6 +41,10 @@ def _worker(rank, world, port, q):
     send = torch.tensor([[rank, d, i, 0, 0] for d in range(world) for i in range(sizes[d])], dtype=torch.int64).reshape(-1, 5)
     recv, in_sizes = M.all_to_all_var(send, sizes)
     before = M.first_found_before(rank == 1, torch.device("cpu"))
+    # cross-rank record stream for shmr_dedup: rank r holds 2 + r records, tagged (rank, i)
+    recs = torch.tensor([[rank, i, 0, 0, 0, 0, 0, 0] for i in range(2 + rank)], dtype=torch.int64).reshape(-1, 8)
+    stream = M.gather_records(recs)
+    assert stream[:, :2].tolist() == [[r, i] for r in range(world) for i in range(2 + r)]  # chunk order, stream order inside
     q.put((rank, {k: v.numpy() for k, v in reads.items()}, l2_all.numpy(), recv.numpy(), in_sizes, before))
     dist.barrier()
     dist.destroy_process_group()
