@@ -11,6 +11,7 @@
 #include <getopt.h>
 #include <assert.h>
 #include <chrono>
+#include <cmath>
 #include <unordered_map>
 #include "../../include/pgb200.h"
 #include "host_util.hpp"
@@ -1336,6 +1337,14 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   if (c->n_shm == 0) { c->sync(); return 0; }
   if (c->n_shm >= (1ull << 31)) throw std::runtime_error("more than 2^31 shimmers in one overlap call");
   ensure_loaded(c);
+  {
+    // rid_pairs is per chunk: with T chunks a read pair is aligned (and accepted) in up to T of them, so the alignment cache
+    // and the pair table of ONE chunk grow relative to its eligible records (measured x1.85 records at T=2, SURVEY 6.2: x4.5
+    // at T=8).  Start large enough to spare the fix-point a restart; an underestimate only costs that restart.
+    const double t = (double)std::min<uint32_t>(T, 16);
+    c->acap_ratio = std::max(c->acap_ratio, 0.75 * pow(t, 0.75));
+    c->ecap_ratio = std::max(c->ecap_ratio, 1.25 * std::max(1.0, t / 4.0));
+  }
   PairSoA R;
   uint32_t nrec = build_pair_records(c, T, mychunk, mc_lower, mc_upper, R);
   if (overlap_core(c, R, nrec, bestn, bw, ovlp_upper) != 0) return -1;
