@@ -1492,7 +1492,7 @@ extern "C" int pgb_overlap_host(pgb_ctx *c, const ovlp_t **out, size_t *n) {
 static void dedup_core(pgb_ctx *c, const ovlp_rec *d_recs, size_t n) {
   c->release(c->d_dedup_text); c->dedup_bytes = 0; c->dedup_kept = 0;
   if (n == 0) return;
-  if (n >= (1ull << 31)) throw std::runtime_error("more than 2^31 records in one dedup call");
+  if (n >= (1ull << 30)) throw std::runtime_error("more than 2^30 records in one dedup call");
   c->tic();
   const uint32_t cap = pow2_at_least(2 * (uint64_t)n + 16);
   uint64_t *keys = c->alloc<uint64_t>(cap);
