@@ -24,6 +24,7 @@ def _mmv_to_np(v, free):
 
 
 _orc = None
+FASTA_CB = C.CFUNCTYPE(None, C.POINTER(C.c_char), C.c_size_t, C.POINTER(C.c_char), C.c_size_t, C.c_void_p)
 
 
 def oracle():
@@ -45,6 +46,15 @@ def oracle():
                                         C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
                                         C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
         L.orc_free.argtypes = [C.c_void_p]
+        # stages next to the path (oracle/stages_oracle.c)
+        L.orc_encode_biseq.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+        L.orc_fasta_records.restype = C.c_size_t
+        L.orc_fasta_records.argtypes = [C.c_char_p, C.c_size_t, FASTA_CB, C.c_void_p]
+        L.orc_dedup.restype = C.c_void_p
+        L.orc_dedup.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.orc_map.restype = C.c_void_p
+        L.orc_map.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32,
+                              C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t)]
         _orc = L
     return _orc
 
@@ -174,4 +184,58 @@ def abi_ovlp_match(L, q, qs, t, ts, bw):
     m = L.ovlp_match(q.ctypes.data, len(q), qs, t.ctypes.data, len(t), ts, bw)
     out = np.array([getattr(m.contents, n) for n, _ in MatchT._fields_], dtype=np.int32)
     L.free_ovlp_match(m)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ stages next to the path
+def orc_mkseqdb(paths):
+    """What shmr_mkseqdb writes for the listed files (plain or gzip): (.idx text, .seqdb bytes), via the oracle's kseq
+    restatement and encode_biseq."""
+    import gzip
+
+    L = oracle()
+    idx, db = [], []
+    state = {"rid": 0, "off": 0}
+
+    def rec(name, nl, seq, sl, _):
+        nm = C.string_at(name, nl)
+        sq = C.string_at(seq, sl)
+        out = np.empty(sl, dtype=np.uint8)
+        L.orc_encode_biseq(sq, sl, out.ctypes.data_as(C.c_void_p))
+        idx.append(b"%09d %s %u %lu\n".replace(b"%lu", b"%d") % (state["rid"], nm, sl, state["off"]))
+        db.append(out.tobytes())
+        state["rid"] += 1
+        state["off"] += sl
+
+    cb = FASTA_CB(rec)
+    for p in paths:
+        raw = open(p, "rb").read()
+        if raw[:2] == b"\x1f\x8b":
+            raw = gzip.decompress(raw)
+        L.orc_fasta_records(raw, len(raw), cb, None)
+    return b"".join(idx), b"".join(db)
+
+
+def orc_dedup(stream: np.ndarray) -> bytes:
+    L = oracle()
+    a = np.ascontiguousarray(stream, dtype=F.OVLP)
+    n = C.c_size_t()
+    p = L.orc_dedup(a.ctypes.data_as(C.c_void_p), len(a), C.byref(n))
+    out = C.string_at(p, n.value)
+    L.orc_free(p)
+    return out
+
+
+def orc_map(ref_mm, mm, mc, rid, ln, T=1, c=1, lower=1, upper=240) -> bytes:
+    L = oracle()
+    ref_mm = np.ascontiguousarray(ref_mm, dtype=F.MM128)
+    mm = np.ascontiguousarray(mm, dtype=F.MM128)
+    mc = np.ascontiguousarray(mc, dtype=F.MMCOUNT)
+    by_rid = np.zeros(int(rid.max()) + 1, dtype=np.uint32)
+    by_rid[rid] = ln
+    n = C.c_size_t()
+    p = L.orc_map(ref_mm.ctypes.data_as(C.c_void_p), len(ref_mm), mm.ctypes.data_as(C.c_void_p), len(mm), mc.ctypes.data_as(C.c_void_p), len(mc),
+                  by_rid.ctypes.data_as(C.c_void_p), T, c, lower, upper, C.byref(n))
+    out = C.string_at(p, n.value)
+    L.orc_free(p)
     return out
