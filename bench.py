@@ -218,6 +218,9 @@ def run_ours(args):
         import faulthandler
 
         faulthandler.dump_traceback_later(240, repeat=True, file=sys.stderr)  # a stuck rank shows where it is stuck
+        killer = threading.Timer(1500, lambda: os._exit(3))  # ... and does not hold 8 GPUs forever
+        killer.daemon = True
+        killer.start()
     # Every rank generates ITS share of the read set (rid % N == (rank+1) % N, src/shmr_index.c:157) straight from the
     # counter-based simulator: read i depends on (seed, i) only, so the shares are exactly the selection of the full set,
     # and no rank ever writes or scans the whole 1.5 GB x N image.
