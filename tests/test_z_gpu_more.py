@@ -46,3 +46,41 @@ def test_replay_tables_overflow_and_restart(workdir, ref_dir, monkeypatch, scale
         oo = ours_overlap(p, rp, 2, os.path.join(workdir, f"ovf/our{T}_{scale}"), T=T)
         for a, b in zip(oo, ro):
             assert_same_ovlp(a, b)
+
+
+def test_cli_chain_like_run_test_sh(workdir, ref_dir):
+    """tools/run_chain.sh = the reference's own shell recipe (test/ecoli_K12/run_test.sh:16-28): shmr_mkseqdb -> shmr_index x 3
+    -> shmr_overlap x 2 (two processes sharing the GPU) -> cat | shmr_dedup, once with bin/ and once with the unmodified
+    reference; preads.ovl and every intermediate file must be identical."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = D.make_sim(workdir, "chain", genome=500_000, cov=15)
+    fa = os.path.join(workdir, "chain", "reads.fa")
+    if not os.path.exists(fa):  # FASTA of the simulated set (decode the low nibbles of the .seqdb image)
+        import numpy as np
+        from peregrine_b200 import formats as F
+
+        rid, ln, off = F.read_idx(p + ".idx")
+        db = np.fromfile(p + ".seqdb", dtype=np.uint8)
+        lut = np.zeros(16, dtype=np.uint8)
+        lut[[1, 2, 4, 8]] = np.frombuffer(b"ACGT", dtype=np.uint8)
+        lut[0] = ord("N")
+        with open(fa, "wb") as f:
+            for i in range(len(rid)):
+                f.write(b">r/%06d/0_%d\n" % (i, ln[i]) + lut[db[int(off[i]): int(off[i]) + int(ln[i])] & 0x0F].tobytes() + b"\n")
+    lst = os.path.join(workdir, "chain", "in.lst")
+    with open(lst, "w") as f:
+        f.write(fa + "\n")
+    outs = {}
+    for tag, bindir in (("ref", ref_dir), ("our", os.path.join(root, "bin"))):
+        wd = os.path.join(workdir, "chain", tag)
+        subprocess.run(["bash", os.path.join(root, "tools", "run_chain.sh"), lst, wd, "3", "2", "2"], env=dict(os.environ, BIN=bindir), check=True,
+                       stdout=subprocess.DEVNULL)
+        outs[tag] = wd
+    for rel in ["asm/preads.ovl", "index/seq_dataset.idx", "index/seq_dataset.seqdb"] + [f"index/shmr-L2-{c:02d}-of-03.dat" for c in (1, 2, 3)]:
+        a, b = (open(os.path.join(outs[t], rel), "rb").read() for t in ("our", "ref"))
+        assert a == b and len(a) > 0, rel
+    for c in ("01", "02"):
+        assert_same_ovlp(os.path.join(outs["our"], "ovlp", "ovlp." + c), os.path.join(outs["ref"], "ovlp", "ovlp." + c))
+    assert open(os.path.join(outs["our"], "asm/preads.ovl"), "rb").read().count(b"\n") > 500
