@@ -145,7 +145,7 @@ def ref_one(prefix, outdir):
     return os.path.getsize(ro[0]) // 64, time.perf_counter() - t
 
 
-def cpu_baseline_single_core(genome=6_000_000, cov=30):
+def cpu_baseline_single_core(genome=15_000_000, cov=30):  # ~12 s of single-core reference work
     from peregrine_b200 import formats as F
 
     p = make_dataset(f"cpu1_g{genome}", genome, cov, seed=1234)
