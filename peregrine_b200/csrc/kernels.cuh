@@ -438,6 +438,37 @@ __global__ void k_reduce(const mm128 *__restrict__ in, const uint64_t *__restric
   if (!WRITE) counts[t] = n;
 }
 
+// Warp per read (EXPERIMENT for the next GPU session, PGB_REDUCE=warp; unmeasured): lane l decides the window ending at
+// in-read offset base + l.  A window emits its pick iff the pick's y differs from the previous window's pick (the first
+// window always emits) - the per-element formulation of shmr_reduce.c:79-88 that tests/hostsim checks against the reference
+// (sim_reduce).  Thread-per-read keeps only ~5 warps per SM busy (100 k reads), each walking ~370 windows sequentially.
+template <bool WRITE>
+__global__ void k_reduce_warp(const mm128 *__restrict__ in, const uint64_t *__restrict__ in_off, uint32_t n_sel, uint32_t rs,
+                              uint32_t *__restrict__ counts, const uint64_t *__restrict__ out_off, mm128 *__restrict__ out) {
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= n_sel) return;  // warp-uniform
+  const mm128 *a = in + in_off[t];
+  const uint32_t n_in = (uint32_t)(in_off[t + 1] - in_off[t]);
+  mm128 *dst = WRITE ? out + out_off[t] : nullptr;
+  uint32_t n = 0;
+  uint64_t carry_y = ~0ULL;  // y of the previous window's pick (none before the first window; a real y carries this read's rid)
+  for (uint32_t base = rs - 1; base < n_in; base += 32) {
+    const uint32_t o = base + lane;
+    const bool valid = o < n_in;
+    mm128 m;
+    m.x = 0; m.y = ~0ULL;
+    if (valid) m = a[reduce_pick(a, o, rs)];
+    uint64_t prev_y = __shfl_up_sync(0xffffffffu, m.y, 1);
+    if (lane == 0) prev_y = carry_y;
+    const bool emit = valid && m.y != prev_y;
+    const uint32_t bal = __ballot_sync(0xffffffffu, emit);
+    if (WRITE && emit) dst[n + __popc(bal & ((1u << lane) - 1u))] = m;
+    n += __popc(bal);
+    carry_y = __shfl_sync(0xffffffffu, m.y, 31);
+  }
+  if (!WRITE && lane == 0) counts[t] = n;
+}
+
 // ------------------------------------------------------------------------------------------------ multiplicity table
 __global__ void k_mc_insert(const mm128 *__restrict__ mm, size_t n, uint64_t *keys, uint32_t *vals, uint32_t mask, int *err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -743,11 +743,20 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   for (int l = 1; l <= levels; l++) {
     c->tic();
     CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
+    const bool reduce_warp = getenv("PGB_REDUCE") && !strcmp(getenv("PGB_REDUCE"), "warp");  // experiment, see k_reduce_warp
+    if (reduce_warp)
+      LAUNCH(c, k_reduce_warp<false>, nblk(ns * 32, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r, counts,
+             (const uint64_t *)nullptr, (mm128 *)nullptr);
+    else
     LAUNCH(c, k_reduce<false>, nblk(ns, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r, counts,
            (const uint64_t *)nullptr, (mm128 *)nullptr);
     c->d_level_off[l] = c->palloc<uint64_t>(ns + 1);
     c->level_n[l] = scan_u32_to_u64(c, counts, c->d_level_off[l], ns + 1);
     c->d_level[l] = c->palloc<mm128>(c->level_n[l]);
+    if (reduce_warp)
+      LAUNCH(c, k_reduce_warp<true>, nblk(ns * 32, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r,
+             (uint32_t *)nullptr, c->d_level_off[l], c->d_level[l]);
+    else
     LAUNCH(c, k_reduce<true>, nblk(ns, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r,
            (uint32_t *)nullptr, c->d_level_off[l], c->d_level[l]);
     c->stats.ms_reduce += c->toc();

@@ -12,3 +12,11 @@ for v in 7 12 13 14; do
 import json,sys
 d=json.loads(sys.stdin.readline()); print({k:d[k] for k in ('ms_align','ms_k_align','ms_replay','overlaps','wall_overlap_s')})"
 done
+# k_reduce_warp: parity (index sweep incl. r = 36, 2, 1-level) then timing
+PGB_REDUCE=warp timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "index_parameter_sweep or single_chunk or multi_chunk or adversarial" 2>&1 | tail -2
+for m in thread warp; do
+  echo "== PGB_REDUCE=$m"
+  PGB_REDUCE=$m python tools/probe.py 50e6 30 3 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline()); print({k:d[k] for k in ('ms_reduce','ms_sketch','overlaps','wall_index_s')})"
+done
