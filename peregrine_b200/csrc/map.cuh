@@ -45,7 +45,8 @@ __global__ void k_map_ref_flags(const mm128 *__restrict__ ref, size_t n, const u
   const uint32_t s = ht_find(mckeys, mcmask, m.x >> 8);
   cnt[i] = s == PGB_NOSLOT ? 0xFFFFFFFFu : mcvals[s];
   const uint32_t xs = ht_find(xkeys, xmask, m.x);
-  if (xs != PGB_NOSLOT && xfirst[xs] != 0xFFFFFFFFu) atomicMin(first_outer, (unsigned long long)i);  // kh_get(MMER0, mmer0.x) hits, :88-89
+  if (xs != PGB_NOSLOT && xfirst[xs] != 0xFFFFFFFFu && (unsigned long long)i < *(volatile unsigned long long *)first_outer)
+    atomicMin(first_outer, (unsigned long long)i);  // kh_get(MMER0, mmer0.x) hits, :88-89
 }
 __global__ void k_map_kept(const uint32_t *__restrict__ cnt, size_t n, uint32_t lower, uint32_t upper, const unsigned long long *first_outer,
                            uint32_t *flags) {
