@@ -694,7 +694,8 @@ __global__ void k_group_gather(const uint32_t *__restrict__ gidx, const uint32_t
     okey[o] = xkeys[(uint32_t)(key >> 32)];
   }
   if (j == n - 1) goff[n_outer] = n;
-  atomicMax(last_seq_all, blast[slot]);
+  const uint32_t ls = blast[slot];
+  if (ls > *(volatile unsigned int *)last_seq_all) atomicMax(last_seq_all, ls);  // one address for every bucket: test before the atomic
 }
 // one thread per outer key: replay its inner khash, write each bucket's visiting position inside the group
 __global__ void k_inner_order(const uint32_t *__restrict__ goff, uint32_t n_outer, GroupedBuckets g, uint32_t *ipos, uint32_t *big_list,
