@@ -730,14 +730,19 @@ __global__ void k_visit_place(GroupedBuckets g, uint32_t n, const uint32_t *__re
                               const uint32_t *__restrict__ ipos, uint32_t ovlp_upper, uint32_t *vis_slot, uint32_t *vis_elig, uint32_t *vis_cnt,
                               unsigned long long *n_cand) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  uint32_t v = vstart[orank[g.oid[j]]] + ipos[j];
-  uint32_t c = g.count[j];
-  bool el = !(c <= 2 || c > ovlp_upper);
-  vis_slot[v] = g.slot[j];
-  vis_elig[v] = el;
-  vis_cnt[v] = el ? c : 0;
-  if (el) atomicAdd(n_cand, (unsigned long long)c * (c - 1) / 2);
+  unsigned long long cand = 0;
+  if (j < n) {
+    uint32_t v = vstart[orank[g.oid[j]]] + ipos[j];
+    uint32_t c = g.count[j];
+    bool el = !(c <= 2 || c > ovlp_upper);
+    vis_slot[v] = g.slot[j];
+    vis_elig[v] = el;
+    vis_cnt[v] = el ? c : 0;
+    if (el) cand = (unsigned long long)c * (c - 1) / 2;
+  }
+  // candidate-pair statistic: one atomic per warp, not one per bucket on a single address (blockDim is a multiple of 32)
+  for (int d = 16; d; d >>= 1) cand += __shfl_down_sync(0xffffffffu, cand, d);
+  if ((threadIdx.x & 31) == 0 && cand) atomicAdd(n_cand, cand);
 }
 __global__ void k_visit_rank(const uint32_t *__restrict__ vis_slot, const uint32_t *__restrict__ vis_elig, const uint32_t *__restrict__ rank_of,
                              const uint32_t *__restrict__ off_of, uint32_t n, uint32_t *slot2rank, uint32_t *rank_off) {
