@@ -1,0 +1,57 @@
+"""peregrine_b200.utils mirrors the SHIMMER helpers of the reference's peregrine/utils.py (same names / arguments / returns).
+CPU: the helper logic bound to the REFERENCE's own library (oracle/_ref/libshimmer_ref.so, ABI mode).
+GPU: the same calls on libpgb200.so must return exactly what they return on the reference library."""
+import os
+
+import numpy as np
+import pytest
+
+from peregrine_b200 import utils as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case():
+    rng = np.random.default_rng(1)
+    g = bytes(rng.choice(list(b"ACGT"), 40000).tolist())
+    noisy = bytearray(g[8000:30000])
+    for p in rng.integers(0, len(noisy), 150):
+        noisy[p] = b"ACGT"[int(rng.integers(0, 4))]
+    return g[:22000], bytes(noisy)
+
+
+def _chains(T):
+    a, b = _case()
+    out = {}
+    for lv in (0, 1, 2):
+        v = T.get_shimmers_from_seq(a, rid=7, levels=lv, reduction_factor=3 if lv else 3)
+        out[f"L{lv}"] = [U.mmer2tuple(v.a[i]) for i in range(v.n)]
+    s0, s1, s1r = T.get_shimmers_from_seq(a, rid=0), T.get_shimmers_from_seq(b, rid=1), T.get_shimmers_from_seq(U.rc(b), rid=2)
+    out["fwd"] = T.get_shimmer_alns(s0, s1, 0)
+    out["rev"] = T.get_shimmer_alns(s0, s1r, 1)
+    out["self_k14"] = T.get_shimmer_alns(T.get_shimmers_from_seq(a, k=14, w=60), T.get_shimmers_from_seq(a, k=14, w=60), 0, max_repeat=2)
+    return out
+
+
+@pytest.fixture(scope="module")
+def ref_tools(ref_dir):
+    return U.ShimmerTools.for_library(os.path.join(ref_dir, "libshimmer_ref.so"))
+
+
+def test_helpers_on_the_reference_library(ref_tools):
+    assert U.rc(b"AACGT") == b"ACGTT"
+    c = _chains(ref_tools)
+    assert len(c["L0"]) > len(c["L1"]) > len(c["L2"]) > 50 and all(t[2] == 7 and t[1] == 16 for t in c["L2"])
+    best = max(c["fwd"], key=lambda x: len(x[0]))
+    assert len(best[0]) > 50 and int(best[1]) == 8000  # b starts 8000 bases into a
+    assert max(len(x[0]) for x in c["rev"]) > 50
+
+
+@pytest.mark.gpu
+def test_helpers_on_libpgb200_match_the_reference_library(ref_tools):
+    from peregrine_b200.shimmer4py import ffi, lib
+
+    ours = _chains(U.ShimmerTools(ffi, lib))
+    want = _chains(ref_tools)
+    for k in want:
+        assert ours[k] == want[k], k
