@@ -145,15 +145,30 @@ def ref_one(prefix, outdir):
     return os.path.getsize(ro[0]) // 64, time.perf_counter() - t
 
 
-def cpu_baseline_single_core(genome=15_000_000, cov=30):  # ~12 s of single-core reference work
-    from peregrine_b200 import formats as F
+def cpu_baseline_single_core(genome=15_000_000, cov=30, device=0):  # ~12 s of single-core reference work
+    """The unmodified reference on one core over a bounded sample of the bench workload (same read model, 15 Mb genome).  Its
+    records are then the checker for OUR engine on the same set: `parity` says whether the two streams are identical
+    (same records, same order); the bench fails if they are not."""
+    from peregrine_b200 import Engine, formats as F
 
     p = make_dataset(f"cpu1_g{genome}", genome, cov, seed=1234)
-    _, ln, _ = F.read_idx(p + ".idx")
-    n, dt = ref_one(p, os.path.join(work_dir(), f"cpu1_g{genome}", "ref"))
+    rid, ln, off = F.read_idx(p + ".idx")
+    outdir = os.path.join(work_dir(), f"cpu1_g{genome}", "ref")
+    n, dt = ref_one(p, outdir)
+    want = F.normalise_ovlp(F.read_ovlp(os.path.join(outdir, "ovlp.01")))
+    eng = Engine(device)
+    eng.load_reads(np.fromfile(p + ".seqdb", dtype=np.uint8), rid, ln, off)
+    P = PARAMS
+    eng.index(P["w"], P["k"], P["r"], P["levels"], 0)
+    eng.set_shimmers_from_index(2)
+    got = eng.overlap(1, 1, P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"])
+    eng.close()
+    same = len(got) == len(want) and got.tobytes() == want.tobytes()
+    parity = {"records": int(len(want)), "records_ours": int(len(got)), "identical": bool(same),
+              "checked": f"ovlp_t stream of this engine vs oracle/_ref shmr_overlap on the {genome/1e6:g} Mb sample, field-normalised, in order"}
     return {"value": n / dt, "unit": "overlaps/s", "cores": 1, "kind": "reference",
             "read_bases_per_s": float(ln.sum()) / dt,
-            "sample": f"oracle/_ref shmr_index+shmr_overlap (unmodified reference), {genome/1e6:g} Mb genome {cov:g}x, T=1, one core, {dt:.1f} s"}
+            "sample": f"oracle/_ref shmr_index+shmr_overlap (unmodified reference), {genome/1e6:g} Mb genome {cov:g}x, T=1, one core, {dt:.1f} s"}, parity
 
 
 def run_reference_arm(args):
@@ -224,13 +239,20 @@ def run_ours(args):
     # Every rank generates ITS share of the read set (rid % N == (rank+1) % N, src/shmr_index.c:157) straight from the
     # counter-based simulator: read i depends on (seed, i) only, so the shares are exactly the selection of the full set,
     # and no rank ever writes or scans the whole 1.5 GB x N image.
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))  # simreads (torchrun pins it to 1)
     prefix = make_dataset(f"g{genome}" if world == 1 else f"g{genome}_c{rank + 1}of{world}", genome, args.cov, mod=world, res=(rank + 1) % world)
     rid, ln, off = F.read_idx(prefix + ".idx")
     nbytes = os.path.getsize(prefix + ".seqdb")
+    if nbytes != int(ln.sum()):
+        raise RuntimeError(f"{prefix}.seqdb has {nbytes} bytes, the .idx table says {int(ln.sum())} (disk full while generating?)")
     pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
     seqdb = pinned.numpy()
     with open(prefix + ".seqdb", "rb") as f:
         f.readinto(memoryview(seqdb))
+    if world > 1:  # a rank's share is only ever read here: do not leave N x 1.5 GB per scaling point in the work directory
+        import shutil
+
+        shutil.rmtree(os.path.dirname(prefix), ignore_errors=True)
     bases = int(ln.sum())
     if world > 1:
         t = torch.tensor([bases], dtype=torch.int64, device=f"cuda:{local}")
@@ -377,7 +399,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_l / K,
                 "kernel_ms_per_step": {k_: v[0] / K for k_, v in kern.items()}}
-    cpu = cpu_baseline_single_core() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    cpu, parity = cpu_baseline_single_core(device=local) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else (None, None)
     out = {
         "metric": "overlaps/s (index+overlap)", "value": n_ovl / (dev_ms * 1e-3), "unit": "overlaps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -399,6 +421,7 @@ def run_ours(args):
     }
     if cpu:
         out["cpu_baseline"] = cpu
+        out["parity"] = parity
     if world > 1:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -406,6 +429,39 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["identical"]:
+        print("bench.py: PARITY FAILURE: this engine's records differ from the reference's on the cpu_baseline sample", file=sys.stderr)
+        sys.exit(4)
+
+
+def run_ours_guarded(args):
+    """A rank that dies must say why: torchrun's summary only has the exit code (SCALE_r01: "rank 7 exitcode 1, error_file
+    <N/A>").  The traceback and the library's last error go to stderr, a one-line JSON error record goes to stdout (rank 0)
+    or stderr (other ranks), and torch's elastic error file is written by `record`."""
+    import traceback
+
+    try:
+        from torch.distributed.elastic.multiprocessing.errors import record
+    except Exception:  # pragma: no cover
+        def record(f):
+            return f
+
+    @record
+    def go():
+        try:
+            run_ours(args)
+        except BaseException as e:  # noqa: BLE001 - report, then re-raise for torchrun
+            if isinstance(e, SystemExit):
+                raise
+            rank = os.environ.get("RANK", "0")
+            tb = traceback.format_exc()
+            sys.stderr.write(f"\n[bench.py rank {rank}] FAILED: {type(e).__name__}: {e}\n{tb}\n")
+            sys.stderr.flush()
+            line = json.dumps({"error": f"{type(e).__name__}: {e}", "rank": int(rank), "n_gpus": args.gpus, "traceback_tail": tb[-1500:]})
+            print(line, file=sys.stdout if rank == "0" else sys.stderr, flush=True)
+            raise
+
+    go()
 
 
 def main():
@@ -423,7 +479,7 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
     else:
-        run_ours(args)
+        run_ours_guarded(args)
 
 
 if __name__ == "__main__":

@@ -174,7 +174,8 @@ int pgb_counts_dump(pgb_ctx *, size_t *n_entries);
 int pgb_counts_set_device(pgb_ctx *, const mm_count_t *entries_device, size_t n);
 int pgb_route_scan(pgb_ctx *, uint32_t mc_lower, uint32_t mc_upper, int *has_first);
 int pgb_route_build(pgb_ctx *, uint32_t total_chunk, uint32_t mc_lower, uint32_t mc_upper, int first_found_before, uint64_t *n_per_chunk);
-int pgb_overlap_routed(pgb_ctx *, const void *records_device, size_t n, uint32_t bestn, uint32_t align_bandwidth, uint32_t ovlp_upper);
+int pgb_overlap_routed(pgb_ctx *, const void *records_device, size_t n, uint32_t bestn, uint32_t align_bandwidth, uint32_t ovlp_upper,
+                       uint32_t total_chunk /* sizes the per-chunk replay tables: rid_pairs is per chunk, src/shmr_overlap.c:202 */);
 
 /* ---- shmr_dedup: raw ovlp_t stream -> preads.ovl text ------------------------------------------------------
  * replaces main() of src/shmr_dedup.c:19-101: keeps the FIRST record of every unordered read pair in stream order (the

@@ -1163,22 +1163,33 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   const char *ts_env = getenv("PGB_TABLE_SCALE");
   const double tscale = ts_env ? atof(ts_env) : 1.0;
   uint64_t ecap64 = (uint64_t)(c->ecap_ratio * tscale * n_elig) + (ts_env ? 64 : 4096);
-  uint64_t acap64 = (uint64_t)(c->acap_ratio * tscale * n_elig) + (ts_env ? 64 : 4096);
+  // The alignment cache (key -> result slot + request queue, 60 B per slot) is only needed once real alignments are asked
+  // for.  The speculative passes count the alignments they had to predict, which is (within a few %) the number the wet
+  // passes will request, so the cache is sized from that count when the first wet pass starts; until then a 1024-slot
+  // empty table answers every lookup with "unknown".  acap64 == 0 means "not sized yet".
+  uint64_t acap64 = 0;
   bool converged = false;
   ReplayState S;
+  memset(&S, 0, sizeof S);
+  // S tables come from the block cache (not the bump arena): a restart hands them back and the next attempt reuses them
+  auto free_S = [&]() { c->release(S.E); c->release(S.akeys); c->release(S.ares); c->release(S.reqs); c->release(S.n_req); };
+  auto alloc_aln_tables = [&](uint64_t cap) {
+    c->release(S.akeys); c->release(S.ares); c->release(S.reqs);
+    S.acap = (uint32_t)cap; S.req_cap = S.acap;
+    S.akeys = c->palloc<uint64_t>(S.acap); S.ares = c->palloc<match_t>(S.acap); S.reqs = c->palloc<AlnReq>(S.req_cap);
+    LAUNCH(c, k_fill_u64, 1184, 256, S.akeys, PGB_EMPTY, (size_t)S.acap);
+  };
   for (int attempt = 0; !converged; attempt++) {
-    if (attempt > 24 || ecap64 >= (1ull << 32) || acap64 >= (1ull << 32)) { free_common(); throw std::runtime_error("replay tables overflow"); }
+    if (attempt > 24 || ecap64 >= (1ull << 32) || acap64 >= (1ull << 32)) { free_S(); free_common(); throw std::runtime_error("replay tables overflow"); }
+    free_S();
     memset(&S, 0, sizeof S);
-    S.ecap = (uint32_t)ecap64; S.acap = (uint32_t)acap64; S.req_cap = S.acap;
-    S.E = c->alloc<EEntry>(S.ecap);
-    S.akeys = c->alloc<uint64_t>(S.acap); S.ares = c->alloc<match_t>(S.acap);
-    S.reqs = c->alloc<AlnReq>(S.req_cap);
-    S.n_req = c->alloc<uint32_t>(1); S.rlen_by_rid = c->d_rlen_by_rid; S.err = c->d_err;
+    S.ecap = (uint32_t)ecap64;
+    S.E = c->palloc<EEntry>(S.ecap);
+    S.n_req = c->palloc<uint32_t>(1); S.rlen_by_rid = c->d_rlen_by_rid; S.err = c->d_err;
     S.ctr = d_ctr;
     S.cur = 0;
-    auto free_S = [&]() { c->release(S.E); c->release(S.akeys); c->release(S.ares); c->release(S.reqs); c->release(S.n_req); };
+    alloc_aln_tables(acap64 ? acap64 : 1024);
     LAUNCH(c, k_e_init, 1184, 256, S.E, (size_t)S.ecap);
-    LAUNCH(c, k_fill_u64, 1184, 256, S.akeys, PGB_EMPTY, (size_t)S.acap);
     CU(cudaMemsetAsync(S.n_req, 0, 4, c->st));
     CU(cudaMemsetAsync(acc, 0, ((size_t)n_ranks + 1) * 4, c->st));
     CU(cudaMemsetAsync(unk_flag, 0, n_ranks, c->st));
@@ -1187,7 +1198,11 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
       LAUNCH(c, k_replay, nblk(n_small, 64), 64, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag);
       LAUNCH(c, k_replay_block, nb, PGB_RB_THREADS, S, nb, list + n_small, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag);
     };
-    bool wet = false, overflow = false;
+    bool wet = MAX_DRY <= 0, overflow = false;
+    if (wet && acap64 == 0) {  // PGB_DRY_PASSES=0: no speculative count to size from
+      acap64 = (uint64_t)(c->acap_ratio * tscale * n_elig) + (ts_env ? 64 : 4096);
+      alloc_aln_tables(acap64);
+    }
     tail_mode = false;
     uint64_t prev_diffs = ~0ULL, last_diffs = ~0ULL;
     uint32_t n_done = 0;
@@ -1225,8 +1240,8 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         if (e & (32 | 64)) {  // a table filled up: grow it and start over
           if (e & 32) { ecap64 *= 2; if (!ts_env) c->ecap_ratio *= 2; }
           if (e & 64) {  // n_req counted every request of the pass, also those that no longer fitted: size for them at once
-            const uint64_t want = std::max(2 * acap64, (uint64_t)n_req + n_req / 2);
-            if (!ts_env) c->acap_ratio *= (double)want / (double)acap64;
+            const uint64_t want = std::max(2 * acap64, 2 * (uint64_t)n_req);
+            if (!ts_env) c->acap_ratio *= (double)want / (double)std::max<uint64_t>(acap64, 1);
             acap64 = want;
           }
           int z = 0;
@@ -1313,9 +1328,13 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         dry_passes++;
         if (ctr[1] <= 16 + ctr[0] / 512 || ctr[1] >= prev_diffs || dry_passes >= MAX_DRY) wet = true;
         prev_diffs = ctr[1];
+        if (wet && acap64 == 0) {  // first wet pass next: size the alignment cache from this pass's count of predicted alignments
+          acap64 = (uint64_t)(2.0 * tscale * (double)ctr[0]) + (ts_env ? 64 : 8192);
+          alloc_aln_tables(acap64);
+        }
       }
     }
-    if (overflow) { free_S(); continue; }
+    if (overflow) continue;
     if (!converged) { free_S(); free_common(); throw std::runtime_error("replay fix-point did not converge in 400 passes"); }
 
     // ---------------- emission pass in visiting order
@@ -1336,6 +1355,16 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   return c->err.empty() ? 0 : -1;
 }
 
+// rid_pairs is per chunk: with T chunks a read pair is aligned (and accepted) in up to T of them, so the pair table of ONE
+// chunk grows relative to its eligible records (measured x1.85 records at T=2, SURVEY 6.2: x4.5 at T=8).  Start large enough
+// to spare the fix-point a restart; an underestimate only costs that restart.  (The alignment cache is sized from the
+// speculative passes' own count of missing alignments, see overlap_core; acap_ratio only covers PGB_DRY_PASSES=0.)
+static void size_tables_for_chunks(pgb_ctx *c, uint32_t T) {
+  const double t = (double)std::min<uint32_t>(std::max<uint32_t>(T, 1), 16);
+  c->acap_ratio = std::max(c->acap_ratio, 0.75 * pow(t, 0.75));
+  c->ecap_ratio = std::max(c->ecap_ratio, 1.25 * std::max(1.0, t / 4.0));
+}
+
 extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t bestn, uint32_t mc_lower, uint32_t mc_upper,
                            uint32_t bw, uint32_t ovlp_upper) {
   API_BEGIN(c)
@@ -1343,20 +1372,14 @@ extern "C" int pgb_overlap(pgb_ctx *c, uint32_t T, uint32_t mychunk, uint32_t be
   if (!c->d_w) throw std::runtime_error("no reads loaded");
   if (!c->d_shm && c->n_shm) throw std::runtime_error("no shimmers set");
   c->release(c->d_ovl); c->n_ovl = 0;
-  if (c->n_shm == 0) { c->sync(); return 0; }
   if (c->n_shm >= (1ull << 31)) throw std::runtime_error("more than 2^31 shimmers in one overlap call");
+  if (c->n_shm != 0) {
   ensure_loaded(c);
-  {
-    // rid_pairs is per chunk: with T chunks a read pair is aligned (and accepted) in up to T of them, so the alignment cache
-    // and the pair table of ONE chunk grow relative to its eligible records (measured x1.85 records at T=2, SURVEY 6.2: x4.5
-    // at T=8).  Start large enough to spare the fix-point a restart; an underestimate only costs that restart.
-    const double t = (double)std::min<uint32_t>(T, 16);
-    c->acap_ratio = std::max(c->acap_ratio, 0.75 * pow(t, 0.75));
-    c->ecap_ratio = std::max(c->ecap_ratio, 1.25 * std::max(1.0, t / 4.0));
-  }
+  size_tables_for_chunks(c, T);
   PairSoA R;
   uint32_t nrec = build_pair_records(c, T, mychunk, mc_lower, mc_upper, R);
-  if (overlap_core(c, R, nrec, bestn, bw, ovlp_upper) != 0) return -1;
+  overlap_core(c, R, nrec, bestn, bw, ovlp_upper);  // failures are left in c->err; API_END syncs, resets the arena and reports them
+  }
   API_END(c)
 }
 
@@ -1413,7 +1436,7 @@ extern "C" int pgb_route_build(pgb_ctx *c, uint32_t T, uint32_t mc_lower, uint32
   c->release(c->d_route); c->n_route = 0;
   for (uint32_t t = 0; t < T; t++) n_per_chunk[t] = 0;
   size_t n = c->n_shm;
-  if (n == 0) { c->sync(); return 0; }
+  if (n != 0) {
   c->tic();
   uint32_t *flags = c->alloc<uint32_t>(n + 1), *pos = c->alloc<uint32_t>(n + 1);
   CU(cudaMemsetAsync(flags, 0, (n + 1) * 4, c->st));
@@ -1455,14 +1478,17 @@ extern "C" int pgb_route_build(pgb_ctx *c, uint32_t T, uint32_t mc_lower, uint32
   c->stats.ms_pairs += c->toc();
   c->stats.n_pair_records += nrec;
   c->check_err("pgb_route_build");
+  }
   API_END(c)
 }
-extern "C" int pgb_overlap_routed(pgb_ctx *c, const void *records_device, size_t n, uint32_t bestn, uint32_t bw, uint32_t ovlp_upper) {
+extern "C" int pgb_overlap_routed(pgb_ctx *c, const void *records_device, size_t n, uint32_t bestn, uint32_t bw, uint32_t ovlp_upper,
+                                  uint32_t T) {
   API_BEGIN(c)
   if (!c->d_w) throw std::runtime_error("no reads loaded");
   if (n >= (1ull << 32)) throw std::runtime_error("more than 2^32 pair records in one overlap call");
   c->release(c->d_ovl); c->n_ovl = 0;
   ensure_loaded(c);
+  size_tables_for_chunks(c, T);
   uint32_t nrec = (uint32_t)n;
   PairSoA R;
   c->tic();
@@ -1470,7 +1496,7 @@ extern "C" int pgb_overlap_routed(pgb_ctx *c, const void *records_device, size_t
   R.seq = c->alloc<uint32_t>(nrec); R.dir = c->alloc<uint8_t>(nrec);
   LAUNCH(c, k_route_unpack, nblk(nrec), 256, (const route_rec *)records_device, nrec, R);
   c->stats.ms_pairs += c->toc();
-  if (overlap_core(c, R, nrec, bestn, bw, ovlp_upper) != 0) return -1;
+  overlap_core(c, R, nrec, bestn, bw, ovlp_upper);
   API_END(c)
 }
 
@@ -1572,7 +1598,7 @@ extern "C" int pgb_map(pgb_ctx *c, const mm128_t *ref_mmers, size_t n_ref, uint3
   if (!c->d_shm && c->n_shm) throw std::runtime_error("no shimmers set");
   if (c->n_shm >= (1ull << 31) || n_ref >= (1ull << 31)) throw std::runtime_error("more than 2^31 shimmers in one map call");
   c->release(c->d_map_text); c->map_bytes = 0; c->map_hits = 0;
-  if (n_ref == 0 || c->n_shm == 0) { c->sync(); return 0; }
+  if (n_ref != 0 && c->n_shm != 0) {
   // ---- pair index of the reads: records, X / B tables, records grouped by bucket in insertion order
   PairSoA R;
   const uint32_t nrec = build_pair_records(c, T, mychunk, mc_lower, mc_upper, R);
@@ -1593,7 +1619,7 @@ extern "C" int pgb_map(pgb_ctx *c, const mm128_t *ref_mmers, size_t n_ref, uint3
     uint32_t *iota = c->alloc<uint32_t>(nrec), *bk_sorted = c->alloc<uint32_t>(nrec), *by_bucket = c->alloc<uint32_t>(nrec);
     LAUNCH(c, k_iota_u32, nblk(nrec), 256, iota, nrec);
     sort_pairs_u32(c, rec_bucket, bk_sorted, iota, by_bucket, nrec);  // stable: records of a bucket stay in insertion order
-    if (c->check_err("pgb_map/buckets")) return -1;
+    if (c->check_err("pgb_map/buckets")) throw std::runtime_error(c->err);
     // ---- contig walk
     mm128 *d_ref = c->alloc<mm128>(n_ref);
     c->h2d(d_ref, ref_mmers, n_ref * sizeof(mm128));
@@ -1629,6 +1655,7 @@ extern "C" int pgb_map(pgb_ctx *c, const mm128_t *ref_mmers, size_t n_ref, uint3
   c->stats.ms_map += c->toc();
   c->stats.n_map_hits += c->map_hits;
   c->check_err("pgb_map");
+  }
   API_END(c)
 }
 extern "C" size_t pgb_map_hits(pgb_ctx *c) { return c ? c->map_hits : 0; }

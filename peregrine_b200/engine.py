@@ -94,7 +94,7 @@ def load_library():
     L.pgb_counts_set_device.argtypes = [vp, vp, C.c_size_t]
     L.pgb_route_scan.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
     L.pgb_route_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u64p]
-    L.pgb_overlap_routed.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.pgb_overlap_routed.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.pgb_dedup.argtypes = [vp, vp, C.c_size_t]
     L.pgb_dedup_device.argtypes = [vp, vp, C.c_size_t]
     L.pgb_dedup_overlaps.argtypes = [vp]
@@ -272,8 +272,8 @@ class Engine:
         self._ck(self.L.pgb_route_build(self.h, total_chunk, mc_lower, mc_upper, int(first_found_before), out), "pgb_route_build")
         return [int(x) for x in out]
 
-    def overlap_routed(self, records_ptr: int, n: int, bestn=4, align_bandwidth=100, ovlp_upper=120, copy=True):
-        self._ck(self.L.pgb_overlap_routed(self.h, C.c_void_p(records_ptr), n, bestn, align_bandwidth, ovlp_upper), "pgb_overlap_routed")
+    def overlap_routed(self, records_ptr: int, n: int, bestn=4, align_bandwidth=100, ovlp_upper=120, copy=True, total_chunk=1):
+        self._ck(self.L.pgb_overlap_routed(self.h, C.c_void_p(records_ptr), n, bestn, align_bandwidth, ovlp_upper, total_chunk), "pgb_overlap_routed")
         if copy is False:
             return self.L.pgb_overlap_size(self.h)
         return self.overlap_records(view=(copy == "view"))

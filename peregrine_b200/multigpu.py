@@ -179,7 +179,7 @@ class ShardedJob:
 
     def overlap(self, bestn=4, mc_lower=2, mc_upper=240, bw=100, ovlp_upper=120, copy=True):
         if self.routed is not None:
-            return self.ovl_eng.overlap_routed(self.routed.data_ptr(), int(self.routed.shape[0]), bestn, bw, ovlp_upper, copy=copy)
+            return self.ovl_eng.overlap_routed(self.routed.data_ptr(), int(self.routed.shape[0]), bestn, bw, ovlp_upper, copy=copy, total_chunk=self.world)
         return self.ovl_eng.overlap(self.world, self.rank + 1, bestn, mc_lower, mc_upper, bw, ovlp_upper, copy=copy)
 
     def dedup_all(self, dedup_eng=None):

@@ -325,7 +325,7 @@ def test_routed_exchange_matches_reference(sim1, workdir, ref_dir):
     M.import_reads(ovl, reads)
     for d in range(T):  # owner of chunk d + 1
         recv = torch.cat([sends[src][int(splits[src][d]): int(splits[src][d + 1])] for src in range(T)]).contiguous()
-        ov = ovl.overlap_routed(recv.data_ptr(), int(recv.shape[0]))
+        ov = ovl.overlap_routed(recv.data_ptr(), int(recv.shape[0]), total_chunk=T)
         want = F.normalise_ovlp(F.read_ovlp(ro[d]))
         assert len(ov) == len(want) and ov.tobytes() == want.tobytes(), f"chunk {d + 1}"
     ovl.close()

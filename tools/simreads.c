@@ -145,7 +145,7 @@ int main(int argc, char **argv) {
       char name[64];
       snprintf(name, sizeof name, "%02d/%06d/0_%u", (int)(rid / per_file), (int)(rid % per_file), r->len);
       for (uint32_t p = 0; p < r->len; p++) enc[p] = (uint8_t)(FWD[r->b[p]] | (REV[r->b[r->len - 1 - p]] << 4));
-      fwrite(enc, 1, r->len, fdb);
+      if (fwrite(enc, 1, r->len, fdb) != r->len) { perror("simreads: write .seqdb"); return 1; }
       fprintf(fidx, "%09d %s %u %lu\n", (int)rid, name, r->len, (unsigned long)offset);
       fprintf(fbed, "%s\t%lu\t%lu\t%d\n", name, (unsigned long)r->start, (unsigned long)(r->start + r->span), r->strand);
       if (ffa) {
@@ -157,7 +157,8 @@ int main(int argc, char **argv) {
       free(r->b);
     }
   }
-  fclose(fdb); fclose(fidx); fclose(fbed); if (ffa) fclose(ffa);
+  if (ferror(fidx) || ferror(fbed) || (ffa && ferror(ffa))) { fprintf(stderr, "simreads: write error\n"); return 1; }
+  if (fclose(fdb) | fclose(fidx) | fclose(fbed) | (ffa ? fclose(ffa) : 0)) { perror("simreads: close"); return 1; }
   fprintf(stderr, "simreads: genome=%lu reads=%lu bases=%lu err=%g seed=%lu -> %s.{seqdb,idx,bed}\n", (unsigned long)G,
           (unsigned long)nsel, (unsigned long)total, perr, (unsigned long)seed, prefix);
   return 0;
