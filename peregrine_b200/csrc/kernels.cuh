@@ -1295,6 +1295,10 @@ __global__ void __launch_bounds__(PGB_AW_WARPS * 32) k_align_warp(const AlnReq *
   }
 }
 
+}  // namespace pgb
+#include "align_quad.cuh"
+namespace pgb {
+
 // ---- pair-table maintenance between passes
 __global__ void k_e_init(EEntry *E, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

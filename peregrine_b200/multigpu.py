@@ -26,24 +26,43 @@ import torch
 READ_KEYS = ("words", "nmask", "row_rid", "row_len", "row_woff", "row_hasn")
 
 
-def all_gather_var(t: torch.Tensor, group=None):
-    """all_gather of 1-D tensors whose length differs per rank (pad to the longest; NCCL needs equal sizes)."""
+def _handoff(device=None):
+    """The collectives run on torch's streams, libpgb200's kernels on the library's own (non-blocking) stream: before a tensor
+    produced here is handed to the library by pointer, everything torch has queued must have finished.  (Round 1 missed this
+    between the all-gather of the count tables and pgb_counts_set_device: at N = 2 the race was won, at N >= 4 the last rank
+    read its table before the gather had written it - "mer missing from count table", SCALE_r01.)"""
+    if device is not None and torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
+
+
+def all_gather_var(t: torch.Tensor, group=None, sizes=None):
+    """all_gather of tensors whose first dimension differs per rank -> ONE tensor, the ranks' blocks concatenated in rank order,
+    plus the per-rank row counts.  NCCL: the blocks are received straight into slices of the result (ProcessGroupNCCL handles
+    uneven outputs as a group of broadcasts), nothing is padded or copied again.  gloo (CPU tests): pad to the longest."""
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    m = max(sizes)
-    if t.dim() == 1:
-        pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+    if sizes is None:
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        all_n = torch.empty(world, dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(all_n, n, group=group)
+        sizes = [int(x) for x in all_n.tolist()]
+    tail = tuple(t.shape[1:])
+    out = torch.empty((sum(sizes),) + tail, dtype=t.dtype, device=t.device)
+    t = t.contiguous()
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather(list(out.split(sizes)), t, group=group)
     else:
-        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    pad[: t.shape[0]] = t
-    outs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(outs, pad, group=group)
-    return [o[:s] for o, s in zip(outs, sizes)]
+        m = max(sizes)
+        pad = torch.zeros((m,) + tail, dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        o = 0
+        for p_, s_ in zip(parts, sizes):
+            out[o: o + s_] = p_[:s_]
+            o += s_
+    return out, sizes
 
 
 def concat_reads(parts):
@@ -62,14 +81,24 @@ def concat_reads(parts):
 
 
 def exchange_reads(part, group=None):
-    gathered = {k: all_gather_var(part[k], group) for k in READ_KEYS}
-    world = len(gathered["words"])
-    return concat_reads([{k: gathered[k][r] for k in READ_KEYS} for r in range(world)])
+    """all-gather of every rank's packed reads + read table; row_woff is rebased onto the concatenated word array."""
+    words, wsizes = all_gather_var(part["words"], group)
+    out = {"words": words}
+    out["nmask"], _ = all_gather_var(part["nmask"], group, sizes=wsizes)
+    out["row_rid"], rsizes = all_gather_var(part["row_rid"], group)
+    for k in ("row_len", "row_hasn", "row_woff"):
+        out[k], _ = all_gather_var(part[k], group, sizes=rsizes)
+    base, o = 0, 0
+    for ws, rs in zip(wsizes, rsizes):  # each rank's block keeps its own guard words, which is harmless
+        out["row_woff"][o: o + rs] += base
+        base += ws
+        o += rs
+    return out
 
 
 def exchange_shimmers(l2: torch.Tensor, group=None):
     """l2: (n, 2) int64 view of this rank's mm128_t list.  Result: all chunks concatenated in chunk (= rank) order."""
-    return torch.cat(all_gather_var(l2, group))
+    return all_gather_var(l2, group)[0]
 
 
 def all_to_all_var(send: torch.Tensor, split_sizes, group=None):
@@ -95,15 +124,15 @@ def first_found_before(has_first: bool, device, group=None) -> bool:
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     f = torch.tensor([1 if has_first else 0], dtype=torch.int64, device=device)
-    fs = [torch.zeros_like(f) for _ in range(world)]
-    dist.all_gather(fs, f, group=group)
-    return any(int(x.item()) for x in fs[:rank])
+    fs = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(fs, f, group=group)
+    return bool(fs[:rank].any().item()) if rank else False
 
 
 def gather_records(mine: torch.Tensor, group=None):
     """`cat ovlp-01.dat ovlp-02.dat ...` across ranks: every rank's ovlp_t records (an (n, 8) int64 view of the 64-byte records)
     concatenated in chunk (= rank) order, which is the stream order shmr_dedup sees (py/scripts/pg_run.py:352)."""
-    return torch.cat(all_gather_var(mine, group))
+    return all_gather_var(mine, group)[0]
 
 
 # ------------------------------------------------------------------------------------------------ engine <-> torch
@@ -169,10 +198,10 @@ class ShardedJob:
         self.idx_eng.index(w, k, r, 2, 0)
         part = export_reads(self.idx_eng, self.device)
         l2 = export_level(self.idx_eng, 2, self.device)
-        torch.cuda.synchronize(self.device)
+        _handoff(self.device)
         reads = exchange_reads(part, self.group)
         l2_all = exchange_shimmers(l2, self.group)
-        torch.cuda.synchronize(self.device)
+        _handoff(self.device)
         import_reads(self.ovl_eng, reads)
         import_shimmers(self.ovl_eng, l2_all)
         return int(reads["words"].shape[0]) * 12 + int(l2_all.shape[0]) * 16  # bytes this rank ends up holding from the exchange
@@ -191,8 +220,9 @@ class ShardedJob:
         mine = torch.empty((n, 8), dtype=torch.int64, device=self.device)
         if n:
             E.buffer_copy_out(E.BUF_OVLP, mine.data_ptr())
-        torch.cuda.synchronize(self.device)
+        _handoff(self.device)
         stream = gather_records(mine, self.group).contiguous()
+        _handoff(self.device)
         if self.rank != 0:
             return None
         return (dedup_eng or E).dedup(device_ptr=stream.data_ptr(), n=int(stream.shape[0]))
@@ -207,16 +237,17 @@ class ShardedJob:
         E.set_shimmers_from_index(2)
         part = export_reads(E, self.device)
         counts = export_counts(E, self.device)
-        torch.cuda.synchronize(self.device)
-        all_counts = torch.cat(all_gather_var(counts, self.group)).contiguous()
+        _handoff(self.device)
+        all_counts, _ = all_gather_var(counts, self.group)
+        _handoff(self.device)  # the library reads all_counts next, on its own stream
         E.counts_set_device(all_counts.data_ptr(), int(all_counts.shape[0]))
         has_first = E.route_scan(mc_lower, mc_upper)
         before = first_found_before(has_first, self.device, self.group)
         per_chunk = E.route_build(self.world, mc_lower, mc_upper, before)
         send = export_route(E, self.device)
-        torch.cuda.synchronize(self.device)
+        _handoff(self.device)
         self.routed, _ = all_to_all_var(send, per_chunk, self.group)  # chunk c is owned by rank c-1
         reads = exchange_reads(part, self.group)
-        torch.cuda.synchronize(self.device)
+        _handoff(self.device)
         import_reads(self.ovl_eng, reads)
         return int(reads["words"].shape[0]) * 12 + int(self.routed.shape[0]) * 40 + int(all_counts.shape[0]) * 16

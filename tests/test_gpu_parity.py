@@ -240,10 +240,12 @@ def test_warp_per_alignment_kernel_on_every_alignment(sim1, workdir, ref_dir, mo
     assert_same_ovlp(oo[0], ro[0])
 
 
-@pytest.mark.parametrize("variant", ["7", "0"])
+@pytest.mark.parametrize("variant", ["7", "0", "20", "21"])
 def test_thread_per_alignment_kernel_on_every_alignment(workdir, ref_dir, monkeypatch, variant):
-    """PGB_ALIGN_WARP_MAX=0 routes every alignment batch through k_align_lean (variant 7: band-row prefetch + register-cached
-    band trim, the production form; variant 0: the plain form), on clean and on 3 %-error reads (wide bands, deep trims)."""
+    """PGB_ALIGN_WARP_MAX=0 routes every alignment batch through the bulk kernel: k_align_lean (variant 7: band-row prefetch +
+    register-cached band trim; variant 0: the plain form) or k_align_quad (20: 4 lanes per alignment, 21: 8 lanes; operand
+    windows staged by cp.async.bulk), on clean and on 3 %-error reads (wide bands, deep trims, multi-chunk rows) and with a
+    narrow band limit (-w 30: the band-limit exit of DWmatch.c:120-122)."""
     monkeypatch.setenv("PGB_ALIGN_WARP_MAX", "0")
     monkeypatch.setenv("PGB_ALIGN_VARIANT", variant)
     for name, kw in (("lean_a", dict(genome=400_000, cov=20)), ("lean_b", dict(genome=150_000, cov=15, err=0.03))):
