@@ -14,6 +14,7 @@
 #include <stdint.h>
 #include "shimmer_core.cuh"
 #include "sketch_tile.cuh"
+#include "sketch_strip.cuh"
 #include "khash_small.cuh"
 
 namespace pgb {
@@ -381,6 +382,28 @@ __global__ void __launch_bounds__(SK_THREADS) k_sketch_tiled(const uint64_t *__r
   }
   if (cnt) sk_phase5_write<HT>(tid, sh, p, emit_mask, tmp + (size_t)tile * tile_cap + pre);
   if (tid == 0) tile_cnt[tile] = total;
+}
+
+// ---- strip kernel plumbing: record budget per row, flagged rows, final placement
+__global__ void k_row_caps(const uint32_t *__restrict__ row_len, uint32_t n_rows, int wsz, uint32_t *caps) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < n_rows) caps[row] = (uint32_t)((6ull * row_len[row]) / (uint32_t)(wsz + 1)) + 64u;  // 3x the expected 2/(w+1) density
+  if (row == n_rows) caps[row] = 0;
+}
+__global__ void k_row_exact_flags(const uint32_t *__restrict__ row_flags, uint32_t n_rows, uint32_t *exact_flag) {
+  uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < n_rows) exact_flag[row] = row_flags[row] != 0;
+}
+// one warp per row: its records from the per-row budget area to their final place
+__global__ void k_row_gather(const uint32_t *__restrict__ cnt_by_row, const uint32_t *__restrict__ row_flags, uint32_t n_rows,
+                             const uint64_t *__restrict__ tmp_off, const mm128 *__restrict__ tmp, const uint64_t *__restrict__ off_by_row,
+                             mm128 *__restrict__ out) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n_rows || row_flags[row]) return;
+  const uint32_t n = cnt_by_row[row];
+  const mm128 *src = tmp + tmp_off[row];
+  mm128 *dst = out + off_by_row[row];
+  for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
 // per row: minimizer count from its tiles, or mark it for the exact automaton

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <unordered_map>
+#include <functional>
 #include "../../include/pgb200.h"
 #include "host_util.hpp"
 #include "fasta_reader.hpp"
@@ -607,7 +608,121 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
   c->d_level_off[0] = c->palloc<uint64_t>(ns + 1);
   const char *force = getenv("PGB_SKETCH");
-  const bool use_tiled = w >= SK_MINW && !(force && !strcmp(force, "exact")) && ns > 0;
+  const bool force_exact = force && !strcmp(force, "exact"), force_tiled = force && !strcmp(force, "tiled");
+  // fast paths: the strip kernel (a warp walks a read, sketch_strip.cuh; default) or round 1's block-tiled kernel (PGB_SKETCH=tiled,
+  // kept as the A/B baseline); tiny windows, k = 1 and PGB_SKETCH=exact run the exact automaton on every read
+  const bool use_strip = w >= SK_MINW && k >= 2 && !force_exact && !force_tiled && ns > 0;
+  const bool use_tiled = w >= SK_MINW && !force_exact && !use_strip && ns > 0;
+  // the reads the fast kernel hands back (flags in row_flags) are redone by the exact automaton, segment-parallel; both fast
+  // paths share this tail: counts[] holds the fast rows' record counts, exact_flag[] marks the others
+  auto exact_tail = [&](uint32_t *row_flags, uint32_t *exact_flag, uint32_t *exact_pos, const std::function<void()> &place_fast) {
+    uint32_t n_exact = scan_u32(c, exact_flag, exact_pos, ns + 1);
+    uint32_t *exact_list = nullptr, *seg_row = nullptr, *seg_lo = nullptr, *seg_first = nullptr, *list_first = nullptr, *seg_cnt = nullptr, *seg_pos = nullptr;
+    uint32_t n_seg = 0;
+    // positions per thread of the exact automaton (plus its warm-up of ~w+k and w trailing slots): the few flagged reads are a
+    // pure latency term (far fewer threads than the GPU holds), so short segments keep them off the critical path
+    const int SEG = getenv("PGB_EXACT_SEG") ? std::max(16, atoi(getenv("PGB_EXACT_SEG"))) : 256;
+    if (n_exact) {
+      exact_list = c->alloc<uint32_t>(n_exact);
+      LAUNCH(c, k_compact_idx, nblk(ns), 256, exact_flag, exact_pos, ns, exact_list);
+      std::vector<uint32_t> h_list(n_exact), h_seg_row, h_seg_lo, h_seg_first, h_list_first(n_exact + 1);
+      c->d2h(h_list.data(), exact_list, (size_t)n_exact * 4);
+      for (uint32_t i = 0; i < n_exact; i++) {
+        uint32_t row = h_list[i], len = c->h_row_len[row];
+        h_list_first[i] = (uint32_t)h_seg_row.size();
+        for (uint32_t lo = 0; lo < len; lo += SEG) { h_seg_row.push_back(row); h_seg_lo.push_back(lo); h_seg_first.push_back(h_list_first[i]); }
+      }
+      n_seg = (uint32_t)h_seg_row.size();
+      h_list_first[n_exact] = n_seg;
+      seg_row = c->alloc<uint32_t>(n_seg); seg_lo = c->alloc<uint32_t>(n_seg); seg_first = c->alloc<uint32_t>(n_seg);
+      list_first = c->alloc<uint32_t>((size_t)n_exact + 1); seg_cnt = c->alloc<uint32_t>((size_t)n_seg + 1); seg_pos = c->alloc<uint32_t>((size_t)n_seg + 1);
+      c->h2d(seg_row, h_seg_row.data(), (size_t)n_seg * 4); c->h2d(seg_lo, h_seg_lo.data(), (size_t)n_seg * 4);
+      c->h2d(seg_first, h_seg_first.data(), (size_t)n_seg * 4); c->h2d(list_first, h_list_first.data(), ((size_t)n_exact + 1) * 4);
+      CU(cudaMemsetAsync(seg_cnt, 0, ((size_t)n_seg + 1) * 4, c->st));
+      c->ktic();
+      LAUNCH(c, k_sketch_exact_seg<false>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
+             c->d_row_woff, c->d_hasn_by_rid, w, k, seg_cnt, (const uint32_t *)nullptr, (const uint64_t *)nullptr, (mm128 *)nullptr);
+      c->stats.ms_k_sketch_count += c->ktoc(); c->stats.n_k_sketch_count++;
+      scan_u32(c, seg_cnt, seg_pos, (size_t)n_seg + 1);
+      LAUNCH(c, k_seg_row_counts, nblk(n_exact), 256, exact_list, list_first, n_exact, seg_pos, counts);
+    }
+    c->stats.n_sketch_fallback_reads += n_exact;
+    c->level_n[0] = scan_u32_to_u64(c, counts, c->d_level_off[0], ns + 1);
+    c->d_level[0] = c->palloc<mm128>(c->level_n[0]);
+    place_fast();
+    if (n_exact) {
+      c->ktic();
+      LAUNCH(c, k_sketch_exact_seg<true>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
+             c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, seg_pos, c->d_level_off[0], c->d_level[0]);
+      c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
+      c->release(exact_list); c->release(seg_row); c->release(seg_lo); c->release(seg_first); c->release(list_first); c->release(seg_cnt); c->release(seg_pos);
+    }
+  };
+  // host->device copy of the .seqdb image in chunks of whole reads on the copy stream while the compute stream packs and
+  // sketches the previous chunk (reads are independent up to the final placement); sketch_rows(r0, r1) launches the fast kernel
+  auto deferred_load = [&](const std::function<void(size_t, size_t)> &sketch_rows) {
+    CU(cudaMemsetAsync(c->d_w, 0, c->n_words * 8, c->st));
+    CU(cudaMemsetAsync(c->d_nm, 0, c->n_words * 4, c->st));
+    CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
+    const uint64_t CH = getenv("PGB_LOAD_CHUNK_MB") ? strtoull(getenv("PGB_LOAD_CHUNK_MB"), 0, 10) << 20 : (uint64_t)96 << 20;
+    uint64_t raw_o = 0, word_o = 2;
+    size_t r0 = 0, n_ev = 0;
+    while (r0 < ns) {
+      size_t r1 = r0;
+      uint64_t bytes = 0, wcount = 0;
+      while (r1 < ns && bytes < CH) { bytes += c->h_row_len[r1]; wcount += ((uint64_t)c->h_row_len[r1] + 31) / 32; r1++; }
+      if (n_ev == c->ev_pool.size()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_pool.push_back(e); }
+      if (bytes) {
+        CU(cudaMemcpyAsync(c->d_raw + raw_o, c->pend.src + raw_o, bytes, cudaMemcpyHostToDevice, c->st_copy));
+        c->stats.h2d_bytes += bytes;
+      }
+      CU(cudaEventRecord(c->ev_pool[n_ev], c->st_copy));
+      CU(cudaStreamWaitEvent(c->st, c->ev_pool[n_ev], 0));
+      n_ev++;
+      if (wcount)
+        LAUNCH(c, k_pack_reads, nblk(wcount), 256, c->d_raw, c->d_row_raw_off, c->d_row_len, c->d_row_woff, c->d_row_rid, (uint32_t)c->n_rows, word_o,
+               wcount, c->d_w, c->d_nm, c->d_hasn_by_rid);
+      sketch_rows(r0, r1);
+      raw_o += bytes; word_o += wcount; r0 = r1;
+    }
+    c->pend.active = false;
+    c->stats.bases_packed += c->sel_bases;
+    if (!c->pend.keep_raw) c->release(c->d_raw);
+  };
+  if (use_strip) {
+    uint32_t *caps = c->alloc<uint32_t>(ns + 1), *row_flags = c->alloc<uint32_t>(ns);
+    uint32_t *exact_flag = c->alloc<uint32_t>(ns + 1), *exact_pos = c->alloc<uint32_t>(ns + 1);
+    uint64_t *tmp_off = c->alloc<uint64_t>(ns + 1);
+    LAUNCH(c, k_row_caps, nblk(ns + 1), 256, c->d_row_len, (uint32_t)ns, w, caps);
+    const uint64_t tmp_n = scan_u32_to_u64(c, caps, tmp_off, ns + 1);
+    mm128 *tmp = c->alloc<mm128>(tmp_n);
+    CU(cudaMemsetAsync(exact_flag, 0, (ns + 1) * 4, c->st));
+    const bool k32 = k <= 16;
+    const size_t smem = k32 ? ss_smem_bytes<uint32_t>() : ss_smem_bytes<uint64_t>();
+    if (k32) CU(cudaFuncSetAttribute(k_sketch_strip<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CU(cudaFuncSetAttribute(k_sketch_strip<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto sketch_rows = [&](size_t r0, size_t r1) {
+      if (r1 <= r0) return;
+      const unsigned grid = nblk(r1 - r0, SS_WARPS);
+      if (k32)
+        k_sketch_strip<uint32_t><<<grid, SS_WARPS * 32, smem, c->st>>>(c->d_w, c->d_row_rid, c->d_row_len, c->d_row_woff, c->d_hasn_by_rid, (uint32_t)r0,
+                                                                        (uint32_t)(r1 - r0), w, k, tmp_off, tmp, counts, row_flags);
+      else
+        k_sketch_strip<uint64_t><<<grid, SS_WARPS * 32, smem, c->st>>>(c->d_w, c->d_row_rid, c->d_row_len, c->d_row_woff, c->d_hasn_by_rid, (uint32_t)r0,
+                                                                        (uint32_t)(r1 - r0), w, k, tmp_off, tmp, counts, row_flags);
+      c->stats.kernel_launches++;
+      CU(cudaGetLastError());
+    };
+    c->ktic();
+    if (c->pend.active) deferred_load(sketch_rows);
+    else sketch_rows(0, ns);
+    c->stats.ms_k_sketch_tiled += c->ktoc(); c->stats.n_k_sketch_tiled++;
+    LAUNCH(c, k_row_exact_flags, nblk(ns), 256, row_flags, (uint32_t)ns, exact_flag);
+    exact_tail(row_flags, exact_flag, exact_pos, [&]() {
+      LAUNCH(c, k_row_gather, nblk(ns * 32, 256), 256, counts, row_flags, (uint32_t)ns, tmp_off, tmp, c->d_level_off[0], c->d_level[0]);
+    });
+    c->release(caps); c->release(row_flags); c->release(exact_flag); c->release(exact_pos); c->release(tmp_off); c->release(tmp);
+  } else
   if (!use_tiled) {
     // exact automaton for every read (tiny windows, or PGB_SKETCH=exact)
     ensure_loaded(c);
@@ -656,83 +771,14 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
       CU(cudaGetLastError());
     };
     c->ktic();
-    if (c->pend.active) {
-      // Deferred load: the .seqdb image is still on the host.  Chunks of whole reads travel on the copy stream; the compute
-      // stream packs and sketches chunk i while chunk i+1 is on the wire (reads are independent up to the L0 gather).
-      CU(cudaMemsetAsync(c->d_w, 0, c->n_words * 8, c->st));
-      CU(cudaMemsetAsync(c->d_nm, 0, c->n_words * 4, c->st));
-      CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
-      const uint64_t CH = getenv("PGB_LOAD_CHUNK_MB") ? strtoull(getenv("PGB_LOAD_CHUNK_MB"), 0, 10) << 20 : (uint64_t)96 << 20;
-      uint64_t raw_o = 0, word_o = 2;
-      size_t r0 = 0, n_ev = 0;
-      while (r0 < ns) {
-        size_t r1 = r0;
-        uint64_t bytes = 0, wcount = 0;
-        while (r1 < ns && bytes < CH) { bytes += c->h_row_len[r1]; wcount += ((uint64_t)c->h_row_len[r1] + 31) / 32; r1++; }
-        if (n_ev == c->ev_pool.size()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_pool.push_back(e); }
-        if (bytes) {
-          CU(cudaMemcpyAsync(c->d_raw + raw_o, c->pend.src + raw_o, bytes, cudaMemcpyHostToDevice, c->st_copy));
-          c->stats.h2d_bytes += bytes;
-        }
-        CU(cudaEventRecord(c->ev_pool[n_ev], c->st_copy));
-        CU(cudaStreamWaitEvent(c->st, c->ev_pool[n_ev], 0));
-        n_ev++;
-        if (wcount)
-          LAUNCH(c, k_pack_reads, nblk(wcount), 256, c->d_raw, c->d_row_raw_off, c->d_row_len, c->d_row_woff, c->d_row_rid, (uint32_t)c->n_rows, word_o,
-                 wcount, c->d_w, c->d_nm, c->d_hasn_by_rid);
-        launch_tiles(h_tile_off[r0], h_tile_off[r1]);
-        raw_o += bytes; word_o += wcount; r0 = r1;
-      }
-      c->pend.active = false;
-      c->stats.bases_packed += c->sel_bases;
-      if (!c->pend.keep_raw) c->release(c->d_raw);
-    } else {
-      launch_tiles(0, n_tiles);
-    }
+    if (c->pend.active) deferred_load([&](size_t r0, size_t r1) { launch_tiles(h_tile_off[r0], h_tile_off[r1]); });
+    else launch_tiles(0, n_tiles);
     c->stats.ms_k_sketch_tiled += c->ktoc(); c->stats.n_k_sketch_tiled++;
     LAUNCH(c, k_row_counts, nblk(ns), 256, tile_off, tile_cnt, row_flags, (uint32_t)ns, counts, exact_flag);
-    uint32_t n_exact = scan_u32(c, exact_flag, exact_pos, ns + 1);
-    uint32_t *exact_list = nullptr, *seg_row = nullptr, *seg_lo = nullptr, *seg_first = nullptr, *list_first = nullptr, *seg_cnt = nullptr, *seg_pos = nullptr;
-    uint32_t n_seg = 0;
-    // positions per thread of the exact automaton (plus its warm-up of ~w+k and w trailing slots): the few flagged reads are a
-    // pure latency term (far fewer threads than the GPU holds), so short segments keep them off the critical path
-    const int SEG = getenv("PGB_EXACT_SEG") ? std::max(16, atoi(getenv("PGB_EXACT_SEG"))) : 256;
-    if (n_exact) {
-      exact_list = c->alloc<uint32_t>(n_exact);
-      LAUNCH(c, k_compact_idx, nblk(ns), 256, exact_flag, exact_pos, ns, exact_list);
-      std::vector<uint32_t> h_list(n_exact), h_seg_row, h_seg_lo, h_seg_first, h_list_first(n_exact + 1);
-      c->d2h(h_list.data(), exact_list, (size_t)n_exact * 4);
-      for (uint32_t i = 0; i < n_exact; i++) {
-        uint32_t row = h_list[i], len = c->h_row_len[row];
-        h_list_first[i] = (uint32_t)h_seg_row.size();
-        for (uint32_t lo = 0; lo < len; lo += SEG) { h_seg_row.push_back(row); h_seg_lo.push_back(lo); h_seg_first.push_back(h_list_first[i]); }
-      }
-      n_seg = (uint32_t)h_seg_row.size();
-      h_list_first[n_exact] = n_seg;
-      seg_row = c->alloc<uint32_t>(n_seg); seg_lo = c->alloc<uint32_t>(n_seg); seg_first = c->alloc<uint32_t>(n_seg);
-      list_first = c->alloc<uint32_t>((size_t)n_exact + 1); seg_cnt = c->alloc<uint32_t>((size_t)n_seg + 1); seg_pos = c->alloc<uint32_t>((size_t)n_seg + 1);
-      c->h2d(seg_row, h_seg_row.data(), (size_t)n_seg * 4); c->h2d(seg_lo, h_seg_lo.data(), (size_t)n_seg * 4);
-      c->h2d(seg_first, h_seg_first.data(), (size_t)n_seg * 4); c->h2d(list_first, h_list_first.data(), ((size_t)n_exact + 1) * 4);
-      CU(cudaMemsetAsync(seg_cnt, 0, ((size_t)n_seg + 1) * 4, c->st));
-      c->ktic();
-      LAUNCH(c, k_sketch_exact_seg<false>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
-             c->d_row_woff, c->d_hasn_by_rid, w, k, seg_cnt, (const uint32_t *)nullptr, (const uint64_t *)nullptr, (mm128 *)nullptr);
-      c->stats.ms_k_sketch_count += c->ktoc(); c->stats.n_k_sketch_count++;
-      scan_u32(c, seg_cnt, seg_pos, (size_t)n_seg + 1);
-      LAUNCH(c, k_seg_row_counts, nblk(n_exact), 256, exact_list, list_first, n_exact, seg_pos, counts);
-    }
-    c->stats.n_sketch_fallback_reads += n_exact;
-    c->level_n[0] = scan_u32_to_u64(c, counts, c->d_level_off[0], ns + 1);
-    c->d_level[0] = c->palloc<mm128>(c->level_n[0]);
-    LAUNCH(c, k_tile_gather, nblk((size_t)n_tiles * 64, 256), 256, tile_off, tile_cnt, row_flags, (uint32_t)ns, n_tiles, c->d_level_off[0], tmp,
-           tile_cap, c->d_level[0]);
-    if (n_exact) {
-      c->ktic();
-      LAUNCH(c, k_sketch_exact_seg<true>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
-             c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, seg_pos, c->d_level_off[0], c->d_level[0]);
-      c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
-      c->release(exact_list); c->release(seg_row); c->release(seg_lo); c->release(seg_first); c->release(list_first); c->release(seg_cnt); c->release(seg_pos);
-    }
+    exact_tail(row_flags, exact_flag, exact_pos, [&]() {
+      LAUNCH(c, k_tile_gather, nblk((size_t)n_tiles * 64, 256), 256, tile_off, tile_cnt, row_flags, (uint32_t)ns, n_tiles, c->d_level_off[0], tmp,
+             tile_cap, c->d_level[0]);
+    });
     c->release(tile_desc);
     c->release(tile_off); c->release(tile_cnt); c->release(row_flags); c->release(exact_flag); c->release(exact_pos); c->release(tmp);
   }
