@@ -74,7 +74,10 @@ struct QaWin {
   uint32_t nwaited;  // how many of them are known to have landed (0..2)
 };
 
-template <int G>
+// BULK = true: a stage is filled by ONE cp.async.bulk (UBLKCP, complete_tx on the stage's mbarrier) issued by the group's first
+// lane.  BULK = false: every lane of the group copies 16-byte pieces with cp.async (LDGSTS) and lets the mbarrier count the
+// completion of its own copies (cp.async.mbarrier.arrive.noinc).  Measured on the bench workload (profiles/r2_align.md).
+template <int G, bool BULK>
 struct QaLane {
   uint32_t gmask, gl, gshift;
   uint32_t ring_s[2];  // shared address of the operand rings
@@ -83,13 +86,26 @@ struct QaLane {
 
   __device__ __forceinline__ void issue(int op, const QaWin &wn, uint32_t blk) {
     __syncwarp(gmask);  // every lane of the group is done reading the stage that is overwritten
-    if (gl == 0) {
-      const uint32_t st = (blk + wn.rot) & 1u, bar = bar_s + 8u * (uint32_t)(op * 2 + st);
+    const uint32_t st = (blk + wn.rot) & 1u, bar = bar_s + 8u * (uint32_t)(op * 2 + st);
+    if (BULK) {
+      if (gl == 0) {
+        if (blk < wn.nblk) {
+          qa_mbar_expect_tx(bar, QA_BLK_BYTES);
+          qa_bulk_g2s(ring_s[op] + st * QA_BLK_BYTES, wn.src0 + (size_t)blk * QA_BLK_BYTES, QA_BLK_BYTES, bar);
+        } else {
+          qa_mbar_arrive(bar);  // past the end of the image: nothing to fetch, complete the phase
+        }
+      }
+    } else {
       if (blk < wn.nblk) {
-        qa_mbar_expect_tx(bar, QA_BLK_BYTES);
-        qa_bulk_g2s(ring_s[op] + st * QA_BLK_BYTES, wn.src0 + (size_t)blk * QA_BLK_BYTES, QA_BLK_BYTES, bar);
+        const char *src = wn.src0 + (size_t)blk * QA_BLK_BYTES;
+        const uint32_t dst = ring_s[op] + st * QA_BLK_BYTES;
+#pragma unroll
+        for (uint32_t i = gl; i < QA_BLK_BYTES / 16; i += G)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16u * i) : "memory");
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");  // arrives when this lane's copies have landed
       } else {
-        qa_mbar_arrive(bar);  // past the end of the image: nothing to fetch, complete the phase
+        qa_mbar_arrive(bar);
       }
     }
   }
@@ -147,7 +163,7 @@ __device__ __forceinline__ int qa_match_len(uint64_t df) {  // leading equal bas
   return lo ? (ctz32(lo) >> 1) : 16 + (ctz32((uint32_t)(df >> 32)) >> 1);
 }
 
-template <int G>
+template <int G, bool BULK>
 __global__ void __launch_bounds__(QA_THREADS) k_align_quad(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint32_t *__restrict__ perm,
                                                             const uint64_t *__restrict__ w, const uint64_t *__restrict__ wrc, uint64_t arr_words,
                                                             const uint64_t *__restrict__ woff_by_rid, const uint32_t *__restrict__ rlen_by_rid,
@@ -159,7 +175,7 @@ __global__ void __launch_bounds__(QA_THREADS) k_align_quad(const AlnReq *__restr
   constexpr uint32_t GBITS = (1u << G) - 1u;
   constexpr uint32_t FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-  QaLane<G> L;
+  QaLane<G, BULK> L;
   L.gl = lane & (G - 1);
   L.gshift = lane & ~(uint32_t)(G - 1);
   L.gmask = GBITS << L.gshift;
@@ -170,7 +186,7 @@ __global__ void __launch_bounds__(QA_THREADS) k_align_quad(const AlnReq *__restr
   L.parity = 0;
   const uint32_t n_blocks = (uint32_t)((arr_words * 8 + QA_BLK_BYTES - 1) / QA_BLK_BYTES);  // (the allocation is a multiple of 512 bytes)
   if (L.gl == 0) {
-    for (int b = 0; b < 4; b++) qa_mbar_init(L.bar_s + 8u * b, 1);
+    for (int b = 0; b < 4; b++) qa_mbar_init(L.bar_s + 8u * b, BULK ? 1 : G);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }

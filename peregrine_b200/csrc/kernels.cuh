@@ -1320,6 +1320,7 @@ __global__ void __launch_bounds__(PGB_AW_WARPS * 32) k_align_warp(const AlnReq *
 
 }  // namespace pgb
 #include "align_quad.cuh"
+#include "align_coop.cuh"
 namespace pgb {
 
 // ---- pair-table maintenance between passes

@@ -1340,29 +1340,38 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
             else
               LAUNCH(c, k_align_stream<true>, grid, PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid,
                      c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases, qhead);
-          } else if (ALIGN_VARIANT == 20 || ALIGN_VARIANT == 21) {
-            // G lanes per alignment, operand windows staged in shared memory by cp.async.bulk (align_quad.cuh)
-            const int G = ALIGN_VARIANT == 20 ? 4 : 8;
+          } else if (ALIGN_VARIANT >= 20 && ALIGN_VARIANT <= 23) {
+            // G lanes per alignment, operand windows staged in shared memory (align_quad.cuh): 20 / 21 = G 4 / 8 with cp.async.bulk,
+            // 22 / 23 = G 4 / 8 with cp.async
+            const int G = (ALIGN_VARIANT & 1) ? 8 : 4;
+            const bool bulk = ALIGN_VARIANT < 22;
             const int vcap_g = (int)bw + 3;
             const size_t smem = (size_t)(QA_THREADS / G) * sizeof(QaGroupSmem);
+            auto kern = G == 4 ? (bulk ? k_align_quad<4, true> : k_align_quad<4, false>) : (bulk ? k_align_quad<8, true> : k_align_quad<8, false>);
             int occ = 1;
-            if (G == 4) {
-              CU(cudaFuncSetAttribute(k_align_quad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-              CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_align_quad<4>, QA_THREADS, smem));
-            } else {
-              CU(cudaFuncSetAttribute(k_align_quad<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-              CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_align_quad<8>, QA_THREADS, smem));
-            }
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QA_THREADS, smem));
             const unsigned grid = std::min(nblk(nn, QA_THREADS / G), (unsigned)(c->sm_count * std::max(occ, 1)));
             unsigned int *qhead = c->alloc<unsigned int>(1);
             int *vscratch = c->alloc<int>((size_t)grid * (QA_THREADS / G) * 2 * vcap_g);
             CU(cudaMemsetAsync(qhead, 0, 4, c->st));
-            if (G == 4)
-              k_align_quad<4><<<grid, QA_THREADS, smem, c->st>>>(S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->n_words, c->d_woff_by_rid, c->d_rlen_by_rid,
-                                                                  c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases, qhead, vscratch, vcap_g);
-            else
-              k_align_quad<8><<<grid, QA_THREADS, smem, c->st>>>(S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->n_words, c->d_woff_by_rid, c->d_rlen_by_rid,
-                                                                  c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases, qhead, vscratch, vcap_g);
+            kern<<<grid, QA_THREADS, smem, c->st>>>(S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->n_words, c->d_woff_by_rid, c->d_rlen_by_rid,
+                                                    c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases, qhead, vscratch, vcap_g);
+            c->stats.kernel_launches++;
+            CU(cudaGetLastError());
+          } else if (ALIGN_VARIANT == 30 || ALIGN_VARIANT == 31) {
+            // G lanes per alignment, branch-free loop, operands read through L1 (align_coop.cuh): 30 = G 4, 31 = G 8
+            const int G = ALIGN_VARIANT == 30 ? 4 : 8;
+            const int vcap_g = (int)bw + 3;
+            auto kern = G == 4 ? k_align_coop<4> : k_align_coop<8>;
+            int occ = 1;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, QC_THREADS, 0));
+            const unsigned grid = std::min(nblk(nn, QC_THREADS / G), (unsigned)(c->sm_count * std::max(occ, 1)));
+            unsigned int *qhead = c->alloc<unsigned int>(1);
+            int *vscratch = c->alloc<int>((size_t)grid * (QC_THREADS / G) * 2 * vcap_g);
+            CU(cudaMemsetAsync(qhead, 0, 4, c->st));
+            kern<<<grid, QC_THREADS, 0, c->st>>>(S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw,
+                                                 S.ares, c->d_align_bases, qhead, vscratch, vcap_g);
             c->stats.kernel_launches++;
             CU(cudaGetLastError());
           } else PGB_LEAN(true, true, 12);

@@ -240,7 +240,7 @@ def test_warp_per_alignment_kernel_on_every_alignment(sim1, workdir, ref_dir, mo
     assert_same_ovlp(oo[0], ro[0])
 
 
-@pytest.mark.parametrize("variant", ["7", "0", "20", "21"])
+@pytest.mark.parametrize("variant", ["7", "0", "20", "21", "22", "23", "30", "31"])
 def test_thread_per_alignment_kernel_on_every_alignment(workdir, ref_dir, monkeypatch, variant):
     """PGB_ALIGN_WARP_MAX=0 routes every alignment batch through the bulk kernel: k_align_lean (variant 7: band-row prefetch +
     register-cached band trim; variant 0: the plain form) or k_align_quad (20: 4 lanes per alignment, 21: 8 lanes; operand
