@@ -102,6 +102,17 @@ const char *pgb_last_error(pgb_ctx *);            /* "" when the last call succe
 int pgb_load_reads(pgb_ctx *, const uint8_t *seqdb, size_t seqdb_bytes, const uint32_t *rid, const uint32_t *len,
                    const uint64_t *offset, size_t n_reads, uint32_t total_chunk, uint32_t mychunk, int keep_raw);
 int pgb_repack(pgb_ctx *);
+/* The 2-bit hand-off.  pgb_pack_2bit: .seqdb bytes of a batch of reads -> their packed form on the host: per read
+ * ceil(len/32) uint64 words (base p at bits 2(p&31) of word p/32, A0 C1 G2 T3, reads in the order given), the parallel N-mask
+ * words (uint32 per 32 bases) and a per-read "contains N" flag.  This library's shmr_mkseqdb writes them next to the .seqdb as
+ * <prefix>.seq2b (the words of all reads in .idx order) and <prefix>.seq2n (uint32 stream {read index, word count, mask words}
+ * for the reads with N); shmr_index / shmr_overlap use them when present and current (PGB_NO_SEQ2B=1: ignore).
+ * pgb_load_reads_2bit: the read set from that image (ALL reads of the table, table order); rows are selected like
+ * pgb_load_reads does; a quarter of the bytes crosses the bus and nothing is packed on the device.  flags: PGB_LOAD_DEFER. */
+int pgb_pack_2bit(pgb_ctx *, const uint8_t *seqdb, size_t seqdb_bytes, const uint64_t *offset, const uint32_t *len, size_t n_reads,
+                  uint64_t *words_out, uint32_t *nmask_out, uint8_t *hasn_out);
+int pgb_load_reads_2bit(pgb_ctx *, const uint64_t *words, size_t n_words_total, const uint32_t *n_records, size_t n_record_words,
+                        const uint32_t *rid, const uint32_t *len, size_t n_reads, uint32_t total_chunk, uint32_t mychunk, int flags);
 /* convenience: parse <prefix>.idx, mmap <prefix>.seqdb, then pgb_load_reads */
 int pgb_load_reads_from_files(pgb_ctx *, const char *seqdb_prefix, uint32_t total_chunk, uint32_t mychunk, int keep_raw);
 

@@ -63,7 +63,8 @@ struct pgb_ctx {
   uint64_t *d_w = nullptr; uint32_t *d_nm = nullptr;
   // deferred bulk copy (pgb_load_reads with PGB_LOAD_DEFER): pgb_index overlaps the host->device copy of the .seqdb image
   // with packing and sketching, chunk by chunk; any other consumer of the reads completes the load first (ensure_loaded)
-  struct { const uint8_t *src = nullptr; bool active = false, keep_raw = false; } pend;
+  struct { const uint8_t *src = nullptr; bool active = false, keep_raw = false;
+           const uint64_t *src_words = nullptr; bool packed = false; } pend;  // packed: src_words is the 2-bit image of the selected rows
   cudaStream_t st_copy = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   uint64_t *d_wrc = nullptr;   // reverse-complement image of d_w (built on first use by the overlap / ovlp_match paths)
@@ -435,6 +436,15 @@ static void ensure_rc(pgb_ctx *c) {
 // completes a deferred bulk copy (no overlap with compute): whoever needs the packed reads before pgb_index ran
 static void ensure_loaded(pgb_ctx *c) {
   if (!c->pend.active) return;
+  if (c->pend.packed) {  // 2-bit image: nothing to pack
+    const uint64_t body = c->n_words - 4;
+    const size_t CHW = (size_t)32 << 20;
+    for (size_t o = 0; o < body; o += CHW) c->h2d(c->d_w + 2 + o, c->pend.src_words + o, std::min(CHW, (size_t)body - o) * 8);
+    c->sync();
+    c->pend.active = false; c->pend.packed = false;
+    c->stats.bases_packed += c->sel_bases;
+    return;
+  }
   const size_t CH = (size_t)256 << 20;
   for (size_t o = 0; o < c->raw_bytes; o += CH) c->h2d(c->d_raw + o, c->pend.src + o, std::min(CH, c->raw_bytes - o));
   do_pack(c);
@@ -533,6 +543,154 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
   API_END(c)
 }
 
+// The 2-bit hand-off ("ideally emitting the 2-bit device image alongside").  pgb_pack_2bit turns .seqdb bytes into
+// the packed form on the device and returns it to the host: per read ceil(len/32) words, reads in the order given, plus the
+// N mask words (all zero for a read without N) and a per-read flag.  shmr_mkseqdb writes these next to the .seqdb
+// (<prefix>.seq2b = the words, <prefix>.seq2n = {read index, word count, mask words} for the reads that contain N).
+extern "C" int pgb_pack_2bit(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_bytes, const uint64_t *offset, const uint32_t *len, size_t n_reads,
+                             uint64_t *words_out, uint32_t *nmask_out, uint8_t *hasn_out) {
+  API_BEGIN(c)
+  if (n_reads >= (1ull << 31)) throw std::runtime_error("too many reads in one pgb_pack_2bit call");
+  std::vector<uint64_t> h_woff(n_reads), h_raw(n_reads);
+  std::vector<uint32_t> h_rid(n_reads);
+  uint64_t words = 0, lo = ~0ULL, hi = 0;
+  for (size_t i = 0; i < n_reads; i++) {
+    if (offset[i] + len[i] > seqdb_bytes) throw std::runtime_error("read extends past the end of the seqdb buffer");
+    h_woff[i] = words; h_rid[i] = (uint32_t)i;
+    words += ((uint64_t)len[i] + 31) / 32;
+    lo = std::min(lo, offset[i]); hi = std::max(hi, offset[i] + len[i]);
+  }
+  if (n_reads && words) {
+    for (size_t i = 0; i < n_reads; i++) h_raw[i] = offset[i] - lo;
+    uint8_t *d_raw = c->alloc<uint8_t>(hi - lo + 64);
+    uint64_t *d_w = c->alloc<uint64_t>(words), *d_woff = c->alloc<uint64_t>(n_reads), *d_rawoff = c->alloc<uint64_t>(n_reads);
+    uint32_t *d_nm = c->alloc<uint32_t>(words), *d_len = c->alloc<uint32_t>(n_reads), *d_rid = c->alloc<uint32_t>(n_reads), *d_hasn = c->alloc<uint32_t>(n_reads);
+    c->tic();
+    c->h2d(d_raw, seqdb + lo, hi - lo);
+    c->h2d(d_woff, h_woff.data(), n_reads * 8); c->h2d(d_rawoff, h_raw.data(), n_reads * 8);
+    c->h2d(d_len, len, n_reads * 4); c->h2d(d_rid, h_rid.data(), n_reads * 4);
+    CU(cudaMemsetAsync(d_hasn, 0, n_reads * 4, c->st));
+    LAUNCH(c, k_pack_reads, nblk(words), 256, d_raw, d_rawoff, d_len, d_woff, d_rid, (uint32_t)n_reads, (uint64_t)0, words, d_w, d_nm, d_hasn);
+    c->d2h(words_out, d_w, words * 8);
+    c->d2h(nmask_out, d_nm, words * 4);
+    std::vector<uint32_t> h_hasn(n_reads);
+    c->d2h(h_hasn.data(), d_hasn, n_reads * 4);
+    for (size_t i = 0; i < n_reads; i++) hasn_out[i] = h_hasn[i] != 0;
+    c->stats.ms_pack += c->toc();
+    c->stats.bases_packed += hi - lo;
+  }
+  API_END(c)
+}
+
+// Read set from the 2-bit image (what pgb_pack_2bit produced for ALL reads of the .idx table, in table order): rows with
+// rid % total_chunk == mychunk % total_chunk are copied to the device as they are - a quarter of the .seqdb bytes over the
+// bus and no packing kernel.  n_records: the .seq2n stream (u32: read index, word count, mask words; ...) or NULL.
+// flags: PGB_LOAD_DEFER as for pgb_load_reads (the words must stay valid until the next pgb_index returns).
+extern "C" int pgb_load_reads_2bit(pgb_ctx *c, const uint64_t *words, size_t n_words_total, const uint32_t *n_records, size_t n_record_words,
+                                   const uint32_t *rid, const uint32_t *len, size_t n_reads, uint32_t T, uint32_t mychunk, int flags) {
+  API_BEGIN(c)
+  if (T == 0 || mychunk == 0 || mychunk > T) throw std::runtime_error("bad chunk spec");
+  c->free_reads();
+  const bool defer = (flags & PGB_LOAD_DEFER) != 0;
+  uint32_t max_rid = 0;
+  for (size_t i = 0; i < n_reads; i++) if (rid[i] > max_rid) max_rid = rid[i];
+  if (n_reads && (uint64_t)max_rid > 8 * (uint64_t)n_reads + (1u << 20)) throw std::runtime_error("read ids too sparse");
+  c->max_rid = max_rid;
+  std::vector<uint64_t> src_woff(n_reads + 1);
+  uint64_t acc = 0;
+  for (size_t i = 0; i < n_reads; i++) { src_woff[i] = acc; acc += ((uint64_t)len[i] + 31) / 32; }
+  src_woff[n_reads] = acc;
+  if (acc != n_words_total) throw std::runtime_error("the 2-bit image does not match the read table (stale .seq2b?)");
+  std::vector<uint32_t> rows;
+  for (size_t i = 0; i < n_reads; i++) if (rid[i] % T == mychunk % T) rows.push_back((uint32_t)i);
+  const size_t nsel = rows.size();
+  std::vector<uint32_t> h_rid(nsel), h_len(nsel), h_rlen_by_rid((size_t)max_rid + 1, 0), h_hasn_by_rid((size_t)max_rid + 1, 0);
+  std::vector<uint64_t> h_woff(nsel), h_woff_by_rid((size_t)max_rid + 1, 0);
+  std::vector<int64_t> row_of_read(n_reads, -1);
+  for (size_t i = 0; i < n_reads; i++) h_rlen_by_rid[rid[i]] = len[i];
+  uint64_t wsum = 2, bases = 0;
+  bool contiguous = true;
+  for (size_t j = 0; j < nsel; j++) {
+    const uint32_t i = rows[j];
+    h_rid[j] = rid[i]; h_len[j] = len[i]; h_woff[j] = wsum;
+    h_woff_by_rid[rid[i]] = wsum;
+    row_of_read[i] = (int64_t)j;
+    if (j && rows[j] != rows[j - 1] + 1) contiguous = false;
+    wsum += ((uint64_t)len[i] + 31) / 32;
+    bases += len[i];
+  }
+  wsum += 2;
+  c->n_rows = nsel; c->n_words = wsum; c->sel_bases = bases; c->raw_bytes = 0;
+  c->h_row_len = h_len;
+  c->d_w = c->palloc<uint64_t>(wsum); c->d_nm = c->palloc<uint32_t>(wsum);
+  c->d_rlen_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1); c->d_hasn_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1);
+  c->d_woff_by_rid = c->palloc<uint64_t>((size_t)max_rid + 1);
+  c->d_row_rid = c->palloc<uint32_t>(nsel); c->d_row_len = c->palloc<uint32_t>(nsel);
+  c->d_row_woff = c->palloc<uint64_t>(nsel); c->d_sel_rows = c->palloc<uint32_t>(nsel);
+  std::vector<uint32_t> ident(nsel);
+  for (size_t j = 0; j < nsel; j++) ident[j] = (uint32_t)j;
+  c->tic();
+  CU(cudaMemsetAsync(c->d_nm, 0, wsum * 4, c->st));
+  CU(cudaMemsetAsync(c->d_w, 0, 2 * 8, c->st));
+  CU(cudaMemsetAsync(c->d_w + (wsum - 2), 0, 2 * 8, c->st));
+  // N masks of the selected reads that have one (sparse)
+  for (size_t p = 0; n_records && p + 2 <= n_record_words;) {
+    const uint32_t i = n_records[p], nw = n_records[p + 1];
+    if (i >= n_reads || p + 2 + nw > n_record_words || nw != ((uint64_t)len[i] + 31) / 32) throw std::runtime_error("malformed N-mask stream (.seq2n)");
+    if (row_of_read[i] >= 0) {
+      c->h2d(c->d_nm + h_woff[(size_t)row_of_read[i]], n_records + p + 2, (size_t)nw * 4);
+      h_hasn_by_rid[rid[i]] = 1;
+    }
+    p += 2 + (size_t)nw;
+  }
+  c->h2d(c->d_rlen_by_rid, h_rlen_by_rid.data(), h_rlen_by_rid.size() * 4);
+  c->h2d(c->d_hasn_by_rid, h_hasn_by_rid.data(), h_hasn_by_rid.size() * 4);
+  c->h2d(c->d_woff_by_rid, h_woff_by_rid.data(), h_woff_by_rid.size() * 8);
+  c->h2d(c->d_row_rid, h_rid.data(), nsel * 4); c->h2d(c->d_row_len, h_len.data(), nsel * 4);
+  c->h2d(c->d_row_woff, h_woff.data(), nsel * 8);
+  c->h2d(c->d_sel_rows, ident.data(), nsel * 4);
+  if (nsel) {
+    if (contiguous && defer) {
+      c->pend.src_words = words + src_woff[rows[0]];
+      c->pend.active = true; c->pend.packed = true; c->pend.keep_raw = false;
+    } else if (contiguous) {
+      const size_t CHW = (size_t)32 << 20;
+      const uint64_t *src = words + src_woff[rows[0]];
+      const uint64_t body = wsum - 4;
+      for (size_t o = 0; o < body; o += CHW) c->h2d(c->d_w + 2 + o, src + o, std::min(CHW, (size_t)body - o) * 8);
+      c->stats.bases_packed += bases;
+    } else {
+      // gather the selected reads' word runs through two pinned staging buffers
+      const size_t CHW = (size_t)8 << 20;
+      uint64_t *stage[2] = {nullptr, nullptr};
+      cudaEvent_t done[2];
+      for (int b = 0; b < 2; b++) { CU(cudaMallocHost((void **)&stage[b], CHW * 8)); CU(cudaEventCreate(&done[b])); }
+      size_t j = 0, dev_o = 2; int b = 0; uint64_t part = 0;
+      while (j < nsel) {
+        CU(cudaEventSynchronize(done[b]));
+        size_t fill = 0;
+        while (j < nsel && fill < CHW) {
+          const uint32_t i = rows[j];
+          const uint64_t nw = src_woff[i + 1] - src_woff[i];
+          const size_t take = (size_t)std::min<uint64_t>(nw - part, CHW - fill);
+          memcpy(stage[b] + fill, words + src_woff[i] + part, take * 8);
+          fill += take; part += take;
+          if (part == nw) { part = 0; j++; }
+        }
+        c->h2d(c->d_w + dev_o, stage[b], fill * 8);
+        CU(cudaEventRecord(done[b], c->st));
+        dev_o += fill; b ^= 1;
+      }
+      c->sync();
+      for (int q = 0; q < 2; q++) { cudaFreeHost(stage[q]); cudaEventDestroy(done[q]); }
+      c->stats.bases_packed += bases;
+    }
+  }
+  c->sync();
+  c->stats.ms_pack += c->toc();
+  API_END(c)
+}
+
 extern "C" int pgb_repack(pgb_ctx *c) {
   API_BEGIN(c)
   ensure_loaded(c);
@@ -565,6 +723,20 @@ extern "C" int pgb_load_reads_from_files(pgb_ctx *c, const char *prefix, uint32_
   ReadTable rt;
   std::string idx = std::string(prefix) + ".idx", db = std::string(prefix) + ".seqdb";
   if (!load_read_table(idx.c_str(), &rt)) { c->err = "cannot open " + idx; return -1; }
+  // the 2-bit side files written by this library's shmr_mkseqdb (<prefix>.seq2b / .seq2n), when they match the read table:
+  // a quarter of the bytes to read and to move over the bus, no packing kernel.  PGB_NO_SEQ2B=1 ignores them.
+  if (!getenv("PGB_NO_SEQ2B") && !(keep_raw & PGB_LOAD_KEEP_RAW)) {
+    uint64_t want_words = 0;
+    for (size_t i = 0; i < rt.n(); i++) want_words += ((uint64_t)rt.len[i] + 31) / 32;
+    MappedFile m2, mn;
+    struct stat s_db, s_2b;
+    const std::string f2b = std::string(prefix) + ".seq2b", f2n = std::string(prefix) + ".seq2n";
+    if (stat(f2b.c_str(), &s_2b) == 0 && stat(db.c_str(), &s_db) == 0 && s_2b.st_mtime >= s_db.st_mtime && (uint64_t)s_2b.st_size == want_words * 8 &&
+        m2.open_ro(f2b.c_str()) && mn.open_ro(f2n.c_str()) && mn.n % 4 == 0) {
+      return pgb_load_reads_2bit(c, (const uint64_t *)m2.p, (size_t)want_words, (const uint32_t *)mn.p, mn.n / 4, rt.rid.data(), rt.len.data(), rt.n(), T,
+                                 mychunk, 0);  // (no deferred copy: the mappings end with this call)
+    }
+  }
   MappedFile mf;
   if (!mf.open_ro(db.c_str())) { c->err = "cannot open " + db; return -1; }
   return pgb_load_reads(c, mf.p, mf.n, rt.rid.data(), rt.len.data(), rt.off.data(), rt.n(), T, mychunk, keep_raw);
@@ -661,9 +833,13 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   // host->device copy of the .seqdb image in chunks of whole reads on the copy stream while the compute stream packs and
   // sketches the previous chunk (reads are independent up to the final placement); sketch_rows(r0, r1) launches the fast kernel
   auto deferred_load = [&](const std::function<void(size_t, size_t)> &sketch_rows) {
-    CU(cudaMemsetAsync(c->d_w, 0, c->n_words * 8, c->st));
-    CU(cudaMemsetAsync(c->d_nm, 0, c->n_words * 4, c->st));
-    CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
+    const bool packed = c->pend.packed;  // 2-bit image on the host (pgb_load_reads_2bit): N masks and flags are already on the device
+    if (!packed) {
+      CU(cudaMemsetAsync(c->d_w, 0, c->n_words * 8, c->st));
+      CU(cudaMemsetAsync(c->d_nm, 0, c->n_words * 4, c->st));
+      CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
+    }
+    // chunk size in .seqdb bytes (= bases): a 2-bit chunk carries a quarter of that over the bus
     const uint64_t CH = getenv("PGB_LOAD_CHUNK_MB") ? strtoull(getenv("PGB_LOAD_CHUNK_MB"), 0, 10) << 20 : (uint64_t)96 << 20;
     uint64_t raw_o = 0, word_o = 2;
     size_t r0 = 0, n_ev = 0;
@@ -672,14 +848,19 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
       uint64_t bytes = 0, wcount = 0;
       while (r1 < ns && bytes < CH) { bytes += c->h_row_len[r1]; wcount += ((uint64_t)c->h_row_len[r1] + 31) / 32; r1++; }
       if (n_ev == c->ev_pool.size()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_pool.push_back(e); }
-      if (bytes) {
+      if (packed) {  // the words travel as they are
+        if (wcount) {
+          CU(cudaMemcpyAsync(c->d_w + word_o, c->pend.src_words + (word_o - 2), wcount * 8, cudaMemcpyHostToDevice, c->st_copy));
+          c->stats.h2d_bytes += wcount * 8;
+        }
+      } else if (bytes) {
         CU(cudaMemcpyAsync(c->d_raw + raw_o, c->pend.src + raw_o, bytes, cudaMemcpyHostToDevice, c->st_copy));
         c->stats.h2d_bytes += bytes;
       }
       CU(cudaEventRecord(c->ev_pool[n_ev], c->st_copy));
       CU(cudaStreamWaitEvent(c->st, c->ev_pool[n_ev], 0));
       n_ev++;
-      if (wcount)
+      if (wcount && !packed)
         LAUNCH(c, k_pack_reads, nblk(wcount), 256, c->d_raw, c->d_row_raw_off, c->d_row_len, c->d_row_woff, c->d_row_rid, (uint32_t)c->n_rows, word_o,
                wcount, c->d_w, c->d_nm, c->d_hasn_by_rid);
       sketch_rows(r0, r1);
@@ -687,7 +868,8 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     }
     c->pend.active = false;
     c->stats.bases_packed += c->sel_bases;
-    if (!c->pend.keep_raw) c->release(c->d_raw);
+    if (packed) c->pend.packed = false;
+    else if (!c->pend.keep_raw) c->release(c->d_raw);
   };
   if (use_strip) {
     uint32_t *caps = c->alloc<uint32_t>(ns + 1), *row_flags = c->alloc<uint32_t>(ns);
@@ -1972,6 +2154,14 @@ extern "C" int pgb_shmr_mkseqdb_main(int argc, char **argv) {
   printf("output seqdb file: %s\n", index_fn.c_str());  // (sic) the reference prints the index name here, src/shmr_mkseqdb.c:92
   FILE *seqdb_file = fopen(seqdb_fn.c_str(), "wb");
   if (!seqdb_file) { fprintf(stderr, "file '%s' open error: %s\n", seqdb_fn.c_str(), strerror(errno)); exit(1); }
+  // the 2-bit image of the same reads for this library's shmr_index / shmr_overlap (not part of the reference's outputs)
+  const std::string f2b = std::string(seqdb_prefix) + ".seq2b", f2n = std::string(seqdb_prefix) + ".seq2n";
+  FILE *w2b = getenv("PGB_NO_SEQ2B") ? nullptr : fopen(f2b.c_str(), "wb");
+  FILE *w2n = w2b ? fopen(f2n.c_str(), "wb") : nullptr;
+  std::vector<uint64_t> b_words;
+  std::vector<uint32_t> b_nmask;
+  std::vector<uint8_t> b_hasn;
+  uint32_t batch_first_read = 0;
   pgb_ctx *c = cli_ctx();
   if (!c) return 1;
   // batch of reads staged in page-locked memory
@@ -1991,6 +2181,27 @@ extern "C" int pgb_shmr_mkseqdb_main(int argc, char **argv) {
       return false;
     }
     fwrite(stage_out, 1, fill, seqdb_file);
+    if (w2b && w2n) {
+      uint64_t nw = 0;
+      for (uint32_t l : b_len) nw += ((uint64_t)l + 31) / 32;
+      b_words.resize(nw); b_nmask.resize(nw); b_hasn.resize(b_len.size());
+      if (pgb_pack_2bit(c, stage_out, fill, b_off.data(), b_len.data(), b_len.size(), b_words.data(), b_nmask.data(), b_hasn.data()) != 0) {
+        fprintf(stderr, "shmr_mkseqdb: %s\n", pgb_last_error(c));
+        return false;
+      }
+      fwrite(b_words.data(), 8, nw, w2b);
+      uint64_t o = 0;
+      for (size_t i = 0; i < b_len.size(); i++) {
+        const uint32_t n_i = (uint32_t)(((uint64_t)b_len[i] + 31) / 32);
+        if (b_hasn[i]) {
+          const uint32_t hdr[2] = {batch_first_read + (uint32_t)i, n_i};
+          fwrite(hdr, 4, 2, w2n);
+          fwrite(b_nmask.data() + o, 4, n_i, w2n);
+        }
+        o += n_i;
+      }
+    }
+    batch_first_read += (uint32_t)b_len.size();
     b_off.clear(); b_len.clear(); fill = 0;
     return true;
   };
@@ -2029,6 +2240,8 @@ extern "C" int pgb_shmr_mkseqdb_main(int argc, char **argv) {
   fclose(lst);
   fclose(index_file);
   fclose(seqdb_file);
+  if (w2b) fclose(w2b);
+  if (w2n) fclose(w2n);
   cudaFreeHost(stage_in); cudaFreeHost(stage_out);
   pgb_destroy(c);
   return rc;

@@ -70,6 +70,8 @@ def load_library():
     L.pgb_last_error.argtypes = [vp]
     L.pgb_load_reads.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int]
     L.pgb_repack.argtypes = [vp]
+    L.pgb_pack_2bit.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_size_t, vp, vp, vp]
+    L.pgb_load_reads_2bit.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int]
     L.pgb_load_reads_from_files.argtypes = [vp, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int]
     L.pgb_index.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.pgb_index_size.restype = C.c_size_t
@@ -178,6 +180,35 @@ class Engine:
     def load_reads_from_files(self, prefix, total_chunk=1, mychunk=1, keep_raw=False):
         self._ck(self.L.pgb_load_reads_from_files(self.h, prefix.encode(), total_chunk, mychunk, int(keep_raw)),
                  "pgb_load_reads_from_files")
+
+    def pack_2bit(self, seqdb, offset, length, words_out=None):
+        """.seqdb bytes -> (words uint64[sum ceil(len/32)], N records uint32[...] in the .seq2n layout): what this library's
+        shmr_mkseqdb writes as <prefix>.seq2b / .seq2n.  words_out: optional preallocated (e.g. pinned) uint64 array."""
+        offset = np.ascontiguousarray(offset, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        nw = (length.astype(np.int64) + 31) // 32
+        total = int(nw.sum())
+        words = words_out if words_out is not None else np.empty(total, dtype=np.uint64)
+        assert words.size == total
+        nmask = np.empty(total, dtype=np.uint32)
+        hasn = np.empty(len(length), dtype=np.uint8)
+        self._ck(self.L.pgb_pack_2bit(self.h, _ptr(seqdb), seqdb.size, _ptr(offset), _ptr(length), len(length), _ptr(words), _ptr(nmask), _ptr(hasn)),
+                 "pgb_pack_2bit")
+        recs = []
+        woff = np.concatenate([[0], np.cumsum(nw)])
+        for i in np.nonzero(hasn)[0]:
+            recs.append(np.array([i, nw[i]], dtype=np.uint32))
+            recs.append(nmask[woff[i]: woff[i + 1]])
+        return words, (np.concatenate(recs) if recs else np.empty(0, dtype=np.uint32))
+
+    def load_reads_2bit(self, words, n_records, rid, length, total_chunk=1, mychunk=1, defer=False):
+        """Read set from the 2-bit image of ALL reads of the table (pack_2bit / .seq2b); defer as for load_reads."""
+        self._seqdb_ref = (words, n_records) if defer else None
+        rid = np.ascontiguousarray(rid, dtype=np.uint32)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        n_records = np.ascontiguousarray(n_records, dtype=np.uint32)
+        self._ck(self.L.pgb_load_reads_2bit(self.h, _ptr(words), words.size, _ptr(n_records), n_records.size, _ptr(rid), _ptr(length), len(rid),
+                                            total_chunk, mychunk, 2 if defer else 0), "pgb_load_reads_2bit")
 
     def repack(self):
         self._ck(self.L.pgb_repack(self.h), "pgb_repack")

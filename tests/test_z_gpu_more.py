@@ -84,3 +84,35 @@ def test_cli_chain_like_run_test_sh(workdir, ref_dir):
     for c in ("01", "02"):
         assert_same_ovlp(os.path.join(outs["our"], "ovlp", "ovlp." + c), os.path.join(outs["ref"], "ovlp", "ovlp." + c))
     assert open(os.path.join(outs["our"], "asm/preads.ovl"), "rb").read().count(b"\n") > 500
+
+
+def test_two_bit_handoff(workdir, ref_dir):
+    """pgb_pack_2bit + pgb_load_reads_2bit (the .seq2b / .seq2n hand-off of this library's shmr_mkseqdb) against the 1-byte/base
+    load: same packed image => same L2 and the same overlap records, on reads with N runs, for a chunked selection (gathered
+    copy), the whole set (one copy) and the deferred form that overlaps the copy with sketching."""
+    import numpy as np
+    from peregrine_b200 import Engine, formats as F
+
+    p = D.make_from_fasta(workdir, "adv2b", D.adversarial_records(seed=11), ref_dir)
+    rid, ln, off = F.read_idx(p + ".idx")
+    seqdb = np.fromfile(p + ".seqdb", dtype=np.uint8)
+    a, b = Engine(0), Engine(0)
+    words, nrec = a.pack_2bit(seqdb, off, ln)
+    assert nrec.size > 0  # the adversarial set has reads with N
+    for T, chunk, defer in ((1, 1, False), (1, 1, True), (3, 2, False), (3, 3, False)):
+        a.load_reads(seqdb, rid, ln, off, T, chunk)
+        b.load_reads_2bit(words, nrec, rid, ln, T, chunk, defer=defer)
+        a.index(80, 16, 6, 2)
+        b.index(80, 16, 6, 2)
+        for lv in (0, 2):
+            assert np.array_equal(a.level(lv), b.level(lv)), (T, chunk, defer, lv)
+    rp = D.ref_index(ref_dir, p, os.path.join(workdir, "adv2b/ref"), T=1, extra=["-m", "0"])
+    ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, "adv2b/ref"), T=1)
+    b.load_reads_2bit(words, nrec, rid, ln)
+    b.index(80, 16, 6, 2)
+    b.set_shimmers_from_index(2)
+    ov = b.overlap(1, 1)
+    want = F.normalise_ovlp(F.read_ovlp(ro[0]))
+    assert len(ov) == len(want) and ov.tobytes() == want.tobytes()
+    a.close()
+    b.close()
