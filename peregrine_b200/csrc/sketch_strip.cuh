@@ -6,8 +6,8 @@
 // (profiles/r1g_ncu.md).  Here lane l of the warp owns positions [512 c + 16 l, 512 c + 16 l + 16) of strip c:
 //   1. it extracts its first k-mer pair from the packed words, rolls 15 more bases through it and hashes the canonical
 //      k-mer of every position (32-bit arithmetic when k <= 16: hash64 masks to 2k bits after every step);
-//   2. suffix minima of its 16 hashes (rightmost on ties, "occurs twice" bit) go to a ring of rows in shared memory
-//      (64 rows of 16 = the last two strips), one row per lane per strip;
+//   2. suffix minima of its 16 hashes (values only) go to a ring of rows in shared memory (64 rows of 16 = the last two
+//      strips), one row per lane per strip;
 //   3. a window [e-w+1, e] ending in the lane's segment is  suffix(row of e-w+1)  +  the whole rows in between  +  prefix of
 //      the own segment: the minimum over the whole rows is computed ONCE per lane and strip (two variants, because the
 //      16 window starts of a lane straddle at most two rows), the prefix is a running minimum in registers, so a window
@@ -29,36 +29,45 @@
 namespace pgb {
 
 enum { SS_SPL = 16, SS_STRIP = 512, SS_ROWS = 64, SS_ROWPAD = 17, SS_WARPS = 4, SS_STAGE = 6, SS_MAXPAL = 8 };
-#define SS_TIE 0x80000000u
 
 template <class HT>
 struct SsWarpSmem {
-  HT sv[SS_ROWS * SS_ROWPAD];        // suffix minimum of the row from this offset on
-  uint32_t sa[SS_ROWS * SS_ROWPAD];  // its arg: (position << 1 | strand) | SS_TIE
-  HT stv[32 * SS_STAGE];             // staged records of the strip: value
-  uint32_t sta[32 * SS_STAGE];       // ... arg
-  int pal[SS_MAXPAL];                // positions of the most recent palindromic k-mers (ring)
+  HT sv[SS_ROWS * SS_ROWPAD];  // suffix minimum (value only) of the row from this offset on; row = (position >> 4) & 63
+  HT stv[32 * SS_STAGE];       // staged records of the strip: window minimum
+  uint16_t stj[32 * SS_STAGE]; // ... in-lane index of the window end | (window reaches one position further back) << 8
+  int pal[SS_MAXPAL];          // positions of the most recent palindromic k-mers (ring)
 };
 
+// 2k-bit window of the packed sequence -> the reference's k-mer pair.  V holds 32 bases, earliest in the low bits (base b at
+// bits 2b); R is V with its 32 two-bit groups reversed.  The k bases that END at base index (k-1+i) of V are, earliest base in
+// the low bits, W = (V >> 2i) & mask: the reverse-complement k-mer of mm_sketch.c:101 is ~W, the forward k-mer (earliest base in
+// the HIGH bits, :100) is the same group range of R.
+// (k <= 16: everything a lane needs, k-1+16 <= 31 bases, sits in one 64-bit value; k > 16 takes the 128-bit form below.)
 template <class HT>
-struct SsMin {
-  HT v;
-  uint32_t a;
-};
-// r lies to the RIGHT of l: ties go to r (the reference keeps the newest of equal k-mers, mm_sketch.c:126,135-138)
-template <class HT>
-__device__ __forceinline__ SsMin<HT> ss_combine(const SsMin<HT> &l, const SsMin<HT> &r) {
-  SsMin<HT> o;
-  const bool lt = r.v < l.v, eq = r.v == l.v;
-  o.v = (lt || eq) ? r.v : l.v;
-  o.a = lt ? r.a : (eq ? (r.a | SS_TIE) : l.a);
-  return o;
+__device__ __forceinline__ void ss_kmers(uint64_t V, uint64_t R, int i, int k, HT mask, HT *kmer0, HT *kmer1) {
+  *kmer1 = (HT)(~(V >> (2 * i))) & mask;
+  *kmer0 = (HT)(R >> (64 - 2 * i - 2 * k)) & mask;
+}
+// 64 bits starting s bits (0..127) into hi:lo
+__device__ __forceinline__ uint64_t ss_field128(uint64_t lo, uint64_t hi, int s) {
+  return s == 0 ? lo : (s < 64 ? (lo >> s) | (hi << (64 - s)) : hi >> (s - 64));
+}
+// the same over 64 bases: Vb:Va hold bases 0..63 (earliest in the low bits of Va), Rb / Ra are rev2(Va) / rev2(Vb), i.e. Ra:Rb... the
+// 128-bit value with all 64 two-bit groups reversed has rev2(Vb) in its low and rev2(Va) in its high half
+__device__ __forceinline__ void ss_kmers128(uint64_t Va, uint64_t Vb, uint64_t RVa, uint64_t RVb, int i, int k, uint64_t mask, uint64_t *kmer0,
+                                            uint64_t *kmer1) {
+  *kmer1 = ~ss_field128(Va, Vb, 2 * i) & mask;
+  *kmer0 = ss_field128(RVb, RVa, 128 - 2 * i - 2 * k) & mask;
 }
 
 // One warp = one read.  Output: cnt_by_row[row] records at tmp + tmp_off[row] (position order); row_flags[row] != 0 when the
 // read must be redone by the exact automaton (its count is then 0).
+//
+// All minima are VALUES only: "which position" is found by a short search when a record is actually emitted (1 window in 40).
+// A tie (the window minimum occurring twice, which changes what the reference emits) is detected conservatively: any
+// combine of two equal non-sentinel values, or a new element equal to the previous window's minimum, flags the read.
 template <class HT>
-__global__ void __launch_bounds__(SS_WARPS * 32) k_sketch_strip(const uint64_t *__restrict__ w, const uint32_t *__restrict__ row_rid,
+__global__ void __launch_bounds__(SS_WARPS * 32, 6) k_sketch_strip(const uint64_t *__restrict__ w, const uint32_t *__restrict__ row_rid,
                                                                 const uint32_t *__restrict__ row_len, const uint64_t *__restrict__ row_woff,
                                                                 const uint32_t *__restrict__ hasn_by_rid, uint32_t row_first, uint32_t n_rows, int wsz, int k,
                                                                 const uint64_t *__restrict__ tmp_off, mm128 *__restrict__ tmp,
@@ -79,69 +88,58 @@ __global__ void __launch_bounds__(SS_WARPS * 32) k_sketch_strip(const uint64_t *
   const int64_t base0 = (int64_t)row_woff[row] * 32;
   const uint64_t mask64 = ((uint64_t)1 << 2 * k) - 1;
   const HT mask = (HT)mask64;
-  const int shift1 = 2 * (k - 1);
   const int e_ff = wsz + k - 2;  // the first full window ends here (l == w+k-1, mm_sketch.c:116) when no palindrome precedes it
-  const int s_eval = e_ff - 1;   // the window before it is evaluated for its tie bit only (first-window special case)
+  const int s_eval = e_ff - 1;   // the window before it is evaluated for its tie check only (first-window special case)
   const uint64_t out0 = tmp_off[row], cap = tmp_off[row + 1] - out0;
   mm128 *out = tmp + out0;
   const uint64_t ridhi = (uint64_t)rid << 32;
   uint32_t n_out = 0, flags = 0;
-  uint32_t carry_a = 0xFFFFFFFFu;  // arg-min of the last window of the previous strip
+  HT carry_v = MAXV;        // minimum of the last window of the previous strip
+  bool have_carry = false;
   int n_pal = 0, last_pal = -0x40000000;
+  auto row_ix = [](int r) -> int { return (r & (SS_ROWS - 1)) * SS_ROWPAD; };
 
   for (int cp = 0; cp < len && !flags; cp += SS_STRIP) {
     const int pos0 = cp + SS_SPL * lane;
+    // a strip is PLAIN when every position has a complete k-mer, every window that ends in it is a full window after the first
+    // one, and no palindromic k-mer is within reach: then no per-position validity test is needed
+    const bool interior = cp > e_ff + 1 && cp + SS_STRIP <= len;
     // ---------------- 1. hashes of the lane's 16 positions
     HT h[SS_SPL];
-    uint32_t zm = 0, palm = 0;
-    {
-      HT kmer0 = 0, kmer1 = 0;
-      if (pos0 >= k - 1 && pos0 + SS_SPL <= len) {  // every position has a complete k-mer (all lanes but a few at the read's ends)
-        const uint64_t v = fetch_fwd64(w, base0 + pos0 - k + 1) & mask64;  // bases pos0-k+1 .. pos0, earliest in the low bits
-        kmer1 = (HT)((~v) & mask64);
-        kmer0 = (HT)(rev2(v) >> (64 - 2 * k));
-        const uint64_t bases = fetch_fwd64(w, base0 + pos0 + 1);
+    uint32_t palm = 0, vm = 0xFFFFu;  // vm: positions that are window slots with a complete k-mer (bit i)
+    const uint64_t V = fetch_fwd64(w, base0 + pos0 - k + 1);  // bases pos0-k+1 .. pos0+32-k (guard words in front of the first read)
+    const uint64_t R = rev2(V);
+    uint64_t V2 = 0, R2 = 0;  // k > 16: the next 32 bases as well
+    if (sizeof(HT) == 8) { V2 = fetch_fwd64(w, base0 + pos0 - k + 33); R2 = rev2(V2); }
 #pragma unroll
-        for (int i = 0; i < SS_SPL; i++) {
-          if (i > 0) {
-            const HT c = (HT)((bases >> (2 * (i - 1))) & 3);
-            kmer0 = (HT)((HT)(kmer0 << 2) | c) & mask;
-            kmer1 = (HT)(kmer1 >> 2) | (HT)((HT)(3 ^ c) << shift1);
-          }
-          const bool z = !(kmer0 < kmer1);
-          const bool p = kmer0 == kmer1;
-          palm |= (uint32_t)p << i;
-          zm |= (uint32_t)z << i;
-          const HT hv = sk_hash<HT>(z ? kmer1 : kmer0, mask);
-          h[i] = p ? MAXV : hv;
-        }
+    for (int i = 0; i < SS_SPL; i++) {
+      HT kmer0, kmer1;
+      if (sizeof(HT) == 8) {
+        uint64_t a, b;
+        ss_kmers128(V, V2, R, R2, i, k, mask64, &a, &b);
+        kmer0 = (HT)a; kmer1 = (HT)b;
       } else {
-        int i0 = k - 1 - pos0;  // first position of this lane whose k-mer is complete
-        if (i0 < 0) i0 = 0;
-        uint64_t bases = 0;
-        if (i0 < SS_SPL && pos0 + i0 < len) {
-          const int pos = pos0 + i0;
-          const uint64_t v = fetch_fwd64(w, base0 + pos - k + 1) & mask64;
-          kmer1 = (HT)((~v) & mask64);
-          kmer0 = (HT)(rev2(v) >> (64 - 2 * k));
-          bases = fetch_fwd64(w, base0 + pos + 1);
-        }
-#pragma unroll
-        for (int i = 0; i < SS_SPL; i++) {
-          h[i] = MAXV;  // past the read's end, or k-mer incomplete (sentinel slot, l < k)
-          if (pos0 + i < len && i >= i0) {
-            if (i > i0) {
-              const HT c = (HT)((bases >> (2 * (i - i0 - 1))) & 3);
-              kmer0 = (HT)((HT)(kmer0 << 2) | c) & mask;
-              kmer1 = (HT)(kmer1 >> 2) | (HT)((HT)(3 ^ c) << shift1);
-            }
-            const bool z = !(kmer0 < kmer1);
-            if (kmer0 == kmer1) palm |= 1u << i;
-            else { zm |= (uint32_t)z << i; h[i] = sk_hash<HT>(z ? kmer1 : kmer0, mask); }
-          }
-        }
+        ss_kmers<HT>(V, R, i, k, mask, &kmer0, &kmer1);
       }
+      if (kmer0 == kmer1) palm |= 1u << i;
+      h[i] = sk_hash<HT>(kmer0 < kmer1 ? kmer0 : kmer1, mask);
     }
+    if (!interior) {  // warp-uniform: the read's first and last strips
+      uint32_t ex = 0;  // positions that exist
+#pragma unroll
+      for (int i = 0; i < SS_SPL; i++) {
+        const bool exists = pos0 + i < len, complete = pos0 + i >= k - 1;
+        if (!(exists && complete)) { vm &= ~(1u << i); palm &= ~(1u << i); }
+        if (exists) ex |= 1u << i;
+      }
+      // an existing position with an incomplete k-mer is a sentinel SLOT (l < k, mm_sketch.c:108-111); one past the end is nothing:
+      // both carry MAXV here, and no window that is evaluated reaches either kind (windows start at k-2 and end before len)
+      (void)ex;
+    }
+    vm &= ~palm;
+#pragma unroll
+    for (int i = 0; i < SS_SPL; i++)
+      if (!((vm >> i) & 1u)) h[i] = MAXV;
     // ---------------- palindromic k-mers of the strip (warp-uniform bookkeeping)
     const uint32_t pal_lanes = __ballot_sync(FULL, palm != 0);
     if (pal_lanes) {
@@ -159,67 +157,64 @@ __global__ void __launch_bounds__(SS_WARPS * 32) k_sketch_strip(const uint64_t *
       __syncwarp();
     }
     const bool slow = last_pal >= cp - wsz - 1;  // some window of this strip may contain a palindromic k-mer
+    const bool plain = interior && !slow;
     // ---------------- 2. suffix minima of the lane's segment -> its row of the ring
+    bool tie = false;
     {
-      const int rbase = ((pos0 >> 4) & (SS_ROWS - 1)) * SS_ROWPAD;
-      SsMin<HT> run;
-      run.v = h[SS_SPL - 1];
-      run.a = (uint32_t)(pos0 + SS_SPL - 1) << 1 | ((zm >> (SS_SPL - 1)) & 1u);
-      sh.sv[rbase + SS_SPL - 1] = run.v;
-      sh.sa[rbase + SS_SPL - 1] = run.a;
+      const int rb = row_ix(pos0 >> 4);
+      HT run = h[SS_SPL - 1];
+      sh.sv[rb + SS_SPL - 1] = run;
 #pragma unroll
       for (int j = SS_SPL - 2; j >= 0; j--) {
-        SsMin<HT> c;
-        c.v = h[j];
-        c.a = (uint32_t)(pos0 + j) << 1 | ((zm >> j) & 1u);
-        run = ss_combine(c, run);
-        sh.sv[rbase + j] = run.v;
-        sh.sa[rbase + j] = run.a;
+        tie |= (h[j] == run) && (plain || run != MAXV);
+        run = h[j] < run ? h[j] : run;
+        sh.sv[rb + j] = run;
       }
     }
     __syncwarp();
     // ---------------- 3. the windows that end in the lane's segment
-    uint32_t n_st = 0;               // staged records of this lane
-    uint32_t first_a = 0xFFFFFFFFu;  // arg-min of the lane's first evaluated window (its emission is decided after the shuffle)
-    uint32_t last_a = 0xFFFFFFFFu;   // ... of its last evaluated window
-    bool first_cond = false;         // stage entry 0 is that first window's record, valid only if it differs from the left neighbour's
-    uint32_t tie = 0;
+    uint32_t n_st = 0;        // staged records of this lane
+    HT first_v = MAXV;        // minimum of the lane's first evaluated window (its emission is decided after the shuffle)
+    HT last_v = MAXV;         // ... of its last evaluated window
+    bool first_cond = false;  // stage entry 0 is that first window's record, valid only if it differs from the left neighbour's minimum
+    bool have_prev = false;
+    const int r_e = pos0 >> 4;
     if (pos0 < len && pos0 + SS_SPL - 1 >= s_eval) {
-      const int lo0 = pos0 - wsz + 1, r_lo0 = lo0 >> 4, r_e = pos0 >> 4;
-      SsMin<HT> m_short, m_long;
-      m_short.v = MAXV; m_short.a = 0;
-      auto row_total = [&](int r) -> SsMin<HT> {
-        SsMin<HT> t;
-        const int ix = (r & (SS_ROWS - 1)) * SS_ROWPAD;
-        t.v = sh.sv[ix];
-        t.a = sh.sa[ix];
-        return t;
-      };
+      const int lo0 = pos0 - wsz + 1, r_lo0 = lo0 >> 4;
+      HT m_short = MAXV, m_long = MAXV;  // minimum over the whole rows between the window's first row and the lane's own row
       if (!slow) {
-        for (int r = (r_lo0 + 2 > 0 ? r_lo0 + 2 : 0); r < r_e; r++) m_short = ss_combine(m_short, row_total(r));
+        for (int r = (r_lo0 + 2 > 0 ? r_lo0 + 2 : 0); r < r_e; r++) {
+          const HT t = sh.sv[row_ix(r)];
+          tie |= (t == m_short) && t != MAXV;
+          m_short = t < m_short ? t : m_short;
+        }
         m_long = m_short;
-        if (r_lo0 + 1 >= 0 && r_lo0 + 1 < r_e) m_long = ss_combine(row_total(r_lo0 + 1), m_short);
+        if (r_lo0 + 1 >= 0 && r_lo0 + 1 < r_e) {
+          const HT t = sh.sv[row_ix(r_lo0 + 1)];
+          tie |= (t == m_short) && t != MAXV;
+          m_long = t < m_short ? t : m_short;
+        }
       }
-      SsMin<HT> pre;
-      pre.v = MAXV; pre.a = 0;
-      uint32_t prev = 0xFFFFFFFFu;
-      bool have_prev = false;
+      // shared-memory word index of the suffix entry of window start lo0 + j: lo0 + j + (row of it) (rows are padded to 17)
+      HT pre = MAXV;
+      HT prev = MAXV;
 #pragma unroll
       for (int j = 0; j < SS_SPL; j++) {
         const int e = pos0 + j;
-        SsMin<HT> c;
-        c.v = h[j];
-        c.a = (uint32_t)e << 1 | ((zm >> j) & 1u);
-        pre = (j == 0) ? c : ss_combine(pre, c);
-        if (e < len && e >= s_eval && !((palm >> j) & 1u)) {
-          SsMin<HT> win;
+        if (j) tie |= (h[j] == pre) && (plain || pre != MAXV);
+        pre = (j == 0 || h[j] < pre) ? h[j] : pre;
+        const bool ev = plain || (e < len && e >= s_eval && ((vm >> j) & 1u));
+        if (ev) {
+          HT win;
+          uint32_t back = 0;
           if (!slow) {
             const int lo = e - wsz + 1;
-            const int ix = ((lo >> 4) & (SS_ROWS - 1)) * SS_ROWPAD + (lo & 15);
-            SsMin<HT> s;
-            s.v = sh.sv[ix];
-            s.a = sh.sa[ix];
-            win = ss_combine(ss_combine(s, (lo >> 4) == r_lo0 ? m_long : m_short), pre);
+            const HT s_ = sh.sv[row_ix(lo >> 4) + (lo & 15)];
+            const HT m_ = (lo >> 4) == r_lo0 ? m_long : m_short;
+            tie |= (s_ == m_) && (plain || m_ != MAXV);
+            const HT old = s_ < m_ ? s_ : m_;
+            tie |= (old == pre) && (plain || pre != MAXV);
+            win = old < pre ? old : pre;
           } else {
             // general form: the window holds w SLOTS; a palindromic k-mer inside it is no slot, so the window reaches one
             // position further back (two of them: exact automaton)
@@ -232,47 +227,71 @@ __global__ void __launch_bounds__(SS_WARPS * 32) k_sketch_strip(const uint64_t *
               edge_pal |= (q == e - wsz);
             }
             if (cpal > 1 || (cpal == 1 && edge_pal)) flags |= SK_FLAG_PAL;
-            const int lo = e - wsz + 1 - (cpal ? 1 : 0);
+            back = cpal ? 1u : 0u;
+            const int lo = e - wsz + 1 - (int)back;
             const int r_lo = lo >> 4;
-            const int ix = (r_lo & (SS_ROWS - 1)) * SS_ROWPAD + (lo & 15);
-            win.v = sh.sv[ix];
-            win.a = sh.sa[ix];
-            for (int r = r_lo + 1; r < r_e; r++) win = ss_combine(win, row_total(r));
-            win = ss_combine(win, pre);
+            win = sh.sv[row_ix(r_lo) + (lo & 15)];
+            for (int r = r_lo + 1; r < r_e; r++) {
+              const HT t = sh.sv[row_ix(r)];
+              tie |= (t == win) && t != MAXV;
+              win = t < win ? t : win;
+            }
+            tie |= (win == pre) && pre != MAXV;
+            win = win < pre ? win : pre;
           }
-          const uint32_t a = win.a & ~SS_TIE;
-          tie |= win.a >> 31;
-          if (e >= e_ff) {
+          if (have_prev) tie |= (h[j] == prev) && (plain || prev != MAXV);  // a new element equal to the previous minimum: a new minimizer the value alone cannot show
+          if (plain || e >= e_ff) {
             const bool is_first = !have_prev;
-            if (e == e_ff || is_first || a != prev) {
+            if ((!plain && e == e_ff) || is_first || win != prev) {
               if (n_st < SS_STAGE) {
-                sh.stv[lane * SS_STAGE + n_st] = win.v;
-                sh.sta[lane * SS_STAGE + n_st] = a;
+                sh.stv[lane * SS_STAGE + n_st] = win;
+                sh.stj[lane * SS_STAGE + n_st] = (uint16_t)(j | (back << 8));
               }
-              if (is_first && e != e_ff) first_cond = true;
+              if (is_first && (plain || e != e_ff)) first_cond = true;
               n_st++;
             }
           }
-          if (!have_prev) { first_a = a; have_prev = true; }
-          prev = a;
-          last_a = a;
+          if (!have_prev) { first_v = win; have_prev = true; }
+          prev = win;
+          last_v = win;
         }
       }
     }
     // ---------------- 4. resolve the lanes' first windows against their left neighbours, then write in position order
     {
-      const uint32_t have = __ballot_sync(FULL, last_a != 0xFFFFFFFFu);
+      const uint32_t have = __ballot_sync(FULL, have_prev);
       const uint32_t below = have & ((1u << lane) - 1u);
       const int src = below ? 31 - __clz((int)below) : 0;
-      uint32_t left = __shfl_sync(FULL, last_a, src);
-      if (!below) left = carry_a;
+      HT left = (HT)__shfl_sync(FULL, last_v, src);
+      bool have_left = below != 0;
+      if (!below) { left = carry_v; have_left = have_carry; }
       uint32_t skip = 0;
-      if (first_cond && first_a == left) { skip = 1; }  // same arg-min as the window before it: not a new minimizer
+      if (have_prev && have_left) {
+        if (first_cond && first_v == left) skip = 1;  // same minimum as the window before it: not a new minimizer
+        // (the lane's first element against the previous window's minimum, as inside the lane)
+        int jf = 0;
+        {
+          const uint32_t evm = plain ? 0xFFFFu : vm;
+          uint32_t cand = evm;
+          if (!plain) {
+            // first evaluated position of this lane
+            cand = 0;
+#pragma unroll
+            for (int j = 0; j < SS_SPL; j++)
+              if (pos0 + j < len && pos0 + j >= s_eval && ((vm >> j) & 1u)) cand |= 1u << j;
+          }
+          jf = cand ? __ffs((int)cand) - 1 : 0;
+        }
+        HT hf = h[0];
+#pragma unroll
+        for (int j = 1; j < SS_SPL; j++) hf = (j == jf) ? h[j] : hf;
+        tie |= (hf == left) && left != MAXV;
+      }
       const uint32_t top = have ? 31 - __clz((int)have) : 0;
-      const uint32_t new_carry = __shfl_sync(FULL, last_a, top);
-      if (have) carry_a = new_carry;
+      const HT new_carry = (HT)__shfl_sync(FULL, last_v, top);
+      if (have) { carry_v = new_carry; have_carry = true; }
       if (__any_sync(FULL, n_st > SS_STAGE)) flags |= SK_FLAG_OVERFLOW;
-      if (__any_sync(FULL, tie != 0)) flags |= SK_FLAG_TIE;
+      if (__any_sync(FULL, tie)) flags |= SK_FLAG_TIE;
       flags = __reduce_or_sync(FULL, flags);
       const uint32_t cnt = n_st - skip;
       uint32_t inc = cnt;
@@ -286,11 +305,39 @@ __global__ void __launch_bounds__(SS_WARPS * 32) k_sketch_strip(const uint64_t *
       if (!flags) {
         uint32_t at = n_out + inc - cnt;
         for (uint32_t i = skip; i < n_st; i++) {
+          // ---- where is the minimum?  rightmost position of the window that holds the value (the window is tie-free)
           const HT v = sh.stv[lane * SS_STAGE + i];
-          const uint32_t a = sh.sta[lane * SS_STAGE + i];
+          const uint32_t sj = sh.stj[lane * SS_STAGE + i];
+          const int j = (int)(sj & 0xFF), e = pos0 + j, lo = e - wsz + 1 - (int)(sj >> 8);
+          int p = -1;
+#pragma unroll
+          for (int jj = 0; jj < SS_SPL; jj++)
+            if (jj <= j && h[jj] == v) p = pos0 + jj;
+          if (p < 0) {
+            const int r_lo = lo >> 4;
+            for (int r = r_e - 1; r >= r_lo && p < 0; r--) {
+              const int o0 = r == r_lo ? (lo & 15) : 0;
+              if (sh.sv[row_ix(r) + o0] == v) {  // the row's suffix from o0 holds it: its last offset with that suffix minimum
+                int o = o0;
+                while (o + 1 < SS_SPL && sh.sv[row_ix(r) + o + 1] == v) o++;
+                p = r * SS_SPL + o;
+              }
+            }
+          }
+          // strand of the canonical k-mer at p (mm_sketch.c:106)
+          const uint64_t Vp_ = fetch_fwd64(w, base0 + p - k + 1);
+          HT kmer0, kmer1;
+          if (sizeof(HT) == 8) {
+            // (the k-mer starts at bit 0 of Vp_: 2k <= 56 bits, one value holds it)
+            kmer1 = (HT)(~Vp_ & mask64);
+            kmer0 = (HT)((rev2(Vp_) >> (64 - 2 * k)) & mask64);
+          } else {
+            ss_kmers<HT>(Vp_, rev2(Vp_), 0, k, mask, &kmer0, &kmer1);
+          }
+          const uint32_t z = kmer0 < kmer1 ? 0u : 1u;
           mm128 m;
           m.x = (uint64_t)v << 8 | (uint64_t)k;
-          m.y = ridhi | (uint64_t)a;
+          m.y = ridhi | (uint64_t)((uint32_t)p << 1 | z);
           out[at++] = m;
         }
         n_out += total;
