@@ -9,7 +9,7 @@ LIB = peregrine_b200/libpgb200.so
 
 all: $(LIB) bin/shmr_index bin/shmr_overlap bin/shmr_dedup bin/shmr_mkseqdb bin/shmr_map build/simreads
 
-$(LIB): $(CSRC)/pgb200.cu $(CSRC)/kernels.cuh $(CSRC)/shimmer_core.cuh $(CSRC)/ovlp_match_lean_body.inc $(CSRC)/sketch_tile.cuh $(CSRC)/khash_small.cuh $(CSRC)/dedup.cuh $(CSRC)/map.cuh $(CSRC)/fasta_reader.hpp $(CSRC)/host_util.hpp include/pgb200.h
+$(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh $(CSRC)/*.inc $(CSRC)/*.hpp) include/pgb200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/pgb200.cu -lz
 
 bin/shmr_index: cli/shmr_index.c $(LIB)
