@@ -440,7 +440,7 @@ def run_ours(args):
         "roofline": roofline,
         "stage_ms_per_step": {k_: st[k_] / K for k_ in st if k_.startswith("ms_") and not k_.startswith("ms_k_")},
         "counts_per_step": {k_: st[k_] // K for k_ in ("n_l0", "n_l1", "n_l2", "n_pair_records", "n_buckets", "n_eligible_buckets", "n_candidates",
-                                                         "n_alignments", "n_replay_passes")},
+                                                         "n_alignments", "n_replay_passes", "n_sketch_fallback_reads")},
     }
     if cpu:
         out["cpu_baseline"] = cpu
