@@ -900,6 +900,18 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     else sketch_rows(0, ns);
     c->stats.ms_k_sketch_tiled += c->ktoc(); c->stats.n_k_sketch_tiled++;
     LAUNCH(c, k_row_exact_flags, nblk(ns), 256, row_flags, (uint32_t)ns, exact_flag);
+    if (getenv("PGB_VERBOSE")) {  // why reads were handed to the exact automaton
+      std::vector<uint32_t> hf(ns);
+      c->d2h(hf.data(), row_flags, ns * 4);
+      size_t n_tie = 0, n_pal = 0, n_ovf = 0, n_short = 0, n_n = 0, n_any = 0;
+      for (uint32_t f : hf) { n_any += f != 0; n_tie += (f & SK_FLAG_TIE) != 0; n_pal += (f & SK_FLAG_PAL) != 0; n_ovf += (f & SK_FLAG_OVERFLOW) != 0;
+                              n_short += (f & SK_FLAG_SHORT) != 0; n_n += (f & SK_FLAG_N) != 0; }
+      fprintf(stderr, "pgb200: strip sketch: %zu of %zu reads to the exact automaton (tie %zu, palindrome %zu, overflow %zu, short %zu, N %zu)\n", n_any, ns,
+              n_tie, n_pal, n_ovf, n_short, n_n);
+      size_t by_bit[32] = {0};
+      for (uint32_t f : hf) for (int b = 8; b < 32; b++) by_bit[b] += (f >> b) & 1u;
+      for (int b = 8; b < 20; b++) if (by_bit[b]) fprintf(stderr, "pgb200:   tie check %d: %zu reads\n", b, by_bit[b]);
+    }
     exact_tail(row_flags, exact_flag, exact_pos, [&]() {
       LAUNCH(c, k_row_gather, nblk(ns * 32, 256), 256, counts, row_flags, (uint32_t)ns, tmp_off, tmp, c->d_level_off[0], c->d_level[0]);
     });
