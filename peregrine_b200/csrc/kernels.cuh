@@ -924,8 +924,9 @@ struct DevReplayCtx {
 __global__ void __launch_bounds__(64) k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ list, const uint32_t *__restrict__ rank_off,
                                                const uint64_t *__restrict__ sy0, const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn,
                                                int request_enabled, int do_emit, uint32_t *acc_count, const uint32_t *__restrict__ out_off,
-                                               ovlp_rec *out, uint8_t *unk_flag) {
+                                               ovlp_rec *out, uint8_t *unk_flag, const uint32_t *__restrict__ cnt_dev) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cnt_dev) n_ranks = cnt_dev[0];  // run list sized on the device (no host round trip): [0] small buckets, [1] all
   if (r >= n_ranks) return;
   if (*(volatile int *)st.err & (32 | 64)) return;  // a table filled up: this pass is void, the host restarts with larger tables
   r = list[r];
@@ -960,7 +961,9 @@ __global__ void __launch_bounds__(PGB_RB_THREADS) k_replay_block(ReplayState st,
                                                                  const uint32_t *__restrict__ rank_off, const uint64_t *__restrict__ sy0,
                                                                  const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn,
                                                                  int request_enabled, int do_emit, uint32_t *acc_count,
-                                                                 const uint32_t *__restrict__ out_off, ovlp_rec *out, uint8_t *unk_flag) {
+                                                                 const uint32_t *__restrict__ out_off, ovlp_rec *out, uint8_t *unk_flag,
+                                                                 const uint32_t *__restrict__ cnt_dev) {
+  if (cnt_dev) { n_ranks = cnt_dev[1] - cnt_dev[0]; list += cnt_dev[0]; }  // the big buckets follow the small ones in the run list
   __shared__ uint8_t code[PGB_RB_MAXN * PGB_RB_MAXN];  // [i * n + j], j > i: kind | type << 2 | accepted << 4
   __shared__ uint64_t s_y0[PGB_RB_MAXN];
   __shared__ uint32_t s_rlen[PGB_RB_MAXN];
@@ -1406,6 +1409,18 @@ __global__ void k_class_flags(const uint32_t *__restrict__ rank_off, uint32_t n_
   const bool big = rank_off[r + 1] - rank_off[r] >= big_n;
   flags[r] = run && !big;
   flags[n_ranks + r] = run && big;
+}
+// what the host needs to know after a pass, gathered into one struct (one device-to-host copy, one synchronisation per pass)
+struct PassOut { unsigned long long unknown, diffs; uint32_t n_req; int err; uint32_t n_small, n_run; unsigned long long align_bases; };
+__global__ void k_run_counts(const uint32_t *__restrict__ dpos, uint32_t n_ranks, uint32_t *cnt) {
+  cnt[0] = dpos[n_ranks];       // small buckets of the run list
+  cnt[1] = dpos[2 * n_ranks];   // all of them
+}
+__global__ void k_pass_out(const unsigned long long *__restrict__ ctr, const uint32_t *__restrict__ n_req, const int *__restrict__ err,
+                           const uint32_t *__restrict__ cnt, const unsigned long long *__restrict__ align_bases, PassOut *out) {
+  PassOut o;
+  o.unknown = ctr[0]; o.diffs = ctr[1]; o.n_req = *n_req; o.err = *err; o.n_small = cnt[0]; o.n_run = cnt[1]; o.align_bases = *align_bases;
+  *out = o;
 }
 __global__ void k_compact_classes(const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos, uint32_t n_ranks, uint32_t *list) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -52,6 +52,8 @@ struct pgb_ctx {
   pgb_stats stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   cudaEvent_t user_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_pass[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // fix-point pass: [0,1] pass, [2,3] k_replay, [4,5] alignment batch
+  PassOut *h_pass = nullptr;  // page-locked mailbox of the fix-point loop
   unsigned long long *d_align_bases = nullptr;
 
   // ---- reads
@@ -325,6 +327,8 @@ extern "C" pgb_ctx *pgb_create(int device) {
     CU(cudaEventCreate(&c->evk0));
     CU(cudaEventCreate(&c->evk1));
     for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->user_ev[i]));
+    for (int i = 0; i < 6; i++) CU(cudaEventCreate(&c->ev_pass[i]));
+    CU(cudaMallocHost((void **)&c->h_pass, sizeof(PassOut)));
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
@@ -360,6 +364,8 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   cudaEventDestroy(c->evk0);
   cudaEventDestroy(c->evk1);
   for (int i = 0; i < 8; i++) cudaEventDestroy(c->user_ev[i]);
+  for (int i = 0; i < 6; i++) cudaEventDestroy(c->ev_pass[i]);
+  if (c->h_pass) cudaFreeHost(c->h_pass);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->st_copy);
   cudaStreamDestroy(c->st);
@@ -1389,9 +1395,40 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   };
   uint32_t n_all = 0;
   const uint32_t n_all_small = class_lists(nullptr, all_list, &n_all);
+  const uint32_t n_all_big = n_all - n_all_small;
+  // upper bound of the CTA-replayed buckets of an incremental pass in tail mode (threshold BIG_TAIL instead of BIG_N)
+  uint32_t n_tail_big = n_all_big;
+  if (BIG_TAIL < BIG_N) {
+    tail_mode = true;
+    std::vector<uint8_t> ones(n_ranks, 1);
+    c->h2d(dirty, ones.data(), n_ranks);
+    uint32_t n_t = 0;
+    const uint32_t n_t_small = class_lists(dirty, dlist, &n_t);
+    n_tail_big = n_t - n_t_small;
+    tail_mode = false;
+  }
+  // the same without a host round trip: the run list's sizes stay on the device (run_cnt), the kernels read them there
+  uint32_t *run_cnt = c->alloc<uint32_t>(2), *all_cnt = c->alloc<uint32_t>(2);
+  PassOut *d_pass = c->alloc<PassOut>(1);
+  {
+    const uint32_t h_all[2] = {n_all_small, n_all};
+    c->h2d(all_cnt, h_all, 8);
+  }
+  auto class_lists_dev = [&](const uint8_t *dirty_flags, uint32_t *list) {
+    CU(cudaMemsetAsync(dflags + 2 * (size_t)n_ranks, 0, 4, c->st));
+    LAUNCH(c, k_class_flags, nblk(n_ranks), 256, d_rank_off, n_ranks, dirty_flags, tail_mode ? std::min(BIG_N, BIG_TAIL) : BIG_N, dflags);
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum((void *)nullptr, tmp_bytes, dflags, dpos, (int)(2 * (size_t)n_ranks + 1), c->st));
+    uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+    CU(cub::DeviceScan::ExclusiveSum((void *)tmp, tmp_bytes, dflags, dpos, (int)(2 * (size_t)n_ranks + 1), c->st));
+    c->stats.kernel_launches += 2;
+    LAUNCH(c, k_run_counts, 1, 1, dpos, n_ranks, run_cnt);
+    LAUNCH(c, k_compact_classes, nblk(2 * (size_t)n_ranks), 256, dflags, dpos, n_ranks, list);
+  };
   auto free_common = [&]() {
     c->release(rid_sorted); c->release(rank_sorted); c->release(bloom); c->release(changed); c->release(unk_flag); c->release(dirty);
     c->release(dflags); c->release(dpos); c->release(dlist); c->release(all_list); c->release(acc); c->release(out_off); c->release(d_ctr);
+    c->release(run_cnt); c->release(all_cnt); c->release(d_pass);
     c->release(sy0); c->release(sy1); c->release(sseq); c->release(sdir); c->release(contained); c->release(d_rank_off);
   };
 
@@ -1433,10 +1470,13 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
     CU(cudaMemsetAsync(S.n_req, 0, 4, c->st));
     CU(cudaMemsetAsync(acc, 0, ((size_t)n_ranks + 1) * 4, c->st));
     CU(cudaMemsetAsync(unk_flag, 0, n_ranks, c->st));
-    auto launch_replay = [&](const uint32_t *list, uint32_t n_small, uint32_t n_total, int request, int emit, const uint32_t *ooff, ovlp_rec *out) {
+    // run list of a pass: host-known sizes (cnt_dev == nullptr) or sizes left on the device by class_lists_dev
+    auto launch_replay = [&](const uint32_t *list, uint32_t n_small, uint32_t n_total, int request, int emit, const uint32_t *ooff, ovlp_rec *out,
+                             const uint32_t *cnt_dev) {
       const uint32_t nb = n_total - n_small;
-      LAUNCH(c, k_replay, nblk(n_small, 64), 64, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag);
-      LAUNCH(c, k_replay_block, nb, PGB_RB_THREADS, S, nb, list + n_small, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag);
+      LAUNCH(c, k_replay, nblk(n_small, 64), 64, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag, cnt_dev);
+      LAUNCH(c, k_replay_block, nb, PGB_RB_THREADS, S, nb, cnt_dev ? list : list + n_small, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff,
+             out, unk_flag, cnt_dev);
     };
     bool wet = MAX_DRY <= 0, overflow = false;
     if (wet && acap64 == 0) {  // PGB_DRY_PASSES=0: no speculative count to size from
@@ -1447,58 +1487,75 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
     uint64_t prev_diffs = ~0ULL, last_diffs = ~0ULL;
     uint32_t n_done = 0;
     int dry_passes = 0;
+    bool align_pending = false;  // an alignment batch was launched whose event pair / base count has not been read yet
+    auto read_align_timing = [&]() {
+      if (!align_pending) return;
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, c->ev_pass[4], c->ev_pass[5]));
+      c->stats.ms_k_align += ms; c->stats.ms_align += ms;
+      align_pending = false;
+    };
+    // ONE host synchronisation per pass: everything the host decides on (convergence, table overflow, the size of the next
+    // alignment batch, the next run list's size class) arrives in one page-locked struct; event times are read after it
     for (int pass = 0; pass < 400; pass++) {
-      c->tic();
+      CU(cudaEventRecord(c->ev_pass[0], c->st));
       CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
       // which buckets run in this pass
-      uint32_t n_run = n_all, n_run_small = n_all_small;
-      const uint32_t *run_list = all_list;
       const bool partial = incremental && pass > 0 && last_diffs <= CHANGED_CAP;
       if (partial) {
         LAUNCH(c, k_dirty_from_unknown, nblk(n_ranks), 256, unk_flag, n_ranks, dirty);
         if (last_diffs) LAUNCH(c, k_mark_dirty_pairs, nblk(last_diffs), 256, changed, (uint32_t)last_diffs, rid_sorted, rank_sorted, n_elig, bloom, dirty);
-        n_run_small = class_lists(dirty, dlist, &n_run);
+        class_lists_dev(dirty, dlist);
         LAUNCH(c, k_e_carry, 1184, 256, S.E, (size_t)S.ecap, S.cur, dirty);
-        run_list = dlist;
       } else {
         LAUNCH(c, k_e_fill_new, 1184, 256, S.E, (size_t)S.ecap, S.cur);
+        CU(cudaMemcpyAsync(run_cnt, all_cnt, 8, cudaMemcpyDeviceToDevice, c->st));
       }
-      c->ktic();
-      launch_replay(run_list, n_run_small, n_run, wet ? 1 : 0, 0, (const uint32_t *)nullptr, (ovlp_rec *)nullptr);
-      const double ms_rp = c->ktoc();
-      c->stats.ms_k_replay += ms_rp; c->stats.n_k_replay++;
+      CU(cudaEventRecord(c->ev_pass[2], c->st));
+      if (partial) launch_replay(dlist, n_ranks, n_ranks + (tail_mode ? n_tail_big : n_all_big), wet ? 1 : 0, 0, (const uint32_t *)nullptr, (ovlp_rec *)nullptr, run_cnt);
+      else launch_replay(all_list, n_all_small, n_all, wet ? 1 : 0, 0, (const uint32_t *)nullptr, (ovlp_rec *)nullptr, (const uint32_t *)nullptr);
+      CU(cudaEventRecord(c->ev_pass[3], c->st));
       LAUNCH(c, k_e_diff_list, 1184, 256, S.E, (size_t)S.ecap, d_ctr + 1, changed, CHANGED_CAP);
-      unsigned long long ctr[2];
-      uint32_t n_req = 0;
-      c->d2h(ctr, d_ctr, 16);
-      c->d2h(&n_req, S.n_req, 4);
-      c->stats.ms_replay += c->toc();
-      c->stats.n_replay_passes++;
+      LAUNCH(c, k_pass_out, 1, 1, d_ctr, S.n_req, c->d_err, run_cnt, c->d_align_bases, d_pass);
+      CU(cudaMemcpyAsync(c->h_pass, d_pass, sizeof(PassOut), cudaMemcpyDeviceToHost, c->st));
+      CU(cudaEventRecord(c->ev_pass[1], c->st));
+      CU(cudaStreamSynchronize(c->st));
+      c->stats.d2h_bytes += sizeof(PassOut);
+      const PassOut po = *c->h_pass;
       {
-        int e = 0;
-        c->d2h(&e, c->d_err, sizeof e);
-        if (e & (32 | 64)) {  // a table filled up: grow it and start over
-          if (e & 32) { ecap64 *= 2; if (!ts_env) c->ecap_ratio *= 2; }
-          if (e & 64) {  // n_req counted every request of the pass, also those that no longer fitted: size for them at once
-            const uint64_t want = std::max(2 * acap64, 2 * (uint64_t)n_req);
-            if (!ts_env) c->acap_ratio *= (double)want / (double)std::max<uint64_t>(acap64, 1);
-            acap64 = want;
-          }
-          int z = 0;
-          c->h2d(c->d_err, &z, sizeof z);
-          c->sync();
-          if (verbose) fprintf(stderr, "pgb200: replay tables too small (flags %d): restarting with pair table %llu, alignment table %llu\n", e,
-                               (unsigned long long)ecap64, (unsigned long long)acap64);
-          overflow = true;
-          break;
-        }
+        float ms_rp = 0, ms_pass = 0;
+        CU(cudaEventElapsedTime(&ms_rp, c->ev_pass[2], c->ev_pass[3]));
+        CU(cudaEventElapsedTime(&ms_pass, c->ev_pass[0], c->ev_pass[1]));
+        c->stats.ms_k_replay += ms_rp; c->stats.n_k_replay++;
+        c->stats.ms_replay += ms_pass;
+        read_align_timing();  // (the batch launched after the previous pass finished before this pass's replay started)
+        if (verbose)
+          fprintf(stderr, "pgb200: replay pass %d %s: buckets=%u/%u unknown=%llu table_diffs=%llu requests=%u  k_replay %.3f ms, pass %.3f ms\n", pass,
+                  wet ? "wet" : "dry", po.n_run, n_ranks, po.unknown, po.diffs, po.n_req, ms_rp, ms_pass);
       }
-      if (c->check_err("pgb_overlap/replay")) { free_S(); free_common(); return -1; }
-      double ms_al = 0;
+      c->stats.n_replay_passes++;
+      const unsigned long long ctr[2] = {po.unknown, po.diffs};
+      const uint32_t n_req = po.n_req;
+      if (po.err & (32 | 64)) {  // a table filled up: grow it and start over
+        if (po.err & 32) { ecap64 *= 2; if (!ts_env) c->ecap_ratio *= 2; }
+        if (po.err & 64) {  // n_req counted every request of the pass, also those that no longer fitted: size for them at once
+          const uint64_t want = std::max(2 * acap64, 2 * (uint64_t)n_req);
+          if (!ts_env) c->acap_ratio *= (double)want / (double)std::max<uint64_t>(acap64, 1);
+          acap64 = want;
+        }
+        int z = 0;
+        c->h2d(c->d_err, &z, sizeof z);
+        c->sync();
+        if (verbose) fprintf(stderr, "pgb200: replay tables too small (flags %d): restarting with pair table %llu, alignment table %llu\n", po.err,
+                             (unsigned long long)ecap64, (unsigned long long)acap64);
+        overflow = true;
+        break;
+      }
+      if (po.err) { c->check_err("pgb_overlap/replay"); free_S(); free_common(); return -1; }
       if (n_req > n_done) {
-        c->tic();
         uint32_t nn = n_req - n_done;
         uint32_t *perm = nullptr;
+        CU(cudaEventRecord(c->ev_pass[4], c->st));
         if (nn > 8192 && nn > ALIGN_WARP_MAX) {  // group alignments of similar predicted length into the same warps
           uint32_t *keys = c->alloc<uint32_t>(nn), *keys2 = c->alloc<uint32_t>(nn), *idx0 = c->alloc<uint32_t>(nn);
           perm = c->alloc<uint32_t>(nn);
@@ -1509,7 +1566,6 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
           CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
           c->stats.kernel_launches += 3;
         }
-        c->ktic();
         if (nn <= ALIGN_WARP_MAX)  // small batch: latency-bound, one warp per alignment
           LAUNCH(c, k_align_warp, nblk(nn, PGB_AW_WARPS), PGB_AW_WARPS * 32, S.reqs, n_done, nn, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid,
                  c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
@@ -1574,27 +1630,17 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         if (c->n_reads_with_n)
           LAUNCH(c, k_align, nblk(nn, 64), 64, S.reqs, n_done, nn, perm, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid,
                  (int)bw, S.ares, c->d_err, c->d_align_bases, 1);
-        ms_al = c->ktoc();
-        c->stats.ms_k_align += ms_al; c->stats.n_k_align++;
-        {
-          unsigned long long ab = 0;
-          c->d2h(&ab, c->d_align_bases, 8);
-          c->stats.n_align_bases += ab;
-          CU(cudaMemsetAsync(c->d_align_bases, 0, 8, c->st));
-        }
-        c->stats.ms_align += c->toc();
+        CU(cudaEventRecord(c->ev_pass[5], c->st));
+        align_pending = true;
+        c->stats.n_k_align++;
         c->stats.n_alignments += nn;
-        if (c->check_err("pgb_overlap/align")) { free_S(); free_common(); return -1; }
       }
       const bool new_requests = n_req > n_done;
       n_done = n_req;
       S.cur ^= 1;
-      if (verbose)
-        fprintf(stderr, "pgb200: replay pass %d %s: buckets=%u/%u unknown=%llu table_diffs=%llu requests=%u  k_replay %.3f ms, k_align %.3f ms\n", pass,
-                wet ? "wet" : "dry", n_run, n_ranks, ctr[0], ctr[1], n_req, ms_rp, ms_al);
       last_diffs = ctr[1];
-      tail_mode = n_run < TAIL_RUN;
-      c->stats.n_replay_buckets += n_run;
+      tail_mode = po.n_run < TAIL_RUN;
+      c->stats.n_replay_buckets += po.n_run;
       if (wet && !new_requests && ctr[0] == 0 && ctr[1] == 0) { converged = true; break; }
       if (!wet) {
         // speculative ("dry") passes settle the time-stamped pair table with predicted alignments only; switch to real
@@ -1608,6 +1654,13 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         }
       }
     }
+    if (align_pending) { c->sync(); read_align_timing(); }
+    {
+      unsigned long long ab = 0;  // bases compared along the final paths of this call's alignments (algorithmic-bytes accounting)
+      c->d2h(&ab, c->d_align_bases, 8);
+      c->stats.n_align_bases += ab;
+      CU(cudaMemsetAsync(c->d_align_bases, 0, 8, c->st));
+    }
     if (overflow) continue;
     if (!converged) { free_S(); free_common(); throw std::runtime_error("replay fix-point did not converge in 400 passes"); }
 
@@ -1617,7 +1670,7 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
     c->d_ovl = c->palloc<ovlp_rec>(n_out); c->n_ovl = n_out;
     LAUNCH(c, k_e_fill_new, 1184, 256, S.E, (size_t)S.ecap, S.cur);
     CU(cudaMemsetAsync(d_ctr, 0, 16, c->st));
-    launch_replay(all_list, n_all_small, n_all, 0, 1, out_off, c->d_ovl);
+    launch_replay(all_list, n_all_small, n_all, 0, 1, out_off, c->d_ovl, (const uint32_t *)nullptr);
     c->sync();
     c->stats.ms_emit += c->toc();
     c->stats.n_overlaps += n_out;
