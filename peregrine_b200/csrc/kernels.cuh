@@ -742,6 +742,12 @@ __global__ void k_inner_order(const uint32_t *__restrict__ goff, uint32_t n_oute
   khs_order(keys, n, last > g.first[b + n - 1], rank);
   for (uint32_t i = 0; i < n; i++) ipos[b + i] = rank[i];
 }
+// [0] start of the last group (= the newest outer key), [1] the sequence number of its first record
+__global__ void k_last_group_first(const uint32_t *__restrict__ goff, uint32_t n_outer, const uint32_t *__restrict__ gfirst, uint32_t *out) {
+  const uint32_t b = goff[n_outer - 1];
+  out[0] = b;
+  out[1] = gfirst[b];
+}
 // group sizes in outer visiting order
 __global__ void k_group_sizes_by_rank(const uint32_t *__restrict__ goff, const uint32_t *__restrict__ orank, uint32_t n_outer, uint32_t *size_by_rank) {
   uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;

@@ -96,6 +96,7 @@ struct pgb_ctx {
   // ---- overlap output
   ovlp_rec *d_ovl = nullptr; size_t n_ovl = 0;
   void *h_ovl = nullptr; size_t h_ovl_cap = 0;  // page-locked staging of the records (pgb_overlap_host)
+  uint64_t *h_okey = nullptr; size_t h_okey_cap = 0;  // page-locked staging of the outer khash keys (overlap_core)
   int *d_err = nullptr;
   KhashEmu outer_emu;  // host replay of the outer khash (visiting order), storage reused between calls
 
@@ -354,6 +355,7 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   c->release(c->d_dedup_text);
   c->release(c->d_map_text);
   if (c->h_ovl) cudaFreeHost(c->h_ovl);
+  if (c->h_okey) cudaFreeHost(c->h_okey);
   c->release(c->d_err);
   c->release(c->d_align_bases);
   cudaStreamSynchronize(c->st);
@@ -421,10 +423,10 @@ static void do_pack(pgb_ctx *c) {
 
 // reverse-complement image + number of reads with N, built once per loaded read set
 static void ensure_loaded(pgb_ctx *c);
-static void ensure_rc(pgb_ctx *c) {
-  ensure_loaded(c);
-  if (c->d_wrc || !c->d_w) return;
-  c->tic();
+// rc_launch only enqueues the kernels (returns the device counter, or null when the image exists); rc_finish reads the counter.
+// overlap_core puts the host's khash replay between the two, so that the image is built while the CPU is busy.
+static unsigned int *rc_launch(pgb_ctx *c) {
+  if (c->d_wrc || !c->d_w) return nullptr;
   c->d_wrc = c->palloc<uint64_t>(c->n_words);
   CU(cudaMemsetAsync(c->d_wrc, 0, c->n_words * 8, c->st));
   uint64_t body = c->n_words - 4;
@@ -432,10 +434,19 @@ static void ensure_rc(pgb_ctx *c) {
   unsigned int *d_n = c->alloc<unsigned int>(1);
   CU(cudaMemsetAsync(d_n, 0, 4, c->st));
   LAUNCH(c, k_count_nonzero_u32, nblk((size_t)c->max_rid + 1), 256, c->d_hasn_by_rid, (size_t)c->max_rid + 1, d_n);
+  return d_n;
+}
+static void rc_finish(pgb_ctx *c, unsigned int *d_n) {
+  if (!d_n) return;
   unsigned int h = 0;
   c->d2h(&h, d_n, 4);
   c->n_reads_with_n = h;
   c->release(d_n);
+}
+static void ensure_rc(pgb_ctx *c) {
+  ensure_loaded(c);
+  c->tic();
+  rc_finish(c, rc_launch(c));
   c->stats.ms_pack += c->toc();
 }
 
@@ -1202,9 +1213,9 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   if (bw + 3 > PGB_MAXV) throw std::runtime_error("align bandwidth (-w) above 256 is not supported by this build");
   if (ovlp_upper > 65535) throw std::runtime_error("ovlp_upper (-n) above 65535 is not supported");
   bestn &= 0xFF;  // uint8_t bestn = atoi(), src/shmr_overlap.c:245,286
-  ensure_rc(c);
+  ensure_loaded(c);
   auto free_R = [&]() { c->release(R.k0); c->release(R.k1); c->release(R.y0); c->release(R.y1); c->release(R.seq); c->release(R.dir); };
-  if (nrec == 0) { free_R(); c->sync(); c->check_err("pgb_overlap/build_map"); return c->err.empty() ? 0 : -1; }
+  if (nrec == 0) { free_R(); ensure_rc(c); c->sync(); c->check_err("pgb_overlap/build_map"); return c->err.empty() ? 0 : -1; }
 
   // ---------------- bucket tables
   c->tic();
@@ -1252,26 +1263,39 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   G.count = c->alloc<uint32_t>(n_buckets); G.oid = c->alloc<uint32_t>(n_buckets); G.k1 = c->alloc<uint64_t>(n_buckets);
   uint32_t *goff = c->alloc<uint32_t>((size_t)n_outer + 1), *ipos = c->alloc<uint32_t>(n_buckets), *big_list = c->alloc<uint32_t>((size_t)n_outer + 1);
   uint64_t *okey = c->alloc<uint64_t>((size_t)n_outer + 1);
-  unsigned int *d_small = c->alloc<unsigned int>(2);  // [0] last_seq_all, [1] n_big
+  unsigned int *d_small = c->alloc<unsigned int>(4);  // [0] last_seq_all, [1] n_big, [2] start of the last group, [3] its first sequence number
   unsigned long long *d_ncand = c->alloc<unsigned long long>(1);
-  CU(cudaMemsetAsync(d_small, 0, 8, c->st));
+  CU(cudaMemsetAsync(d_small, 0, 16, c->st));
   CU(cudaMemsetAsync(d_ncand, 0, 8, c->st));
   LAUNCH(c, k_group_gather, nblk(n_buckets), 256, gidx, goid_sorted, n_buckets, sslot, bkeys, xkeys, bfirst, blast, bcount, G, goff, n_outer, okey,
          d_small);
   // (d) inner khash replay, one thread per outer key
   LAUNCH(c, k_inner_order, nblk(n_outer, 128), 128, goff, n_outer, G, ipos, big_list, d_small + 1);
-  std::vector<uint64_t> h_okey(n_outer);
-  std::vector<uint32_t> h_goff_last(2);
-  unsigned int h_small[2];
-  c->d2h(h_okey.data(), okey, (size_t)n_outer * 8);
-  c->d2h(h_small, d_small, 8);
-  uint32_t newest_outer_seq = 0;
-  {
-    uint32_t last_group_start = 0;
-    c->d2h(&last_group_start, goff + (n_outer - 1), 4);
-    c->d2h(&newest_outer_seq, G.first + last_group_start, 4);
+  // the outer keys go to a page-locked buffer; the reverse-complement image of the reads (needed by the alignments only) is
+  // built behind that copy, while the host replays the outer khash
+  if (c->h_okey_cap < (size_t)n_outer + 4) {
+    if (c->h_okey) cudaFreeHost(c->h_okey);
+    c->h_okey = nullptr; c->h_okey_cap = 0;
+    const size_t cap = (size_t)n_outer + (n_outer >> 2) + 1024;
+    CU(cudaMallocHost((void **)&c->h_okey, cap * 8));
+    c->h_okey_cap = cap;
   }
-  c->stats.ms_buckets += c->toc();
+  uint64_t *h_okey_p = c->h_okey;
+  unsigned int *h_small = reinterpret_cast<unsigned int *>(h_okey_p + n_outer);  // 4 x u32 (see d_small)
+  LAUNCH(c, k_last_group_first, 1, 1, goff, n_outer, G.first, (uint32_t *)(d_small + 2));
+  CU(cudaMemcpyAsync(h_okey_p, okey, (size_t)n_outer * 8, cudaMemcpyDeviceToHost, c->st));
+  CU(cudaMemcpyAsync(h_small, d_small, 16, cudaMemcpyDeviceToHost, c->st));
+  c->stats.d2h_bytes += (size_t)n_outer * 8 + 16;
+  CU(cudaEventRecord(c->ev_pass[0], c->st));
+  unsigned int *d_rc_count = rc_launch(c);
+  CU(cudaEventSynchronize(c->ev_pass[0]));
+  const uint32_t newest_outer_seq = h_small[3];
+  {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev_pass[0]));
+    c->stats.ms_buckets += ms;
+  }
+  struct OkeyView { const uint64_t *p; const uint64_t *data() const { return p; } } h_okey{h_okey_p};
   // (e) host: outer khash replay (keys only) -> visiting rank of every outer key; inner replay of the few oversized groups
   double t_host0 = now_ms();
   std::vector<uint32_t> orank(n_outer);
@@ -1310,6 +1334,7 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
     }
   }
   c->stats.ms_host_order += now_ms() - t_host0;
+  rc_finish(c, d_rc_count);
   // (f) visiting positions, eligibility, ranks
   c->tic();
   uint32_t *d_orank = c->alloc<uint32_t>(n_outer), *size_by_rank = c->alloc<uint32_t>((size_t)n_outer + 1), *vstart = c->alloc<uint32_t>((size_t)n_outer + 1);
@@ -2674,7 +2699,7 @@ extern "C" void build_shimmer_map4py(py_mmer_t *py, char *seqdb_prefix, char *sh
       uint32_t *big_list = c->alloc<uint32_t>((size_t)h->n_outer + 1);
       uint64_t *okey = c->alloc<uint64_t>((size_t)h->n_outer + 1);
       unsigned int *d_small = c->alloc<unsigned int>(2);
-      CU(cudaMemsetAsync(d_small, 0, 8, c->st));
+      CU(cudaMemsetAsync(d_small, 0, 16, c->st));
       CU(cudaMemsetAsync(G.count, 0, ((size_t)nb + 1) * 4, c->st));
       LAUNCH(c, k_group_gather, nblk(nb), 256, gidx, goid_sorted, nb, sslot, bkeys, h->xkeys, bfirst, blast, bcount, G, h->goff, h->n_outer, okey, d_small);
       LAUNCH(c, k_inner_order, nblk(h->n_outer, 128), 128, h->goff, h->n_outer, G, h->ipos, big_list, d_small + 1);
