@@ -349,6 +349,8 @@ def run_ours(args):
     pinned_w = torch.empty(nw_total, dtype=torch.int64, pin_memory=True)
     words2b, nrec2b = engines[0].pack_2bit(seqdb, off, ln, words_out=pinned_w.numpy().view(np.uint64))
 
+    e2e_steps = []  # rank 0's per-step host times of the two end-to-end loops (a stall in one step shows here)
+
     def time_e2e(step):  # (this also warms the allocator pool)
         for _ in range(max(args.warmup, 1)):
             n = step()
@@ -356,11 +358,15 @@ def run_ours(args):
             e.stats_reset()
         barrier()
         t0 = time.perf_counter()
+        per_step = []
         for _ in range(args.steps):
+            t1 = time.perf_counter()
             n = step()
+            per_step.append(round((time.perf_counter() - t1) * 1e3, 2))
         barrier()
         sec = max_over_ranks((time.perf_counter() - t0) / args.steps)
         st_ = all_stats()
+        e2e_steps.append(per_step)
         return n, sec, int(sum_over_ranks(st_["h2d_bytes"])), int(sum_over_ranks(st_["d2h_bytes"]))  # bytes of the whole job
 
     # ---- end-to-end: from the reference's 1-byte/base image, then from the 2-bit image (the headline `e2e`)
@@ -443,9 +449,11 @@ def run_ours(args):
                                  else "NCCL all-gather of packed reads + L2 lists")) if world > 1 else "single GPU"},
         "e2e": {"value": n_ovl / e2e_s, "unit": "overlaps/s", "h2d_bytes_per_step": h2d_all // K, "d2h_bytes_per_step": d2h_all // K,
                 "ms_per_step": e2e_s * 1e3, "read_bases_per_s": bases / e2e_s,
-                "input": "pinned host 2-bit image (<prefix>.seq2b as written by this library's shmr_mkseqdb) -> ovlp_t records in pinned host memory"},
+                "input": "pinned host 2-bit image (<prefix>.seq2b as written by this library's shmr_mkseqdb) -> ovlp_t records in pinned host memory",
+                "steps_ms_rank0": e2e_steps[1]},
         "e2e_seqdb": {"value": n_ovl / e2e_db_s, "unit": "overlaps/s", "h2d_bytes_per_step": h2d_db // K, "d2h_bytes_per_step": d2h_db // K,
-                      "ms_per_step": e2e_db_s * 1e3, "input": "pinned host 1-byte/base .seqdb image (the reference's own format)"},
+                      "ms_per_step": e2e_db_s * 1e3, "input": "pinned host 1-byte/base .seqdb image (the reference's own format)",
+                      "steps_ms_rank0": e2e_steps[0]},
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": clocks,
         "roofline": roofline,
@@ -469,6 +477,146 @@ def run_ours(args):
         sys.exit(4)
 
 
+# ------------------------------------------------------------------------------------------------ our arm, T chunks on N GPUs
+def run_chunked(args):
+    """BASELINE.json configs[2]/[3]-style jobs: ONE genome of --genome-mb (total), T = --chunks index chunks and T hash chunks
+    (README.md:155-165 runs human data as 24 / 24 chunks) on N GPUs, T a multiple of N.  Rank r owns index chunks and hash
+    chunks c = r + 1 + j N.  A step = every rank sketches its index chunks -> the packed reads and the per-chunk SHIMMER lists are
+    all-gathered in chunk order (what the reference's processes find on the shared file system, src/shmr_overlap.c:359-382) ->
+    every rank runs build_map + process_overlaps for its hash chunks.  Records per chunk are the reference's `shmr_overlap -t T -c c`
+    (tests/test_gpu_parity.py::test_sharded_exchange_matches_reference checks this path chunk by chunk)."""
+    import shutil
+
+    import torch
+    import torch.distributed as dist
+
+    from peregrine_b200 import Engine, formats as F, multigpu as M
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    T = args.chunks
+    if T % world:
+        raise SystemExit("--chunks must be a multiple of the number of GPUs")
+    per = T // world
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    genome = int(args.genome_mb * 1e6)
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+    mine = [rank + 1 + j * world for j in range(per)]
+    shares = []
+    for ci in mine:  # one share at a time: generate, read into page-locked memory, delete
+        prefix = make_dataset(f"g{genome}_c{ci}of{T}", genome, args.cov, mod=T, res=ci % T)
+        rid, ln, off = F.read_idx(prefix + ".idx")
+        nbytes = os.path.getsize(prefix + ".seqdb")
+        if nbytes != int(ln.sum()):
+            raise RuntimeError(f"{prefix}.seqdb is truncated (disk full?)")
+        pinned = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        with open(prefix + ".seqdb", "rb") as f:
+            f.readinto(memoryview(pinned.numpy()))
+        shutil.rmtree(os.path.dirname(prefix), ignore_errors=True)
+        shares.append((pinned, rid, ln, off))
+    bases_mine = sum(int(s_[2].sum()) for s_ in shares)
+    P = PARAMS
+    idx_eng, ovl_eng = Engine(local), Engine(local)
+    sampler = ClockSampler(local)
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        parts, lists = [], []
+        for pinned, rid, ln, off in shares:
+            idx_eng.load_reads(pinned.numpy(), rid, ln, off, 1, 1, keep_raw=False, defer=True)
+            idx_eng.index(P["w"], P["k"], P["r"], P["levels"], 0)
+            parts.append(M.export_reads(idx_eng, dev))
+            lists.append(M.export_level(idx_eng, 2, dev))
+        M._handoff(dev)
+        if world > 1:
+            blocks = [M.exchange_reads(p_) for p_ in parts]  # block j = chunks 1 + jN .. N + jN in chunk order
+            l2_all = torch.cat([M.exchange_shimmers(l_) for l_ in lists])
+        else:
+            blocks, l2_all = parts, torch.cat(lists)
+        reads = M.concat_reads(blocks) if len(blocks) > 1 else blocks[0]
+        M._handoff(dev)
+        M.import_reads(ovl_eng, reads)
+        M.import_shimmers(ovl_eng, l2_all.contiguous())
+        del reads, blocks, parts, lists
+        n = 0
+        for c_ in mine:
+            n += len(ovl_eng.overlap(T, c_, P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy="view"))
+        return n
+
+    for _ in range(max(args.warmup, 1)):
+        n_mine = step()
+    for e in (idx_eng, ovl_eng):
+        e.stats_reset()
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_mine = step()
+    barrier()
+    sec = allmax((time.perf_counter() - t0) / args.steps)
+    clocks = sampler.stop()
+    st = {}
+    for e in (idx_eng, ovl_eng):
+        for k_, v in e.stats().items():
+            st[k_] = st.get(k_, 0) + v
+    n_ovl = int(allsum(n_mine))
+    bases = int(allsum(bases_mine))
+    n_aln = int(allsum(st["n_alignments"])) // args.steps
+    launches = int(st["kernel_launches"])
+    h2d, d2h = int(allsum(st["h2d_bytes"])) // args.steps, int(allsum(st["d2h_bytes"])) // args.steps
+    idx_eng.close()
+    ovl_eng.close()
+    if rank == 0:
+        K = args.steps
+        out = {
+            "metric": "overlaps/s (index+overlap)", "value": n_ovl / sec, "unit": "overlaps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "read_bases_per_s": bases / sec,
+            "config": {"workload": f"synthetic {args.genome_mb:g} Mb genome, {args.cov:g}x 15 kb reads @99.5%, k=16 w=80 r=6 l=2, T={T} index chunks and {T} "
+                                   f"hash chunks on {world} GPU(s), {per} of each per GPU",
+                       "bases": bases, "overlaps_per_step": n_ovl, "alignments_per_step": n_aln,
+                       "timing": "host clock around barrier + synchronize (the step spans two engines and the NCCL streams); inputs are host buffers: "
+                                 "the same number is the end-to-end figure",
+                       "l2_flush": "inputs exceed the 126 MB L2",
+                       "sharding": "index chunks by rid % T, hash chunks by (hash % T); all-gather of packed reads + per-chunk SHIMMER lists in chunk order"},
+            "e2e": {"value": n_ovl / sec, "unit": "overlaps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3,
+                    "read_bases_per_s": bases / sec},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        out["stage_ms_per_step"] = {k_: st[k_] / K for k_ in st if k_.startswith("ms_") and not k_.startswith("ms_k_")}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours_guarded(args):
     """A rank that dies must say why: torchrun's summary only has the exit code (SCALE_r01: "rank 7 exitcode 1, error_file
     <N/A>").  The traceback and the library's last error go to stderr, a one-line JSON error record goes to stdout (rank 0)
@@ -484,7 +632,10 @@ def run_ours_guarded(args):
     @record
     def go():
         try:
-            run_ours(args)
+            if args.chunks:
+                run_chunked(args)
+            else:
+                run_ours(args)
         except BaseException as e:  # noqa: BLE001 - report, then re-raise for torchrun
             if isinstance(e, SystemExit):
                 raise
@@ -507,6 +658,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-mb", type=float, default=50.0, help="genome size per GPU (BASELINE.json configs[1]: 50 Mb)")
     ap.add_argument("--cov", type=float, default=30.0)
+    ap.add_argument("--chunks", type=int, default=0, help="T index chunks and T hash chunks of ONE genome of --genome-mb (total) on the N GPUs "
+                                                          "(strong-scaling / configs[2..3] mode; T must be a multiple of N)")
     ap.add_argument("--ref-genome-mb", type=float, default=4.0, help="reference arm: genome size of each per-core sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="routed", choices=["routed", "gathered"], help="multi-GPU exchange step (N > 1)")
