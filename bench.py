@@ -211,7 +211,11 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
+    import gc
+
     import torch
+
+    gc.disable()  # a generation-2 collection inside a 60 ms step is a 30 ms outlier (seen as 1 step in 12); nothing here needs the collector
 
     from peregrine_b200 import Engine, formats as F
 
