@@ -549,6 +549,8 @@ def run_chunked(args):
         if world > 1:
             dist.barrier()
 
+    free_min = [torch.cuda.mem_get_info(dev)[0]]
+
     def step():
         parts, lists = [], []
         for pinned, rid, ln, off in shares:
@@ -557,19 +559,18 @@ def run_chunked(args):
             parts.append(M.export_reads(idx_eng, dev))
             lists.append(M.export_level(idx_eng, 2, dev))
         M._handoff(dev)
-        if world > 1:
-            blocks = [M.exchange_reads(p_) for p_ in parts]  # block j = chunks 1 + jN .. N + jN in chunk order
-            l2_all = torch.cat([M.exchange_shimmers(l_) for l_ in lists])
-        else:
-            blocks, l2_all = parts, torch.cat(lists)
-        reads = M.concat_reads(blocks) if len(blocks) > 1 else blocks[0]
+        reads, l2_all = M.gather_chunks(parts, lists)  # straight into buffers in chunk order 1..T
+        del parts, lists
         M._handoff(dev)
         M.import_reads(ovl_eng, reads)
-        M.import_shimmers(ovl_eng, l2_all.contiguous())
-        del reads, blocks, parts, lists
+        M.import_shimmers(ovl_eng, l2_all)
+        del reads, l2_all
+        torch.cuda.empty_cache()  # the gathered copies go back to the driver before the overlap stage sizes its tables
+        free_min[0] = min(free_min[0], torch.cuda.mem_get_info(dev)[0])
         n = 0
         for c_ in mine:
             n += len(ovl_eng.overlap(T, c_, P["bestn"], P["mc_lower"], P["mc_upper"], P["bw"], P["ovlp_upper"], copy="view"))
+            free_min[0] = min(free_min[0], torch.cuda.mem_get_info(dev)[0])
         return n
 
     for _ in range(max(args.warmup, 1)):
@@ -606,7 +607,7 @@ def run_chunked(args):
                        "bases": bases, "overlaps_per_step": n_ovl, "alignments_per_step": n_aln,
                        "timing": "host clock around barrier + synchronize (the step spans two engines and the NCCL streams); inputs are host buffers: "
                                  "the same number is the end-to-end figure",
-                       "l2_flush": "inputs exceed the 126 MB L2",
+                       "l2_flush": "inputs exceed the 126 MB L2", "hbm_free_min_gb_rank0": round(free_min[0] / 1e9, 1),
                        "sharding": "index chunks by rid % T, hash chunks by (hash % T); all-gather of packed reads + per-chunk SHIMMER lists in chunk order"},
             "e2e": {"value": n_ovl / sec, "unit": "overlaps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3,
                     "read_bases_per_s": bases / sec},

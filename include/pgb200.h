@@ -188,6 +188,14 @@ int pgb_route_build(pgb_ctx *, uint32_t total_chunk, uint32_t mc_lower, uint32_t
 int pgb_overlap_routed(pgb_ctx *, const void *records_device, size_t n, uint32_t bestn, uint32_t align_bandwidth, uint32_t ovlp_upper,
                        uint32_t total_chunk /* sizes the per-chunk replay tables: rid_pairs is per chunk, src/shmr_overlap.c:202 */);
 
+/* ---- batched ovlp_match for the cffi callers (py/scripts/path_to_contig.py:82-105 stitches contigs with one call per
+ * overlap; py/peregrine/utils.py).  Pair i aligns seq[q_off[i], +q_len[i]) read on strand q_strand[i] with seq[t_off[i], +t_len[i]) on
+ * t_strand[i]; seq holds .seqdb bytes (the strand selects the nibble, src/DWmatch.c:90-91).  out[i] = what ovlp_match returns
+ * for that pair.  One upload, one warp per pair, one download; the context's loaded reads are not touched. */
+int pgb_ovlp_match_batch(pgb_ctx *, const uint8_t *seq, size_t seq_bytes, size_t n_pairs, const uint64_t *q_off, const uint32_t *q_len,
+                         const uint8_t *q_strand, const uint64_t *t_off, const uint32_t *t_len, const uint8_t *t_strand, int band_tolerance,
+                         ovlp_match_t *out);
+
 /* ---- shmr_dedup: raw ovlp_t stream -> preads.ovl text ------------------------------------------------------
  * replaces main() of src/shmr_dedup.c:19-101: keeps the FIRST record of every unordered read pair in stream order (the
  * concatenation of the chunk files, `cat ovlp-*.dat | shmr_dedup`, py/scripts/pg_run.py:352) and prints

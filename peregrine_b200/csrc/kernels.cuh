@@ -19,6 +19,8 @@
 
 namespace pgb {
 
+struct AlnReqPOD { uint32_t rid0, start0, rid1, strands, slot; };  // = AlnReq (defined with the replay tables below)
+
 // ------------------------------------------------------------------------------------------------ hash table (u64 keys)
 #define PGB_EMPTY 0xFFFFFFFFFFFFFFFFULL
 #define PGB_NOSLOT 0xFFFFFFFFu
@@ -134,6 +136,45 @@ __global__ void k_pack_reads(const uint8_t *__restrict__ raw, const uint64_t *__
   w[word] = bits;
   nm[word] = nmask;
   if (nmask) atomicOr(&hasn_by_rid[row_rid[row]], 1u);
+}
+
+// Operands of the cffi ovlp_match calls: .seqdb bytes whose strand picks the nibble (src/DWmatch.c:90-91,136-137).  One thread
+// builds one packed word of one operand from the nibble its strand selects (shift 0 or 4); anything but A/C/G/T sets the N bit.
+__global__ void k_pack_nibbles(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ row_raw_off, const uint32_t *__restrict__ row_len,
+                               const uint64_t *__restrict__ row_woff, const uint8_t *__restrict__ row_shift, uint32_t n_rows, uint64_t n_words,
+                               uint64_t *__restrict__ w, uint32_t *__restrict__ nm, uint32_t *__restrict__ hasn_by_row) {
+  uint64_t word = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (word >= n_words) return;
+  uint32_t lo = 0, hi = n_rows;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (row_woff[mid] <= word) lo = mid; else hi = mid;
+  }
+  const uint32_t row = lo, len = row_len[row], sh = row_shift[row];
+  const uint64_t p0 = (word - row_woff[row]) * 32;
+  uint64_t bits = 0;
+  uint32_t nmask = 0;
+  if (word >= row_woff[row] && p0 < len) {
+    const uint8_t *s = raw + row_raw_off[row] + p0;
+    const uint32_t cnt = (len - p0) < 32 ? (uint32_t)(len - p0) : 32u;
+    for (uint32_t j = 0; j < cnt; j++) {
+      const uint32_t nib = (s[j] >> sh) & 0xF;
+      const uint32_t code = (nib == 2) ? 1u : (nib == 4) ? 2u : (nib == 8) ? 3u : 0u;
+      const uint32_t isn = !(nib == 1 || nib == 2 || nib == 4 || nib == 8);
+      bits |= (uint64_t)code << (2 * j);
+      nmask |= isn << j;
+    }
+    if (nmask) atomicOr(&hasn_by_row[row], 1u);
+  }
+  w[word] = bits;
+  nm[word] = nmask;
+}
+__global__ void k_pair_requests(uint32_t n, AlnReqPOD *reqs) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  AlnReqPOD q;
+  q.rid0 = 2 * i; q.start0 = 0; q.rid1 = 2 * i + 1; q.strands = 0; q.slot = i;  // the strands were applied when the nibbles were packed
+  reqs[i] = q;
 }
 
 // Reverse-complement image of the packed reads (same word offsets as the forward image): base p of read r in wrc is

@@ -2497,34 +2497,82 @@ extern "C" void mm_reduce(mm128_v *in, mm128_v *out, uint8_t rs) {
   }
 }
 
+// ovlp_match for a batch of operand pairs given as .seqdb bytes (the cffi callers: py/scripts/path_to_contig.py:82-105,
+// py/peregrine/utils.py).  Nothing of the context's loaded read set is touched: the operands are packed into scratch memory
+// from the nibble their strand selects, one request per pair runs through the warp-per-alignment kernel (pairs with N
+// through the generic one), and the results come back in one copy.
+static void match_batch_core(pgb_ctx *c, const uint8_t *seq, size_t seq_bytes, size_t n, const uint64_t *q_off, const uint32_t *q_len, const uint8_t *q_strand,
+                             const uint64_t *t_off, const uint32_t *t_len, const uint8_t *t_strand, int band_tolerance, ovlp_match_t *out) {
+  static_assert(sizeof(AlnReqPOD) == sizeof(AlnReq), "request layout");
+  if (band_tolerance + 3 > PGB_MAXV || band_tolerance < 0) throw std::runtime_error("ovlp_match: band_tolerance outside [0, 261]");
+  if (n == 0) return;
+  if (n >= (1ull << 30)) throw std::runtime_error("too many pairs in one batch");
+  const size_t rows = 2 * n;
+  // one host block: [raw offsets u64 x rows][word offsets u64 x rows][lengths u32 x rows][shifts u8 x rows]
+  std::vector<uint64_t> meta(2 * rows + (rows + 1) / 2 + (rows + 7) / 8 + 1);
+  uint64_t *h_raw = meta.data(), *h_woff = meta.data() + rows;
+  uint32_t *h_len = reinterpret_cast<uint32_t *>(meta.data() + 2 * rows);
+  uint8_t *h_shift = reinterpret_cast<uint8_t *>(meta.data() + 2 * rows + (rows + 1) / 2);
+  uint64_t words = 2, lo = ~0ULL, hi = 0;
+  for (size_t i = 0; i < n; i++) {
+    for (int s_ = 0; s_ < 2; s_++) {
+      const uint64_t off = s_ ? t_off[i] : q_off[i];
+      const uint32_t len = s_ ? t_len[i] : q_len[i];
+      if (off + len > seq_bytes) throw std::runtime_error("ovlp_match: operand extends past the end of the buffer");
+      const size_t r = 2 * i + s_;
+      h_raw[r] = off; h_len[r] = len; h_woff[r] = words; h_shift[r] = (s_ ? t_strand[i] : q_strand[i]) ? 4 : 0;
+      words += ((uint64_t)len + 31) / 32;
+      if (len) { lo = std::min(lo, off); hi = std::max(hi, off + len); }
+    }
+  }
+  words += 2;
+  if (hi <= lo) { lo = 0; hi = 0; }
+  for (size_t r = 0; r < rows; r++) h_raw[r] -= std::min(h_raw[r], lo);
+  uint8_t *d_raw = c->alloc<uint8_t>(hi - lo + 64);
+  uint64_t *d_meta = c->alloc<uint64_t>(meta.size());
+  uint64_t *d_w = c->alloc<uint64_t>(words);
+  uint32_t *d_nm = c->alloc<uint32_t>(words), *d_hasn = c->alloc<uint32_t>(rows);
+  AlnReq *d_req = c->alloc<AlnReq>(n);
+  match_t *d_res = c->alloc<match_t>(n);
+  c->h2d(d_raw, seq + lo, hi - lo);
+  c->h2d(d_meta, meta.data(), meta.size() * 8);
+  const uint64_t *d_rawoff = d_meta, *d_woff = d_meta + rows;
+  const uint32_t *d_len = reinterpret_cast<const uint32_t *>(d_meta + 2 * rows);
+  const uint8_t *d_shift = reinterpret_cast<const uint8_t *>(d_meta + 2 * rows + (rows + 1) / 2);
+  CU(cudaMemsetAsync(d_hasn, 0, rows * 4, c->st));
+  LAUNCH(c, k_pack_nibbles, nblk(words), 256, d_raw, d_rawoff, d_len, d_woff, d_shift, (uint32_t)rows, words, d_w, d_nm, d_hasn);
+  LAUNCH(c, k_pair_requests, nblk(n), 256, (uint32_t)n, reinterpret_cast<AlnReqPOD *>(d_req));
+  // (rid = row index: the by-rid tables of the kernels are the row tables)
+  LAUNCH(c, k_align_warp, nblk(n, PGB_AW_WARPS), PGB_AW_WARPS * 32, d_req, 0u, (uint32_t)n, d_w, d_w, d_woff, d_len, d_hasn, band_tolerance, d_res,
+         c->d_align_bases);
+  LAUNCH(c, k_align, nblk(n, 64), 64, d_req, 0u, (uint32_t)n, (const uint32_t *)nullptr, d_w, d_nm, d_woff, d_len, d_hasn, band_tolerance, d_res, c->d_err,
+         c->d_align_bases, 1);
+  c->d2h(out, d_res, n * sizeof(match_t));
+  CU(cudaMemsetAsync(c->d_align_bases, 0, 8, c->st));
+  if (c->check_err("ovlp_match")) throw std::runtime_error(c->err);
+}
+extern "C" int pgb_ovlp_match_batch(pgb_ctx *c, const uint8_t *seq, size_t seq_bytes, size_t n, const uint64_t *q_off, const uint32_t *q_len,
+                                    const uint8_t *q_strand, const uint64_t *t_off, const uint32_t *t_len, const uint8_t *t_strand, int band_tolerance,
+                                    ovlp_match_t *out) {
+  API_BEGIN(c)
+  match_batch_core(c, seq, seq_bytes, n, q_off, q_len, q_strand, t_off, t_len, t_strand, band_tolerance, out);
+  API_END(c)
+}
+
 extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_t q_strand, uint8_t *target_seq, seq_coor_t t_len,
                                     uint8_t t_strand, seq_coor_t band_tolerance) {
-  // The operands arrive as .seqdb bytes; the strand picks the nibble (src/DWmatch.c:90-91,136-137).  The selected nibbles
-  // are staged as two forward "reads" and one alignment request is run through the same k_align kernel.
+  // a batch of one through the same path (src/DWmatch.c:66-204); the result is calloc'd like the reference's (:105)
   ovlp_match_t *rtn = (ovlp_match_t *)calloc(1, sizeof(ovlp_match_t));
   if (q_len <= 0 || t_len <= 0) return rtn;
-  if (band_tolerance + 3 > PGB_MAXV || band_tolerance < 0) { fprintf(stderr, "pgb200: ovlp_match band_tolerance %d unsupported\n", band_tolerance); exit(1); }
   pgb_ctx *c = shared_ctx();
+  // the two operands may live anywhere: stage them back to back
   std::vector<uint8_t> img((size_t)q_len + (size_t)t_len);
-  int qs = q_strand == 0 ? 0 : 4, ts = t_strand == 0 ? 0 : 4;
-  for (int i = 0; i < q_len; i++) img[i] = (query_seq[i] >> qs) & 0x0F;
-  for (int i = 0; i < t_len; i++) img[(size_t)q_len + i] = (target_seq[i] >> ts) & 0x0F;
-  uint32_t rids[2] = {0, 1}, lens[2] = {(uint32_t)q_len, (uint32_t)t_len};
-  uint64_t offs[2] = {0, (uint64_t)q_len};
-  CLI_CHECK(c, pgb_load_reads(c, img.data(), img.size(), rids, lens, offs, 2, 1, 1, 0));
-  try {
-    AlnReq q; q.rid0 = 0; q.start0 = 0; q.rid1 = 1; q.strands = 0; q.slot = 0;
-    AlnReq *d_q = c->alloc<AlnReq>(1);
-    match_t *d_m = c->alloc<match_t>(1);
-    c->h2d(d_q, &q, sizeof q);
-    LAUNCH(c, k_align, 1, 32, d_q, 0u, 1u, (const uint32_t *)nullptr, c->d_w, c->d_nm, c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)band_tolerance, d_m, c->d_err, c->d_align_bases, 0);
-    c->d2h(rtn, d_m, sizeof(match_t));
-    c->release(d_q); c->release(d_m);
-    c->sync();
-    c->scratch_reset();
-    if (c->check_err("ovlp_match")) { fprintf(stderr, "pgb200: %s\n", pgb_last_error(c)); exit(1); }
-  } catch (std::exception &e) {
-    fprintf(stderr, "pgb200: ovlp_match failed: %s\n", e.what());
+  memcpy(img.data(), query_seq, (size_t)q_len);
+  memcpy(img.data() + q_len, target_seq, (size_t)t_len);
+  const uint64_t qo = 0, to = (uint64_t)q_len;
+  const uint32_t ql = (uint32_t)q_len, tl = (uint32_t)t_len;
+  if (pgb_ovlp_match_batch(c, img.data(), img.size(), 1, &qo, &ql, &q_strand, &to, &tl, &t_strand, band_tolerance, rtn) != 0) {
+    fprintf(stderr, "pgb200: ovlp_match failed: %s\n", pgb_last_error(c));
     exit(1);
   }
   return rtn;

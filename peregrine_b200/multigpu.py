@@ -35,7 +35,7 @@ def _handoff(device=None):
         torch.cuda.synchronize(device)
 
 
-def all_gather_var(t: torch.Tensor, group=None, sizes=None):
+def all_gather_var(t: torch.Tensor, group=None, sizes=None, out=None):
     """all_gather of tensors whose first dimension differs per rank -> ONE tensor, the ranks' blocks concatenated in rank order,
     plus the per-rank row counts.  NCCL: the blocks are received straight into slices of the result (ProcessGroupNCCL handles
     uneven outputs as a group of broadcasts), nothing is padded or copied again.  gloo (CPU tests): pad to the longest."""
@@ -48,7 +48,9 @@ def all_gather_var(t: torch.Tensor, group=None, sizes=None):
         dist.all_gather_into_tensor(all_n, n, group=group)
         sizes = [int(x) for x in all_n.tolist()]
     tail = tuple(t.shape[1:])
-    out = torch.empty((sum(sizes),) + tail, dtype=t.dtype, device=t.device)
+    if out is None:
+        out = torch.empty((sum(sizes),) + tail, dtype=t.dtype, device=t.device)
+    assert out.shape[0] == sum(sizes)  # (a caller may hand in a slice of a larger preallocated buffer)
     t = t.contiguous()
     if dist.get_backend(group) == "nccl":
         dist.all_gather(list(out.split(sizes)), t, group=group)
@@ -94,6 +96,55 @@ def exchange_reads(part, group=None):
         base += ws
         o += rs
     return out
+
+
+def gather_chunks(parts, lists, group=None):
+    """Several chunks per rank (T = per x N chunks, chunk c = r + 1 + j N held by rank r as its j-th): all-gather every rank's
+    packed reads and SHIMMER lists straight into buffers laid out in chunk order 1..T - block j (chunks 1 + jN .. N + jN, rank
+    order) follows block j - 1 -, without intermediate copies.  parts[j] / lists[j]: this rank's j-th chunk (export_reads /
+    export_level).  Returns (reads dict with row_woff rebased onto the concatenated word array, l2_all)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    per = len(parts)
+    dev = parts[0]["words"].device
+    mine = torch.tensor([[p_["words"].shape[0], p_["row_rid"].shape[0], l_.shape[0]] for p_, l_ in zip(parts, lists)], dtype=torch.int64, device=dev)
+    if world > 1:
+        allm = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allm, mine.contiguous(), group=group)
+    else:
+        allm = mine[None]
+    allm = allm.cpu().numpy()  # [rank][j][kind]
+    n_w = [[int(allm[r][j][0]) for r in range(world)] for j in range(per)]
+    n_r = [[int(allm[r][j][1]) for r in range(world)] for j in range(per)]
+    n_l = [[int(allm[r][j][2]) for r in range(world)] for j in range(per)]
+    tot_w, tot_r, tot_l = sum(map(sum, n_w)), sum(map(sum, n_r)), sum(map(sum, n_l))
+    out = {"words": torch.empty(tot_w, dtype=torch.int64, device=dev), "nmask": torch.empty(tot_w, dtype=torch.int32, device=dev),
+           "row_rid": torch.empty(tot_r, dtype=torch.int32, device=dev), "row_len": torch.empty(tot_r, dtype=torch.int32, device=dev),
+           "row_hasn": torch.empty(tot_r, dtype=torch.int32, device=dev), "row_woff": torch.empty(tot_r, dtype=torch.int64, device=dev)}
+    l2_all = torch.empty((tot_l, 2), dtype=torch.int64, device=dev)
+    ow = orow = ol = 0
+    for j in range(per):
+        sw, sr, sl = sum(n_w[j]), sum(n_r[j]), sum(n_l[j])
+        for key, o_, s_, sizes in (("words", ow, sw, n_w[j]), ("nmask", ow, sw, n_w[j]), ("row_rid", orow, sr, n_r[j]), ("row_len", orow, sr, n_r[j]),
+                                   ("row_hasn", orow, sr, n_r[j]), ("row_woff", orow, sr, n_r[j])):
+            if world > 1:
+                all_gather_var(parts[j][key], group, sizes=sizes, out=out[key][o_: o_ + s_])
+            else:
+                out[key][o_: o_ + s_] = parts[j][key]
+        if world > 1:
+            all_gather_var(lists[j], group, sizes=n_l[j], out=l2_all[ol: ol + sl])
+        else:
+            l2_all[ol: ol + sl] = lists[j]
+        base, o2 = ow, orow
+        for r in range(world):  # each chunk keeps its own guard words; rebase its rows onto the concatenated word array
+            out["row_woff"][o2: o2 + n_r[j][r]] += base
+            base += n_w[j][r]
+            o2 += n_r[j][r]
+        ow += sw
+        orow += sr
+        ol += sl
+    return out, l2_all
 
 
 def exchange_shimmers(l2: torch.Tensor, group=None):

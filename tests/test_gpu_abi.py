@@ -184,3 +184,59 @@ def test_shimmer4py_index_handle_vs_reference(ours, workdir, ref_dir):
             assert a == b, (c, T, x)
             n_hits += len(a)
         assert n_hits > 100
+
+
+def test_ovlp_match_batch_vs_reference(ours):
+    """pgb_ovlp_match_batch (one upload, a warp per pair, one download) against the reference's ovlp_match pair by pair: all
+    four strand combinations, operands with N runs (nibble 0 equals only nibble 0), empty-ish operands, three band limits;
+    and the single-call ovlp_match, which is a batch of one through the same path."""
+    import time
+
+    ref = O.reflib()
+    if ref is None:
+        pytest.skip("oracle/_ref not present")
+    from peregrine_b200 import Engine
+
+    rnd = np.random.default_rng(23)
+    B = np.array(list("ACGT"))
+    bufs, pairs = [], []
+    off = 0
+    for trial in range(60):
+        n = int(rnd.integers(40, 9000))
+        s = "".join(rnd.choice(B, n))
+        t = list(s[int(rnd.integers(0, min(300, n // 2))):])
+        for _ in range(int(len(t) * 0.01 * (trial % 4))):
+            p = int(rnd.integers(0, len(t)))
+            t[p] = str(rnd.choice(B)) if rnd.random() < 0.5 else ""
+        t = "".join(t)
+        if trial % 6 == 0 and len(t) > 200:
+            t = t[:90] + "N" * 9 + t[99:]
+        if trial % 9 == 0:
+            s = s[:30] + "N" + s[31:]
+        q, tt = O.encode_biseq(s), O.encode_biseq(t)
+        bufs += [q, tt]
+        pairs.append((off, len(q), trial & 1, off + len(q), len(tt), (trial >> 1) & 1))
+        off += len(q) + len(tt)
+    seq = np.concatenate(bufs)
+    eng = Engine(0)
+    L = eng.L
+    L.pgb_ovlp_match_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    P = np.array(pairs, dtype=np.int64)
+    arrs = [np.ascontiguousarray(P[:, 0], np.uint64), np.ascontiguousarray(P[:, 1], np.uint32), np.ascontiguousarray(P[:, 2], np.uint8),
+            np.ascontiguousarray(P[:, 3], np.uint64), np.ascontiguousarray(P[:, 4], np.uint32), np.ascontiguousarray(P[:, 5], np.uint8)]
+    for bw in (20, 100, 200):
+        out = np.zeros((len(pairs), 8), dtype=np.int32)
+        rc = L.pgb_ovlp_match_batch(eng.h, seq.ctypes.data, seq.size, len(pairs), *[a.ctypes.data for a in arrs], bw, out.ctypes.data)
+        assert rc == 0, L.pgb_last_error(eng.h)
+        for i, (qo, ql, qs, to, tl, ts) in enumerate(pairs):
+            want = O.abi_ovlp_match(ref, seq[qo:qo + ql], qs, seq[to:to + tl], ts, bw)
+            assert list(map(int, want)) == list(map(int, out[i])), (bw, i, pairs[i])
+    # single calls: the same answers, and cheap enough to be called in a Python loop
+    qo, ql, qs, to, tl, ts = pairs[3]
+    t0 = time.perf_counter()
+    for _ in range(20):
+        got = O.abi_ovlp_match(ours, seq[qo:qo + ql], qs, seq[to:to + tl], ts, 100)
+    per_call = (time.perf_counter() - t0) / 20
+    assert list(map(int, got)) == list(map(int, O.abi_ovlp_match(ref, seq[qo:qo + ql], qs, seq[to:to + tl], ts, 100)))
+    print(f"single ovlp_match call ({ql} x {tl} bases): {per_call * 1e6:.0f} us")
+    eng.close()

@@ -45,6 +45,14 @@ def _worker(rank, world, port, q):
     recs = torch.tensor([[rank, i, 0, 0, 0, 0, 0, 0] for i in range(2 + rank)], dtype=torch.int64).reshape(-1, 8)
     stream = M.gather_records(recs)
     assert stream[:, :2].tolist() == [[r, i] for r in range(world) for i in range(2 + r)]  # chunk order, stream order inside
+    # several chunks per rank (T = 2 x world): chunk c = rank + 1 + j * world; the gather must come back in chunk order 1..T
+    cparts = [_part(10 * j + rank) for j in range(2)]
+    clists = [torch.full((3 + j + rank, 2), 100 * j + rank, dtype=torch.int64) for j in range(2)]
+    creads, cl2 = M.gather_chunks(cparts, clists)
+    want_c = M.concat_reads([_part(10 * j + r) for j in range(2) for r in range(world)])
+    for k in M.READ_KEYS:
+        assert torch.equal(creads[k], want_c[k]), k
+    assert cl2[:, 0].tolist() == [100 * j + r for j in range(2) for r in range(world) for _ in range(3 + j + r)]
     q.put((rank, {k: v.numpy() for k, v in reads.items()}, l2_all.numpy(), recv.numpy(), in_sizes, before))
     dist.barrier()
     dist.destroy_process_group()
