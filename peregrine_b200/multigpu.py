@@ -110,8 +110,9 @@ def gather_chunks(parts, lists, group=None):
     dev = parts[0]["words"].device
     mine = torch.tensor([[p_["words"].shape[0], p_["row_rid"].shape[0], l_.shape[0]] for p_, l_ in zip(parts, lists)], dtype=torch.int64, device=dev)
     if world > 1:
-        allm = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allm, mine.contiguous(), group=group)
+        flat = torch.empty(world * per * 3, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(flat, mine.reshape(-1).contiguous(), group=group)
+        allm = flat.reshape(world, per, 3)
     else:
         allm = mine[None]
     allm = allm.cpu().numpy()  # [rank][j][kind]
