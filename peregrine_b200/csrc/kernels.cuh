@@ -75,7 +75,8 @@ __global__ void k_fill_u32(uint32_t *p, uint32_t v, size_t n) {
 __global__ void k_pack_reads(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ row_raw_off,
                              const uint32_t *__restrict__ row_len, const uint64_t *__restrict__ row_woff,
                              const uint32_t *__restrict__ row_rid, uint32_t n_rows, uint64_t first_word, uint64_t n_words,
-                             uint64_t *__restrict__ w, uint32_t *__restrict__ nm, uint32_t *__restrict__ hasn_by_rid) {
+                             uint64_t *__restrict__ w, uint32_t *__restrict__ nm, uint32_t *__restrict__ hasn_by_rid, uint64_t raw_shift = 0) {
+  // raw_shift: `raw` is a staging window that holds the image from byte raw_shift on (pgb_load_reads packs big inputs window by window)
   uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_words) return;
   uint64_t word = first_word + g;
@@ -93,7 +94,7 @@ __global__ void k_pack_reads(const uint8_t *__restrict__ raw, const uint64_t *__
     nm[word] = 0;
     return;
   }
-  const uint8_t *s = raw + row_raw_off[row] + p0;
+  const uint8_t *s = raw + (row_raw_off[row] - raw_shift) + p0;
   uint32_t cnt = (len - p0) < 32 ? (uint32_t)(len - p0) : 32u;
   uint64_t bits = 0;
   uint32_t nmask = 0;

@@ -62,6 +62,7 @@ struct pgb_ctx {
   uint64_t n_words = 0;     // packed words incl. guards
   uint64_t sel_bases = 0;
   uint8_t *d_raw = nullptr; size_t raw_bytes = 0;
+  size_t raw_ring = 0;  // != 0: d_raw is a ring of two staging windows of this many bytes, not the whole image (keep_raw = 0)
   uint64_t *d_w = nullptr; uint32_t *d_nm = nullptr;
   // deferred bulk copy (pgb_load_reads with PGB_LOAD_DEFER): pgb_index overlaps the host->device copy of the .seqdb image
   // with packing and sketching, chunk by chunk; any other consumer of the reads completes the load first (ensure_loaded)
@@ -462,6 +463,31 @@ static void ensure_loaded(pgb_ctx *c) {
     c->stats.bases_packed += c->sel_bases;
     return;
   }
+  if (c->raw_ring) {  // window by window through the ring (see pgb_load_reads)
+    CU(cudaMemsetAsync(c->d_w, 0, c->n_words * 8, c->st));
+    CU(cudaMemsetAsync(c->d_nm, 0, c->n_words * 4, c->st));
+    CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
+    uint64_t raw_o = 0, word_o = 2;
+    size_t r0 = 0;
+    int half = 0;
+    const size_t ns = c->n_rows;
+    while (r0 < ns) {
+      size_t r1 = r0;
+      uint64_t bytes = 0, wcount = 0;
+      while (r1 < ns && bytes + c->h_row_len[r1] <= c->raw_ring) { bytes += c->h_row_len[r1]; wcount += ((uint64_t)c->h_row_len[r1] + 31) / 32; r1++; }
+      uint8_t *win = c->d_raw + (size_t)half * c->raw_ring;
+      c->h2d(win, c->pend.src + raw_o, bytes);
+      if (wcount)
+        LAUNCH(c, k_pack_reads, nblk(wcount), 256, win, c->d_row_raw_off, c->d_row_len, c->d_row_woff, c->d_row_rid, (uint32_t)c->n_rows, word_o, wcount, c->d_w,
+               c->d_nm, c->d_hasn_by_rid, raw_o);
+      raw_o += bytes; word_o += wcount; r0 = r1; half ^= 1;
+    }
+    c->stats.bases_packed += c->sel_bases;
+    c->sync();
+    c->pend.active = false;
+    c->release(c->d_raw);
+    return;
+  }
   const size_t CH = (size_t)256 << 20;
   for (size_t o = 0; o < c->raw_bytes; o += CH) c->h2d(c->d_raw + o, c->pend.src + o, std::min(CH, c->raw_bytes - o));
   do_pack(c);
@@ -480,7 +506,7 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
   // the by-rid tables cover every read (lengths are needed for any rid an index file mentions)
   uint32_t max_rid = 0;
   for (size_t i = 0; i < n_reads; i++) if (rid[i] > max_rid) max_rid = rid[i];
-  if (n_reads && (uint64_t)max_rid > 8 * (uint64_t)n_reads + (1u << 20)) throw std::runtime_error("read ids too sparse");
+  if (n_reads && (uint64_t)max_rid > 64 * (uint64_t)n_reads + (1u << 24)) throw std::runtime_error("read ids too sparse");
   c->max_rid = max_rid;
   std::vector<uint32_t> rows;
   for (size_t i = 0; i < n_reads; i++) {
@@ -504,7 +530,13 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
   words += 2;
   c->n_rows = nsel; c->n_words = words; c->sel_bases = raw; c->raw_bytes = raw;
   c->h_row_len = h_len;
-  c->d_raw = c->palloc<uint8_t>(raw + 64);
+  // keep_raw = 0 and one contiguous source range: the 1-byte/base image never sits whole in HBM, it passes through a ring of two
+  // staging windows (the packed form is 3/8 byte per base; at 90 Gbase the whole image would be 90 GB of a 180 GB device)
+  uint32_t longest = 0;
+  for (size_t j = 0; j < nsel; j++) longest = std::max(longest, h_len[j]);
+  const size_t RING = std::max<size_t>((size_t)256 << 20, (size_t)longest + 64);
+  c->raw_ring = (!keep_raw && contiguous && raw > 2 * RING) ? RING : 0;
+  c->d_raw = c->palloc<uint8_t>((c->raw_ring ? 2 * c->raw_ring : raw) + 64);
   c->d_w = c->palloc<uint64_t>(words); c->d_nm = c->palloc<uint32_t>(words);
   c->d_rlen_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1); c->d_hasn_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1);
   c->d_woff_by_rid = c->palloc<uint64_t>((size_t)max_rid + 1);
@@ -518,6 +550,7 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
   c->h2d(c->d_row_woff, h_woff.data(), nsel * 8); c->h2d(c->d_row_raw_off, h_rawoff.data(), nsel * 8);
   c->h2d(c->d_sel_rows, ident.data(), nsel * 4);
   // raw bytes of the selected reads
+  bool packed_already = false;
   if (nsel) {
     if (contiguous && defer) {
       c->pend.src = seqdb + offset[rows[0]];
@@ -525,6 +558,32 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
       c->pend.keep_raw = keep_raw != 0;
       c->sync();
       return 0;  // (API_END's bookkeeping is not needed: nothing was taken from the scratch arena)
+    } else if (contiguous && c->raw_ring) {
+      // window by window: whole reads up to the window size, copy into one half of the ring, pack from there
+      const uint8_t *src = seqdb + offset[rows[0]];
+      CU(cudaMemsetAsync(c->d_w, 0, c->n_words * 8, c->st));
+      CU(cudaMemsetAsync(c->d_nm, 0, c->n_words * 4, c->st));
+      CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
+      c->tic();
+      uint64_t raw_o = 0, word_o = 2;
+      size_t r0 = 0;
+      int half = 0;
+      while (r0 < nsel) {
+        size_t r1 = r0;
+        uint64_t bytes = 0, wcount = 0;
+        while (r1 < nsel && bytes + h_len[r1] <= c->raw_ring) { bytes += h_len[r1]; wcount += ((uint64_t)h_len[r1] + 31) / 32; r1++; }
+        uint8_t *win = c->d_raw + (size_t)half * c->raw_ring;
+        c->h2d(win, src + raw_o, bytes);  // (same stream as the pack kernels: a window is reused only after its pack finished)
+        if (wcount)
+          LAUNCH(c, k_pack_reads, nblk(wcount), 256, win, c->d_row_raw_off, c->d_row_len, c->d_row_woff, c->d_row_rid, (uint32_t)c->n_rows, word_o, wcount,
+                 c->d_w, c->d_nm, c->d_hasn_by_rid, raw_o);
+        raw_o += bytes; word_o += wcount; r0 = r1; half ^= 1;
+      }
+      c->stats.ms_pack += c->toc();
+      c->stats.bases_packed += c->sel_bases;
+      c->sync();
+      c->release(c->d_raw);
+      packed_already = true;
     } else if (contiguous) {
       const uint8_t *src = seqdb + offset[rows[0]];
       const size_t CH = (size_t)256 << 20;
@@ -554,9 +613,11 @@ extern "C" int pgb_load_reads(pgb_ctx *c, const uint8_t *seqdb, size_t seqdb_byt
       for (int q = 0; q < 2; q++) { cudaFreeHost(stage[q]); cudaEventDestroy(done[q]); }
     }
   }
-  do_pack(c);
-  c->sync();
-  if (!keep_raw) c->release(c->d_raw);
+  if (!packed_already) {
+    do_pack(c);
+    c->sync();
+    if (!keep_raw) c->release(c->d_raw);
+  }
   API_END(c)
 }
 
@@ -611,7 +672,7 @@ extern "C" int pgb_load_reads_2bit(pgb_ctx *c, const uint64_t *words, size_t n_w
   const bool defer = (flags & PGB_LOAD_DEFER) != 0;
   uint32_t max_rid = 0;
   for (size_t i = 0; i < n_reads; i++) if (rid[i] > max_rid) max_rid = rid[i];
-  if (n_reads && (uint64_t)max_rid > 8 * (uint64_t)n_reads + (1u << 20)) throw std::runtime_error("read ids too sparse");
+  if (n_reads && (uint64_t)max_rid > 64 * (uint64_t)n_reads + (1u << 24)) throw std::runtime_error("read ids too sparse");
   c->max_rid = max_rid;
   std::vector<uint64_t> src_woff(n_reads + 1);
   uint64_t acc = 0;
@@ -857,13 +918,16 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
       CU(cudaMemsetAsync(c->d_hasn_by_rid, 0, ((size_t)c->max_rid + 1) * 4, c->st));
     }
     // chunk size in .seqdb bytes (= bases): a 2-bit chunk carries a quarter of that over the bus
-    const uint64_t CH = getenv("PGB_LOAD_CHUNK_MB") ? strtoull(getenv("PGB_LOAD_CHUNK_MB"), 0, 10) << 20 : (uint64_t)96 << 20;
+    uint64_t CH = getenv("PGB_LOAD_CHUNK_MB") ? strtoull(getenv("PGB_LOAD_CHUNK_MB"), 0, 10) << 20 : (uint64_t)96 << 20;
+    const bool ring = !packed && c->raw_ring != 0;  // the raw image passes through two staging windows (pgb_load_reads)
+    if (ring) CH = std::min<uint64_t>(CH, c->raw_ring);
+    std::vector<cudaEvent_t> packed_ev;  // ring: window h may be overwritten once the pack kernel of the chunk before last is done
     uint64_t raw_o = 0, word_o = 2;
-    size_t r0 = 0, n_ev = 0;
+    size_t r0 = 0, n_ev = 0, chunk_no = 0;
     while (r0 < ns) {
       size_t r1 = r0;
       uint64_t bytes = 0, wcount = 0;
-      while (r1 < ns && bytes < CH) { bytes += c->h_row_len[r1]; wcount += ((uint64_t)c->h_row_len[r1] + 31) / 32; r1++; }
+      while (r1 < ns && (ring ? bytes + c->h_row_len[r1] <= CH : bytes < CH)) { bytes += c->h_row_len[r1]; wcount += ((uint64_t)c->h_row_len[r1] + 31) / 32; r1++; }
       if (n_ev == c->ev_pool.size()) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->ev_pool.push_back(e); }
       if (packed) {  // the words travel as they are
         if (wcount) {
@@ -871,17 +935,29 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
           c->stats.h2d_bytes += wcount * 8;
         }
       } else if (bytes) {
-        CU(cudaMemcpyAsync(c->d_raw + raw_o, c->pend.src + raw_o, bytes, cudaMemcpyHostToDevice, c->st_copy));
+        uint8_t *dst = ring ? c->d_raw + (chunk_no & 1) * c->raw_ring : c->d_raw + raw_o;
+        if (ring && chunk_no >= 2) CU(cudaStreamWaitEvent(c->st_copy, packed_ev[chunk_no - 2], 0));
+        CU(cudaMemcpyAsync(dst, c->pend.src + raw_o, bytes, cudaMemcpyHostToDevice, c->st_copy));
         c->stats.h2d_bytes += bytes;
       }
       CU(cudaEventRecord(c->ev_pool[n_ev], c->st_copy));
       CU(cudaStreamWaitEvent(c->st, c->ev_pool[n_ev], 0));
       n_ev++;
       if (wcount && !packed)
-        LAUNCH(c, k_pack_reads, nblk(wcount), 256, c->d_raw, c->d_row_raw_off, c->d_row_len, c->d_row_woff, c->d_row_rid, (uint32_t)c->n_rows, word_o,
-               wcount, c->d_w, c->d_nm, c->d_hasn_by_rid);
+        LAUNCH(c, k_pack_reads, nblk(wcount), 256, ring ? c->d_raw + (chunk_no & 1) * c->raw_ring : c->d_raw, c->d_row_raw_off, c->d_row_len, c->d_row_woff,
+               c->d_row_rid, (uint32_t)c->n_rows, word_o, wcount, c->d_w, c->d_nm, c->d_hasn_by_rid, ring ? raw_o : (uint64_t)0);
+      if (ring) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventRecord(e, c->st));
+        packed_ev.push_back(e);
+      }
       sketch_rows(r0, r1);
-      raw_o += bytes; word_o += wcount; r0 = r1;
+      raw_o += bytes; word_o += wcount; r0 = r1; chunk_no++;
+    }
+    if (!packed_ev.empty()) {
+      CU(cudaStreamSynchronize(c->st));
+      for (auto e : packed_ev) cudaEventDestroy(e);
     }
     c->pend.active = false;
     c->stats.bases_packed += c->sel_bases;
@@ -1134,7 +1210,7 @@ extern "C" int pgb_load_packed_device(pgb_ctx *c, const uint64_t *words, const u
   LAUNCH(c, k_max_u32, nblk(n_rows), 256, row_rid, (uint32_t)n_rows, d_max);
   uint32_t max_rid = 0;
   c->d2h(&max_rid, d_max, 4);
-  if (n_rows && (uint64_t)max_rid > 8 * (uint64_t)n_rows + (1u << 20)) throw std::runtime_error("read ids too sparse");
+  if (n_rows && (uint64_t)max_rid > 64 * (uint64_t)n_rows + (1u << 24)) throw std::runtime_error("read ids too sparse");
   c->max_rid = max_rid; c->n_rows = n_rows; c->n_words = n_words;
   c->d_w = c->palloc<uint64_t>(n_words); c->d_nm = c->palloc<uint32_t>(n_words);
   c->d_rlen_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1); c->d_hasn_by_rid = c->palloc<uint32_t>((size_t)max_rid + 1);
@@ -1934,7 +2010,7 @@ extern "C" int pgb_set_read_lengths(pgb_ctx *c, const uint32_t *rid, const uint3
   c->free_reads();
   uint32_t max_rid = 0;
   for (size_t i = 0; i < n_reads; i++) if (rid[i] > max_rid) max_rid = rid[i];
-  if (n_reads && (uint64_t)max_rid > 8 * (uint64_t)n_reads + (1u << 20)) throw std::runtime_error("read ids too sparse");
+  if (n_reads && (uint64_t)max_rid > 64 * (uint64_t)n_reads + (1u << 24)) throw std::runtime_error("read ids too sparse");
   std::vector<uint32_t> by_rid((size_t)max_rid + 1, 0);
   for (size_t i = 0; i < n_reads; i++) by_rid[rid[i]] = len[i];
   c->max_rid = max_rid;
