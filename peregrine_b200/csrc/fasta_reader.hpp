@@ -12,6 +12,7 @@
 //   * after a FASTQ record the scanner looks for the next header from scratch (last_char = 0, :221).
 // Only the byte-level grammar lives here (plain C++, also compiled into tests/hostsim); encoding the bases is the GPU's job.
 #pragma once
+#include <algorithm>
 #include <stdint.h>
 #include <string.h>
 #include <string>
@@ -28,6 +29,11 @@ struct FastaRecord {
 class FastaScanner {
  public:
   FastaScanner(const char *buf, size_t n) : b_(buf), n_(n) {}
+  // streaming use (GzRecordStream below): the scanner is a function of the byte stream and one remembered header character, so
+  // a record can be re-scanned from its first byte once more of the file is in the buffer
+  FastaScanner(const char *buf, size_t n, int last_char) : b_(buf), n_(n), last_char_(last_char) {}
+  size_t pos() const { return pos_; }
+  int last_char() const { return last_char_; }
   // next record into r; false at end of input or at a malformed FASTQ record (both end the file in the reference)
   bool next(FastaRecord &r) {
     if (last_char_ == 0) {
@@ -87,6 +93,52 @@ class FastaScanner {
   size_t n_, pos_ = 0;
   int last_char_ = 0;
   std::string qual_;
+};
+
+// Records of one (optionally gzip-compressed) file without holding the file in memory: the text is read in blocks; a record whose
+// scan touched the end of the buffered text while the file has more is scanned again after the next block arrived, so the
+// buffer holds one block plus at most one record (the reference's kseq streams the same way, src/kseq.h:92-130).
+class GzRecordStream {
+ public:
+  explicit GzRecordStream(const char *path, size_t block = (size_t)64 << 20) : block_(block) {
+    f_ = gzopen(path, "r");
+    if (f_) gzbuffer(f_, 1 << 20);
+  }
+  ~GzRecordStream() { if (f_) gzclose(f_); }
+  bool ok() const { return f_ != nullptr; }
+  bool next(FastaRecord &r) {
+    for (;;) {
+      FastaScanner sc(buf_.data() + start_, buf_.size() - start_, last_char_);
+      const bool got = sc.next(r);
+      if (!eof_ && start_ + sc.pos() >= buf_.size()) {  // the scan ran into the end of what is buffered: more text may belong to it
+        fill();
+        continue;
+      }
+      if (!got) return false;  // end of file, or a malformed FASTQ record (both end the file in the reference)
+      start_ += sc.pos();
+      last_char_ = sc.last_char();
+      return true;
+    }
+  }
+
+ private:
+  void fill() {
+    if (start_) { buf_.erase(buf_.begin(), buf_.begin() + (ptrdiff_t)start_); start_ = 0; }
+    const size_t old = buf_.size();
+    buf_.resize(old + block_);
+    size_t got_total = 0;
+    while (got_total < block_) {
+      const int got = gzread(f_, buf_.data() + old + got_total, (unsigned)std::min<size_t>(block_ - got_total, (size_t)1 << 30));
+      if (got <= 0) { eof_ = true; break; }
+      got_total += (size_t)got;
+    }
+    buf_.resize(old + got_total);
+  }
+  gzFile f_ = nullptr;
+  size_t block_, start_ = 0;
+  std::vector<char> buf_;
+  int last_char_ = 0;
+  bool eof_ = false;
 };
 
 // whole file into memory through zlib (plain and gzip-compressed files alike, as gzopen/gzread do for the reference)

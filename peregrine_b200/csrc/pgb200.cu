@@ -2374,11 +2374,10 @@ extern "C" int pgb_shmr_mkseqdb_main(int argc, char **argv) {
   char fn[8192];
   uint32_t rid = 0;
   size_t offset = 0;
-  std::vector<char> text;
   int rc = 0;
   while (rc == 0 && fscanf(lst, "%8191s", fn) != EOF) {
-    if (!slurp_gz(fn, text)) { fprintf(stderr, "file '%s' open error: %s\n", fn, strerror(errno)); exit(1); }
-    FastaScanner sc(text.data(), text.size());
+    GzRecordStream sc(fn);  // block-wise: a 100 GB fastq.gz does not have to fit in memory
+    if (!sc.ok()) { fprintf(stderr, "file '%s' open error: %s\n", fn, strerror(errno)); exit(1); }
     FastaRecord r;
     while (sc.next(r)) {
       const size_t l = r.seq.size();

@@ -573,7 +573,8 @@ static int cmd_dedup() {
   return 0;
 }
 
-static int cmd_fastaidx(const char *lst) {
+// block > 0: through GzRecordStream with that block size (what shmr_mkseqdb uses; tiny blocks stress the re-scan at block ends)
+static int cmd_fastaidx(const char *lst, size_t block) {
   FILE *f = fopen(lst, "r");
   if (!f) return 1;
   char fn[8192];
@@ -581,6 +582,17 @@ static int cmd_fastaidx(const char *lst) {
   size_t offset = 0;
   std::vector<char> buf;
   while (fscanf(f, "%8191s", fn) != EOF) {
+    if (block) {
+      GzRecordStream st(fn, block);
+      if (!st.ok()) return 1;
+      FastaRecord r;
+      while (st.next(r)) {
+        printf("%09d %s %u %lu\n", rid, r.name.c_str(), (unsigned)r.seq.size(), offset);
+        rid++;
+        offset += r.seq.size();
+      }
+      continue;
+    }
     if (!slurp_gz(fn, buf)) return 1;
     FastaScanner sc(buf.data(), buf.size());
     FastaRecord r;
@@ -597,7 +609,7 @@ static int cmd_fastaidx(const char *lst) {
 int main(int argc, char **argv) {
   if (argc < 2) { fprintf(stderr, "usage: hostsim sketch|match|overlap|dedup|fastaidx ...\n"); return 1; }
   if (!strcmp(argv[1], "dedup")) return cmd_dedup();
-  if (!strcmp(argv[1], "fastaidx") && argc > 2) return cmd_fastaidx(argv[2]);
+  if (!strcmp(argv[1], "fastaidx") && argc > 2) return cmd_fastaidx(argv[2], argc > 3 ? (size_t)strtoull(argv[3], 0, 10) : 0);
   load_ref();
   if (!strcmp(argv[1], "sketch")) return cmd_sketch(argc, argv);
   if (!strcmp(argv[1], "match")) return cmd_match(argc, argv);

@@ -64,6 +64,11 @@ def test_fasta_scanner_on_host(tmp_path, ref_dir):
     want_idx, want_db = ref_mkseqdb(ref_dir, lst, str(tmp_path / "ref"))
     got = subprocess.run([os.path.join(ROOT, "build", "hostsim"), "fastaidx", lst], stdout=subprocess.PIPE, check=True).stdout
     assert want_idx.count(b"\n") >= 12 and got == want_idx
+    # the block-wise reader shmr_mkseqdb uses (GzRecordStream): every block size, down to blocks far smaller than a record, must
+    # give the same records (a record that touches the end of the buffered text is scanned again once more text arrived)
+    for block in (1, 3, 7, 64, 333, 1 << 20):
+        got = subprocess.run([os.path.join(ROOT, "build", "hostsim"), "fastaidx", lst, str(block)], stdout=subprocess.PIPE, check=True).stdout
+        assert got == want_idx, block
 
 
 @pytest.mark.gpu
