@@ -135,7 +135,9 @@ inline std::vector<std::string> glob_sorted(const std::string &pattern) {
   std::vector<std::string> r;
   glob_t g;
   memset(&g, 0, sizeof g);
-  if (glob(pattern.c_str(), 0, NULL, &g) == 0)
+  // GLOB_NOCHECK: with no match the pattern itself comes back, as wordexp does in the reference (src/shmr_overlap.c:362): opening
+  // it then fails with the reference's message and exit 1 instead of silently producing an empty result
+  if (glob(pattern.c_str(), GLOB_NOCHECK, NULL, &g) == 0)
     for (size_t i = 0; i < g.gl_pathc; i++) r.push_back(g.gl_pathv[i]);
   globfree(&g);
   return r;

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <unordered_map>
+#include <mutex>
 #include <functional>
 #include "../../include/pgb200.h"
 #include "host_util.hpp"
@@ -2497,12 +2498,17 @@ extern "C" mm128_v read_mmlist(char *fn) {
 }
 
 static pgb_ctx *g_ctx = nullptr;  // lazily created context behind the single-call cffi functions
-static pgb_ctx *shared_ctx() {
-  if (!g_ctx) {
-    g_ctx = cli_ctx();
+// The reference's functions keep no state and may be called from several threads; ours share one device context, so every
+// single-call entry point takes this lock for its duration (SharedCtx).
+static std::recursive_mutex g_ctx_mu;
+struct SharedCtx {
+  std::lock_guard<std::recursive_mutex> guard;
+  pgb_ctx *c;
+  SharedCtx() : guard(g_ctx_mu) {
+    if (!g_ctx) g_ctx = cli_ctx();
+    c = g_ctx;
   }
-  return g_ctx;
-}
+};
 static void mm128v_append(mm128_v *p, const mm128_t *src, size_t n) {
   if (p->n + n > p->m) {
     size_t m = p->m ? p->m : 16;
@@ -2526,7 +2532,8 @@ extern "C" void mm_sketch(void *km, const char *str, int len, int w, int k, uint
   (void)km;
   assert(len > 0 && (w > 0 && w < 256) && (k > 0 && k <= 28));  // src/mm_sketch.c:77-78
   if (is_hpc) { fprintf(stderr, "pgb200: mm_sketch with is_hpc != 0 is not supported (no reference caller uses it)\n"); exit(1); }
-  pgb_ctx *c = shared_ctx();
+  SharedCtx shared_;
+  pgb_ctx *c = shared_.c;
   std::vector<uint8_t> img((size_t)len);
   for (int i = 0; i < len; i++) img[i] = ascii_to_nibble(str[i]);
   uint32_t one_rid = 0, one_len = (uint32_t)len; uint64_t one_off = 0;
@@ -2541,7 +2548,8 @@ extern "C" void mm_sketch(void *km, const char *str, int len, int w, int k, uint
 extern "C" void mm_reduce(mm128_v *in, mm128_v *out, uint8_t rs) {
   // runs of equal rid are the "reads" of src/shmr_reduce.c:72-77 (the ring is reset whenever the rid changes)
   if (!in || in->n == 0) return;
-  pgb_ctx *c = shared_ctx();
+  SharedCtx shared_;
+  pgb_ctx *c = shared_.c;
   try {
     CU(cudaSetDevice(c->device));
     size_t n = in->n;
@@ -2639,7 +2647,8 @@ extern "C" ovlp_match_t *ovlp_match(uint8_t *query_seq, seq_coor_t q_len, uint8_
   // a batch of one through the same path (src/DWmatch.c:66-204); the result is calloc'd like the reference's (:105)
   ovlp_match_t *rtn = (ovlp_match_t *)calloc(1, sizeof(ovlp_match_t));
   if (q_len <= 0 || t_len <= 0) return rtn;
-  pgb_ctx *c = shared_ctx();
+  SharedCtx shared_;
+  pgb_ctx *c = shared_.c;
   // the two operands may live anywhere: stage them back to back
   std::vector<uint8_t> img((size_t)q_len + (size_t)t_len);
   memcpy(img.data(), query_seq, (size_t)q_len);
@@ -2664,7 +2673,8 @@ extern "C" shmr_aln_v *shmr_aln(mm128_v *mmers0, mm128_v *mmers1, uint8_t direct
   shmr_aln_v *alns = (shmr_aln_v *)calloc(sizeof(shmr_aln_v), 1);
   const size_t n0 = mmers0 ? mmers0->n : 0, n1 = mmers1 ? mmers1->n : 0;
   if (!n0 || !n1) return alns;
-  pgb_ctx *c = shared_ctx();
+  SharedCtx shared_;
+  pgb_ctx *c = shared_.c;
   try {
     CU(cudaSetDevice(c->device));
     mm128 *d0 = c->alloc<mm128>(n0), *d1 = c->alloc<mm128>(n1);
@@ -2722,6 +2732,7 @@ struct PyMmerHandle {
 
 extern "C" void build_shimmer_map4py(py_mmer_t *py, char *seqdb_prefix, char *shimmer_prefix, uint32_t mychunk, uint32_t total_chunk,
                                      uint32_t lower, uint32_t upper) {
+  std::lock_guard<std::recursive_mutex> lock_(g_ctx_mu);
   assert(total_chunk > 0);
   assert(mychunk > 0 && mychunk <= total_chunk);
   const char *sp = seqdb_prefix ? seqdb_prefix : "seq_dataset", *lp = shimmer_prefix ? shimmer_prefix : "shimmer-L2";
@@ -2879,6 +2890,7 @@ extern "C" void get_shimmers_for_read(mm128_v *out, py_mmer_t *py, uint32_t rid)
 }
 
 extern "C" uint32_t get_mmer_count(py_mmer_t *py, uint64_t mhash) {
+  std::lock_guard<std::recursive_mutex> lock_(g_ctx_mu);  // one device context behind the handle: calls are serialised
   PyMmerHandle *h = (PyMmerHandle *)py->mcmap;
   pgb_ctx *c = h->c;
   uint32_t v = 0;
@@ -2894,6 +2906,7 @@ extern "C" uint32_t get_mmer_count(py_mmer_t *py, uint64_t mhash) {
 }
 
 extern "C" void get_shimmer_hits(mp256_v *out, py_mmer_t *py, uint64_t mhash0, uint32_t span) {
+  std::lock_guard<std::recursive_mutex> lock_(g_ctx_mu);  // one device context behind the handle: calls are serialised
   PyMmerHandle *h = (PyMmerHandle *)py->mmer0_map;
   pgb_ctx *c = h->c;
   if (!h->xkeys) return;
