@@ -1167,13 +1167,16 @@ __global__ void __launch_bounds__(PGB_RB_THREADS) k_replay_block(ReplayState st,
 // sort key of an alignment request = predicted overlap length in 256-base units: warps then hold alignments of similar
 // length and finish together
 __global__ void k_align_keys(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n, const uint32_t *__restrict__ rlen_by_rid,
-                             uint32_t *keys, uint32_t *idx) {
+                             uint32_t *keys, uint32_t *idx, int mode) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   AlnReq q = reqs[first + i];
   uint32_t a = rlen_by_rid[q.rid0] - q.start0, b = rlen_by_rid[q.rid1];
   uint32_t e = (a < b ? a : b) >> 8;
-  keys[i] = 255u - (e > 255 ? 255 : e);  // longest first: the tail of the launch is made of short alignments
+  const uint32_t lk = 255u - (e > 255 ? 255 : e);  // longest first: the tail of the launch is made of short alignments
+  // mode 1 (experiment PGB_ALIGN_SORT=target): alignments against the same target read side by side (their lanes then walk the
+  // same cache lines of the target), length class (2 kb) as the major key so that warps still finish together
+  keys[i] = mode == 1 ? ((lk >> 3) << 26) | (q.rid1 & 0x3FFFFFFu) : lk;
   idx[i] = i;
 }
 // 1 thread = 1 alignment, flattened state machine (ovlp_match_flat) over (read, strand) views with N masks; the result goes

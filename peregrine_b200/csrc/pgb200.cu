@@ -1661,11 +1661,13 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         if (nn > 8192 && nn > ALIGN_WARP_MAX) {  // group alignments of similar predicted length into the same warps
           uint32_t *keys = c->alloc<uint32_t>(nn), *keys2 = c->alloc<uint32_t>(nn), *idx0 = c->alloc<uint32_t>(nn);
           perm = c->alloc<uint32_t>(nn);
-          LAUNCH(c, k_align_keys, nblk(nn), 256, S.reqs, n_done, nn, c->d_rlen_by_rid, keys, idx0);
+          const int sort_mode = (getenv("PGB_ALIGN_SORT") && !strcmp(getenv("PGB_ALIGN_SORT"), "target")) ? 1 : 0;
+          const int key_bits = sort_mode ? 31 : 8;
+          LAUNCH(c, k_align_keys, nblk(nn), 256, S.reqs, n_done, nn, c->d_rlen_by_rid, keys, idx0, sort_mode);
           size_t tmp_bytes = 0;
-          CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
+          CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, key_bits, c->st));
           uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
-          CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, 8, c->st));
+          CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, keys2, idx0, perm, (int)nn, 0, key_bits, c->st));
           c->stats.kernel_launches += 3;
         }
         if (nn <= ALIGN_WARP_MAX)  // small batch: latency-bound, one warp per alignment
