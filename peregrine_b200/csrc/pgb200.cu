@@ -2175,11 +2175,16 @@ extern "C" int pgb_shmr_index_main(int argc, char **argv) {
   snprintf(path, sizeof path, "%s.seqdb", seqdb_prefix);
   fprintf(stderr, "using seqdb file: %s\n", path);
 
+  const bool vt = getenv("PGB_VERBOSE") != nullptr;
+  const double t_0 = now_ms();
   pgb_ctx *c = cli_ctx();
+  const double t_ctx = now_ms();
   CLI_CHECK(c, pgb_load_reads_from_files(c, seqdb_prefix, (uint32_t)total_chunk, (uint32_t)mychunk, 0));
+  const double t_load = now_ms();
   int levels = number_layers == 1 ? 1 : (number_layers > 1 ? 2 : 0);
   int with_counts = (output_L0 == 1 ? 1 : 0) | (levels == 1 ? 2 : 0) | (levels == 2 ? 4 : 0);
   CLI_CHECK(c, pgb_index(c, window_size, kmer_size, reduction_factor, levels, with_counts));
+  const double t_index = now_ms();
   auto write_level = [&](int level, const char *tag, bool data_msg_stderr) {
     std::vector<mm128_t> v(pgb_index_size(c, level));
     CLI_CHECK(c, pgb_index_copy(c, level, v.data()));
@@ -2195,6 +2200,8 @@ extern "C" int pgb_shmr_index_main(int argc, char **argv) {
   if (output_L0 == 1) write_level(0, "L0", true);   // src/shmr_index.c:165-197
   if (levels == 1) write_level(1, "L1", false);      // :201-214
   if (levels == 2) write_level(2, "L2", true);       // :216-232
+  if (vt) fprintf(stderr, "pgb200: shmr_index timing: context %.0f ms, load %.0f ms, index %.0f ms, write %.0f ms\n", t_ctx - t_0, t_load - t_ctx,
+                  t_index - t_load, now_ms() - t_index);
   pgb_destroy(c);
   return 0;
 }
