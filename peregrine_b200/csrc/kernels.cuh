@@ -503,7 +503,7 @@ __global__ void k_reduce(const mm128 *__restrict__ in, const uint64_t *__restric
   if (!WRITE) counts[t] = n;
 }
 
-// Warp per read (EXPERIMENT for the next GPU session, PGB_REDUCE=warp; unmeasured): lane l decides the window ending at
+// Warp per read (the default; 0.93 ms per step against 2.03 ms for k_reduce on the bench workload): lane l decides the window ending at
 // in-read offset base + l.  A window emits its pick iff the pick's y differs from the previous window's pick (the first
 // window always emits) - the per-element formulation of shmr_reduce.c:79-88 that tests/hostsim checks against the reference
 // (sim_reduce).  Thread-per-read keeps only ~5 warps per SM busy (100 k reads), each walking ~370 windows sequentially.
@@ -1209,7 +1209,7 @@ __global__ void k_align(const AlnReq *__restrict__ reqs, uint32_t first, uint32_
 #ifndef PGB_ALIGN_MINBLOCKS
 #define PGB_ALIGN_MINBLOCKS 16
 #endif
-template <bool PRE, bool TRIMREG, int MINBLOCKS, bool PF = false>
+template <bool PRE, bool TRIMREG, int MINBLOCKS>
 __global__ void __launch_bounds__(PGB_ALIGN_THREADS, MINBLOCKS) k_align_lean(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n,
                                                                   const uint32_t *__restrict__ perm, const uint64_t *__restrict__ w,
                                                                   const uint64_t *__restrict__ wrc, const uint64_t *__restrict__ woff_by_rid,
@@ -1225,43 +1225,9 @@ __global__ void __launch_bounds__(PGB_ALIGN_THREADS, MINBLOCKS) k_align_lean(con
   const uint64_t *tw = ((q.strands & 2) ? wrc : w) + woff_by_rid[q.rid1];
   int V[2 * PGB_MAXV];
   match_t m;
-  ovlp_match_lean_t<PRE, TRIMREG, PF>(qw, q.start0, (int)(rl0 - q.start0), tw, 0u, (int)rl1, bw, V, PGB_MAXV, &m);
+  ovlp_match_lean_t<PRE, TRIMREG>(qw, q.start0, (int)(rl0 - q.start0), tw, 0u, (int)rl1, bw, V, PGB_MAXV, &m);
   results[q.slot] = m;
   atomicAdd(bases_total, (unsigned long long)(m.q_end + m.t_end));
-}
-
-// Persistent form of k_align_lean (EXPERIMENT for the next GPU session, selected with PGB_ALIGN_VARIANT=13/14, not yet
-// measured): the grid is sized to the machine (12 CTAs per SM) and every lane takes the next request from a global queue
-// head when its alignment ends (ovlp_match_lean_stream; checked against the reference on the CPU in tests/hostsim).
-template <bool PF>
-__global__ void __launch_bounds__(PGB_ALIGN_THREADS, 12) k_align_stream(const AlnReq *__restrict__ reqs, uint32_t first, uint32_t n,
-                                                                         const uint32_t *__restrict__ perm, const uint64_t *__restrict__ w,
-                                                                         const uint64_t *__restrict__ wrc, const uint64_t *__restrict__ woff_by_rid,
-                                                                         const uint32_t *__restrict__ rlen_by_rid, const uint32_t *__restrict__ hasn_by_rid,
-                                                                         int bw, match_t *results, unsigned long long *bases_total, unsigned int *queue_head) {
-  int V[2 * PGB_MAXV];
-  uint32_t slot = 0;
-  unsigned long long bases = 0;
-  auto fetch = [&](const uint64_t *&qw, uint32_t &qo, int &q_len, const uint64_t *&tw, uint32_t &to, int &t_len) -> bool {
-    for (;;) {
-      uint32_t i = atomicAdd(queue_head, 1u);
-      if (i >= n) return false;
-      if (perm) i = perm[i];
-      const AlnReq q = reqs[first + i];
-      if (hasn_by_rid[q.rid0] | hasn_by_rid[q.rid1]) continue;  // left to k_align(only_n = 1)
-      const uint32_t rl0 = rlen_by_rid[q.rid0], rl1 = rlen_by_rid[q.rid1];
-      qw = ((q.strands & 1) ? wrc : w) + woff_by_rid[q.rid0]; qo = q.start0; q_len = (int)(rl0 - q.start0);
-      tw = ((q.strands & 2) ? wrc : w) + woff_by_rid[q.rid1]; to = 0u; t_len = (int)rl1;
-      slot = q.slot;
-      return true;
-    }
-  };
-  auto store = [&](const match_t &m) {
-    results[slot] = m;
-    bases += (unsigned long long)(m.q_end + m.t_end);
-  };
-  ovlp_match_lean_stream<true, true, PF>(fetch, store, bw, V, PGB_MAXV);
-  if (bases) atomicAdd(bases_total, bases);
 }
 
 // Low-latency form for the small alignment batches of the fix-point's tail passes: 1 warp = 1 alignment.  Same algorithm
@@ -1582,14 +1548,6 @@ __global__ void k_aln_chain(const mm128 *__restrict__ a0, const mm128 *__restric
   }
   n_out[0] = n_hits;
   n_out[1] = n_chains;
-}
-
-__global__ void k_table_diff(const uint64_t *__restrict__ a, const uint64_t *__restrict__ b, size_t n, unsigned long long *diffs) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  unsigned int local = 0;
-  for (; i < n; i += stride) local += a[i] != b[i];
-  if (local) atomicAdd(diffs, (unsigned long long)local);
 }
 
 }  // namespace pgb

@@ -1077,7 +1077,8 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   for (int l = 1; l <= levels; l++) {
     c->tic();
     CU(cudaMemsetAsync(counts, 0, (ns + 1) * 4, c->st));
-    const bool reduce_warp = getenv("PGB_REDUCE") && !strcmp(getenv("PGB_REDUCE"), "warp");  // experiment, see k_reduce_warp
+    // warp per read (measured 0.93 ms per step against 2.03 ms for thread per read, profiles/r2_notes.md); PGB_REDUCE=thread: the old form
+    const bool reduce_warp = !(getenv("PGB_REDUCE") && !strcmp(getenv("PGB_REDUCE"), "thread"));
     if (reduce_warp)
       LAUNCH(c, k_reduce_warp<false>, nblk(ns * 32, 128), 128, c->d_level[l - 1], c->d_level_off[l - 1], (uint32_t)ns, (uint32_t)r, counts,
              (const uint64_t *)nullptr, (mm128 *)nullptr);
@@ -1681,20 +1682,7 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
           // step against 26.2 ms for the plain form at 16 CTAs/SM, whose 64-register cap forces spills (profiles/r1g_ncu.md);
           // PGB_ALIGN_VARIANT=0 selects the plain form (kept as the A/B baseline of the parity tests)
           if (ALIGN_VARIANT == 0) PGB_LEAN(false, false, 16);
-          else if (ALIGN_VARIANT == 12)  // experiment for the next GPU session: + L2 prefetch of the next operand line (unmeasured)
-            LAUNCH(c, (k_align_lean<true, true, 12, true>), nblk(nn, PGB_ALIGN_THREADS), PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc,
-                   c->d_woff_by_rid, c->d_rlen_by_rid, c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases);
-          else if (ALIGN_VARIANT == 13 || ALIGN_VARIANT == 14) {  // experiment: persistent lanes with a global request queue (unmeasured)
-            unsigned int *qhead = c->alloc<unsigned int>(1);
-            CU(cudaMemsetAsync(qhead, 0, 4, c->st));
-            const unsigned grid = std::min(nblk(nn, PGB_ALIGN_THREADS), (unsigned)(c->sm_count * 12));
-            if (ALIGN_VARIANT == 13)
-              LAUNCH(c, k_align_stream<false>, grid, PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid,
-                     c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases, qhead);
-            else
-              LAUNCH(c, k_align_stream<true>, grid, PGB_ALIGN_THREADS, S.reqs, n_done, nn, perm, c->d_w, c->d_wrc, c->d_woff_by_rid, c->d_rlen_by_rid,
-                     c->d_hasn_by_rid, (int)bw, S.ares, c->d_align_bases, qhead);
-          } else if (ALIGN_VARIANT >= 20 && ALIGN_VARIANT <= 23) {
+          else if (ALIGN_VARIANT >= 20 && ALIGN_VARIANT <= 23) {
             // G lanes per alignment, operand windows staged in shared memory (align_quad.cuh): 20 / 21 = G 4 / 8 with cp.async.bulk,
             // 22 / 23 = G 4 / 8 with cp.async
             const int G = (ALIGN_VARIANT & 1) ? 8 : 4;

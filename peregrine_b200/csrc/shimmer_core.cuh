@@ -407,16 +407,9 @@ PGB_HD uint64_t window64(uint64_t A, uint64_t B, uint32_t s2) {
 // qw / tw: first packed word of the read in the image of the operand's strand; qo / to: base offset of logical base 0.
 // V: caller scratch of 2*cap ints, cap >= band_tolerance + 2.
 // PRE: load V[d-1][k+3] one cell ahead; TRIMREG: serve the first two trim steps per side from registers
-// PF: when a continued snake enters a new 128-byte line of an operand, ask L2 for the line after it (a hint only; the
-// walk is sequential, so the DRAM latency of the next line overlaps the 16 word-steps spent in the current one)
-PGB_HD void prefetch_l2(const void *p) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
-template <bool PRE, bool TRIMREG, bool PF = false>
+// (Measured and dropped in round 2, profiles/r2_align.md: an L2 prefetch of the next operand line, 20.6 vs 20.2 ms, and a
+// persistent form in which a lane takes the next alignment from a queue when its own ends, 22.6 ms.)
+template <bool PRE, bool TRIMREG>
 PGB_HD void ovlp_match_lean_t(const uint64_t *qw, uint32_t qo, int q_len, const uint64_t *tw, uint32_t to, int t_len,
                               int band_tolerance, int *V, int cap, match_t *out) {
   match_t r;
@@ -453,59 +446,6 @@ PGB_HD void ovlp_match_lean_t(const uint64_t *qw, uint32_t qo, int q_len, const 
 PGB_HD void ovlp_match_lean(const uint64_t *qw, uint32_t qo, int q_len, const uint64_t *tw, uint32_t to, int t_len,
                             int band_tolerance, int *V, int cap, match_t *out) {
   ovlp_match_lean_t<true, true>(qw, qo, q_len, tw, to, t_len, band_tolerance, V, cap, out);
-}
-
-// Streaming form: one lane works through a queue of alignments.  fetch(qw, qo, q_len, tw, to, t_len) -> false when the queue
-// is empty; store(result) is called once per fetched alignment.  When an alignment ends the lane fetches the next one
-// inside the same loop, so the lanes of a warp stay busy until the queue is drained (in ovlp_match_lean_t a lane that
-// finished early idles until the longest alignment of its warp ends: 6 of 32 lanes on average, profiles/r1g_ncu.md).
-// Same results as ovlp_match_lean_t call by call (tests/hostsim `match`).
-template <bool PRE, bool TRIMREG, bool PF, class Fetch, class Store>
-PGB_HD void ovlp_match_lean_stream(Fetch &&fetch, Store &&store, int band_tolerance, int *V, int cap) {
-  const uint64_t *qw = nullptr, *tw = nullptr;
-  uint32_t qo = 0, to = 0;
-  int q_len = 0, t_len = 0;
-  match_t r;
-  int max_d = 0;
-  const int band_size = band_tolerance * 2;
-  uint32_t longest_match = 0;
-  bool start = false, matched = false;
-  int best_m = -1, k_best = 0, u_first = 0;
-  int min_k = 0, max_k = 0, d = 0, k = 0, idx = 0, x = 0, x1 = 0;
-  int *Vc = V, *Vp = V + cap;
-  int vcarry = 0, vpre = 0, poff = 0;
-  int u1 = 0, u2 = 0, ul0 = 0, ul1 = 0, ul2 = 0;
-  const uint64_t *qp = nullptr, *tp = nullptr;
-  uint32_t qs = 0, ts = 0;
-  uint64_t qA = 0, qB = 0, tA = 0, tB = 0;
-  bool fresh = true, running = false, active = true;
-  auto begin = [&]() -> bool {
-    if (!fetch(qw, qo, q_len, tw, to, t_len)) return false;
-    r.m_size = r.dist = r.q_bgn = r.q_end = r.t_bgn = r.t_end = r.t_m_end = r.q_m_end = 0;
-    max_d = (int)(0.3 * (double)(q_len + t_len));  // DWmatch.c:96
-    longest_match = 0;
-    start = false; matched = false;
-    best_m = -1; k_best = 0; u_first = 0;
-    min_k = 0; max_k = 0; d = 0; k = 0; idx = 0; x = 0; x1 = 0;
-    Vc = V; Vp = V + cap;
-    vcarry = 0; vpre = 0; poff = 0;
-    qp = qw + (qo >> 5); tp = tw + (to >> 5);
-    qs = (qo & 31) * 2; ts = (to & 31) * 2;
-    fresh = true;
-    running = max_d > 0;
-    return true;
-  };
-  active = begin();
-  while (active) {
-    if (running) {
-#include "ovlp_match_lean_body.inc"
-    }
-    if (!running) {  // the alignment ended in this iteration (or never started: max_d == 0)
-      if (!matched) { r.q_bgn = 0; r.t_bgn = 0; }  // DWmatch.c:196-199
-      store(r);
-      active = begin();
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------- mm_sketch (exact automaton)

@@ -96,7 +96,7 @@ static void load_packed(const char *prefix, Packed *P) {
   }
 }
 struct LeanCase { size_t r0; uint32_t start0; int s0; size_t r1; int s1; match_t want; };
-static std::vector<LeanCase> g_lean_cases;  // replayed through ovlp_match_lean_stream at the end of `match`
+static std::vector<LeanCase> g_lean_cases;
 static bool lean_match(const Packed &P, size_t r0, uint32_t start0, int s0, size_t r1, int s1, int bw, match_t *m) {
   if (P.has_n[r0] || P.has_n[r1]) return false;  // reads with N take ovlp_match_flat in the product too
   std::vector<int> V(2 * (bw + 2));
@@ -309,25 +309,7 @@ static int cmd_match(int argc, char **argv) {
     if (it % 4 == 1) st = 0;
     one_match(P, r0, st, (int)(rnd() & 1), r1, (int)(rnd() & 1), bw, &bad);
   }
-  // the streaming form: a few "lanes" work through the recorded pairs as queues; every result must equal the per-call one
-  size_t stream_bad = 0, stream_n = 0;
-  for (int lanes : {1, 3}) {
-    for (int lane = 0; lane < lanes; lane++) {
-      std::vector<int> V(2 * (bw + 2));
-      size_t next = (size_t)lane, cur = 0;
-      auto fetch = [&](const uint64_t *&qw, uint32_t &qo, int &q_len, const uint64_t *&tw, uint32_t &to, int &t_len) -> bool {
-        if (next >= g_lean_cases.size()) return false;
-        cur = next; next += (size_t)lanes;
-        const LeanCase &c = g_lean_cases[cur];
-        qw = (c.s0 ? P.wrc.data() : P.w.data()) + P.woff[c.r0]; qo = c.start0; q_len = (int)(P.rt.len[c.r0] - c.start0);
-        tw = (c.s1 ? P.wrc.data() : P.w.data()) + P.woff[c.r1]; to = 0; t_len = (int)P.rt.len[c.r1];
-        return true;
-      };
-      auto store = [&](const match_t &m) { stream_n++; if (!same_match(m, g_lean_cases[cur].want)) stream_bad++; };
-      ovlp_match_lean_stream<true, true, false>(fetch, store, bw, V.data(), bw + 2);
-    }
-  }
-  if (stream_n != 2 * g_lean_cases.size()) stream_bad++;
+  const size_t stream_bad = 0, stream_n = 0;  // (the streaming form of ovlp_match_lean was measured and dropped in round 2)
   printf("match: pairs=%zu mismatches=%zu stream_results=%zu stream_mismatches=%zu\n", npairs, bad, stream_n, stream_bad);
   return (bad || stream_bad) ? 3 : 0;
 }
