@@ -272,13 +272,16 @@ __global__ void k_sketch_exact(const uint64_t *__restrict__ w, const uint32_t *_
 
 // Segment-parallel form of the exact automaton for the reads the tiled kernel hands back: one thread replays one
 // SEG-position segment of one read (warm-up before it, w slots after it; see sketch_exact_range).
-template <bool WRITE>
+// MODE 0: count per segment.  MODE 1: write at the final place (needs the counts' scan).  MODE 2: count AND stage the records
+// in a per-segment buffer of `stage_cap` records (one pass of the automaton instead of two; a segment that overflows its
+// buffer raises *overflow and the caller falls back to MODE 1).
+template <int MODE>
 __global__ void k_sketch_exact_seg(const uint64_t *__restrict__ w, const uint32_t *__restrict__ nm, const uint32_t *__restrict__ seg_row,
                                    const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_first, uint32_t n_seg, int seg_len,
                                    const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ row_len,
                                    const uint64_t *__restrict__ row_woff, const uint32_t *__restrict__ hasn_by_rid, int wsz, int k,
                                    uint32_t *__restrict__ seg_cnt, const uint32_t *__restrict__ seg_pos,
-                                   const uint64_t *__restrict__ off_by_row, mm128 *__restrict__ out) {
+                                   const uint64_t *__restrict__ off_by_row, mm128 *__restrict__ out, uint32_t stage_cap, int *overflow) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_seg) return;
   const uint32_t row = seg_row[s];
@@ -289,9 +292,9 @@ __global__ void k_sketch_exact_seg(const uint64_t *__restrict__ w, const uint32_
   uint64_t ring_x[256];
   uint32_t ring_p[256];
   uint32_t n = 0;
-  mm128 *dst = WRITE ? out + off_by_row[row] + (seg_pos[s] - seg_pos[seg_first[s]]) : nullptr;
+  mm128 *dst = MODE == 1 ? out + off_by_row[row] + (seg_pos[s] - seg_pos[seg_first[s]]) : (MODE == 2 ? out + (size_t)s * stage_cap : nullptr);
   auto em = [&](uint64_t x, uint64_t y) {
-    if (WRITE) {
+    if (MODE == 1 || (MODE == 2 && n < stage_cap)) {
       dst[n].x = x;
       dst[n].y = y;
     }
@@ -304,7 +307,18 @@ __global__ void k_sketch_exact_seg(const uint64_t *__restrict__ w, const uint32_
     n = 0;  // warm-up too short (palindrome-dense stretch): replay from the read start
     sketch_exact_range(w, nmp, row_woff[row], len, wsz, k, rid, 0, lo, hi, ring_x, ring_p, em);
   }
-  if (!WRITE) seg_cnt[s] = n;
+  if (MODE != 1) seg_cnt[s] = n;
+  if (MODE == 2 && n > stage_cap) atomicOr(overflow, 1);
+}
+// staged records of a segment -> their final place
+__global__ void k_seg_place(const uint32_t *__restrict__ seg_row, const uint32_t *__restrict__ seg_first, uint32_t n_seg, const uint32_t *__restrict__ seg_pos,
+                            const uint64_t *__restrict__ off_by_row, const mm128 *__restrict__ stage, uint32_t stage_cap, mm128 *__restrict__ out) {
+  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l = threadIdx.x & 7;  // 8 lanes per segment
+  if (s >= n_seg) return;
+  const uint32_t n = seg_pos[s + 1] - seg_pos[s];
+  mm128 *dst = out + off_by_row[seg_row[s]] + (seg_pos[s] - seg_pos[seg_first[s]]);
+  const mm128 *src = stage + (size_t)s * stage_cap;
+  for (uint32_t i = l; i < n; i += 8) dst[i] = src[i];
 }
 __global__ void k_seg_row_counts(const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_first_seg, uint32_t n_list,
                                  const uint32_t *__restrict__ seg_pos, uint32_t *cnt_by_row) {

@@ -869,7 +869,9 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   auto exact_tail = [&](uint32_t *row_flags, uint32_t *exact_flag, uint32_t *exact_pos, const std::function<void()> &place_fast) {
     uint32_t n_exact = scan_u32(c, exact_flag, exact_pos, ns + 1);
     uint32_t *exact_list = nullptr, *seg_row = nullptr, *seg_lo = nullptr, *seg_first = nullptr, *list_first = nullptr, *seg_cnt = nullptr, *seg_pos = nullptr;
-    uint32_t n_seg = 0;
+    uint32_t n_seg = 0, stage_cap = 0;
+    mm128 *seg_stage = nullptr;
+    bool staged_ok = false;
     // positions per thread of the exact automaton (plus its warm-up of ~w+k and w trailing slots): the few flagged reads are a
     // pure latency term (far fewer threads than the GPU holds), so short segments keep them off the critical path
     const int SEG = getenv("PGB_EXACT_SEG") ? std::max(16, atoi(getenv("PGB_EXACT_SEG"))) : 256;
@@ -890,10 +892,20 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
       c->h2d(seg_row, h_seg_row.data(), (size_t)n_seg * 4); c->h2d(seg_lo, h_seg_lo.data(), (size_t)n_seg * 4);
       c->h2d(seg_first, h_seg_first.data(), (size_t)n_seg * 4); c->h2d(list_first, h_list_first.data(), ((size_t)n_exact + 1) * 4);
       CU(cudaMemsetAsync(seg_cnt, 0, ((size_t)n_seg + 1) * 4, c->st));
+      // ONE pass of the automaton: the records are staged per segment (budget: 4x the expected 2/(w+1) density, at least 32) and
+      // placed once the counts are scanned; only a segment that overflows its budget costs the second pass
+      stage_cap = std::max<uint32_t>(32, (uint32_t)(8 * SEG / (w + 1)) + 8);
+      seg_stage = c->alloc<mm128>((size_t)n_seg * stage_cap);
+      int *d_ovf = c->alloc<int>(1);
+      CU(cudaMemsetAsync(d_ovf, 0, 4, c->st));
       c->ktic();
-      LAUNCH(c, k_sketch_exact_seg<false>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
-             c->d_row_woff, c->d_hasn_by_rid, w, k, seg_cnt, (const uint32_t *)nullptr, (const uint64_t *)nullptr, (mm128 *)nullptr);
+      LAUNCH(c, k_sketch_exact_seg<2>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
+             c->d_row_woff, c->d_hasn_by_rid, w, k, seg_cnt, (const uint32_t *)nullptr, (const uint64_t *)nullptr, seg_stage, stage_cap, d_ovf);
       c->stats.ms_k_sketch_count += c->ktoc(); c->stats.n_k_sketch_count++;
+      int h_ovf = 0;
+      c->d2h(&h_ovf, d_ovf, 4);
+      staged_ok = h_ovf == 0;
+      c->release(d_ovf);
       scan_u32(c, seg_cnt, seg_pos, (size_t)n_seg + 1);
       LAUNCH(c, k_seg_row_counts, nblk(n_exact), 256, exact_list, list_first, n_exact, seg_pos, counts);
     }
@@ -903,9 +915,13 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     place_fast();
     if (n_exact) {
       c->ktic();
-      LAUNCH(c, k_sketch_exact_seg<true>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
-             c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, seg_pos, c->d_level_off[0], c->d_level[0]);
+      if (staged_ok)
+        LAUNCH(c, k_seg_place, nblk((size_t)n_seg * 8, 256), 256, seg_row, seg_first, n_seg, seg_pos, c->d_level_off[0], seg_stage, stage_cap, c->d_level[0]);
+      else
+        LAUNCH(c, k_sketch_exact_seg<1>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
+               c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, seg_pos, c->d_level_off[0], c->d_level[0], 0u, (int *)nullptr);
       c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
+      c->release(seg_stage);
       c->release(exact_list); c->release(seg_row); c->release(seg_lo); c->release(seg_first); c->release(list_first); c->release(seg_cnt); c->release(seg_pos);
     }
   };
