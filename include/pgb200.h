@@ -196,6 +196,17 @@ int pgb_ovlp_match_batch(pgb_ctx *, const uint8_t *seq, size_t seq_bytes, size_t
                          const uint8_t *q_strand, const uint64_t *t_off, const uint32_t *t_len, const uint8_t *t_strand, int band_tolerance,
                          ovlp_match_t *out);
 
+/* ---- batched shmr_aln for the cffi callers (py/peregrine/utils.py:52-73 get_shimmer_alns; src/shmr_align.c:21-160).  Pair p chains
+ * mm0[off0[p], off0[p+1]) against mm1[off1[p], off1[p+1]) with the reference's parameters.  On return the hits of pair p are
+ * (*hits)[hit_off[p] .. hit_off[p+1]) in the order the reference appends them (idx0 / idx1 index the pair's own lists, chain = the
+ * position of the chain in the reference's shmr_aln_v), n_chains[p] = alns->n.  *hits is malloc'd: release it with pgb_host_free.
+ * One upload, one radix sort for the hash -> index map of all pairs, one warp per pair for the greedy chaining, one download. */
+typedef struct { uint32_t chain, idx0, idx1; } pgb_aln_hit_t;
+int pgb_shmr_aln_batch(pgb_ctx *, const mm128_t *mm0, const uint64_t *off0, const mm128_t *mm1, const uint64_t *off1, uint32_t n_pairs,
+                       uint8_t direction, uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat, uint64_t *hit_off /* [n_pairs+1] */,
+                       uint32_t *n_chains /* [n_pairs] or NULL */, pgb_aln_hit_t **hits);
+void pgb_host_free(void *);
+
 /* ---- shmr_dedup: raw ovlp_t stream -> preads.ovl text ------------------------------------------------------
  * replaces main() of src/shmr_dedup.c:19-101: keeps the FIRST record of every unordered read pair in stream order (the
  * concatenation of the chunk files, `cat ovlp-*.dat | shmr_dedup`, py/scripts/pg_run.py:352) and prints
@@ -251,6 +262,8 @@ typedef struct {
   uint64_t n_k_encode, bases_encoded;
   double ms_map;                 /* pgb_map after the pair records are built */
   uint64_t n_map_hits;
+  uint64_t n_device_mallocs;     /* cudaMalloc calls (block-cache misses + new scratch slabs): 0 per step in a steady-state job */
+  uint64_t n_replay_restarts;    /* fix-point restarts after a replay table filled up */
 } pgb_stats;
 void pgb_stats_reset(pgb_ctx *);
 /* CUDA events on the context's stream (the stream every kernel of this library is launched on): record slot 0..7, then

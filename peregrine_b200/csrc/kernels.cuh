@@ -986,13 +986,14 @@ struct DevReplayCtx {
 __global__ void __launch_bounds__(64) k_replay(ReplayState st, uint32_t n_ranks, const uint32_t *__restrict__ list, const uint32_t *__restrict__ rank_off,
                                                const uint64_t *__restrict__ sy0, const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn,
                                                int request_enabled, int do_emit, uint32_t *acc_count, const uint32_t *__restrict__ out_off,
-                                               ovlp_rec *out, uint8_t *unk_flag, const uint32_t *__restrict__ cnt_dev) {
+                                               ovlp_rec *out, uint8_t *unk_flag, const uint32_t *__restrict__ cnt_dev, uint32_t warp_min, uint32_t warp_max) {
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (cnt_dev) n_ranks = cnt_dev[0];  // run list sized on the device (no host round trip): [0] small buckets, [1] all
   if (r >= n_ranks) return;
   if (*(volatile int *)st.err & (32 | 64)) return;  // a table filled up: this pass is void, the host restarts with larger tables
   r = list[r];
   uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
+  if (n >= warp_min && n < warp_max) return;  // walked by a warp (k_replay_warp)
   DevReplayCtx c;
   c.s = st;
   c.rank = r;
@@ -1003,6 +1004,158 @@ __global__ void __launch_bounds__(64) k_replay(ReplayState st, uint32_t n_ranks,
   acc_count[r] = acc;
   unk_flag[r] = unk != 0;
   if (unk) atomicAdd(&st.ctr[0], (unsigned long long)unk);
+}
+
+// Lane-group form for MEDIUM buckets (min_n <= n < max_n).  A thread that walks such a bucket alone performs one dependent table
+// probe after the other (several per row, rows n-2 .. 0): an incremental pass lasts as long as its slowest thread.  Here G lanes
+// walk the rows of one bucket (32/G buckets per warp) and probe G candidates of the row IN PARALLEL; the row's sequential
+// semantics (stop at bestn overlaps, a CONTAINED result ends the row, src/shmr_overlap.c:97-176) are then applied to the
+// classified candidates with ballots: the candidates up to the cut-off are exactly those the reference visits, only they cause
+// table updates, requests and records.  G is small on purpose: candidates probed beyond the cut-off are wasted random accesses
+// (a whole warp per bucket, G = 32, doubles the time of a full pass).  Valid when no read has two records in the bucket (every
+// read pair then occurs once in the bucket, so the rows do not see each other's table entries); other buckets are walked by
+// the group's first lane with the generic replay_bucket.  The warp never diverges in the main loop: every ballot is full-mask
+// and a group that is done idles under predicates.
+#define PGB_RW_WARPS 4
+#define PGB_RW_MAXN 64
+template <int G>
+__global__ void __launch_bounds__(PGB_RW_WARPS * 32) k_replay_group(ReplayState st, uint32_t n_list, const uint32_t *__restrict__ list,
+                                                                    const uint32_t *__restrict__ rank_off, const uint64_t *__restrict__ sy0,
+                                                                    const uint8_t *__restrict__ sdir, uint8_t *contained, uint32_t bestn,
+                                                                    int request_enabled, int do_emit, uint32_t *acc_count,
+                                                                    const uint32_t *__restrict__ out_off, ovlp_rec *out, uint8_t *unk_flag,
+                                                                    const uint32_t *__restrict__ cnt_dev, uint32_t min_n, uint32_t max_n) {
+  constexpr int NG = 32 / G, GPB = PGB_RW_WARPS * NG;
+  constexpr uint32_t FULL = 0xffffffffu, GM = G == 32 ? FULL : ((1u << (G & 31)) - 1u);
+  __shared__ uint64_t s_y0[GPB][PGB_RW_MAXN];
+  __shared__ uint32_t s_rlen[GPB][PGB_RW_MAXN];
+  __shared__ uint8_t s_dir[GPB][PGB_RW_MAXN], s_cont[GPB][PGB_RW_MAXN];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane / G, gl = lane % G, gsh = g * G;
+  const uint32_t slot = wid * NG + g, li = blockIdx.x * GPB + slot;
+  if (cnt_dev) n_list = cnt_dev[0];
+  bool have = li < n_list && !(*(volatile int *)st.err & (32 | 64));  // (a table filled up: this pass is void)
+  uint32_t r = 0, b = 0, n = 0;
+  if (have) {
+    r = list[li];
+    b = rank_off[r];
+    n = rank_off[r + 1] - b;
+    have = n >= min_n && n < max_n;  // the others: thread-walked (k_replay) or CTA-walked (k_replay_block)
+  }
+  if (!__any_sync(FULL, have)) return;
+  DevReplayCtx c;
+  c.s = st;
+  c.rank = r;
+  c.request_enabled = request_enabled != 0;
+  c.out = (do_emit && have) ? out + out_off[r] : nullptr;
+  uint64_t *y0s = s_y0[slot];
+  uint32_t *rl = s_rlen[slot];
+  uint8_t *dr = s_dir[slot], *ct = s_cont[slot];
+  bool dup = false;
+  if (have) {
+    for (uint32_t t = gl; t < n; t += G) {
+      const uint64_t y = sy0[b + t];
+      y0s[t] = y;
+      rl[t] = st.rlen_by_rid[(uint32_t)(y >> 32)];
+      dr[t] = sdir[b + t];
+      ct[t] = 0;
+    }
+  }
+  __syncwarp();
+  if (have)  // a read with two records in the bucket?
+    for (uint32_t t = gl; t < n; t += G) {
+      const uint32_t rid = (uint32_t)(y0s[t] >> 32);
+      for (uint32_t u = t + 1; u < n; u++) dup |= (uint32_t)(y0s[u] >> 32) == rid;
+    }
+  dup = ((__ballot_sync(FULL, dup) >> gsh) & GM) != 0;
+  const uint64_t NONE = ~0ULL;
+  uint32_t n_acc = 0, n_unk = 0, overlap_count = 0;
+  uint32_t k0 = (have && !dup) ? n - 1 : 0;  // current row is k0 - 1, its candidates start at k0; 0 = this group is done
+  uint32_t base = k0;
+  while (__any_sync(FULL, k0 > 0)) {
+    const bool act = k0 > 0;
+    const uint32_t i = act ? k0 - 1 : 0, j = base + gl;
+    const bool valid = act && j < n && !ct[j];  // (rid0 != rid1: no read occurs twice in this bucket)
+    bool hit = false, known = true, accepted = false;
+    uint32_t type = 0, rid0 = 0, pos0 = 0, rlen0 = 0, rid1 = 0, rlen1 = 0, pos1 = 0;
+    uint64_t y0 = 0, y1 = 0, ridp = 0;
+    match_t m;
+    if (valid) {
+      y0 = y0s[i];
+      rid0 = (uint32_t)(y0 >> 32); pos0 = (uint32_t)((y0 & 0xFFFFFFFFULL) >> 1) + 1; rlen0 = rl[i];
+      y1 = y0s[j];
+      rid1 = (uint32_t)(y1 >> 32);
+      ridp = rid0 < rid1 ? ((uint64_t)rid0 << 32) | rid1 : ((uint64_t)rid1 << 32) | rid0;
+      uint64_t v, vnew;
+      c.pair_get(ridp, &v, &vnew);
+      hit = (v != NONE) && ((uint32_t)(v >> 2) < r);
+      if (!hit) {
+        v = vnew;
+        hit = (v != NONE) && ((uint32_t)(v >> 2) <= r);
+      }
+      if (hit) {
+        type = (uint32_t)(v & 3);
+      } else {
+        pos1 = (uint32_t)((y1 & 0xFFFFFFFFULL) >> 1) + 1;
+        rlen1 = rl[j];
+        known = c.aln_get(i, j, &m);
+        if (!known) predict_match(rlen0, rlen1, pos0 - pos1, &m);
+        accepted = classify_match(m, rlen0, rlen1, rlen0 - pos0 + pos1, rlen1, &type);
+      }
+    }
+    // the row in candidate order: overlap_count rises on a rid_pairs hit of type OVERLAP and on an accepted OVERLAP; the
+    // candidate that brings it to bestn is the last one visited; an accepted CONTAINED ends the row after its candidate
+    const bool inc = valid && type == OVL_OVERLAP && (hit || accepted);
+    const bool ends = valid && !hit && accepted && type == OVL_CONTAINED;
+    const uint32_t incm = (__ballot_sync(FULL, inc) >> gsh) & GM, endm = (__ballot_sync(FULL, ends) >> gsh) & GM;
+    const uint32_t need = bestn - overlap_count;  // >= 1 for an active group
+    uint32_t cut = G;                             // candidates of lanes <= cut are visited
+    bool row_done = false;
+    if (act && (uint32_t)__popc(incm) >= need) cut = __fns(incm, 0, (int)need);
+    if (endm) {
+      const uint32_t e = __ffs((int)endm) - 1;
+      if (e <= cut) { cut = e; row_done = true; }
+    }
+    const uint32_t vis = cut >= G - 1 ? GM : ((2u << cut) - 1u);
+    const bool mine = valid && ((vis >> gl) & 1u);
+    const uint32_t accm = (__ballot_sync(FULL, mine && !hit && accepted) >> gsh) & GM;
+    const uint32_t unkm = (__ballot_sync(FULL, mine && !hit && !known) >> gsh) & GM;
+    if (mine && !hit) {
+      if (!known) c.aln_request(i, j, rid0, pos0 - pos1, dr[i], rid1, dr[j]);
+      if (accepted) {
+        if (type == OVL_CONTAINS) ct[j] = 1;
+        c.pair_set(ridp, ((uint64_t)r << 2) | type);
+        if (do_emit) {
+          ovlp_rec o;
+          o.y0 = y0; o.y1 = y1; o.rl0 = rlen0; o.rl1 = rlen1;
+          o.strand0 = dr[i]; o.strand1 = dr[j]; o.ovlp_type = (uint8_t)type; o.pad0 = 0;
+          o.match = m;
+          o.pad1 = 0;
+          c.out[n_acc + __popc(accm & ((1u << gl) - 1u))] = o;
+        }
+      }
+    }
+    overlap_count += __popc(incm & vis);
+    n_acc += __popc(accm);
+    n_unk += __popc(unkm);
+    const bool next_row = act && (row_done || overlap_count >= bestn || base + G >= n);
+    if (act && row_done && gl == 0) ct[i] = 1;
+    if (act && !next_row) base += G;
+    __syncwarp();
+    if (next_row) {  // the next row that is not contained (src/shmr_overlap.c:71)
+      k0--;
+      while (k0 > 0 && ct[k0 - 1]) k0--;
+      base = k0;
+      overlap_count = 0;
+    }
+  }
+  if (have && gl == 0) {
+    if (dup) {
+      n_acc = replay_bucket(c, r, sy0 + b, sdir + b, n, contained + b, bestn, do_emit != 0, &n_unk);
+    }
+    acc_count[r] = n_acc;
+    unk_flag[r] = n_unk != 0;
+    if (n_unk) atomicAdd(&st.ctr[0], (unsigned long long)n_unk);
+  }
 }
 
 // Block-cooperative form of the same scan for BIG buckets (one CTA of 128 threads = one bucket of up to PGB_RB_MAXN records).
@@ -1188,9 +1341,10 @@ __global__ void k_align_keys(const AlnReq *__restrict__ reqs, uint32_t first, ui
   uint32_t a = rlen_by_rid[q.rid0] - q.start0, b = rlen_by_rid[q.rid1];
   uint32_t e = (a < b ? a : b) >> 8;
   const uint32_t lk = 255u - (e > 255 ? 255 : e);  // longest first: the tail of the launch is made of short alignments
-  // mode 1 (experiment PGB_ALIGN_SORT=target): alignments against the same target read side by side (their lanes then walk the
-  // same cache lines of the target), length class (2 kb) as the major key so that warps still finish together
-  keys[i] = mode == 1 ? ((lk >> 3) << 26) | (q.rid1 & 0x3FFFFFFu) : lk;
+  // mode m > 0 (default m = 4): alignments against the same target read side by side -- every alignment starts at base 0 of its
+  // target, so the lanes of a warp walk the same cache lines of it in step (one L1 tag look-up instead of one per lane) -- with
+  // the length class (2^(m-1) x 256 bases) as the major key so that warps still finish together.  mode 0: length only.
+  keys[i] = mode > 0 ? ((lk >> (mode - 1)) << 23) | (q.rid1 & 0x7FFFFFu) : lk;
   idx[i] = i;
 }
 // 1 thread = 1 alignment, flattened state machine (ovlp_match_flat) over (read, strand) views with N masks; the result goes
@@ -1484,33 +1638,82 @@ __global__ void k_outer_lookup(const uint64_t *__restrict__ xkeys, uint32_t xmas
 }
 
 // ------------------------------------------------------------------------------------------------ shmr_aln (co-linear chaining)
-// src/shmr_align.c:21-160.  k_aln_match_count/fill: for every minimizer of list 1 the ascending indices of the minimizers
-// of list 0 with the same hash (the reference's MMIDX hash map, :40-57).  k_aln_chain: the greedy chaining itself is
-// sequential in the hits (every hit extends the best existing chain or opens a new one, :97-147), so one thread walks the
-// hits; it emits (chain id, idx0, idx1) per hit.
-__global__ void k_aln_match_count(const mm128 *__restrict__ a0, uint32_t n0, const mm128 *__restrict__ a1, uint32_t n1, uint32_t *cnt) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n1) return;
-  uint64_t key = a1[s].x >> 8;
-  uint32_t c = 0;
-  for (uint32_t i = 0; i < n0; i++) c += (a0[i].x >> 8) == key;
-  cnt[s] = c;
-}
-__global__ void k_aln_match_fill(const mm128 *__restrict__ a0, uint32_t n0, const mm128 *__restrict__ a1, uint32_t n1,
-                                 const uint32_t *__restrict__ off, uint32_t *midx) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n1) return;
-  uint64_t key = a1[s].x >> 8;
-  uint32_t at = off[s];
-  for (uint32_t i = 0; i < n0; i++)
-    if ((a0[i].x >> 8) == key) midx[at++] = i;
-}
+// src/shmr_align.c:21-160, batched: pair p chains list0[off0[p], off0[p+1]) against list1[off1[p], off1[p+1]).
+//  * the reference's MMIDX hash map (:40-57: hash -> ascending indices into list 0) is one radix sort of all list-0 elements by
+//    (pair, low 40 hash bits) with the element index as the value (k_aln_keys0; the sort is stable, so equal keys stay in
+//    ascending index order; elements of a pair stay inside the pair's own range [off0[p], off0[p+1]));
+//  * k_aln_lookup<false/true>: one thread per list-1 element binary-searches its pair's range and counts / writes the list-0
+//    indices whose FULL hash equals its own;
+//  * k_aln_chain_warp: the greedy chaining is sequential in the hits (every hit extends the best existing chain or opens a new one,
+//    :97-147), so one WARP walks a pair's hits in order and its lanes evaluate the existing chains in parallel (arg-min of
+//    (diff, chain id) by shuffle = the reference's first chain with the smallest diff); it emits (chain id, idx0, idx1) per hit.
 struct AlnHit { uint32_t chain, i0, i1; };
+struct AlnChain { uint32_t last_i0, lp0; int32_t delta1; uint32_t n; };
 __device__ __forceinline__ int64_t aln_abs_u32(uint32_t v) { int32_t x = (int32_t)v; return x < 0 ? -(int64_t)x : (int64_t)x; }  // abs((int)uint32)
-__global__ void k_aln_chain(const mm128 *__restrict__ a0, const mm128 *__restrict__ a1, uint32_t n1, const uint32_t *__restrict__ off,
-                            const uint32_t *__restrict__ midx, uint32_t direction, uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat,
-                            uint32_t *chain_last0, uint32_t *chain_last1, uint32_t *chain_n, AlnHit *hits, uint32_t *n_out /* [0]=hits [1]=chains */) {
-  if (blockIdx.x || threadIdx.x) return;
+#define PGB_ALN_HBITS 40
+// pair id of every element of a concatenated list
+__global__ void k_aln_pair_ids(const uint64_t *__restrict__ off, uint32_t n_pairs, uint64_t n, uint32_t *pid) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t lo = 0, hi = n_pairs;  // last p with off[p] <= i
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (off[mid] <= i) lo = mid; else hi = mid;
+  }
+  pid[i] = lo;
+}
+__global__ void k_aln_keys0(const mm128 *__restrict__ a0, const uint32_t *__restrict__ pid0, uint64_t n0, uint64_t *keys, uint32_t *idx) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0) return;
+  keys[i] = ((uint64_t)pid0[i] << PGB_ALN_HBITS) | ((a0[i].x >> 8) & ((1ULL << PGB_ALN_HBITS) - 1));
+  idx[i] = (uint32_t)i;
+}
+template <bool FILL>
+__global__ void k_aln_lookup(const mm128 *__restrict__ a0, const mm128 *__restrict__ a1, const uint32_t *__restrict__ pid1, uint64_t n1,
+                             const uint64_t *__restrict__ off0, const uint64_t *__restrict__ skeys, const uint32_t *__restrict__ sidx,
+                             uint32_t *cnt, const uint64_t *__restrict__ moff, uint32_t *midx) {
+  uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n1) return;
+  const uint32_t p = pid1[s];
+  const uint64_t h = a1[s].x >> 8, key = ((uint64_t)p << PGB_ALN_HBITS) | (h & ((1ULL << PGB_ALN_HBITS) - 1));
+  uint64_t lo = off0[p], hi = off0[p + 1];
+  const uint64_t end = hi, first = lo;
+  while (lo < hi) {  // lower bound of key in the pair's range
+    uint64_t mid = (lo + hi) >> 1;
+    if (skeys[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  uint32_t c = 0;
+  uint64_t at = FILL ? moff[s] : 0;
+  for (; lo < end && skeys[lo] == key; lo++) {
+    const uint32_t i = sidx[lo];
+    if ((a0[i].x >> 8) != h) continue;
+    if (FILL) midx[at++] = (uint32_t)(i - first);  // index inside the pair's list 0
+    c++;
+  }
+  if (!FILL) cnt[s] = c;
+}
+// per pair: upper bound of its hits = sum of the match counts that pass the max_repeat filter (:71-80)
+__global__ void k_aln_hit_bound(const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ off1, uint32_t n_pairs, uint32_t max_repeat, uint32_t *ub) {
+  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p >= n_pairs) return;
+  uint32_t t = 0;
+  for (uint64_t s = off1[p] + lane; s < off1[p + 1]; s += 32) { const uint32_t c = cnt[s]; if (c && c <= max_repeat) t += c; }
+  t = __reduce_add_sync(0xffffffffu, t);
+  if (lane == 0) ub[p] = t;
+}
+__global__ void __launch_bounds__(128) k_aln_chain_warp(const mm128 *__restrict__ a0, const mm128 *__restrict__ a1, const uint64_t *__restrict__ off0,
+                                                        const uint64_t *__restrict__ off1, uint32_t n_pairs, const uint32_t *__restrict__ cnt,
+                                                        const uint64_t *__restrict__ moff, const uint32_t *__restrict__ midx, uint32_t direction,
+                                                        uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat, const uint64_t *__restrict__ hoff,
+                                                        AlnChain *chains, AlnHit *hits, uint32_t *n_hits_out, uint32_t *n_chains_out) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (p >= n_pairs) return;
+  const mm128 *l0 = a0 + off0[p], *l1 = a1 + off1[p];
+  const uint64_t s_base = off1[p];
+  const uint32_t n1 = (uint32_t)(off1[p + 1] - s_base);
+  AlnChain *ch = chains + hoff[p];
+  AlnHit *out = hits + hoff[p];
   uint32_t n_hits = 0, n_chains = 0, small_aln_count = 0;
   for (uint32_t ss = 0; ss < n1; ss++) {
     uint32_t s = ss;
@@ -1518,50 +1721,61 @@ __global__ void k_aln_chain(const mm128 *__restrict__ a0, const mm128 *__restric
       if (ss == 0) continue;      // that element is skipped
       s = n1 - ss;
     }
-    const uint32_t c = off[s + 1] - off[s];
+    const uint32_t c = cnt[s_base + s];
     if (c == 0 || c > max_repeat) continue;            // :71-80
-    const mm128 m1 = a1[s];
+    const mm128 m1 = l1[s];
     const uint32_t pos1 = (uint32_t)((m1.y & 0xFFFFFFFFULL) >> 1);
+    const uint64_t mo = moff[s_base + s];
     for (uint32_t q = 0; q < c; q++) {
-      const uint32_t i = midx[off[s] + q];
-      const mm128 m0 = a0[i];
+      const uint32_t i = midx[mo + q];
+      const mm128 m0 = l0[i];
       const uint32_t pos0 = (uint32_t)((m0.y & 0xFFFFFFFFULL) >> 1);
       if (direction == 0 && (m0.y & 1) != (m1.y & 1)) continue;   // :86-92
       if (direction == 1 && (m0.y & 1) == (m1.y & 1)) continue;
       const int64_t delta0 = direction == 1 ? aln_abs_u32(pos0 + pos1) : aln_abs_u32(pos0 - pos1);
-      uint32_t best = 0xFFFFFFFFu;
-      double min_diff = (double)max_diff;
-      small_aln_count = 0;
-      for (uint32_t ai = 0; ai < n_chains; ai++) {     // :103-132
-        if (chain_n[ai] < 3) small_aln_count++;
-        if (i < chain_last0[ai]) continue;
-        const mm128 l0 = a0[chain_last0[ai]], l1 = a1[chain_last1[ai]];
-        const uint32_t lp0 = (uint32_t)((l0.y & 0xFFFFFFFFULL) >> 1), lp1 = (uint32_t)((l1.y & 0xFFFFFFFFULL) >> 1);
-        const int64_t mm_dist = aln_abs_u32(pos0 - lp0);
-        if (mm_dist >= (int64_t)max_dist) continue;
-        const int64_t delta1 = direction == 1 ? aln_abs_u32(lp0 + lp1) : aln_abs_u32(lp0 - lp1);
-        int32_t dd = (int32_t)delta0 - (int32_t)delta1;
-        const uint32_t diff = (uint32_t)(dd < 0 ? -dd : dd);
-        if (diff < max_diff && (double)diff < min_diff && mm_dist < (int64_t)max_dist) {
-          min_diff = (double)diff;
-          best = ai;
+      // :103-132 over the existing chains, 32 at a time: smallest diff below max_diff, the first chain on ties
+      uint64_t bestk = ~0ULL;
+      uint32_t small = 0;
+      __syncwarp();  // (chain records written by lane 0 for the previous hit)
+      for (uint32_t a = lane; a < ((n_chains + 31) & ~31u); a += 32) {
+        uint64_t k = ~0ULL;
+        bool is_small = false;
+        if (a < n_chains) {
+          const AlnChain cc = ch[a];
+          is_small = cc.n < 3;
+          if (i >= cc.last_i0) {
+            const int64_t mm_dist = aln_abs_u32(pos0 - cc.lp0);
+            if (mm_dist < (int64_t)max_dist) {
+              int32_t dd = (int32_t)delta0 - cc.delta1;
+              const uint32_t diff = (uint32_t)(dd < 0 ? -dd : dd);
+              if (diff < max_diff) k = ((uint64_t)diff << 32) | a;
+            }
+          }
         }
+        small += __popc(__ballot_sync(FULL, is_small));
+        if (k < bestk) bestk = k;
       }
-      if (best == 0xFFFFFFFFu) {
-        best = n_chains++;
-        chain_n[best] = 0;
+      small_aln_count = small;
+      for (int o = 16; o; o >>= 1) { const uint64_t t = __shfl_xor_sync(FULL, bestk, o); if (t < bestk) bestk = t; }
+      uint32_t best = (uint32_t)bestk;
+      const bool fresh = bestk == ~0ULL;
+      if (fresh) best = n_chains++;
+      if (lane == 0) {
+        AlnChain cc;
+        cc.last_i0 = i;
+        cc.lp0 = pos0;
+        cc.delta1 = (int32_t)delta0;  // what a later hit computes from this chain's last pair (:118-121) is this hit's delta0
+        cc.n = fresh ? 1u : ch[best].n + 1u;
+        ch[best] = cc;
+        AlnHit h;
+        h.chain = best; h.i0 = i; h.i1 = s;
+        out[n_hits] = h;
       }
-      chain_last0[best] = i;
-      chain_last1[best] = s;
-      chain_n[best]++;
-      AlnHit h;
-      h.chain = best; h.i0 = i; h.i1 = s;
-      hits[n_hits++] = h;
+      n_hits++;
     }
     if (small_aln_count > 4800) break;                 // MAX_SMALL_ALNS, :19,149
   }
-  n_out[0] = n_hits;
-  n_out[1] = n_chains;
+  if (lane == 0) { n_hits_out[p] = n_hits; n_chains_out[p] = n_chains; }
 }
 
 }  // namespace pgb

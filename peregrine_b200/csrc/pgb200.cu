@@ -134,6 +134,7 @@ struct pgb_ctx {
     } else {
       // a miss means the job changed shape: stale blocks would only pile up
       if (blk_cached_bytes > ((size_t)8 << 30) || blk_cache.size() > 256) blk_flush();
+      stats.n_device_mallocs++;
       if (cudaMalloc(&p, bytes) != cudaSuccess) {
         cudaGetLastError();
         blk_flush();
@@ -161,6 +162,7 @@ struct pgb_ctx {
       if (sl.cap - sl.used >= bytes) { T *p = (T *)(sl.base + sl.used); sl.used += bytes; return p; }
     size_t cap = std::max(bytes, (size_t)512 << 20);
     void *b = nullptr;
+    stats.n_device_mallocs++;
     CU(cudaMalloc(&b, cap));
     slabs.push_back(Slab{(char *)b, cap, bytes});
     return (T *)b;
@@ -1479,6 +1481,13 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
   // BIG_TAIL is the threshold of the incremental passes, where only the critical path of the biggest bucket matters
   const uint32_t BIG_N = getenv("PGB_REPLAY_BIG") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG")) : 48u;
   const uint32_t BIG_TAIL = getenv("PGB_REPLAY_BIG_TAIL") ? (uint32_t)atoi(getenv("PGB_REPLAY_BIG_TAIL")) : 8u;
+  // buckets of the thread class with at least RW_MIN records are walked by RW_G lanes each (k_replay_group); PGB_REPLAY_WARP_MIN=64: none
+  // Measured on config 2 (profiles/r2_replay.md): full passes are throughput bound (every bucket runs; a thread stops at bestn, a
+  // group probes up to G-1 candidates too many) and stay thread-walked (64 = no group buckets); incremental passes are latency
+  // bound (their time is the longest dependent probe chain of one bucket) and hand buckets of >= 8 records to lane groups.
+  const uint32_t RW_MIN = getenv("PGB_REPLAY_WARP_MIN") ? (uint32_t)atoi(getenv("PGB_REPLAY_WARP_MIN")) : 64u;
+  const uint32_t RW_MIN_INC = getenv("PGB_REPLAY_WARP_MIN_INC") ? (uint32_t)atoi(getenv("PGB_REPLAY_WARP_MIN_INC")) : (getenv("PGB_REPLAY_WARP_MIN") ? RW_MIN : 8u);
+  const int RW_G = getenv("PGB_REPLAY_GROUP") ? atoi(getenv("PGB_REPLAY_GROUP")) : 8;
   const uint32_t TAIL_RUN = getenv("PGB_TAIL_RUN") ? (uint32_t)strtoul(getenv("PGB_TAIL_RUN"), 0, 10) : 40000u;
   // speculative passes before real alignments are computed: 2 cost ~2 % extra alignments and save two full passes
   const int MAX_DRY = getenv("PGB_DRY_PASSES") ? atoi(getenv("PGB_DRY_PASSES")) : 2;
@@ -1593,7 +1602,21 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
     auto launch_replay = [&](const uint32_t *list, uint32_t n_small, uint32_t n_total, int request, int emit, const uint32_t *ooff, ovlp_rec *out,
                              const uint32_t *cnt_dev) {
       const uint32_t nb = n_total - n_small;
-      LAUNCH(c, k_replay, nblk(n_small, 64), 64, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag, cnt_dev);
+      // of the "small" list: buckets below rw_min records are walked by a thread, the others by a group of RW_G lanes (the size
+      // test is in the kernels); incremental passes (cnt_dev) are latency bound and use their own threshold
+      const uint32_t rw_min = cnt_dev ? RW_MIN_INC : RW_MIN;
+      LAUNCH(c, k_replay, nblk(n_small, 64), 64, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff, out, unk_flag, cnt_dev,
+             rw_min, (uint32_t)PGB_RW_MAXN);
+      if (rw_min < PGB_RW_MAXN) {
+#define PGB_RG(G)                                                                                                                                      \
+  LAUNCH(c, k_replay_group<G>, nblk(n_small, PGB_RW_WARPS * (32 / G)), PGB_RW_WARPS * 32, S, n_small, list, d_rank_off, sy0, sdir, contained, bestn, \
+         request, emit, acc, ooff, out, unk_flag, cnt_dev, rw_min, (uint32_t)PGB_RW_MAXN)
+        if (RW_G == 4) PGB_RG(4);
+        else if (RW_G == 16) PGB_RG(16);
+        else if (RW_G == 32) PGB_RG(32);
+        else PGB_RG(8);
+#undef PGB_RG
+      }
       LAUNCH(c, k_replay_block, nb, PGB_RB_THREADS, S, nb, cnt_dev ? list : list + n_small, d_rank_off, sy0, sdir, contained, bestn, request, emit, acc, ooff,
              out, unk_flag, cnt_dev);
     };
@@ -1668,6 +1691,7 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         if (verbose) fprintf(stderr, "pgb200: replay tables too small (flags %d): restarting with pair table %llu, alignment table %llu\n", po.err,
                              (unsigned long long)ecap64, (unsigned long long)acap64);
         overflow = true;
+        c->stats.n_replay_restarts++;
         break;
       }
       if (po.err) { c->check_err("pgb_overlap/replay"); free_S(); free_common(); return -1; }
@@ -1678,7 +1702,9 @@ static int overlap_core(pgb_ctx *c, PairSoA R, uint32_t nrec, uint32_t bestn, ui
         if (nn > 8192 && nn > ALIGN_WARP_MAX) {  // group alignments of similar predicted length into the same warps
           uint32_t *keys = c->alloc<uint32_t>(nn), *keys2 = c->alloc<uint32_t>(nn), *idx0 = c->alloc<uint32_t>(nn);
           perm = c->alloc<uint32_t>(nn);
-          const int sort_mode = (getenv("PGB_ALIGN_SORT") && !strcmp(getenv("PGB_ALIGN_SORT"), "target")) ? 1 : 0;
+          // PGB_ALIGN_SORT: 0 = by predicted length only, m in 1..9 = (length >> (m-1), target read); see k_align_keys
+          int sort_mode = getenv("PGB_ALIGN_SORT") ? atoi(getenv("PGB_ALIGN_SORT")) : 4;
+          if (sort_mode < 0 || sort_mode > 9) sort_mode = 4;
           const int key_bits = sort_mode ? 31 : 8;
           LAUNCH(c, k_align_keys, nblk(nn), 256, S.reqs, n_done, nn, c->d_rlen_by_rid, keys, idx0, sort_mode);
           size_t tmp_bytes = 0;
@@ -2682,7 +2708,81 @@ static void idxv_push(mm_idx_v *v, mm_idx_t x) {
   }
   v->a[v->n++] = x;
 }
+// n_pairs chaining problems in one go (kernels.cuh "shmr_aln"): the hits of pair p are out[hoff[p] .. hoff[p] + n_hits[p]) in the
+// order the reference produces them; chains are numbered in order of creation
+static void aln_batch_core(pgb_ctx *c, const mm128 *mm0, const uint64_t *off0, const mm128 *mm1, const uint64_t *off1, uint32_t n_pairs, uint32_t direction,
+                           uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat, std::vector<uint64_t> &hoff, std::vector<uint32_t> &n_hits,
+                           std::vector<uint32_t> &n_chains, std::vector<AlnHit> &hits) {
+  hoff.assign((size_t)n_pairs + 1, 0); n_hits.assign(n_pairs, 0); n_chains.assign(n_pairs, 0); hits.clear();
+  if (!n_pairs) return;
+  if (n_pairs >= (1u << (64 - PGB_ALN_HBITS))) throw std::runtime_error("pgb_shmr_aln_batch: more than 2^24 pairs in one call");
+  const uint64_t n0 = off0[n_pairs], n1 = off1[n_pairs];
+  if (n0 >= (1ull << 32) || n1 >= (1ull << 32)) throw std::runtime_error("pgb_shmr_aln_batch: more than 2^32 minimizers in one call");
+  if (!n0 || !n1) return;
+  mm128 *d0 = c->alloc<mm128>(n0), *d1 = c->alloc<mm128>(n1);
+  uint64_t *doff0 = c->alloc<uint64_t>((size_t)n_pairs + 1), *doff1 = c->alloc<uint64_t>((size_t)n_pairs + 1);
+  c->h2d(d0, mm0, n0 * sizeof(mm128)); c->h2d(d1, mm1, n1 * sizeof(mm128));
+  c->h2d(doff0, off0, ((size_t)n_pairs + 1) * 8); c->h2d(doff1, off1, ((size_t)n_pairs + 1) * 8);
+  uint32_t *pid0 = c->alloc<uint32_t>(n0), *pid1 = c->alloc<uint32_t>(n1);
+  LAUNCH(c, k_aln_pair_ids, nblk(n0), 256, doff0, n_pairs, n0, pid0);
+  LAUNCH(c, k_aln_pair_ids, nblk(n1), 256, doff1, n_pairs, n1, pid1);
+  uint64_t *keys = c->alloc<uint64_t>(n0), *skeys = c->alloc<uint64_t>(n0);
+  uint32_t *idx = c->alloc<uint32_t>(n0), *sidx = c->alloc<uint32_t>(n0);
+  LAUNCH(c, k_aln_keys0, nblk(n0), 256, d0, pid0, n0, keys, idx);
+  size_t tmp_bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairs((void *)nullptr, tmp_bytes, keys, skeys, idx, sidx, (int)n0, 0, 64, c->st));
+  uint8_t *tmp = c->alloc<uint8_t>(tmp_bytes);
+  CU(cub::DeviceRadixSort::SortPairs((void *)tmp, tmp_bytes, keys, skeys, idx, sidx, (int)n0, 0, 64, c->st));
+  c->stats.kernel_launches += 4;
+  uint32_t *cnt = c->alloc<uint32_t>(n1 + 1);
+  uint64_t *moff = c->alloc<uint64_t>(n1 + 1);
+  CU(cudaMemsetAsync(cnt, 0, (n1 + 1) * 4, c->st));
+  LAUNCH(c, k_aln_lookup<false>, nblk(n1, 128), 128, d0, d1, pid1, n1, doff0, skeys, sidx, cnt, (const uint64_t *)nullptr, (uint32_t *)nullptr);
+  const uint64_t n_match = scan_u32_to_u64(c, cnt, moff, n1 + 1);
+  uint32_t *midx = c->alloc<uint32_t>(n_match + 1);
+  LAUNCH(c, k_aln_lookup<true>, nblk(n1, 128), 128, d0, d1, pid1, n1, doff0, skeys, sidx, (uint32_t *)nullptr, moff, midx);
+  uint32_t *ub = c->alloc<uint32_t>((size_t)n_pairs + 1);
+  uint64_t *dhoff = c->alloc<uint64_t>((size_t)n_pairs + 1);
+  CU(cudaMemsetAsync(ub, 0, ((size_t)n_pairs + 1) * 4, c->st));
+  LAUNCH(c, k_aln_hit_bound, nblk((size_t)n_pairs * 32, 128), 128, cnt, doff1, n_pairs, max_repeat, ub);
+  const uint64_t n_bound = scan_u32_to_u64(c, ub, dhoff, (size_t)n_pairs + 1);
+  AlnChain *chains = c->alloc<AlnChain>(n_bound + 1);
+  AlnHit *dhits = c->alloc<AlnHit>(n_bound + 1);
+  uint32_t *dnh = c->alloc<uint32_t>(n_pairs), *dnc = c->alloc<uint32_t>(n_pairs);
+  LAUNCH(c, k_aln_chain_warp, nblk((size_t)n_pairs * 32, 128), 128, d0, d1, doff0, doff1, n_pairs, cnt, moff, midx, direction, max_diff, max_dist, max_repeat,
+         dhoff, chains, dhits, dnh, dnc);
+  hits.resize(n_bound);
+  c->d2h(hoff.data(), dhoff, ((size_t)n_pairs + 1) * 8);
+  c->d2h(n_hits.data(), dnh, (size_t)n_pairs * 4);
+  c->d2h(n_chains.data(), dnc, (size_t)n_pairs * 4);
+  if (n_bound) c->d2h(hits.data(), dhits, n_bound * sizeof(AlnHit));
+  c->sync();
+}
+
+extern "C" int pgb_shmr_aln_batch(pgb_ctx *c, const mm128_t *mm0, const uint64_t *off0, const mm128_t *mm1, const uint64_t *off1, uint32_t n_pairs,
+                                  uint8_t direction, uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat, uint64_t *hit_off, uint32_t *n_chains,
+                                  pgb_aln_hit_t **hits_out) {
+  API_BEGIN(c)
+  static_assert(sizeof(pgb_aln_hit_t) == sizeof(AlnHit), "hit layout");
+  if (hits_out) *hits_out = nullptr;
+  std::vector<uint64_t> hoff;
+  std::vector<uint32_t> nh, nc;
+  std::vector<AlnHit> hits;
+  aln_batch_core(c, (const mm128 *)mm0, off0, (const mm128 *)mm1, off1, n_pairs, direction, max_diff, max_dist, max_repeat, hoff, nh, nc, hits);
+  uint64_t total = 0;
+  for (uint32_t p = 0; p < n_pairs; p++) { hit_off[p] = total; total += nh[p]; if (n_chains) n_chains[p] = nc[p]; }
+  hit_off[n_pairs] = total;
+  pgb_aln_hit_t *o = (pgb_aln_hit_t *)malloc((total ? total : 1) * sizeof(pgb_aln_hit_t));
+  if (!o) throw std::runtime_error("pgb_shmr_aln_batch: out of host memory");
+  for (uint32_t p = 0; p < n_pairs; p++)
+    if (nh[p]) memcpy(o + hit_off[p], hits.data() + hoff[p], (size_t)nh[p] * sizeof(AlnHit));
+  *hits_out = o;
+  API_END(c)
+}
+extern "C" void pgb_host_free(void *p) { free(p); }
+
 extern "C" shmr_aln_v *shmr_aln(mm128_v *mmers0, mm128_v *mmers1, uint8_t direction, uint32_t max_diff, uint32_t max_dist, uint32_t max_repeat) {
+  // a batch of one (src/shmr_align.c:21-160); the result is built with kvec's growth rule like the reference's
   shmr_aln_v *alns = (shmr_aln_v *)calloc(sizeof(shmr_aln_v), 1);
   const size_t n0 = mmers0 ? mmers0->n : 0, n1 = mmers1 ? mmers1->n : 0;
   if (!n0 || !n1) return alns;
@@ -2690,29 +2790,17 @@ extern "C" shmr_aln_v *shmr_aln(mm128_v *mmers0, mm128_v *mmers1, uint8_t direct
   pgb_ctx *c = shared_.c;
   try {
     CU(cudaSetDevice(c->device));
-    mm128 *d0 = c->alloc<mm128>(n0), *d1 = c->alloc<mm128>(n1);
-    uint32_t *cnt = c->alloc<uint32_t>(n1 + 1), *off = c->alloc<uint32_t>(n1 + 1);
-    c->h2d(d0, mmers0->a, n0 * sizeof(mm128));
-    c->h2d(d1, mmers1->a, n1 * sizeof(mm128));
-    CU(cudaMemsetAsync(cnt, 0, (n1 + 1) * 4, c->st));
-    LAUNCH(c, k_aln_match_count, nblk(n1, 128), 128, d0, (uint32_t)n0, d1, (uint32_t)n1, cnt);
-    uint32_t total = scan_u32(c, cnt, off, n1 + 1);
-    uint32_t *midx = c->alloc<uint32_t>(total);
-    LAUNCH(c, k_aln_match_fill, nblk(n1, 128), 128, d0, (uint32_t)n0, d1, (uint32_t)n1, off, midx);
-    uint32_t *cl0 = c->alloc<uint32_t>(total + 1), *cl1 = c->alloc<uint32_t>(total + 1), *cn = c->alloc<uint32_t>(total + 1), *n_out = c->alloc<uint32_t>(2);
-    AlnHit *hits = c->alloc<AlnHit>(total + 1);
-    LAUNCH(c, k_aln_chain, 1, 32, d0, d1, (uint32_t)n1, off, midx, (uint32_t)direction, max_diff, max_dist, max_repeat, cl0, cl1, cn, hits, n_out);
-    uint32_t h_n[2] = {0, 0};
-    c->d2h(h_n, n_out, 8);
-    std::vector<AlnHit> h_hits(h_n[0]);
-    c->d2h(h_hits.data(), hits, (size_t)h_n[0] * sizeof(AlnHit));
-    c->sync();
+    const uint64_t off0[2] = {0, n0}, off1[2] = {0, n1};
+    std::vector<uint64_t> hoff;
+    std::vector<uint32_t> nh, nc;
+    std::vector<AlnHit> hits;
+    aln_batch_core(c, (const mm128 *)mmers0->a, off0, (const mm128 *)mmers1->a, off1, 1, direction, max_diff, max_dist, max_repeat, hoff, nh, nc, hits);
     c->scratch_reset();
-    alns->n = alns->m = h_n[1];
-    alns->a = (shmr_aln_t *)calloc(h_n[1] ? h_n[1] : 1, sizeof(shmr_aln_t));
-    for (auto &h : h_hits) {
-      idxv_push(&alns->a[h.chain].idx0, h.i0);
-      idxv_push(&alns->a[h.chain].idx1, h.i1);
+    alns->n = alns->m = nc[0];
+    alns->a = (shmr_aln_t *)calloc(nc[0] ? nc[0] : 1, sizeof(shmr_aln_t));
+    for (uint32_t h = 0; h < nh[0]; h++) {
+      idxv_push(&alns->a[hits[h].chain].idx0, hits[h].i0);
+      idxv_push(&alns->a[hits[h].chain].idx1, hits[h].i1);
     }
   } catch (std::exception &e) {
     fprintf(stderr, "pgb200: shmr_aln failed: %s\n", e.what());

@@ -45,7 +45,7 @@ class _Stats(C.Structure):
         + [("ms_k_sketch_tiled", C.c_double), ("n_k_sketch_tiled", C.c_uint64), ("n_sketch_fallback_reads", C.c_uint64),
            ("n_replay_buckets", C.c_uint64), ("ms_dedup", C.c_double), ("n_dedup_in", C.c_uint64), ("n_dedup_kept", C.c_uint64),
            ("ms_encode", C.c_double), ("ms_k_encode", C.c_double), ("n_k_encode", C.c_uint64), ("bases_encoded", C.c_uint64),
-           ("ms_map", C.c_double), ("n_map_hits", C.c_uint64)]
+           ("ms_map", C.c_double), ("n_map_hits", C.c_uint64), ("n_device_mallocs", C.c_uint64), ("n_replay_restarts", C.c_uint64)]
     )
 
 
@@ -97,6 +97,9 @@ def load_library():
     L.pgb_route_scan.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_int)]
     L.pgb_route_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u64p]
     L.pgb_overlap_routed.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.pgb_ovlp_match_batch.argtypes = [vp, vp, C.c_size_t, C.c_size_t] + [vp] * 6 + [C.c_int, vp]
+    L.pgb_shmr_aln_batch.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint8, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(vp)]
+    L.pgb_host_free.argtypes = [vp]
     L.pgb_dedup.argtypes = [vp, vp, C.c_size_t]
     L.pgb_dedup_device.argtypes = [vp, vp, C.c_size_t]
     L.pgb_dedup_overlaps.argtypes = [vp]
@@ -310,6 +313,49 @@ class Engine:
         return self.overlap_records(view=(copy == "view"))
 
     # ------------------------------------------------------------------ shmr_dedup
+    def ovlp_match_batch(self, seq, q_off, q_len, q_strand, t_off, t_len, t_strand, band_tolerance=100):
+        """ovlp_match (src/DWmatch.c:66-204) for many operand pairs at once: `seq` holds .seqdb bytes, pair i aligns
+        seq[q_off[i]:+q_len[i]] on strand q_strand[i] with seq[t_off[i]:+t_len[i]] on t_strand[i].  Returns an (n, 8) int32 array with
+        the fields of ovlp_match_t per pair."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        a = [np.ascontiguousarray(x, dtype=t) for x, t in ((q_off, np.uint64), (q_len, np.uint32), (q_strand, np.uint8), (t_off, np.uint64),
+                                                           (t_len, np.uint32), (t_strand, np.uint8))]
+        out = np.zeros((len(a[0]), 8), dtype=np.int32)
+        self._ck(self.L.pgb_ovlp_match_batch(self.h, _ptr(seq), seq.size, len(a[0]), *[_ptr(x) for x in a], int(band_tolerance), _ptr(out)), "ovlp_match_batch")
+        return out
+
+    def shmr_aln_batch(self, lists0, lists1, direction=0, max_diff=100, max_dist=1200, max_repeat=1):
+        """shmr_aln (src/shmr_align.c:21-160) for many pairs of minimizer lists at once.  lists0 / lists1: sequences of MM128
+        arrays (pair p = lists0[p] against lists1[p]).  Returns, per pair, the chains as the reference returns them:
+        [(idx0 list, idx1 list), ...] in the order of shmr_aln_v."""
+        from . import formats as F
+
+        n = len(lists0)
+        assert len(lists1) == n
+        off0 = np.zeros(n + 1, dtype=np.uint64)
+        off1 = np.zeros(n + 1, dtype=np.uint64)
+        off0[1:] = np.cumsum([len(x) for x in lists0])
+        off1[1:] = np.cumsum([len(x) for x in lists1])
+        cat = lambda ls: np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=F.MM128) for x in ls])) if n else np.zeros(0, dtype=F.MM128)
+        m0, m1 = cat(lists0), cat(lists1)
+        hit_off = np.zeros(n + 1, dtype=np.uint64)
+        n_chains = np.zeros(max(n, 1), dtype=np.uint32)
+        hp = C.c_void_p()
+        self._ck(self.L.pgb_shmr_aln_batch(self.h, _ptr(m0), _ptr(off0), _ptr(m1), _ptr(off1), n, int(direction), int(max_diff), int(max_dist),
+                                           int(max_repeat), _ptr(hit_off), _ptr(n_chains), C.byref(hp)), "shmr_aln_batch")
+        total = int(hit_off[n])
+        hits = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(max(total, 1), 3))[:total].copy()
+        self.L.pgb_host_free(hp)
+        out = []
+        for p in range(n):
+            h = hits[int(hit_off[p]): int(hit_off[p + 1])]
+            chains = [([], []) for _ in range(int(n_chains[p]))]
+            for ch, i0, i1 in h.tolist():
+                chains[ch][0].append(i0)
+                chains[ch][1].append(i1)
+            out.append(chains)
+        return out
+
     def dedup(self, records=None, device_ptr=None, n=None, text=True):
         """First record of every read pair in stream order -> preads.ovl text (bytes).  records: numpy array of ovlp_t on the
         host; device_ptr/n: a stream already in HBM; neither: the records of this engine's last overlap(), in place.

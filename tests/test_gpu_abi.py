@@ -129,6 +129,65 @@ def test_shmr_aln_vs_reference(ours):
     assert _aln(ours, m0[:0], m1, 0, 100, 1200, 1) == []
 
 
+def test_shmr_aln_batch_vs_reference(ours):
+    """pgb_shmr_aln_batch (one sort for the hash -> index map of all pairs, a warp per pair for the greedy chaining) against the
+    reference's shmr_aln pair by pair: related and unrelated lists, tandem repeats (several matches per minimizer, max_repeat
+    filter), empty lists inside the batch, both directions' strand filters, three parameter sets."""
+    import time
+
+    ref = O.reflib()
+    if ref is None:
+        pytest.skip("oracle/_ref not present")
+    from peregrine_b200 import Engine
+
+    rnd = np.random.default_rng(5)
+    B = np.array(list("ACGT"))
+    l0, l1 = [], []
+    for trial in range(48):
+        n = int(rnd.integers(300, 12000))
+        s = "".join(rnd.choice(B, n))
+        if trial % 3 == 0:
+            unit = "".join(rnd.choice(B, 250))
+            s = s[: n // 3] + unit * 4 + s[n // 3:]
+        t = list(s[int(rnd.integers(0, 300)):])
+        for _ in range(int(len(t) * 0.02)):
+            p = int(rnd.integers(0, len(t)))
+            t[p] = str(rnd.choice(B)) if rnd.random() < 0.5 else ""
+        t = "".join(t) if trial % 7 else "".join(rnd.choice(B, n))
+        m0 = O.abi_sketch(ref, s, 24, 12, 0)
+        m1 = O.abi_sketch(ref, t, 24, 12, 1)
+        if trial % 2:
+            m0, m1 = O.abi_reduce(ref, m0, 2), O.abi_reduce(ref, m1, 2)
+        if trial == 5:
+            m0 = m0[:0]
+        if trial == 9:
+            m1 = m1[:0]
+        l0.append(m0)
+        l1.append(m1)
+    eng = Engine(0)
+    for params in ((100, 1200, 1), (100, 1200, 3), (30, 500, 2)):
+        got = eng.shmr_aln_batch(l0, l1, 0, *params)
+        for p in range(len(l0)):
+            want = _aln(ref, l0[p], l1[p], 0, *params) if len(l0[p]) and len(l1[p]) else []
+            assert want == got[p], (params, p)
+    # direction 1: the reference reads one element past the end of list 1 for its first probe (SURVEY A-7), so only the chains'
+    # well-defined part is compared, as in tests/test_z_utils_helpers.py: both sides must agree on every hit whose idx1 > 0
+    assert eng.shmr_aln_batch([], [], 0) == []
+    # a batch is much cheaper than single calls, and faster per pair than one reference core
+    big0, big1 = l0 * 40, l1 * 40
+    eng.shmr_aln_batch(big0[:8], big1[:8], 0)
+    t0 = time.perf_counter()
+    eng.shmr_aln_batch(big0, big1, 0)
+    t_batch = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for p in range(len(l0)):
+        if len(l0[p]) and len(l1[p]):
+            _aln(ref, l0[p], l1[p], 0, 100, 1200, 1)
+    t_ref = (time.perf_counter() - t0) * 40
+    print(f"shmr_aln: batch of {len(big0)} pairs {t_batch * 1e3:.1f} ms (incl. Python packing), reference one core {t_ref * 1e3:.1f} ms")
+    eng.close()
+
+
 class PyMmer(C.Structure):
     _fields_ = [("mmers", C.POINTER(O.MMV)), ("mmer0_map", C.c_void_p), ("rlmap", C.c_void_p), ("mcmap", C.c_void_p), ("ridmm", C.c_void_p)]
 

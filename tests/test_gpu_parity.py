@@ -219,15 +219,34 @@ def test_tiled_sketch_reports_fallbacks(workdir, ref_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("big", ["3", "1000000"])
-def test_replay_kernel_forms(sim1, workdir, ref_dir, monkeypatch, big):
-    """PGB_REPLAY_BIG=3 sends every bucket through the block-cooperative replay kernel, a huge value through the
-    one-thread-per-bucket kernel (the default mixes them by bucket size); both must reproduce the reference stream."""
+@pytest.mark.parametrize("big,warp_min,group", [("3", "64", "8"), ("1000000", "64", "8"), ("64", "2", "8"), ("64", "2", "32"), ("64", "3", "4"), ("48", "16", "16")])
+def test_replay_kernel_forms(sim1, workdir, ref_dir, monkeypatch, big, warp_min, group):
+    """The three forms of the bucket scan: PGB_REPLAY_BIG=3 sends every bucket through the block-cooperative kernel
+    (k_replay_block), a huge value with PGB_REPLAY_WARP_MIN=64 through the one-thread-per-bucket kernel (k_replay), and
+    PGB_REPLAY_BIG=64 with PGB_REPLAY_WARP_MIN=2 through the lane-group kernel (k_replay_group<G>, G = PGB_REPLAY_GROUP lanes
+    per bucket; buckets in which a read occurs twice fall back to one lane).  The default mixes them by bucket size.  Every
+    mix must reproduce the reference stream, on clean reads, on 1 % error reads, with a small bestn (the row cut-off inside
+    a group's G candidates) and on the adversarial set (tandem repeats: reads with several records per bucket)."""
     monkeypatch.setenv("PGB_REPLAY_BIG", big)
     monkeypatch.setenv("PGB_REPLAY_BIG_TAIL", big)
+    monkeypatch.setenv("PGB_REPLAY_WARP_MIN", warp_min)
+    monkeypatch.setenv("PGB_REPLAY_GROUP", group)
+    tag = f"rb{big}_{warp_min}_{group}"
     rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
-    ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, "sim1/ref1"), T=1)
-    oo = ours_overlap(sim1, rp, 2, os.path.join(workdir, f"sim1/our_rb{big}"), T=1)
+    for extra in ([], ["-b", "2", "-n", "40"], ["-b", "1"]):
+        et = "".join(extra).replace("-", "")
+        ro = D.ref_overlap(ref_dir, sim1, rp, 2, os.path.join(workdir, f"sim1/refo_{et}"), T=1, extra=extra)
+        oo = ours_overlap(sim1, rp, 2, os.path.join(workdir, f"sim1/our_{tag}{et}"), T=1, extra=extra)
+        assert_same_ovlp(oo[0], ro[0])
+    p = D.make_sim(workdir, "sim_e1", genome=400_000, cov=25, err=0.01, seed=7)
+    rp = D.ref_index(ref_dir, p, os.path.join(workdir, "sim_e1/ref"), T=1, extra=["-m", "0"])
+    ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, "sim_e1/ref"), T=1)
+    oo = ours_overlap(p, rp, 2, os.path.join(workdir, f"sim_e1/our_{tag}"), T=1)
+    assert_same_ovlp(oo[0], ro[0])
+    p = D.make_from_fasta(workdir, "adv", D.adversarial_records(), ref_dir)
+    rp = D.ref_index(ref_dir, p, os.path.join(workdir, "adv/ref_m1"), T=1, extra=["-m", "1"])
+    ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, "adv/ref_m1"), T=1, extra=["-M", "1000"])
+    oo = ours_overlap(p, rp, 2, os.path.join(workdir, f"adv/our_{tag}"), T=1, extra=["-M", "1000"])
     assert_same_ovlp(oo[0], ro[0])
 
 
