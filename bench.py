@@ -140,8 +140,8 @@ def ref_one(prefix, outdir):
     import datasets as D
 
     t = time.perf_counter()
-    rp = D.ref_index(REF, prefix, outdir, T=1, extra=["-m", "0"])
-    ro = D.ref_overlap(REF, prefix, rp, 2, outdir, T=1)
+    rp = D.ref_index(REF, prefix, outdir, T=1, extra=["-m", "0", "-k", str(PARAMS["k"]), "-w", str(PARAMS["w"])])
+    ro = D.ref_overlap(REF, prefix, rp, 2, outdir, T=1, extra=["-w", str(PARAMS["bw"])])
     return os.path.getsize(ro[0]) // 64, time.perf_counter() - t
 
 
@@ -203,7 +203,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "overlaps/s (index+overlap)", "value": v, "unit": "overlaps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "read_bases_per_s": bases * args.steps / tot_t,
-        "config": {"workload": "synthetic 30x 15 kb reads @99.5%, k=16 w=80 r=6 l=2, T=1 (bounded sample of configs[1])", "sample": sample},
+        "config": {"workload": "synthetic 30x 15 kb reads @99.5%, k=%d w=%d r=6 l=2, T=1 (bounded sample of configs[1])" % (PARAMS["k"], PARAMS["w"]), "sample": sample},
         "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "overlaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -431,7 +431,9 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": n_l / K,
-                "kernel_ms_per_step": {k_: v[0] / K for k_, v in kern.items()}}
+                "kernel_ms_per_step": {**{k_: v[0] / K for k_, v in kern.items()},
+                                       # the exact automaton on the reads the fast sketch kernel hands back (automaton pass + placement)
+                                       "k_sketch_exact": (st["ms_k_sketch_count"] + st["ms_k_sketch_write"]) / K}}
     # the same figure for each of the three heavy kernels (north_star asks for mm_sketch and the chaining kernels, not only the top
     # one); `limiter` = what the committed ncu captures (profiles/) show each kernel is actually bound by
     limiter = {"k_sketch_tiled": "integer ALU pipe (ncu: 58 % of the ALU pipe's peak, issue active 50 %; ~120 thread-instructions per base)",
@@ -448,7 +450,7 @@ def run_ours(args):
         "metric": "overlaps/s (index+overlap)", "value": n_ovl / (dev_ms * 1e-3), "unit": "overlaps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "read_bases_per_s": bases / (dev_ms * 1e-3),
-        "config": {"workload": f"synthetic {args.genome_mb * world:g} Mb genome, {args.cov:g}x 15 kb reads @99.5%, k=16 w=80 r=6 l=2, T={T}",
+        "config": {"workload": f"synthetic {args.genome_mb * world:g} Mb genome, {args.cov:g}x 15 kb reads @99.5%, k={P['k']} w={P['w']} r=6 l=2, T={T}",
                    "reads_per_rank": int(len(rid)), "bases": bases, "overlaps_per_step": int(n_ovl), "l2_flush": "inputs (1.5 GB image) exceed the 126 MB L2",
                    "wall_ms_per_step_device_resident": dev_wall * 1e3,
                    "sharding": ("reads by rid % N for the index, SHIMMER-hash chunk c of T=N for the overlap; " +
@@ -605,7 +607,7 @@ def run_chunked(args):
             "metric": "overlaps/s (index+overlap)", "value": n_ovl / sec, "unit": "overlaps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "read_bases_per_s": bases / sec,
-            "config": {"workload": f"synthetic {args.genome_mb:g} Mb genome, {args.cov:g}x 15 kb reads @99.5%, k=16 w=80 r=6 l=2, T={T} index chunks and {T} "
+            "config": {"workload": f"synthetic {args.genome_mb:g} Mb genome, {args.cov:g}x 15 kb reads @99.5%, k={P['k']} w={P['w']} r=6 l=2, T={T} index chunks and {T} "
                                    f"hash chunks on {world} GPU(s), {per} of each per GPU",
                        "bases": bases, "overlaps_per_step": n_ovl, "alignments_per_step": n_aln,
                        "timing": "host clock around barrier + synchronize (the step spans two engines and the NCCL streams); inputs are host buffers: "
@@ -669,9 +671,13 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="T index chunks and T hash chunks of ONE genome of --genome-mb (total) on the N GPUs "
                                                           "(strong-scaling / configs[2..3] mode; T must be a multiple of N)")
     ap.add_argument("--ref-genome-mb", type=float, default=4.0, help="reference arm: genome size of each per-core sample")
+    ap.add_argument("--k", type=int, default=16, help="k-mer size (BASELINE.json configs[4] sweeps 14/16/18; k > 16 takes the 64-bit sketch kernel)")
+    ap.add_argument("--w", type=int, default=80, help="minimizer window (configs[4]: 60/80/120)")
+    ap.add_argument("--aln-bw", type=int, default=100, help="ovlp_match band tolerance, shmr_overlap -w (configs[4]: 50/100/200)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="routed", choices=["routed", "gathered"], help="multi-GPU exchange step (N > 1)")
     args = ap.parse_args()
+    PARAMS.update(k=args.k, w=args.w, bw=args.aln_bw)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -275,22 +275,35 @@ __global__ void k_sketch_exact(const uint64_t *__restrict__ w, const uint32_t *_
 // MODE 0: count per segment.  MODE 1: write at the final place (needs the counts' scan).  MODE 2: count AND stage the records
 // in a per-segment buffer of `stage_cap` records (one pass of the automaton instead of two; a segment that overflows its
 // buffer raises *overflow and the caller falls back to MODE 1).
+// A segment is a "piece" [seg_lo, seg_hi) of a read.  seg_kind 0: redone by the automaton (this kernel).  seg_kind 1 (reads of
+// which only some strips are redone, sketch_strip.cuh): the fast path's records with positions in the piece stand; this kernel
+// skips such pieces, k_seg_fast_count counts them and k_seg_place copies them.
 template <int MODE>
 __global__ void k_sketch_exact_seg(const uint64_t *__restrict__ w, const uint32_t *__restrict__ nm, const uint32_t *__restrict__ seg_row,
-                                   const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_first, uint32_t n_seg, int seg_len,
-                                   const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ row_len,
+                                   const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi, const uint8_t *__restrict__ seg_kind,
+                                   const uint32_t *__restrict__ seg_first, uint32_t n_seg, const uint32_t *__restrict__ row_rid, const uint32_t *__restrict__ row_len,
                                    const uint64_t *__restrict__ row_woff, const uint32_t *__restrict__ hasn_by_rid, int wsz, int k,
                                    uint32_t *__restrict__ seg_cnt, const uint32_t *__restrict__ seg_pos,
-                                   const uint64_t *__restrict__ off_by_row, mm128 *__restrict__ out, uint32_t stage_cap, int *overflow) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_seg) return;
+                                   const uint64_t *__restrict__ off_by_row, mm128 *__restrict__ out, uint32_t stage_cap, int *overflow,
+                                   uint32_t lane_stride) {
+  // Only every lane_stride-th lane takes a piece.  The lanes of a warp rescan their rings at different positions (whenever a
+  // lane's minimum leaves its window), and a rescan is a chain of ~2w dependent shared-memory loads that every other lane of the
+  // warp waits for: with few pieces (the usual case: a handful of bad strips) one piece per warp is 10x faster than 32.
+  if (threadIdx.x % lane_stride) return;
+  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) / lane_stride;
+  if (s >= n_seg || seg_kind[s]) return;
   const uint32_t row = seg_row[s];
   const uint32_t rid = row_rid[row];
   const int len = (int)row_len[row];
-  const int lo = (int)seg_lo[s];
-  const int hi = lo + seg_len < len ? lo + seg_len : len;
-  uint64_t ring_x[256];
-  uint32_t ring_p[256];
+  const int lo = (int)seg_lo[s], hi = (int)seg_hi[s];
+  // the w-slot rings of the CTA's threads, interleaved in shared memory (slot j of thread t at [j * blockDim.x + t]: conflict
+  // free).  The automaton rescans its ring whenever the minimum leaves the window (every ~w/2 positions per thread, so in
+  // nearly every step of a warp); with the rings in local memory that rescan ran at L2 latency and the kernel took 1.5 ms for
+  // the 0.4 % of the reads that need it
+  extern __shared__ uint64_t seg_smem[];
+  const int rs = (int)(blockDim.x / lane_stride);
+  uint64_t *ring_x = seg_smem + threadIdx.x / lane_stride;
+  uint32_t *ring_p = (uint32_t *)(seg_smem + (size_t)wsz * rs) + threadIdx.x / lane_stride;
   uint32_t n = 0;
   mm128 *dst = MODE == 1 ? out + off_by_row[row] + (seg_pos[s] - seg_pos[seg_first[s]]) : (MODE == 2 ? out + (size_t)s * stage_cap : nullptr);
   auto em = [&](uint64_t x, uint64_t y) {
@@ -303,21 +316,47 @@ __global__ void k_sketch_exact_seg(const uint64_t *__restrict__ w, const uint32_
   const uint32_t *nmp = hasn_by_rid[rid] ? nm : nullptr;
   int st = lo - sketch_warmup_len(wsz, k);
   if (st < 0) st = 0;
-  if (!sketch_exact_range(w, nmp, row_woff[row], len, wsz, k, rid, st, lo, hi, ring_x, ring_p, em)) {
+  if (!sketch_exact_range(w, nmp, row_woff[row], len, wsz, k, rid, st, lo, hi, ring_x, ring_p, em, rs)) {
     n = 0;  // warm-up too short (palindrome-dense stretch): replay from the read start
-    sketch_exact_range(w, nmp, row_woff[row], len, wsz, k, rid, 0, lo, hi, ring_x, ring_p, em);
+    sketch_exact_range(w, nmp, row_woff[row], len, wsz, k, rid, 0, lo, hi, ring_x, ring_p, em, rs);
   }
   if (MODE != 1) seg_cnt[s] = n;
   if (MODE == 2 && n > stage_cap) atomicOr(overflow, 1);
 }
-// staged records of a segment -> their final place
-__global__ void k_seg_place(const uint32_t *__restrict__ seg_row, const uint32_t *__restrict__ seg_first, uint32_t n_seg, const uint32_t *__restrict__ seg_pos,
-                            const uint64_t *__restrict__ off_by_row, const mm128 *__restrict__ stage, uint32_t stage_cap, mm128 *__restrict__ out) {
-  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l = threadIdx.x & 7;  // 8 lanes per segment
+// pieces of kind 1: rank range of the read's fast-path records (position order in its slab) with seg_lo <= position < seg_hi
+__global__ void k_seg_fast_count(const uint32_t *__restrict__ seg_row, const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi,
+                                 const uint8_t *__restrict__ seg_kind, uint32_t n_seg, const uint64_t *__restrict__ tmp_off, const mm128 *__restrict__ tmp,
+                                 const uint32_t *__restrict__ fast_cnt, uint32_t *__restrict__ seg_cnt, uint32_t *__restrict__ seg_src) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg || !seg_kind[s]) return;
+  const uint32_t row = seg_row[s], n = fast_cnt[row];
+  const mm128 *a = tmp + tmp_off[row];
+  auto rank = [&](uint32_t pos) -> uint32_t {  // records with position < pos
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if ((((uint32_t)a[mid].y) >> 1) < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const uint32_t r0 = rank(seg_lo[s]), r1 = rank(seg_hi[s]);
+  seg_src[s] = r0;
+  seg_cnt[s] = r1 - r0;
+}
+// records of a piece -> their final place: staged automaton records (kind 0, unless they were written in place: !place_exact) or
+// the fast path's records of that position range (kind 1)
+__global__ void k_seg_place(const uint32_t *__restrict__ seg_row, const uint32_t *__restrict__ seg_first, const uint8_t *__restrict__ seg_kind,
+                            const uint32_t *__restrict__ seg_src, uint32_t n_seg, const uint32_t *__restrict__ seg_pos,
+                            const uint64_t *__restrict__ off_by_row, const mm128 *__restrict__ stage, uint32_t stage_cap,
+                            const uint64_t *__restrict__ tmp_off, const mm128 *__restrict__ tmp, mm128 *__restrict__ out, int place_exact) {
+  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l = threadIdx.x & 7;  // 8 lanes per piece
   if (s >= n_seg) return;
+  const uint32_t kind = seg_kind[s];
+  if (!kind && !place_exact) return;
   const uint32_t n = seg_pos[s + 1] - seg_pos[s];
-  mm128 *dst = out + off_by_row[seg_row[s]] + (seg_pos[s] - seg_pos[seg_first[s]]);
-  const mm128 *src = stage + (size_t)s * stage_cap;
+  const uint32_t row = seg_row[s];
+  mm128 *dst = out + off_by_row[row] + (seg_pos[s] - seg_pos[seg_first[s]]);
+  const mm128 *src = kind ? tmp + tmp_off[row] + seg_src[s] : stage + (size_t)s * stage_cap;
   for (uint32_t i = l; i < n; i += 8) dst[i] = src[i];
 }
 __global__ void k_seg_row_counts(const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_first_seg, uint32_t n_list,

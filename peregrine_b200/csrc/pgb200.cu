@@ -120,6 +120,15 @@ struct pgb_ctx {
   }
   void *blk_alloc(size_t bytes) {
     bytes = (bytes + 511) & ~(size_t)511;
+    // size classes (8 per octave) above 1 MB: table sizes that follow data-dependent counts (e.g. the alignment cache, sized from a
+    // pass's count of predicted alignments, which depends on the order in which concurrent buckets saw each other's entries)
+    // differ by a few entries from step to step; without classes a request just above the cached block's size is a miss, and a
+    // cudaMalloc in the middle of a step costs ~100 ms (bench.py e2e.device_mallocs shows them)
+    if (bytes >= ((size_t)1 << 20)) {
+      int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+      const size_t q = (size_t)1 << (lg - 3);
+      bytes = (bytes + q - 1) & ~(q - 1);
+    }
     int best = -1;
     for (int i = 0; i < (int)blk_cache.size(); i++)
       if (blk_cache[i].bytes >= bytes && blk_cache[i].bytes <= bytes + bytes / 4 + (1 << 20) && (best < 0 || blk_cache[i].bytes < blk_cache[best].bytes))
@@ -259,6 +268,14 @@ struct pgb_ctx {
   }
 };
 
+#define LAUNCH_SMEM(ctx, kern, grid, block, smem, ...)           \
+  do {                                                           \
+    if ((grid) > 0) {                                            \
+      kern<<<(grid), (block), (smem), (ctx)->st>>>(__VA_ARGS__); \
+      (ctx)->stats.kernel_launches++;                            \
+      CU(cudaGetLastError());                                    \
+    }                                                            \
+  } while (0)
 #define LAUNCH(ctx, kern, grid, block, ...)                      \
   do {                                                           \
     if ((grid) > 0) {                                            \
@@ -868,41 +885,91 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
   const bool use_tiled = w >= SK_MINW && !force_exact && !use_strip && ns > 0;
   // the reads the fast kernel hands back (flags in row_flags) are redone by the exact automaton, segment-parallel; both fast
   // paths share this tail: counts[] holds the fast rows' record counts, exact_flag[] marks the others
-  auto exact_tail = [&](uint32_t *row_flags, uint32_t *exact_flag, uint32_t *exact_pos, const std::function<void()> &place_fast) {
+  // (strip path only) row_bad / fast_cnt / tmp_off / tmp: reads of which only some strips are redone (SK_FLAG_PARTIAL, sketch_strip.cuh)
+  auto exact_tail = [&](uint32_t *row_flags, uint32_t *exact_flag, uint32_t *exact_pos, const std::function<void()> &place_fast, const uint64_t *row_bad,
+                        const uint32_t *fast_cnt, const uint64_t *tmp_off, const mm128 *tmp) {
     uint32_t n_exact = scan_u32(c, exact_flag, exact_pos, ns + 1);
-    uint32_t *exact_list = nullptr, *seg_row = nullptr, *seg_lo = nullptr, *seg_first = nullptr, *list_first = nullptr, *seg_cnt = nullptr, *seg_pos = nullptr;
+    uint32_t *exact_list = nullptr, *seg_row = nullptr, *seg_lo = nullptr, *seg_hi = nullptr, *seg_first = nullptr, *list_first = nullptr, *seg_cnt = nullptr,
+             *seg_pos = nullptr, *seg_src = nullptr;
+    uint8_t *seg_kind = nullptr;
     uint32_t n_seg = 0, stage_cap = 0;
     mm128 *seg_stage = nullptr;
     bool staged_ok = false;
-    // positions per thread of the exact automaton (plus its warm-up of ~w+k and w trailing slots): the few flagged reads are a
-    // pure latency term (far fewer threads than the GPU holds), so short segments keep them off the critical path
+    // positions per thread of the exact automaton (plus its warm-up of ~2(w+k) and w trailing slots)
     const int SEG = getenv("PGB_EXACT_SEG") ? std::max(16, atoi(getenv("PGB_EXACT_SEG"))) : 256;
+    // one warp per CTA: its w-slot rings (12 B per slot and thread) live in shared memory, 30 KB at w = 80
+    const unsigned SEG_THREADS = 32;
+    unsigned seg_stride = 1;  // lanes per piece (only the first of them works, see k_sketch_exact_seg): sized once the pieces are known
+    size_t seg_smem = 0;
     if (n_exact) {
       exact_list = c->alloc<uint32_t>(n_exact);
       LAUNCH(c, k_compact_idx, nblk(ns), 256, exact_flag, exact_pos, ns, exact_list);
-      std::vector<uint32_t> h_list(n_exact), h_seg_row, h_seg_lo, h_seg_first, h_list_first(n_exact + 1);
+      std::vector<uint32_t> h_list(n_exact), h_seg_row, h_seg_lo, h_seg_hi, h_seg_first, h_list_first(n_exact + 1);
+      std::vector<uint8_t> h_seg_kind;
+      std::vector<uint64_t> h_bad;
       c->d2h(h_list.data(), exact_list, (size_t)n_exact * 4);
+      if (row_bad) { h_bad.resize(ns); c->d2h(h_bad.data(), row_bad, ns * 8); }
+      size_t n_partial = 0;
+      auto push = [&](uint32_t row, uint32_t lo, uint32_t hi, uint8_t kind, uint32_t first) {
+        h_seg_row.push_back(row); h_seg_lo.push_back(lo); h_seg_hi.push_back(hi); h_seg_kind.push_back(kind); h_seg_first.push_back(first);
+      };
       for (uint32_t i = 0; i < n_exact; i++) {
-        uint32_t row = h_list[i], len = c->h_row_len[row];
-        h_list_first[i] = (uint32_t)h_seg_row.size();
-        for (uint32_t lo = 0; lo < len; lo += SEG) { h_seg_row.push_back(row); h_seg_lo.push_back(lo); h_seg_first.push_back(h_list_first[i]); }
+        const uint32_t row = h_list[i], len = c->h_row_len[row];
+        const uint32_t first = (uint32_t)h_seg_row.size();
+        h_list_first[i] = first;
+        const uint64_t bad = row_bad ? h_bad[row] : 0;
+        if (!bad) {  // the whole read
+          for (uint32_t lo = 0; lo < len; lo += SEG) push(row, lo, std::min<uint32_t>(lo + SEG, len), 0, first);
+          continue;
+        }
+        // pieces in position order: a bad strip c is redone as a whole, and so are the last w + SS_MAXPAL positions before it (the
+        // positions a window that ends in strip c can contain); everything between two such intervals keeps the fast path's records
+        n_partial++;
+        const uint32_t n_strips = (len + SS_STRIP - 1) / SS_STRIP, reach = (uint32_t)w + SS_MAXPAL;
+        uint32_t at = 0;  // positions below `at` are covered by the pieces so far
+        auto redo = [&](uint32_t lo, uint32_t hi) {
+          if (hi > len) hi = len;
+          if (lo < at) lo = at;
+          if (lo >= hi) return;
+          if (lo > at) push(row, at, lo, 1, first);
+          for (uint32_t x = lo; x < hi; x += SEG) push(row, x, std::min<uint32_t>(x + SEG, hi), 0, first);
+          at = hi;
+        };
+        for (uint32_t cs = 0; cs < n_strips && cs < 64; cs++) {
+          if (!((bad >> cs) & 1)) continue;
+          const uint32_t s0 = cs * SS_STRIP;
+          redo(s0 > reach ? s0 - reach : 0, s0 + SS_STRIP);
+        }
+        if (at < len) push(row, at, len, 1, first);
       }
       n_seg = (uint32_t)h_seg_row.size();
       h_list_first[n_exact] = n_seg;
-      seg_row = c->alloc<uint32_t>(n_seg); seg_lo = c->alloc<uint32_t>(n_seg); seg_first = c->alloc<uint32_t>(n_seg);
+      while (seg_stride < 32 && (size_t)n_seg * seg_stride * 2 <= 100000) seg_stride *= 2;  // about 100 k lanes fill the GPU
+      if (getenv("PGB_EXACT_STRIDE")) seg_stride = (unsigned)std::min(32, std::max(1, atoi(getenv("PGB_EXACT_STRIDE"))));
+      while (32 % seg_stride) seg_stride--;
+      seg_smem = (size_t)w * (SEG_THREADS / seg_stride) * 12;
+      if (getenv("PGB_VERBOSE")) fprintf(stderr, "pgb200: exact automaton: %u reads (%zu of them in part), %u pieces\n", n_exact, n_partial, n_seg);
+      seg_row = c->alloc<uint32_t>(n_seg); seg_lo = c->alloc<uint32_t>(n_seg); seg_hi = c->alloc<uint32_t>(n_seg); seg_first = c->alloc<uint32_t>(n_seg);
+      seg_kind = c->alloc<uint8_t>(n_seg); seg_src = c->alloc<uint32_t>(n_seg);
       list_first = c->alloc<uint32_t>((size_t)n_exact + 1); seg_cnt = c->alloc<uint32_t>((size_t)n_seg + 1); seg_pos = c->alloc<uint32_t>((size_t)n_seg + 1);
-      c->h2d(seg_row, h_seg_row.data(), (size_t)n_seg * 4); c->h2d(seg_lo, h_seg_lo.data(), (size_t)n_seg * 4);
+      c->h2d(seg_row, h_seg_row.data(), (size_t)n_seg * 4); c->h2d(seg_lo, h_seg_lo.data(), (size_t)n_seg * 4); c->h2d(seg_hi, h_seg_hi.data(), (size_t)n_seg * 4);
+      c->h2d(seg_kind, h_seg_kind.data(), (size_t)n_seg);
       c->h2d(seg_first, h_seg_first.data(), (size_t)n_seg * 4); c->h2d(list_first, h_list_first.data(), ((size_t)n_exact + 1) * 4);
       CU(cudaMemsetAsync(seg_cnt, 0, ((size_t)n_seg + 1) * 4, c->st));
-      // ONE pass of the automaton: the records are staged per segment (budget: 4x the expected 2/(w+1) density, at least 32) and
-      // placed once the counts are scanned; only a segment that overflows its budget costs the second pass
+      CU(cudaMemsetAsync(seg_src, 0, (size_t)n_seg * 4, c->st));
+      // ONE pass of the automaton: the records are staged per piece (budget: 4x the expected 2/(w+1) density, at least 32) and
+      // placed once the counts are scanned; only a piece that overflows its budget costs the second pass
       stage_cap = std::max<uint32_t>(32, (uint32_t)(8 * SEG / (w + 1)) + 8);
       seg_stage = c->alloc<mm128>((size_t)n_seg * stage_cap);
       int *d_ovf = c->alloc<int>(1);
       CU(cudaMemsetAsync(d_ovf, 0, 4, c->st));
       c->ktic();
-      LAUNCH(c, k_sketch_exact_seg<2>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
-             c->d_row_woff, c->d_hasn_by_rid, w, k, seg_cnt, (const uint32_t *)nullptr, (const uint64_t *)nullptr, seg_stage, stage_cap, d_ovf);
+      CU(cudaFuncSetAttribute(k_sketch_exact_seg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
+      LAUNCH_SMEM(c, k_sketch_exact_seg<2>, nblk((size_t)n_seg * seg_stride, SEG_THREADS), SEG_THREADS, seg_smem, c->d_w, c->d_nm, seg_row, seg_lo, seg_hi, seg_kind, seg_first, n_seg,
+                  c->d_row_rid, c->d_row_len, c->d_row_woff, c->d_hasn_by_rid, w, k, seg_cnt, (const uint32_t *)nullptr, (const uint64_t *)nullptr, seg_stage,
+                  stage_cap, d_ovf, seg_stride);
+      if (n_partial)
+        LAUNCH(c, k_seg_fast_count, nblk(n_seg, 128), 128, seg_row, seg_lo, seg_hi, seg_kind, n_seg, tmp_off, tmp, fast_cnt, seg_cnt, seg_src);
       c->stats.ms_k_sketch_count += c->ktoc(); c->stats.n_k_sketch_count++;
       int h_ovf = 0;
       c->d2h(&h_ovf, d_ovf, 4);
@@ -917,14 +984,18 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     place_fast();
     if (n_exact) {
       c->ktic();
-      if (staged_ok)
-        LAUNCH(c, k_seg_place, nblk((size_t)n_seg * 8, 256), 256, seg_row, seg_first, n_seg, seg_pos, c->d_level_off[0], seg_stage, stage_cap, c->d_level[0]);
-      else
-        LAUNCH(c, k_sketch_exact_seg<1>, nblk(n_seg, 64), 64, c->d_w, c->d_nm, seg_row, seg_lo, seg_first, n_seg, SEG, c->d_row_rid, c->d_row_len,
-               c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, seg_pos, c->d_level_off[0], c->d_level[0], 0u, (int *)nullptr);
+      if (!staged_ok) {
+        CU(cudaFuncSetAttribute(k_sketch_exact_seg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seg_smem));
+        LAUNCH_SMEM(c, k_sketch_exact_seg<1>, nblk((size_t)n_seg * seg_stride, SEG_THREADS), SEG_THREADS, seg_smem, c->d_w, c->d_nm, seg_row, seg_lo, seg_hi, seg_kind, seg_first,
+                    n_seg, c->d_row_rid, c->d_row_len, c->d_row_woff, c->d_hasn_by_rid, w, k, (uint32_t *)nullptr, seg_pos, c->d_level_off[0], c->d_level[0], 0u,
+                    (int *)nullptr, seg_stride);
+      }
+      LAUNCH(c, k_seg_place, nblk((size_t)n_seg * 8, 256), 256, seg_row, seg_first, seg_kind, seg_src, n_seg, seg_pos, c->d_level_off[0], seg_stage, stage_cap,
+             tmp_off, tmp, c->d_level[0], staged_ok ? 1 : 0);
       c->stats.ms_k_sketch_write += c->ktoc(); c->stats.n_k_sketch_write++;
       c->release(seg_stage);
-      c->release(exact_list); c->release(seg_row); c->release(seg_lo); c->release(seg_first); c->release(list_first); c->release(seg_cnt); c->release(seg_pos);
+      c->release(exact_list); c->release(seg_row); c->release(seg_lo); c->release(seg_hi); c->release(seg_first); c->release(list_first); c->release(seg_cnt);
+      c->release(seg_pos); c->release(seg_kind); c->release(seg_src);
     }
   };
   // host->device copy of the .seqdb image in chunks of whole reads on the copy stream while the compute stream packs and
@@ -984,9 +1055,9 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     else if (!c->pend.keep_raw) c->release(c->d_raw);
   };
   if (use_strip) {
-    uint32_t *caps = c->alloc<uint32_t>(ns + 1), *row_flags = c->alloc<uint32_t>(ns);
+    uint32_t *caps = c->alloc<uint32_t>(ns + 1), *row_flags = c->alloc<uint32_t>(ns), *fast_cnt = c->alloc<uint32_t>(ns);
     uint32_t *exact_flag = c->alloc<uint32_t>(ns + 1), *exact_pos = c->alloc<uint32_t>(ns + 1);
-    uint64_t *tmp_off = c->alloc<uint64_t>(ns + 1);
+    uint64_t *tmp_off = c->alloc<uint64_t>(ns + 1), *row_bad = c->alloc<uint64_t>(ns);
     LAUNCH(c, k_row_caps, nblk(ns + 1), 256, c->d_row_len, (uint32_t)ns, w, caps);
     const uint64_t tmp_n = scan_u32_to_u64(c, caps, tmp_off, ns + 1);
     mm128 *tmp = c->alloc<mm128>(tmp_n);
@@ -1000,10 +1071,10 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
       const unsigned grid = nblk(r1 - r0, SS_WARPS);
       if (k32)
         k_sketch_strip<uint32_t><<<grid, SS_WARPS * 32, smem, c->st>>>(c->d_w, c->d_row_rid, c->d_row_len, c->d_row_woff, c->d_hasn_by_rid, (uint32_t)r0,
-                                                                        (uint32_t)(r1 - r0), w, k, tmp_off, tmp, counts, row_flags);
+                                                                        (uint32_t)(r1 - r0), w, k, tmp_off, tmp, counts, row_flags, row_bad, fast_cnt);
       else
         k_sketch_strip<uint64_t><<<grid, SS_WARPS * 32, smem, c->st>>>(c->d_w, c->d_row_rid, c->d_row_len, c->d_row_woff, c->d_hasn_by_rid, (uint32_t)r0,
-                                                                        (uint32_t)(r1 - r0), w, k, tmp_off, tmp, counts, row_flags);
+                                                                        (uint32_t)(r1 - r0), w, k, tmp_off, tmp, counts, row_flags, row_bad, fast_cnt);
       c->stats.kernel_launches++;
       CU(cudaGetLastError());
     };
@@ -1015,18 +1086,19 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     if (getenv("PGB_VERBOSE")) {  // why reads were handed to the exact automaton
       std::vector<uint32_t> hf(ns);
       c->d2h(hf.data(), row_flags, ns * 4);
-      size_t n_tie = 0, n_pal = 0, n_ovf = 0, n_short = 0, n_n = 0, n_any = 0;
-      for (uint32_t f : hf) { n_any += f != 0; n_tie += (f & SK_FLAG_TIE) != 0; n_pal += (f & SK_FLAG_PAL) != 0; n_ovf += (f & SK_FLAG_OVERFLOW) != 0;
+      size_t n_tie = 0, n_pal = 0, n_ovf = 0, n_short = 0, n_n = 0, n_any = 0, n_part = 0;
+      for (uint32_t f : hf) { n_any += f != 0; n_part += (f & SK_FLAG_PARTIAL) != 0; n_tie += (f & SK_FLAG_TIE) != 0; n_pal += (f & SK_FLAG_PAL) != 0; n_ovf += (f & SK_FLAG_OVERFLOW) != 0;
                               n_short += (f & SK_FLAG_SHORT) != 0; n_n += (f & SK_FLAG_N) != 0; }
-      fprintf(stderr, "pgb200: strip sketch: %zu of %zu reads to the exact automaton (tie %zu, palindrome %zu, overflow %zu, short %zu, N %zu)\n", n_any, ns,
-              n_tie, n_pal, n_ovf, n_short, n_n);
+      fprintf(stderr, "pgb200: strip sketch: %zu of %zu reads to the exact automaton (single strips of %zu; whole reads: tie %zu, palindrome %zu, overflow %zu, "
+                      "short %zu, N %zu)\n", n_any, ns, n_part, n_tie, n_pal, n_ovf, n_short, n_n);
       size_t by_bit[32] = {0};
       for (uint32_t f : hf) for (int b = 8; b < 32; b++) by_bit[b] += (f >> b) & 1u;
       for (int b = 8; b < 20; b++) if (by_bit[b]) fprintf(stderr, "pgb200:   tie check %d: %zu reads\n", b, by_bit[b]);
     }
     exact_tail(row_flags, exact_flag, exact_pos, [&]() {
       LAUNCH(c, k_row_gather, nblk(ns * 32, 256), 256, counts, row_flags, (uint32_t)ns, tmp_off, tmp, c->d_level_off[0], c->d_level[0]);
-    });
+    }, row_bad, fast_cnt, tmp_off, tmp);
+    c->release(row_bad); c->release(fast_cnt);
     c->release(caps); c->release(row_flags); c->release(exact_flag); c->release(exact_pos); c->release(tmp_off); c->release(tmp);
   } else
   if (!use_tiled) {
@@ -1084,7 +1156,7 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
     exact_tail(row_flags, exact_flag, exact_pos, [&]() {
       LAUNCH(c, k_tile_gather, nblk((size_t)n_tiles * 64, 256), 256, tile_off, tile_cnt, row_flags, (uint32_t)ns, n_tiles, c->d_level_off[0], tmp,
              tile_cap, c->d_level[0]);
-    });
+    }, (const uint64_t *)nullptr, (const uint32_t *)nullptr, (const uint64_t *)nullptr, (const mm128 *)nullptr);
     c->release(tile_desc);
     c->release(tile_off); c->release(tile_cnt); c->release(row_flags); c->release(exact_flag); c->release(exact_pos); c->release(tmp);
   }

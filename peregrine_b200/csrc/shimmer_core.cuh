@@ -534,7 +534,8 @@ PGB_HD void sketch_exact(const uint64_t *w, const uint32_t *nm, uint64_t word_of
 // Returns false when start_pos > 0 and the warm-up condition was not met (caller retries with start_pos = 0).
 template <class Emit>
 PGB_HD bool sketch_exact_range(const uint64_t *w, const uint32_t *nm, uint64_t word_off, int len, int wsz, int k, uint32_t rid,
-                               int start_pos, int seg_lo, int seg_hi, uint64_t *ring_x, uint32_t *ring_p, Emit &&emit) {
+                               int start_pos, int seg_lo, int seg_hi, uint64_t *ring_x, uint32_t *ring_p, Emit &&emit, int rs = 1) {
+  // (slot j of the ring lives at index j * rs: rs = 1 for a private ring, rs = CTA size for rings interleaved in shared memory)
   const uint64_t shift1 = 2 * (uint64_t)(k - 1), mask = (1ULL << 2 * k) - 1;
   const uint64_t XMAX = ~0ULL;
   const uint32_t PMAX = ~0u;
@@ -543,8 +544,8 @@ PGB_HD bool sketch_exact_range(const uint64_t *w, const uint32_t *nm, uint64_t w
   uint64_t min_x = XMAX;
   uint32_t min_p = PMAX;
   for (int j = 0; j < wsz; j++) {
-    ring_x[j] = XMAX;
-    ring_p[j] = PMAX;
+    ring_x[(j) * rs] = XMAX;
+    ring_p[(j) * rs] = PMAX;
   }
   const uint64_t ridhi = (uint64_t)rid << 32;
   const uint32_t plo = (uint32_t)seg_lo << 1, phi = (uint32_t)seg_hi << 1;
@@ -588,13 +589,13 @@ PGB_HD bool sketch_exact_range(const uint64_t *w, const uint32_t *nm, uint64_t w
     }
     if (i < seg_lo) slots_before++;
     if (i >= seg_hi) slots_after++;
-    ring_x[buf_pos] = info_x;
-    ring_p[buf_pos] = info_p;
+    ring_x[(buf_pos) * rs] = info_x;
+    ring_p[(buf_pos) * rs] = info_p;
     if (l == wsz + k - 1 && min_x != XMAX) {
       for (int j = buf_pos + 1; j < wsz; ++j)
-        if (min_x == ring_x[j] && ring_p[j] != min_p) PGB_EMIT_IF(ring_x[j], ring_p[j]);
+        if (min_x == ring_x[(j) * rs] && ring_p[(j) * rs] != min_p) PGB_EMIT_IF(ring_x[(j) * rs], ring_p[(j) * rs]);
       for (int j = 0; j < buf_pos; ++j)
-        if (min_x == ring_x[j] && ring_p[j] != min_p) PGB_EMIT_IF(ring_x[j], ring_p[j]);
+        if (min_x == ring_x[(j) * rs] && ring_p[(j) * rs] != min_p) PGB_EMIT_IF(ring_x[(j) * rs], ring_p[(j) * rs]);
     }
     if (info_x <= min_x) {
       if (l >= wsz + k && min_x != XMAX) PGB_EMIT_IF(min_x, min_p);
@@ -605,14 +606,14 @@ PGB_HD bool sketch_exact_range(const uint64_t *w, const uint32_t *nm, uint64_t w
       if (l >= wsz + k - 1 && min_x != XMAX) PGB_EMIT_IF(min_x, min_p);
       min_x = XMAX;
       for (int j = buf_pos + 1; j < wsz; ++j)
-        if (min_x >= ring_x[j]) min_x = ring_x[j], min_p = ring_p[j], min_pos = j;
+        if (min_x >= ring_x[(j) * rs]) min_x = ring_x[(j) * rs], min_p = ring_p[(j) * rs], min_pos = j;
       for (int j = 0; j <= buf_pos; ++j)
-        if (min_x >= ring_x[j]) min_x = ring_x[j], min_p = ring_p[j], min_pos = j;
+        if (min_x >= ring_x[(j) * rs]) min_x = ring_x[(j) * rs], min_p = ring_p[(j) * rs], min_pos = j;
       if (l >= wsz + k - 1 && min_x != XMAX) {
         for (int j = buf_pos + 1; j < wsz; ++j)
-          if (min_x == ring_x[j] && min_p != ring_p[j]) PGB_EMIT_IF(ring_x[j], ring_p[j]);
+          if (min_x == ring_x[(j) * rs] && min_p != ring_p[(j) * rs]) PGB_EMIT_IF(ring_x[(j) * rs], ring_p[(j) * rs]);
         for (int j = 0; j <= buf_pos; ++j)
-          if (min_x == ring_x[j] && min_p != ring_p[j]) PGB_EMIT_IF(ring_x[j], ring_p[j]);
+          if (min_x == ring_x[(j) * rs] && min_p != ring_p[(j) * rs]) PGB_EMIT_IF(ring_x[(j) * rs], ring_p[(j) * rs]);
       }
     }
     if (++buf_pos == wsz) buf_pos = 0;

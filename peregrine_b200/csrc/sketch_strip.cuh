@@ -15,10 +15,15 @@
 //   4. a position is emitted when it becomes the window's (rightmost) arg-min; emitted records are staged per lane and
 //      leave in position order after one warp scan per strip.
 // Exactness: on tie-free, N-free data "rightmost arg-min of every full window, reported when it changes" IS the reference
-// output.  Everything else is detected and the whole read is handed to the exact automaton
-// (k_sketch_exact_seg): reads with N, reads shorter than one window, any evaluated window whose minimum occurs twice,
-// a palindromic k-mer before the first full window, two palindromic k-mers within one window, a lane with more than
-// SS_STAGE records in a strip, a read that overflows its record budget.
+// output.  Everything else is detected and handed to the exact automaton (k_sketch_exact_seg):
+//  * whole reads: reads with N, reads shorter than one window, a lane with more than SS_STAGE records in a strip, a read that
+//    overflows its record budget, more than SS_MAXPAL palindromic k-mers, a bad window beyond strip 63;
+//  * single strips ("bad" strips, bit c of the read's mask): a strip in which some evaluated window's minimum occurs twice, or
+//    holds two palindromic k-mers, or a palindromic k-mer precedes the first full window (strip 0).  The automaton's state is a
+//    function of the last w window slots, so a record at position p is decided by the windows that contain p alone: every
+//    position inside a bad window ("tainted": at most w + SS_MAXPAL positions back from the window's end) is redone by the
+//    automaton, the fast path's records at tainted positions are dropped, all its other records stand (the walk continues
+//    through a bad strip: the minimum carried into the next strip is that of a window, whatever happened before it).
 // Palindromic k-mers (src/mm_sketch.c:104-105: they occupy NO window slot) are rare (4^-k/2 per position) but hit 20 % of
 // 15 kb reads at k = 16: a strip within w positions of one takes a slower, general window evaluation in which the windows
 // that contain the palindrome reach one position further back.
@@ -38,6 +43,7 @@ struct SsWarpSmem {
   HT stv[32 * SS_STAGE];             // staged records of the strip: hash
   uint32_t stp[32 * SS_STAGE];       // ... position
   int pal[SS_MAXPAL];                // positions of the most recent palindromic k-mers (ring)
+  unsigned long long bad;            // strips (bit c = positions [512 c, 512 c + 512)) with a window the fast path cannot decide; lane 0 writes
 };
 
 // a running minimum: value, "occurs twice" flag, position
@@ -106,7 +112,7 @@ __device__ __forceinline__ void ss_strip(SsState<HT> &S, SsWarpSmem<HT> &sh, con
   auto row_ix = [](int r) -> int { return (r & (SS_ROWS - 1)) * SS_ROWPAD; };
   const int pos0 = cp + SS_SPL * lane, wsz = S.wsz, len = S.len, e_ff = S.e_ff, s_eval = S.s_eval;
   const int r_e = pos0 >> 4;
-  bool tie = false;
+  bool tie = false;  // this lane saw a window of the strip that the fast path cannot decide (tie, or palindromes beyond its reach)
   // ---------------- suffix minima of the lane's segment -> its row of the ring
   {
     const int rb = row_ix(r_e);
@@ -187,7 +193,7 @@ __device__ __forceinline__ void ss_strip(SsState<HT> &S, SsWarpSmem<HT> &sh, con
             cpal += (q >= e - wsz + 1 && q <= e);
             edge_pal |= (q == e - wsz);
           }
-          if (cpal > 1 || (cpal == 1 && edge_pal)) S.flags |= SK_FLAG_PAL;
+          if (cpal > 1 || (cpal == 1 && edge_pal)) tie = true;
           const int lo = e - wsz + 1 - (cpal ? 1 : 0);
           const int r_lo = lo >> 4, ix = row_ix(r_lo) + (lo & 15);
           win.v = sh.sv[ix];
@@ -233,7 +239,10 @@ __device__ __forceinline__ void ss_strip(SsState<HT> &S, SsWarpSmem<HT> &sh, con
     const HT new_carry = (HT)__shfl_sync(FULL, last_v, top);
     if (have) { S.carry_v = new_carry; S.have_carry = true; }
     if (__any_sync(FULL, n_st > SS_STAGE)) S.flags |= SK_FLAG_OVERFLOW;
-    if (__any_sync(FULL, tie)) S.flags |= SK_FLAG_TIE;
+    if (__any_sync(FULL, tie)) {  // redo this strip (and the w + SS_MAXPAL positions before it) with the exact automaton
+      if ((cp >> 9) >= 64) S.flags |= SK_FLAG_TIE;
+      else if (lane == 0) sh.bad |= 1ull << (cp >> 9);
+    }
     S.flags = __reduce_or_sync(FULL, S.flags);
     const uint32_t cnt = n_st - skip;
     uint32_t inc = cnt;
@@ -263,14 +272,15 @@ __device__ __forceinline__ void ss_strip(SsState<HT> &S, SsWarpSmem<HT> &sh, con
   __syncwarp();  // the stage and the ring rows are rewritten by the next strip
 }
 
-// One warp = one read.  Output: cnt_by_row[row] records at tmp + tmp_off[row] (position order); row_flags[row] != 0 when the
-// read must be redone by the exact automaton (its count is then 0).
+// One warp = one read.  Output: fast_cnt[row] records at tmp + tmp_off[row] (position order); row_flags[row] != 0 when the read
+// (SK_FLAG_PARTIAL: only the strips in row_bad[row]) must be redone by the exact automaton; cnt_by_row[row] is then 0.
 template <class HT>
-__global__ void __launch_bounds__(SS_WARPS * 32, 6) k_sketch_strip(const uint64_t *__restrict__ w, const uint32_t *__restrict__ row_rid,
+__global__ void __launch_bounds__(SS_WARPS * 32, sizeof(HT) == 8 ? 4 : 6) k_sketch_strip(const uint64_t *__restrict__ w, const uint32_t *__restrict__ row_rid,
                                                                    const uint32_t *__restrict__ row_len, const uint64_t *__restrict__ row_woff,
                                                                    const uint32_t *__restrict__ hasn_by_rid, uint32_t row_first, uint32_t n_rows, int wsz, int k,
                                                                    const uint64_t *__restrict__ tmp_off, mm128 *__restrict__ tmp,
-                                                                   uint32_t *__restrict__ cnt_by_row, uint32_t *__restrict__ row_flags) {
+                                                                   uint32_t *__restrict__ cnt_by_row, uint32_t *__restrict__ row_flags,
+                                                                   uint64_t *__restrict__ row_bad, uint32_t *__restrict__ fast_cnt) {
   extern __shared__ __align__(16) unsigned char ss_smem[];
   constexpr uint32_t FULL = 0xffffffffu;
   const HT MAXV = (HT) ~(HT)0;
@@ -283,7 +293,10 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 6) k_sketch_strip(const uint64_
   S.w = w;
   S.len = (int)row_len[row];
   if (hasn_by_rid[rid] || S.len < sk_min_len(wsz, k)) {
-    if (lane == 0) { row_flags[row] = hasn_by_rid[rid] ? (uint32_t)SK_FLAG_N : (uint32_t)SK_FLAG_SHORT; cnt_by_row[row] = 0; }
+    if (lane == 0) {
+      row_flags[row] = hasn_by_rid[rid] ? (uint32_t)SK_FLAG_N : (uint32_t)SK_FLAG_SHORT;
+      cnt_by_row[row] = 0; row_bad[row] = 0; fast_cnt[row] = 0;
+    }
     return;
   }
   S.base0 = (int64_t)row_woff[row] * 32;
@@ -297,6 +310,7 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 6) k_sketch_strip(const uint64_
   S.out = tmp + out0;
   S.ridhi = (uint64_t)rid << 32;
   S.n_out = 0; S.flags = 0;
+  if (lane == 0) sh.bad = 0;
   S.carry_v = MAXV; S.have_carry = false;
   S.n_pal = 0; S.last_pal = -0x40000000;
   const int len = S.len;
@@ -340,7 +354,8 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 6) k_sketch_strip(const uint64_
         uint32_t pm = __shfl_sync(FULL, palm, src);
         for (; pm; pm &= pm - 1) {
           const int q = cp + SS_SPL * src + (__ffs((int)pm) - 1);
-          if (q <= S.e_ff + 1 || S.n_pal >= SS_MAXPAL) S.flags |= SK_FLAG_PAL;  // before the first full window / too many: exact automaton
+          if (q <= S.e_ff + 1 && lane == 0) sh.bad |= 1ull;   // before the first full window (it moves): strip 0 is redone
+          if (S.n_pal >= SS_MAXPAL) S.flags |= SK_FLAG_PAL;   // too many for the ring: whole read
           if (lane == 0) sh.pal[S.n_pal & (SS_MAXPAL - 1)] = q;
           S.n_pal++;
           S.last_pal = q;
@@ -360,8 +375,12 @@ __global__ void __launch_bounds__(SS_WARPS * 32, 6) k_sketch_strip(const uint64_
     }
   }
   if (lane == 0) {
-    row_flags[row] = S.flags;
-    cnt_by_row[row] = S.flags ? 0u : S.n_out;
+    const unsigned long long bad = sh.bad;
+    const bool partial = !S.flags && bad;
+    row_flags[row] = partial ? (uint32_t)SK_FLAG_PARTIAL : S.flags;
+    row_bad[row] = partial ? bad : 0ull;
+    fast_cnt[row] = S.flags ? 0u : S.n_out;            // records in the read's slab (a partial read: incl. those at tainted positions)
+    cnt_by_row[row] = (S.flags || bad) ? 0u : S.n_out;  // final count, known now only for clean reads
   }
 }
 

@@ -29,7 +29,9 @@ namespace pgb {
 #endif
 enum { SK_THREADS = 256, SK_G = PGB_SK_G, SK_R = SK_THREADS * SK_G /* region positions */, SK_PALPAD = 16, SK_CAP = 512 /* records per tile */,
        SK_MINW = 17 /* smallest window the tiled kernel takes */ };
-enum { SK_FLAG_TIE = 1, SK_FLAG_PAL = 2, SK_FLAG_OVERFLOW = 4, SK_FLAG_SHORT = 8, SK_FLAG_N = 16 };
+// reasons for redoing a whole read with the exact automaton; PARTIAL (strip kernel only): no such reason, but some strips of the read
+// hold a window the fast path cannot decide (tie / palindrome): only those strips are redone (row_bad = their bit mask)
+enum { SK_FLAG_TIE = 1, SK_FLAG_PAL = 2, SK_FLAG_OVERFLOW = 4, SK_FLAG_SHORT = 8, SK_FLAG_N = 16, SK_FLAG_PARTIAL = 32 };
 
 PGB_HD int sk_halo(int wsz) { return wsz + SK_PALPAD; }
 PGB_HD int sk_tile_len(int wsz) { return SK_R - sk_halo(wsz); }

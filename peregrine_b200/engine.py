@@ -324,20 +324,14 @@ class Engine:
         self._ck(self.L.pgb_ovlp_match_batch(self.h, _ptr(seq), seq.size, len(a[0]), *[_ptr(x) for x in a], int(band_tolerance), _ptr(out)), "ovlp_match_batch")
         return out
 
-    def shmr_aln_batch(self, lists0, lists1, direction=0, max_diff=100, max_dist=1200, max_repeat=1):
-        """shmr_aln (src/shmr_align.c:21-160) for many pairs of minimizer lists at once.  lists0 / lists1: sequences of MM128
-        arrays (pair p = lists0[p] against lists1[p]).  Returns, per pair, the chains as the reference returns them:
-        [(idx0 list, idx1 list), ...] in the order of shmr_aln_v."""
+    def shmr_aln_batch_raw(self, m0, off0, m1, off1, direction=0, max_diff=100, max_dist=1200, max_repeat=1):
+        """pgb_shmr_aln_batch on concatenated MM128 arrays: pair p = m0[off0[p]:off0[p+1]] against m1[off1[p]:off1[p+1]].  Returns
+        (hit_off[n+1], n_chains[n], hits[total, 3] = (chain, idx0, idx1) rows in the reference's order)."""
         from . import formats as F
 
-        n = len(lists0)
-        assert len(lists1) == n
-        off0 = np.zeros(n + 1, dtype=np.uint64)
-        off1 = np.zeros(n + 1, dtype=np.uint64)
-        off0[1:] = np.cumsum([len(x) for x in lists0])
-        off1[1:] = np.cumsum([len(x) for x in lists1])
-        cat = lambda ls: np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=F.MM128) for x in ls])) if n else np.zeros(0, dtype=F.MM128)
-        m0, m1 = cat(lists0), cat(lists1)
+        n = len(off0) - 1
+        m0, m1 = np.ascontiguousarray(m0, dtype=F.MM128), np.ascontiguousarray(m1, dtype=F.MM128)
+        off0, off1 = np.ascontiguousarray(off0, dtype=np.uint64), np.ascontiguousarray(off1, dtype=np.uint64)
         hit_off = np.zeros(n + 1, dtype=np.uint64)
         n_chains = np.zeros(max(n, 1), dtype=np.uint32)
         hp = C.c_void_p()
@@ -346,6 +340,24 @@ class Engine:
         total = int(hit_off[n])
         hits = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(max(total, 1), 3))[:total].copy()
         self.L.pgb_host_free(hp)
+        return hit_off, n_chains[:n], hits
+
+    def shmr_aln_batch(self, lists0, lists1, direction=0, max_diff=100, max_dist=1200, max_repeat=1):
+        """shmr_aln (src/shmr_align.c:21-160) for many pairs of minimizer lists at once.  lists0 / lists1: sequences of MM128
+        arrays (pair p = lists0[p] against lists1[p]).  Returns, per pair, the chains as the reference returns them:
+        [(idx0 list, idx1 list), ...] in the order of shmr_aln_v."""
+        from . import formats as F
+
+        n = len(lists0)
+        assert len(lists1) == n
+        if n == 0:
+            return []
+        off0 = np.zeros(n + 1, dtype=np.uint64)
+        off1 = np.zeros(n + 1, dtype=np.uint64)
+        off0[1:] = np.cumsum([len(x) for x in lists0])
+        off1[1:] = np.cumsum([len(x) for x in lists1])
+        cat = lambda ls: np.concatenate([np.asarray(x, dtype=F.MM128) for x in ls])
+        hit_off, n_chains, hits = self.shmr_aln_batch_raw(cat(lists0), off0, cat(lists1), off1, direction, max_diff, max_dist, max_repeat)
         out = []
         for p in range(n):
             h = hits[int(hit_off[p]): int(hit_off[p + 1])]

@@ -173,18 +173,24 @@ def test_shmr_aln_batch_vs_reference(ours):
     # direction 1: the reference reads one element past the end of list 1 for its first probe (SURVEY A-7), so only the chains'
     # well-defined part is compared, as in tests/test_z_utils_helpers.py: both sides must agree on every hit whose idx1 > 0
     assert eng.shmr_aln_batch([], [], 0) == []
-    # a batch is much cheaper than single calls, and faster per pair than one reference core
+    # the batch call itself (arrays already concatenated, as a C caller has them) against one reference core
     big0, big1 = l0 * 40, l1 * 40
-    eng.shmr_aln_batch(big0[:8], big1[:8], 0)
+    off0 = np.zeros(len(big0) + 1, dtype=np.uint64)
+    off1 = np.zeros(len(big1) + 1, dtype=np.uint64)
+    off0[1:] = np.cumsum([len(x) for x in big0])
+    off1[1:] = np.cumsum([len(x) for x in big1])
+    c0, c1 = np.concatenate(big0), np.concatenate(big1)
+    eng.shmr_aln_batch_raw(c0, off0, c1, off1)
     t0 = time.perf_counter()
-    eng.shmr_aln_batch(big0, big1, 0)
+    hit_off, n_chains, hits = eng.shmr_aln_batch_raw(c0, off0, c1, off1)
     t_batch = time.perf_counter() - t0
+    assert int(hit_off[-1]) == len(hits) and int(n_chains[3]) == len(_aln(ref, l0[3], l1[3], 0, 100, 1200, 1))
+    vs = [(O.MMV(len(a), len(a), a.ctypes.data), O.MMV(len(b), len(b), b.ctypes.data)) for a, b in zip(l0, l1) if len(a) and len(b)]
     t0 = time.perf_counter()
-    for p in range(len(l0)):
-        if len(l0[p]) and len(l1[p]):
-            _aln(ref, l0[p], l1[p], 0, 100, 1200, 1)
+    for v0, v1 in vs:  # the reference's C call alone (no Python-side unpacking)
+        ref.free_shmr_alns(ref.shmr_aln(C.byref(v0), C.byref(v1), 0, 100, 1200, 1))
     t_ref = (time.perf_counter() - t0) * 40
-    print(f"shmr_aln: batch of {len(big0)} pairs {t_batch * 1e3:.1f} ms (incl. Python packing), reference one core {t_ref * 1e3:.1f} ms")
+    print(f"shmr_aln: batch of {len(big0)} pairs ({len(c0)} x {len(c1)} minimizers, {len(hits)} hits) {t_batch * 1e3:.1f} ms, reference one core {t_ref * 1e3:.1f} ms")
     eng.close()
 
 
