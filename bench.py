@@ -413,7 +413,7 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     K = args.steps
     kern = {
-        "k_sketch_tiled": (st["ms_k_sketch_tiled"], st["n_k_sketch_tiled"], bases / 4.0 + 16.0 * st["n_l0"] / K),
+        "k_sketch_tiled": (st["ms_k_sketch_tiled"], st["n_k_sketch_tiled"], (st["bases_sketched"] / 4.0 + 16.0 * st["n_l0"]) / max(st["n_k_sketch_tiled"], 1)),  # (rank 0's own reads)
         "k_align": (st["ms_k_align"], st["n_k_align"], (st["n_align_bases"] / 4.0 + 64.0 * st["n_alignments"]) / max(st["n_k_align"], 1)),
         # n_candidates = candidate pairs of the eligible buckets, counted once per step: per launch = total over the steps / launches
         "k_replay": (st["ms_k_replay"], st["n_k_replay"], (16.0 * st["n_candidates"] + 9.0 * st["n_pair_records"]) / max(st["n_k_replay"], 1)),
@@ -436,9 +436,9 @@ def run_ours(args):
                                        "k_sketch_exact": (st["ms_k_sketch_count"] + st["ms_k_sketch_write"]) / K}}
     # the same figure for each of the three heavy kernels (north_star asks for mm_sketch and the chaining kernels, not only the top
     # one); `limiter` = what the committed ncu captures (profiles/) show each kernel is actually bound by
-    limiter = {"k_sketch_tiled": "integer ALU pipe (ncu: 58 % of the ALU pipe's peak, issue active 50 %; ~120 thread-instructions per base)",
-               "k_align": "L1 tag stage + dependent-load latency (ncu: issue active 44 %, 15 of 32 lanes live, DRAM 5 % of peak)",
-               "k_replay": "L2 latency of dependent hash-table probes (ncu: 6 of 32 lanes live, DRAM 9 % of peak)"}
+    limiter = {"k_sketch_tiled": "integer ALU pipe (ncu: 65 % of the ALU pipe's peak, issue active 49 %; 117 thread-instructions per base; DRAM reads 0.255 B/base = the packed words once)",
+               "k_align": "dependent-load latency + divergence (ncu: issue active 54 %, 14.7 of 32 lanes live, 36 % occupancy, DRAM 6 % of peak)",
+               "k_replay": "latency of dependent random probes into a 1.5 GB table (ncu: 6 of 32 lanes live, DRAM 0.45 TB/s = 7 % of peak in full passes)"}
     rooflines = {}
     for k_, (ms_k, n_k, b_k) in kern.items():
         a_ms = ms_k / max(n_k, 1)
