@@ -216,6 +216,12 @@ void pgb_host_free(void *);
 int pgb_shmr_dedup_main(int argc, char **argv);
 int pgb_dedup(pgb_ctx *, const ovlp_t *records, size_t n);               /* host stream                                   */
 int pgb_dedup_device(pgb_ctx *, const ovlp_t *records_device, size_t n); /* stream already in HBM                         */
+/* the same stream in bounded batches (what bin/shmr_dedup does with stdin): the pair table persists on the device between the pushes, a
+ * push leaves the lines of the records IT keeps (pgb_dedup_text_bytes / pgb_dedup_text_copy); the concatenation of the pushes' texts is
+ * the text of the whole stream.  Host memory: one batch; device memory: 16 B per distinct pair at load <= 0.5 + one batch. */
+int pgb_dedup_stream_begin(pgb_ctx *);
+int pgb_dedup_stream_push(pgb_ctx *, const ovlp_t *records, size_t n);
+int pgb_dedup_stream_end(pgb_ctx *);
 int pgb_dedup_overlaps(pgb_ctx *);                                       /* the records of the last pgb_overlap, in place */
 size_t pgb_dedup_kept(pgb_ctx *);
 size_t pgb_dedup_text_bytes(pgb_ctx *);

@@ -163,8 +163,11 @@ __global__ void k_encode_biseq(const uint8_t *__restrict__ ascii, const EncTile 
   for (uint32_t p = t.p0 + threadIdx.x; p < p1; p += blockDim.x) o[p] = (uint8_t)(biseq_f(s[p]) | (biseq_r(s[t.len - 1 - p]) << 4));
 }
 
+// The pair table (keys / first) persists over the batches of one record stream: first[slot] = stream index of the first record of the
+// pair, `base` = stream index of this batch's record 0.  A record is kept iff it holds its pair's minimum, i.e. no earlier batch
+// and no earlier record of this batch had the pair (src/shmr_dedup.c:36-47 keeps the first record of every unordered pair).
 __global__ void k_dedup_insert(const ovlp_rec *__restrict__ recs, size_t n, uint64_t *keys, uint32_t mask, unsigned long long *first,
-                               uint32_t *slot_of, int *err) {
+                               uint32_t *slot_of, int *err, unsigned long long base) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = dedup_pair_key(recs[i]);
@@ -172,15 +175,26 @@ __global__ void k_dedup_insert(const ovlp_rec *__restrict__ recs, size_t n, uint
   const uint32_t s = ht_insert(keys, mask, key);
   slot_of[i] = s;
   if (s == PGB_NOSLOT) { atomicOr(err, 256); return; }
-  atomicMin(&first[s], (unsigned long long)i);
+  atomicMin(&first[s], base + (unsigned long long)i);
+}
+// the table grew: move every (pair, first) entry into the new one
+__global__ void k_dedup_rehash(const uint64_t *__restrict__ old_keys, const unsigned long long *__restrict__ old_first, size_t old_cap, uint64_t *keys,
+                               uint32_t mask, unsigned long long *first, int *err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= old_cap) return;
+  const uint64_t key = old_keys[i];
+  if (key == PGB_EMPTY) return;
+  const uint32_t s = ht_insert(keys, mask, key);
+  if (s == PGB_NOSLOT) { atomicOr(err, 256); return; }
+  first[s] = old_first[i];
 }
 __global__ void k_dedup_len(const ovlp_rec *__restrict__ recs, size_t n, const unsigned long long *__restrict__ first,
-                            const uint32_t *__restrict__ slot_of, uint32_t *len, unsigned long long *n_kept) {
+                            const uint32_t *__restrict__ slot_of, uint32_t *len, unsigned long long *n_kept, unsigned long long base) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t s = slot_of[i];
   uint32_t l = 0;
-  if (s != PGB_NOSLOT && first[s] == (unsigned long long)i) {
+  if (s != PGB_NOSLOT && first[s] == base + (unsigned long long)i) {
     char buf[192];
     l = (uint32_t)dedup_format(recs[i], buf);
     const unsigned m = __activemask();  // one atomic per converged group of kept records

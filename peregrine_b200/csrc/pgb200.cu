@@ -93,6 +93,9 @@ struct pgb_ctx {
   char *d_map_text = nullptr; size_t map_bytes = 0, map_hits = 0;
   // ---- dedup output (preads.ovl text)
   char *d_dedup_text = nullptr; size_t dedup_bytes = 0, dedup_kept = 0;
+  // pair table of a record stream that is deduplicated in batches (pgb_dedup_stream_*): persists between the pushes
+  uint64_t *dd_keys = nullptr; unsigned long long *dd_first = nullptr; uint32_t dd_cap = 0; unsigned long long dd_base = 0, dd_occ = 0;
+  bool dd_open = false;
   // ---- replay table sizing relative to the eligible record count (learned: doubled whenever a table overflowed)
   double ecap_ratio = 1.25, acap_ratio = 0.75;
   // ---- overlap output
@@ -374,6 +377,7 @@ extern "C" void pgb_destroy(pgb_ctx *c) {
   c->free_reads();
   c->release(c->d_ovl);
   c->release(c->d_dedup_text);
+  c->release(c->dd_keys); c->release(c->dd_first);
   c->release(c->d_map_text);
   if (c->h_ovl) cudaFreeHost(c->h_ovl);
   if (c->h_okey) cudaFreeHost(c->h_okey);
@@ -2057,31 +2061,56 @@ extern "C" int pgb_overlap_host(pgb_ctx *c, const ovlp_t **out, size_t *n) {
 
 // ================================================================================================ shmr_dedup
 // first record of every unordered read pair, in stream order, as preads.ovl text (src/shmr_dedup.c:19-101)
-static void dedup_core(pgb_ctx *c, const ovlp_rec *d_recs, size_t n) {
-  c->release(c->d_dedup_text); c->dedup_bytes = 0; c->dedup_kept = 0;
-  if (n == 0) return;
-  if (n >= (1ull << 30)) throw std::runtime_error("more than 2^30 records in one dedup call");
-  c->tic();
-  const uint32_t cap = pow2_at_least(2 * (uint64_t)n + 16);
-  uint64_t *keys = c->alloc<uint64_t>(cap);
-  unsigned long long *first = c->alloc<unsigned long long>(cap), *d_kept = c->alloc<unsigned long long>(1);
-  uint32_t *slot_of = c->alloc<uint32_t>(n), *len = c->alloc<uint32_t>(n + 1);
-  uint64_t *off = c->alloc<uint64_t>(n + 1);
+static void dedup_table_free(pgb_ctx *c) {
+  c->release(c->dd_keys); c->release(c->dd_first);
+  c->dd_cap = 0; c->dd_base = 0; c->dd_occ = 0; c->dd_open = false;
+}
+// room for `n` more pairs at load <= 0.5: allocate, or grow and move the entries over
+static void dedup_table_reserve(pgb_ctx *c, size_t n) {
+  const uint64_t want = 2 * (c->dd_occ + (uint64_t)n) + 16;
+  if (want > (1ull << 31)) throw std::runtime_error("shmr_dedup: more than 2^30 distinct read pairs in one stream");
+  if (c->dd_cap && want <= c->dd_cap) return;
+  const uint32_t cap = pow2_at_least(c->dd_cap ? std::max<uint64_t>(want, 2ull * c->dd_cap) : want);
+  uint64_t *keys = c->palloc<uint64_t>(cap);
+  unsigned long long *first = c->palloc<unsigned long long>(cap);
   LAUNCH(c, k_fill_u64, 1184, 256, keys, PGB_EMPTY, (size_t)cap);
   CU(cudaMemsetAsync(first, 0xFF, (size_t)cap * 8, c->st));
-  CU(cudaMemsetAsync(d_kept, 0, 8, c->st));
+  if (c->dd_cap) LAUNCH(c, k_dedup_rehash, nblk(c->dd_cap), 256, c->dd_keys, c->dd_first, (size_t)c->dd_cap, keys, cap - 1, first, c->d_err);
+  c->sync();
+  c->release(c->dd_keys); c->release(c->dd_first);
+  c->dd_keys = keys; c->dd_first = first; c->dd_cap = cap;
+}
+// one batch of the stream: the kept records' lines become the context's dedup text
+static void dedup_push(pgb_ctx *c, const ovlp_rec *d_recs, size_t n) {
+  c->release(c->d_dedup_text); c->dedup_bytes = 0; c->dedup_kept = 0;
+  if (n == 0) return;
+  if (n >= (1ull << 30)) throw std::runtime_error("more than 2^30 records in one dedup batch");
+  c->tic();
+  dedup_table_reserve(c, n);
+  unsigned long long *d_kept = c->alloc<unsigned long long>(2);
+  uint32_t *slot_of = c->alloc<uint32_t>(n), *len = c->alloc<uint32_t>(n + 1);
+  uint64_t *off = c->alloc<uint64_t>(n + 1);
+  CU(cudaMemsetAsync(d_kept, 0, 16, c->st));
   CU(cudaMemsetAsync(len + n, 0, 4, c->st));
-  LAUNCH(c, k_dedup_insert, nblk(n), 256, d_recs, n, keys, cap - 1, first, slot_of, c->d_err);
-  LAUNCH(c, k_dedup_len, nblk(n), 256, d_recs, n, first, slot_of, len, d_kept);
+  LAUNCH(c, k_dedup_insert, nblk(n), 256, d_recs, n, c->dd_keys, c->dd_cap - 1, c->dd_first, slot_of, c->d_err, c->dd_base);
+  LAUNCH(c, k_dedup_len, nblk(n), 256, d_recs, n, c->dd_first, slot_of, len, d_kept, c->dd_base);
   const uint64_t bytes = scan_u32_to_u64(c, len, off, n + 1);
   c->d_dedup_text = c->palloc<char>(bytes);
   LAUNCH(c, k_dedup_write, nblk(n), 256, d_recs, n, len, off, c->d_dedup_text);
   unsigned long long kept = 0;
   c->d2h(&kept, d_kept, 8);
   c->dedup_bytes = bytes; c->dedup_kept = kept;
+  c->dd_base += n;
+  c->dd_occ += kept;  // every kept record is the first of a pair the table did not hold
   c->stats.ms_dedup += c->toc();
   c->stats.n_dedup_in += n; c->stats.n_dedup_kept += kept;
   c->check_err("pgb_dedup");
+}
+// a whole stream in one call
+static void dedup_core(pgb_ctx *c, const ovlp_rec *d_recs, size_t n) {
+  dedup_table_free(c);
+  dedup_push(c, d_recs, n);
+  dedup_table_free(c);
 }
 extern "C" int pgb_dedup(pgb_ctx *c, const ovlp_t *records, size_t n) {
   API_BEGIN(c)
@@ -2098,6 +2127,27 @@ extern "C" int pgb_dedup_device(pgb_ctx *c, const ovlp_t *records_device, size_t
 extern "C" int pgb_dedup_overlaps(pgb_ctx *c) {
   API_BEGIN(c)
   dedup_core(c, c->d_ovl, c->n_ovl);
+  API_END(c)
+}
+// the stream in bounded batches: begin, push x N (each push leaves the lines of ITS kept records, read with pgb_dedup_text_*), end
+extern "C" int pgb_dedup_stream_begin(pgb_ctx *c) {
+  API_BEGIN(c)
+  dedup_table_free(c);
+  c->dd_open = true;
+  API_END(c)
+}
+extern "C" int pgb_dedup_stream_push(pgb_ctx *c, const ovlp_t *records, size_t n) {
+  API_BEGIN(c)
+  if (!c->dd_open) throw std::runtime_error("pgb_dedup_stream_push without pgb_dedup_stream_begin");
+  ovlp_rec *d = c->alloc<ovlp_rec>(n);
+  c->h2d(d, records, n * sizeof(ovlp_rec));
+  dedup_push(c, d, n);
+  API_END(c)
+}
+extern "C" int pgb_dedup_stream_end(pgb_ctx *c) {
+  API_BEGIN(c)
+  dedup_table_free(c);
+  c->release(c->d_dedup_text); c->dedup_bytes = 0;
   API_END(c)
 }
 extern "C" size_t pgb_dedup_kept(pgb_ctx *c) { return c ? c->dedup_kept : 0; }
@@ -2373,30 +2423,46 @@ extern "C" int pgb_shmr_overlap_main(int argc, char **argv) {
 // shmr_dedup: raw ovlp_t stream on stdin -> preads.ovl text on stdout (src/shmr_dedup.c:19-101; no options)
 extern "C" int pgb_shmr_dedup_main(int argc, char **argv) {
   (void)argc; (void)argv;
-  std::vector<char> in;
-  {
-    char buf[1 << 16];
-    size_t got;
-    while ((got = fread(buf, 1, sizeof buf, stdin)) > 0) in.insert(in.end(), buf, buf + got);
+  // stdin is consumed in batches of PGB_DEDUP_BATCH records (default 8 M = 512 MB); the pair table stays on the device between them,
+  // so host memory is bounded by one batch and device memory by the table (16 B per distinct pair at load <= 0.5) plus one batch
+  size_t batch = getenv("PGB_DEDUP_BATCH") ? (size_t)strtoull(getenv("PGB_DEDUP_BATCH"), 0, 10) : ((size_t)8 << 20);
+  if (batch < 1) batch = 1;
+  if (batch > ((size_t)1 << 29)) batch = (size_t)1 << 29;
+  std::vector<char> in(batch * sizeof(ovlp_t)), text;
+  pgb_ctx *c = nullptr;
+  size_t have = 0;  // bytes of an incomplete record carried over
+  for (;;) {
+    size_t got = have;
+    while (got < in.size()) {
+      const size_t r = fread(in.data() + got, 1, in.size() - got, stdin);
+      if (r == 0) break;
+      got += r;
+    }
+    const size_t n = got / sizeof(ovlp_t);  // a truncated trailing record is ignored
+    if (n == 0) break;
+    if (!c) {
+      c = cli_ctx();
+      if (!c) return 1;
+      if (pgb_dedup_stream_begin(c) != 0) { fprintf(stderr, "shmr_dedup: %s\n", pgb_last_error(c)); pgb_destroy(c); return 1; }
+    }
+    if (pgb_dedup_stream_push(c, (const ovlp_t *)in.data(), n) != 0) {
+      fprintf(stderr, "shmr_dedup: %s\n", pgb_last_error(c));
+      pgb_destroy(c);
+      return 1;
+    }
+    text.resize(pgb_dedup_text_bytes(c));
+    if (!text.empty() && pgb_dedup_text_copy(c, text.data()) != 0) {
+      fprintf(stderr, "shmr_dedup: %s\n", pgb_last_error(c));
+      pgb_destroy(c);
+      return 1;
+    }
+    fwrite(text.data(), 1, text.size(), stdout);
+    have = got - n * sizeof(ovlp_t);
+    if (have) memmove(in.data(), in.data() + n * sizeof(ovlp_t), have);
+    if (got < in.size()) break;  // end of the stream
   }
-  const size_t n = in.size() / sizeof(ovlp_t);  // a truncated trailing record is ignored
-  if (n == 0) return 0;
-  pgb_ctx *c = cli_ctx();
-  if (!c) return 1;
-  if (pgb_dedup(c, (const ovlp_t *)in.data(), n) != 0) {
-    fprintf(stderr, "shmr_dedup: %s\n", pgb_last_error(c));
-    pgb_destroy(c);
-    return 1;
-  }
-  std::vector<char> text(pgb_dedup_text_bytes(c));
-  if (pgb_dedup_text_copy(c, text.data()) != 0) {
-    fprintf(stderr, "shmr_dedup: %s\n", pgb_last_error(c));
-    pgb_destroy(c);
-    return 1;
-  }
-  fwrite(text.data(), 1, text.size(), stdout);
   fflush(stdout);
-  pgb_destroy(c);
+  if (c) { pgb_dedup_stream_end(c); pgb_destroy(c); }
   return 0;
 }
 

@@ -109,3 +109,42 @@ def test_dedup_cli_and_in_place(workdir, ref_dir):
     ov = eng.overlap(1, 1)
     assert eng.dedup() == ref_dedup(ref_dir, ov.tobytes())
     eng.close()
+
+
+@pytest.mark.gpu
+def test_dedup_in_bounded_batches(workdir, ref_dir):
+    """bin/shmr_dedup reads stdin in batches (PGB_DEDUP_BATCH records) and keeps the pair table on the device between them: batch
+    sizes from 1 record up (the table grows and is rehashed several times on the way), a stream with a truncated trailing
+    record, and the stream API of the library; the text must be the reference's for the whole stream."""
+    import ctypes as C
+
+    from peregrine_b200 import Engine
+
+    tool = os.path.join(ROOT, "bin", "shmr_dedup")
+    big = adversarial_stream(200_000, seed=3).tobytes()
+    for stream, batches in ((real_stream(workdir, ref_dir), ("7", "1000", "65536")), (big, ("3001", "50000")), (adversarial_stream(40, seed=2).tobytes(), ("1",))):
+        want = ref_dedup(ref_dir, stream)
+        for b in batches:
+            got = subprocess.run([tool], input=stream, stdout=subprocess.PIPE, check=True, env=dict(os.environ, PGB_DEDUP_BATCH=b)).stdout
+            assert got == want, (len(stream), b)
+    cut = big[: 64 * 1000 + 17]  # 1000 records and a torn one
+    got = subprocess.run([tool], input=cut, stdout=subprocess.PIPE, check=True, env=dict(os.environ, PGB_DEDUP_BATCH="333")).stdout
+    assert got == ref_dedup(ref_dir, cut[: 64 * 1000])
+    eng = Engine(0)
+    L = eng.L
+    for f in (L.pgb_dedup_stream_begin, L.pgb_dedup_stream_end):
+        f.argtypes = [C.c_void_p]
+    L.pgb_dedup_stream_push.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    recs = np.frombuffer(big, dtype=F.OVLP)
+    assert L.pgb_dedup_stream_begin(eng.h) == 0
+    out = []
+    for lo in range(0, len(recs), 77_777):
+        part = np.ascontiguousarray(recs[lo: lo + 77_777])
+        assert L.pgb_dedup_stream_push(eng.h, part.ctypes.data, len(part)) == 0, L.pgb_last_error(eng.h)
+        buf = np.empty(L.pgb_dedup_text_bytes(eng.h), dtype=np.uint8)
+        if buf.size:
+            assert L.pgb_dedup_text_copy(eng.h, buf.ctypes.data) == 0
+        out.append(buf.tobytes())
+    assert L.pgb_dedup_stream_end(eng.h) == 0
+    assert b"".join(out) == ref_dedup(ref_dir, big)
+    eng.close()
