@@ -203,7 +203,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "overlaps/s (index+overlap)", "value": v, "unit": "overlaps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "read_bases_per_s": bases * args.steps / tot_t,
-        "config": {"workload": "synthetic 30x 15 kb reads @99.5%, k=%d w=%d r=6 l=2, T=1 (bounded sample of configs[1])" % (PARAMS["k"], PARAMS["w"]), "sample": sample},
+        "config": {"workload": f"synthetic 30x 15 kb reads @99.5%, k={PARAMS['k']} w={PARAMS['w']} r=6 l=2, T=1 (bounded sample of configs[1])", "sample": sample},
         "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "overlaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
