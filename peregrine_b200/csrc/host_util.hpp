@@ -148,6 +148,28 @@ inline std::vector<std::string> glob_sorted(const std::string &pattern) {
 // 64-bit keys and no deletions: same hash (khash.h:373), same triangular probing, same 0.77 load-factor growth with
 // the in-place kick-out rehash.  order() returns the keys' indices (in insertion order numbering) by ascending slot,
 // which is the order `for (i = kh_begin; i != kh_end; ++i) if (kh_exist(i))` visits them.
+// ---------------------------------------------------------------------------------------------- sketch fallback pieces
+// A read of which only some 512-position strips must be redone by the exact automaton (sketch_strip.cuh) is cut into pieces in
+// position order: kind 0 = redone by the automaton, kind 1 = the fast path's records with positions in the piece stand.  A bad
+// strip c is redone as a whole, and so are the last `reach` positions before it (the positions a window that ends in strip c
+// can contain: w plus the palindromic k-mers the window may skip); automaton pieces are at most `seg` positions long.
+struct SketchPiece { uint32_t lo, hi; uint8_t kind; };
+inline void build_sketch_pieces(uint32_t len, uint64_t bad, uint32_t strip, uint32_t reach, uint32_t seg, std::vector<SketchPiece> &out) {
+  const uint32_t n_strips = (len + strip - 1) / strip;
+  uint32_t at = 0;  // positions below `at` are covered by the pieces so far
+  for (uint32_t cs = 0; cs < n_strips && cs < 64; cs++) {
+    if (!((bad >> cs) & 1)) continue;
+    const uint32_t s0 = cs * strip;
+    uint32_t lo = s0 > reach ? s0 - reach : 0, hi = std::min<uint32_t>(s0 + strip, len);
+    if (lo < at) lo = at;
+    if (lo >= hi) continue;
+    if (lo > at) out.push_back(SketchPiece{at, lo, 1});
+    for (uint32_t x = lo; x < hi; x += seg) out.push_back(SketchPiece{x, std::min<uint32_t>(x + seg, hi), 0});
+    at = hi;
+  }
+  if (at < len) out.push_back(SketchPiece{at, len, 1});
+}
+
 struct KhashEmu {
   // One 8-byte slot per bucket: the key's 32-bit khash value (placement depends on the key only through it; keys are
   // distinct by contract, so equality is never tested) and insertion number + 1 with a generation bit on top

@@ -926,25 +926,12 @@ extern "C" int pgb_index(pgb_ctx *c, int w, int k, int r, int levels, int with_c
           for (uint32_t lo = 0; lo < len; lo += SEG) push(row, lo, std::min<uint32_t>(lo + SEG, len), 0, first);
           continue;
         }
-        // pieces in position order: a bad strip c is redone as a whole, and so are the last w + SS_MAXPAL positions before it (the
-        // positions a window that ends in strip c can contain); everything between two such intervals keeps the fast path's records
+        // pieces in position order (build_sketch_pieces, host_util.hpp): bad strips and the w + SS_MAXPAL positions before them are
+        // redone, everything between keeps the fast path's records
         n_partial++;
-        const uint32_t n_strips = (len + SS_STRIP - 1) / SS_STRIP, reach = (uint32_t)w + SS_MAXPAL;
-        uint32_t at = 0;  // positions below `at` are covered by the pieces so far
-        auto redo = [&](uint32_t lo, uint32_t hi) {
-          if (hi > len) hi = len;
-          if (lo < at) lo = at;
-          if (lo >= hi) return;
-          if (lo > at) push(row, at, lo, 1, first);
-          for (uint32_t x = lo; x < hi; x += SEG) push(row, x, std::min<uint32_t>(x + SEG, hi), 0, first);
-          at = hi;
-        };
-        for (uint32_t cs = 0; cs < n_strips && cs < 64; cs++) {
-          if (!((bad >> cs) & 1)) continue;
-          const uint32_t s0 = cs * SS_STRIP;
-          redo(s0 > reach ? s0 - reach : 0, s0 + SS_STRIP);
-        }
-        if (at < len) push(row, at, len, 1, first);
+        std::vector<SketchPiece> pieces;
+        build_sketch_pieces(len, bad, SS_STRIP, (uint32_t)w + SS_MAXPAL, (uint32_t)SEG, pieces);
+        for (const SketchPiece &pc : pieces) push(row, pc.lo, pc.hi, pc.kind, first);
       }
       n_seg = (uint32_t)h_seg_row.size();
       h_list_first[n_exact] = n_seg;

@@ -110,3 +110,51 @@ def ref_overlap(ref_dir, prefix, idx_prefix, level, outdir, T=1, extra=()):
         run([os.path.join(ref_dir, "shmr_overlap"), "-p", prefix, "-l", f"{idx_prefix}-L{level}", "-t", str(T), "-c", str(c), "-o", o, *extra])
         outs.append(o)
     return outs
+
+
+def bad_strip_records(seed=41, n_reads=60):
+    """Random reads with planted trouble for the strip sketch kernel's per-strip fallback (sketch_strip.cuh): tandem duplications
+    (equal k-mer hashes inside one window: ties) in the middle of a read, in two adjacent strips, across a strip boundary, in the
+    last partial strip and beyond strip 63 (> 32 kb: whole-read fallback); palindromic k-mers (no window slot) before the first
+    full window, two within one window, and one next to a duplication."""
+    rnd = random.Random(seed)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    rs = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))
+    rc = lambda s: "".join(comp[c] for c in reversed(s))
+
+    def plant_dup(s, at, unit):  # s[at:at+unit] twice in a row
+        return s[:at + unit] + s[at:at + unit] + s[at + unit:]
+
+    def plant_pal(s, at, half):  # a reverse-complement palindrome of 2*half bases at `at`
+        h = rs(half)
+        return s[:at] + h + rc(h) + s[at + 2 * half:]
+
+    recs = []
+    for i in range(n_reads):
+        n = rnd.choice([700, 3000, 9000, 15000, 20000])
+        s = rs(n)
+        kind = i % 10
+        if kind == 0 and n > 2500:
+            s = plant_dup(s, 1700, 30)
+        elif kind == 1 and n > 2500:
+            s = plant_dup(plant_dup(s, 1000, 25), 1500, 40)          # adjacent strips 1/2 and 2/3
+        elif kind == 2 and n > 2500:
+            s = plant_dup(s, 2030, 28)                                # across the boundary at 2048
+        elif kind == 3:
+            s = plant_dup(s, len(s) - 120, 35)                        # last (partial) strip
+        elif kind == 4:
+            s = plant_pal(s, 20, rnd.choice([6, 7, 8, 9]))            # before the first full window
+        elif kind == 5 and n > 2500:
+            h = rnd.choice([6, 7, 8, 9])
+            s = plant_pal(plant_pal(s, 1200, h), 1240, h)             # two in one window
+        elif kind == 6 and n > 2500:
+            s = plant_dup(plant_pal(s, 2500, 8), 2530, 30)
+        elif kind == 7 and n > 2500:
+            s = plant_pal(plant_pal(s, 600, 7), 2100, 9)              # k = 14 / k = 18 palindromes
+        elif kind == 8:
+            for at in range(100, len(s) - 200, 900):
+                s = plant_dup(s, at, rnd.choice([17, 24, 33, 50]))
+        recs.append((f"r/{i}/0_{len(s)}", s))
+    long_read = rs(40000)
+    recs.append(("r/long/0_1", plant_dup(plant_dup(long_read, 5000, 30), 35000, 30)))  # bad windows before and beyond strip 63
+    return recs

@@ -176,6 +176,70 @@ static uint32_t sketch_tiled_host(const Packed &P, size_t row, int wsz, int k, s
   return 0;
 }
 
+// Host MODEL of what the strip sketch kernel (peregrine_b200/csrc/sketch_strip.cuh) decides, used to check the splice argument of
+// its fallback on the CPU: per full window the rightmost arg-min over the last w SLOTS (palindromic k-mers are no slots), a
+// record when the minimum changes, and the same "cannot decide" conditions as the kernel (a minimum that occurs twice, a new
+// element equal to the previous window's minimum, two palindromic k-mers in reach, a palindromic k-mer before the first full
+// window), recorded per 512-position strip.  Returns false when the kernel would hand over the whole read.
+static bool sketch_fast_model(const char *seq, uint32_t len, int w, int k, uint32_t rid, std::vector<mm128> &recs, uint64_t *bad_out) {
+  const uint64_t MAXV = ~0ULL, mask = (1ULL << 2 * k) - 1, shift1 = 2 * (uint64_t)(k - 1);
+  *bad_out = 0;
+  if ((int)len < sk_min_len(w, k)) return false;
+  struct Slot { uint64_t v; uint32_t pos, strand; };
+  std::vector<Slot> slots;
+  std::vector<uint32_t> pals;
+  uint64_t kmer0 = 0, kmer1 = 0, bad = 0;
+  int l = 0;
+  const int e_ff = w + k - 2;
+  for (uint32_t p = 0; p < len; p++) {
+    int c;
+    switch (seq[p]) { case 'A': case 'a': c = 0; break; case 'C': case 'c': c = 1; break; case 'G': case 'g': c = 2; break; case 'T': case 't': c = 3; break; default: return false; }
+    kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
+    kmer1 = (kmer1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+    if (kmer0 == kmer1) {
+      if (p + 1 >= (uint32_t)k) {  // (the kernel looks at complete k-mers only)
+        if ((int)p <= e_ff + 1) bad |= 1;
+        if (pals.size() >= 8) return false;
+        pals.push_back(p);
+      }
+      continue;
+    }
+    const uint32_t z = kmer0 < kmer1 ? 0 : 1;
+    ++l;
+    slots.push_back(Slot{l >= k ? hash64(z ? kmer1 : kmer0, mask) : MAXV, p, z});
+  }
+  const uint64_t cap = (6ull * len) / (uint32_t)(w + 1) + 64;
+  uint64_t prev = MAXV;
+  bool have_prev = false;
+  std::vector<uint32_t> per16((len >> 4) + 2, 0);
+  for (size_t s = 0; s < slots.size(); s++) {
+    const int e = (int)slots[s].pos;
+    if (e < e_ff - 1 || (int)s < w - 1) continue;  // evaluated from the window before the first full one (its tie check only)
+    uint64_t v = MAXV;
+    uint32_t arg = 0, strand = 0, cnt = 0;
+    for (size_t t = s + 1 - (size_t)w; t <= s; t++) {
+      if (slots[t].v < v) { v = slots[t].v; cnt = 0; }
+      if (slots[t].v == v) { arg = slots[t].pos; strand = slots[t].strand; cnt++; }
+    }
+    bool undecided = cnt > 1 && v != MAXV;
+    if (have_prev && slots[s].v == prev && prev != MAXV) undecided = true;
+    uint32_t cpal = 0;
+    for (uint32_t q : pals) cpal += (q >= slots[s + 1 - (size_t)w].pos && q <= (uint32_t)e);
+    if (cpal > 1) undecided = true;
+    if (undecided) { if ((e >> 9) >= 64) return false; bad |= 1ull << (e >> 9); }
+    const bool full = (int)s >= w + k - 2;  // l >= w+k-1
+    if (full && (!have_prev || v != prev || (int)s == w + k - 2)) {
+      recs.push_back(mm128{v << 8 | (uint64_t)k, (uint64_t)rid << 32 | (uint64_t)(arg << 1 | strand)});
+      if (++per16[e >> 4] > 8) return false;  // the kernel stages at most 8 records per lane and strip
+    }
+    prev = v;
+    have_prev = true;
+  }
+  if (recs.size() > cap) return false;
+  *bad_out = bad;
+  return true;
+}
+
 static int cmd_sketch(int argc, char **argv) {
   if (argc < 5) return 1;
   for (int B = 9; B <= 129; B++)
@@ -187,6 +251,10 @@ static int cmd_sketch(int argc, char **argv) {
   int rs = argc > 5 ? atoi(argv[5]) : 6;
   std::vector<uint64_t> rx(256); std::vector<uint32_t> rp(256);
   size_t bad = 0, total = 0, bad_tiled = 0, n_fallback = 0, bad_seg = 0, n_seg_retry = 0; uint32_t fallback_flags = 0;
+  size_t n_model = 0, n_model_partial = 0, n_model_pieces = 0, bad_splice = 0;
+  // PGB_SPLICE_REACH: positions before a bad strip that are redone as well (default: the product's w + 8); a value that is too small
+  // must make the splice check fail (the test uses this to show that the check can fail)
+  const int splice_reach = getenv("PGB_SPLICE_REACH") ? atoi(getenv("PGB_SPLICE_REACH")) : -1;
   std::vector<mm128> all_mine;
   mm128_v all_ref = {0, 0, 0};
   for (size_t i = 0; i < P.rt.n(); i++) {
@@ -232,12 +300,50 @@ static int cmd_sketch(int argc, char **argv) {
         bad_tiled++;
       }
     }
+    if (w >= SK_MINW && !P.has_n[i]) {  // strip-kernel model + per-strip fallback, spliced by position (sketch_strip.cuh, build_sketch_pieces)
+      std::vector<mm128> fast, spliced;
+      uint64_t badmask = 0;
+      if (sketch_fast_model(seq.data(), len, w, k, P.rt.rid[i], fast, &badmask)) {
+        n_model++;
+        if (badmask) n_model_partial++;
+        std::vector<SketchPiece> pieces;
+        if (badmask) build_sketch_pieces(len, badmask, 512, splice_reach >= 0 ? (uint32_t)splice_reach : (uint32_t)w + 8, 256, pieces);
+        else pieces.push_back(SketchPiece{0, len, 1});
+        for (const SketchPiece &pc : pieces) {
+          if (pc.kind) {
+            for (const mm128 &m : fast) { const uint32_t pos = (uint32_t)m.y >> 1; if (pos >= pc.lo && pos < pc.hi) spliced.push_back(m); }
+          } else {
+            n_model_pieces++;
+            int st = std::max(0, (int)pc.lo - sketch_warmup_len(w, k));
+            auto em = [&](uint64_t x, uint64_t y) { spliced.push_back(mm128{x, y}); };
+            size_t mark = spliced.size();
+            if (!sketch_exact_range(P.w.data(), nullptr, P.woff[i], (int)len, w, k, P.rt.rid[i], st, (int)pc.lo, (int)pc.hi, rx.data(), rp.data(), em)) {
+              spliced.resize(mark);
+              sketch_exact_range(P.w.data(), nullptr, P.woff[i], (int)len, w, k, P.rt.rid[i], 0, (int)pc.lo, (int)pc.hi, rx.data(), rp.data(), em);
+            }
+          }
+        }
+        if (spliced.size() != nr || memcmp(all_ref.a + n0, spliced.data(), nr * 16) != 0) {
+          if (bad_splice < 5) {
+            fprintf(stderr, "SPLICE mismatch read row %zu rid %u len %u bad 0x%llx: ref %zu spliced %zu\n", i, P.rt.rid[i], len, (unsigned long long)badmask, nr,
+                    spliced.size());
+            for (size_t q = 0; q < std::min(nr, spliced.size()); q++)
+              if (memcmp(&all_ref.a[n0 + q], &spliced[q], 16)) {
+                fprintf(stderr, "  first diff at %zu: ref pos %u spliced pos %u\n", q, (uint32_t)(all_ref.a[n0 + q].y & 0xFFFFFFFF) >> 1, (uint32_t)(spliced[q].y & 0xFFFFFFFF) >> 1);
+                break;
+              }
+          }
+          bad_splice++;
+        }
+      }
+    }
     if (nr != nmine || memcmp(all_ref.a + n0, all_mine.data() + m0, nr * 16) != 0) {
       if (bad < 5) fprintf(stderr, "sketch mismatch read row %zu rid %u len %u: ref %zu mine %zu\n", i, P.rt.rid[i], len, nr, nmine);
       bad++;
     }
   }
   printf("sketch: reads=%zu L0=%zu mismatching_reads=%zu ; tiled kernel: mismatching=%zu fallback_reads=%zu (flags 0x%x) ; segmented exact: mismatching=%zu retries=%zu\n", P.rt.n(), total, bad, bad_tiled, n_fallback, fallback_flags, bad_seg, n_seg_retry);
+  printf("strip model + per-strip fallback: reads=%zu of them in part=%zu automaton pieces=%zu mismatching=%zu\n", n_model, n_model_partial, n_model_pieces, bad_splice);
   // reduce twice
   mm128_v r1 = {0, 0, 0}, r2 = {0, 0, 0};
   ref_mm_reduce(&all_ref, &r1, (uint8_t)rs);
@@ -249,7 +355,7 @@ static int cmd_sketch(int argc, char **argv) {
   bool ok2 = r2.n == m2.size() && (r2.n == 0 || memcmp(r2.a, m2.data(), r2.n * 16) == 0);
   printf("reduce: L1 ref=%zu mine=%zu %s ; L2 ref=%zu mine=%zu %s\n", r1.n, m1.size(), ok1 ? "OK" : "MISMATCH", r2.n, m2.size(),
          ok2 ? "OK" : "MISMATCH");
-  return (bad || bad_tiled || bad_seg || !ok1 || !ok2) ? 3 : 0;
+  return (bad || bad_tiled || bad_seg || bad_splice || !ok1 || !ok2) ? 3 : 0;
 }
 
 static uint64_t rng_state = 0x12345;

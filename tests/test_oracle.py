@@ -186,6 +186,17 @@ def test_kernel_logic_on_host(workdir, ref_dir):
     p = D.make_from_fasta(workdir, "adv_h", D.adversarial_records(seed=11), ref_dir)
     for w, k, r in ((80, 16, 6), (24, 12, 2), (120, 18, 3)):
         subprocess.check_call([hs, "sketch", p, str(w), str(k), str(r)], env=env, stdout=subprocess.DEVNULL)
+    # the strip sketch kernel's per-strip fallback: a host model of the kernel's window decisions + the exact automaton on the bad
+    # strips, spliced by position, must give the reference's minimizers (planted ties and palindromic k-mers; even and odd k)
+    pb = D.make_from_fasta(workdir, "badstrips_h", D.bad_strip_records(seed=43, n_reads=150), ref_dir)
+    for w, k in ((80, 16), (40, 14), (120, 18), (33, 15), (64, 12)):
+        out = subprocess.run([hs, "sketch", pb, str(w), str(k), "6"], env=env, stdout=subprocess.PIPE, check=True).stdout.decode()
+        line = [x for x in out.splitlines() if x.startswith("strip model")][0]
+        f = dict(kv.split("=") for kv in line.replace("of them in part", "partial").replace("automaton pieces", "pieces").split(":")[1].split())
+        assert int(f["partial"]) > 10 and int(f["pieces"]) > 10 and int(f["mismatching"]) == 0, line
+    # ... and the check can fail: without the positions before a bad strip the splice is wrong
+    r = subprocess.run([hs, "sketch", pb, "80", "16", "6"], env=dict(env, PGB_SPLICE_REACH="0"), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+    assert r.returncode == 3 and b"mismatching=0\n" not in [x for x in r.stdout.splitlines(True) if x.startswith(b"strip model")][0]
     subprocess.check_call([hs, "match", p, "1500", "50"], env=env, stdout=subprocess.DEVNULL)
     rp = D.ref_index(ref_dir, p, os.path.join(workdir, "adv_h/ref"), T=2, extra=["-m", "0", "-k", "18", "-w", "120", "-r", "3"])
     ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, "adv_h/ref"), T=1)

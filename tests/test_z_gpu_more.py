@@ -125,50 +125,10 @@ def test_sketch_bad_strips_are_spliced(workdir, ref_dir, monkeypatch):
     strip 63 (> 32 kb: whole-read fallback); palindromic k-mers (no window slot) before the first full window, two within one
     window, and one next to a duplication.  L0 must be byte-identical to the reference for three (k, w) and the counters must show
     that reads were redone in part."""
-    import random
-
     import numpy as np
     from peregrine_b200 import Engine, formats as F
 
-    rnd = random.Random(41)
-    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
-    rs = lambda n: "".join(rnd.choice("ACGT") for _ in range(n))
-    rc = lambda s: "".join(comp[c] for c in reversed(s))
-
-    def plant_dup(s, at, unit):  # s[at:at+unit] twice in a row
-        return s[:at + unit] + s[at:at + unit] + s[at + unit:]
-
-    def plant_pal(s, at, half):  # a reverse-complement palindrome of 2*half bases at `at`
-        h = rs(half)
-        return s[:at] + h + rc(h) + s[at + 2 * half:]
-
-    recs = []
-    for i in range(60):
-        n = rnd.choice([700, 3000, 9000, 15000, 20000])
-        s = rs(n)
-        kind = i % 10
-        if kind == 0 and n > 2500:
-            s = plant_dup(s, 1700, 30)
-        elif kind == 1 and n > 2500:
-            s = plant_dup(plant_dup(s, 1000, 25), 1500, 40)          # adjacent strips 1/2 and 2/3
-        elif kind == 2 and n > 2500:
-            s = plant_dup(s, 2030, 28)                                # across the boundary at 2048
-        elif kind == 3:
-            s = plant_dup(s, len(s) - 120, 35)                        # last (partial) strip
-        elif kind == 4:
-            s = plant_pal(s, 20, 8)                                   # before the first full window (k = 16)
-        elif kind == 5 and n > 2500:
-            s = plant_pal(plant_pal(s, 1200, 8), 1240, 8)             # two in one window
-        elif kind == 6 and n > 2500:
-            s = plant_dup(plant_pal(s, 2500, 8), 2530, 30)
-        elif kind == 7 and n > 2500:
-            s = plant_pal(plant_pal(s, 600, 7), 2100, 9)              # k = 14 / k = 18 palindromes
-        elif kind == 8:
-            for at in range(100, len(s) - 200, 900):
-                s = plant_dup(s, at, rnd.choice([17, 24, 33, 50]))
-        recs.append((f"r/{i}/0_{len(s)}", s))
-    long_read = rs(40000)
-    recs.append(("r/long/0_1", plant_dup(plant_dup(long_read, 5000, 30), 35000, 30)))  # bad windows before and beyond strip 63
+    recs = D.bad_strip_records()
     p = D.make_from_fasta(workdir, "badstrips", recs, ref_dir)
     rid, ln, off = F.read_idx(p + ".idx")
     seqdb = np.fromfile(p + ".seqdb", dtype=np.uint8)
