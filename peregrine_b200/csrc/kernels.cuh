@@ -1032,7 +1032,7 @@ __global__ void __launch_bounds__(64) k_replay(ReplayState st, uint32_t n_ranks,
   if (*(volatile int *)st.err & (32 | 64)) return;  // a table filled up: this pass is void, the host restarts with larger tables
   r = list[r];
   uint32_t b = rank_off[r], n = rank_off[r + 1] - b;
-  if (n >= warp_min && n < warp_max) return;  // walked by a warp (k_replay_warp)
+  if (n >= warp_min && n < warp_max) return;  // walked by a lane group (k_replay_group)
   DevReplayCtx c;
   c.s = st;
   c.rank = r;
