@@ -1108,7 +1108,7 @@ __global__ void __launch_bounds__(PGB_RW_WARPS * 32) k_replay_group(ReplayState 
   dup = ((__ballot_sync(FULL, dup) >> gsh) & GM) != 0;
   const uint64_t NONE = ~0ULL;
   uint32_t n_acc = 0, n_unk = 0, overlap_count = 0;
-  uint32_t k0 = (have && !dup) ? n - 1 : 0;  // current row is k0 - 1, its candidates start at k0; 0 = this group is done
+  uint32_t k0 = (have && !dup && bestn > 0) ? n - 1 : 0;  // current row is k0 - 1, its candidates start at k0; 0 = this group is done
   uint32_t base = k0;
   while (__any_sync(FULL, k0 > 0)) {
     const bool act = k0 > 0;

@@ -2842,7 +2842,7 @@ static void aln_batch_core(pgb_ctx *c, const mm128 *mm0, const uint64_t *off0, c
   if (!n_pairs) return;
   if (n_pairs >= (1u << (64 - PGB_ALN_HBITS))) throw std::runtime_error("pgb_shmr_aln_batch: more than 2^24 pairs in one call");
   const uint64_t n0 = off0[n_pairs], n1 = off1[n_pairs];
-  if (n0 >= (1ull << 32) || n1 >= (1ull << 32)) throw std::runtime_error("pgb_shmr_aln_batch: more than 2^32 minimizers in one call");
+  if (n0 >= (1ull << 31) || n1 >= (1ull << 31)) throw std::runtime_error("pgb_shmr_aln_batch: more than 2^31 minimizers in one call");
   if (!n0 || !n1) return;
   mm128 *d0 = c->alloc<mm128>(n0), *d1 = c->alloc<mm128>(n1);
   uint64_t *doff0 = c->alloc<uint64_t>((size_t)n_pairs + 1), *doff1 = c->alloc<uint64_t>((size_t)n_pairs + 1);

@@ -99,7 +99,8 @@ def test_index_parameter_sweep(sim1, workdir, ref_dir, k, w, r, l):
     compare_index(rp, op, 1, levels=("L0", f"L{l}"))
 
 
-@pytest.mark.parametrize("extra", [["-w", "50"], ["-w", "200"], ["-b", "2", "-n", "40"], ["-m", "3", "-M", "60"], ["-b", "8", "-n", "500", "-M", "1000"]])
+@pytest.mark.parametrize("extra", [["-w", "50"], ["-w", "200"], ["-b", "2", "-n", "40"], ["-m", "3", "-M", "60"], ["-b", "8", "-n", "500", "-M", "1000"],
+                                   ["-b", "256"]])  # (bestn is a uint8_t: 256 wraps to 0 and no candidate is visited, src/shmr_overlap.c:245)
 def test_overlap_parameter_sweep(sim1, workdir, ref_dir, extra):
     tag = "_".join(x.strip("-") for x in extra)
     rp = D.ref_index(ref_dir, sim1, os.path.join(workdir, "sim1/ref1"), T=1, extra=["-m", "1"])
