@@ -190,6 +190,7 @@ def gather_records(mine: torch.Tensor, group=None):
 # ------------------------------------------------------------------------------------------------ engine <-> torch
 def export_reads(eng, device):
     """Copy the engine's packed reads + read table into fresh torch tensors on `device` (a CUDA device)."""
+    _handoff(device)  # (a recycled block of torch's allocator may still be in use by work queued on torch's stream)
     E = eng
     spec = (("words", E.BUF_WORDS, torch.int64), ("nmask", E.BUF_NMASK, torch.int32), ("row_rid", E.BUF_ROW_RID, torch.int32),
             ("row_len", E.BUF_ROW_LEN, torch.int32), ("row_woff", E.BUF_ROW_WOFF, torch.int64), ("row_hasn", E.BUF_ROW_HASN, torch.int32))
@@ -202,6 +203,7 @@ def export_reads(eng, device):
 
 
 def export_level(eng, level, device):
+    _handoff(device)
     n = eng.buffer_elems(eng.BUF_LEVEL0 + level)
     t = torch.empty((n, 2), dtype=torch.int64, device=device)
     eng.buffer_copy_out(eng.BUF_LEVEL0 + level, t.data_ptr())
@@ -210,6 +212,7 @@ def export_level(eng, level, device):
 
 def export_counts(eng, device):
     """This rank's partial multiplicity table as an (n, 2) int64 tensor of (mer, count) rows (mm_count_t, 16 bytes)."""
+    _handoff(device)
     n = eng.counts_dump()
     t = torch.empty((n, 2), dtype=torch.int64, device=device)
     eng.buffer_copy_out(eng.BUF_COUNTS, t.data_ptr())
@@ -218,6 +221,7 @@ def export_counts(eng, device):
 
 def export_route(eng, device):
     """The routed SHIMMER-pair records of pgb_route_build: (n, 5) int64 rows {x0, x1, y0, y1, direction}, grouped by owner."""
+    _handoff(device)
     n = eng.buffer_elems(eng.BUF_ROUTE)
     t = torch.empty((n, 5), dtype=torch.int64, device=device)
     eng.buffer_copy_out(eng.BUF_ROUTE, t.data_ptr())
@@ -225,13 +229,16 @@ def export_route(eng, device):
 
 
 def import_reads(eng, reads):
+    """Hand torch tensors (e.g. the result of concat_reads) to the engine by pointer: torch's queued work is finished first."""
     r = {k: v.contiguous() for k, v in reads.items()}
+    _handoff(r["words"].device)
     eng.load_packed_device(r["words"].data_ptr(), r["nmask"].data_ptr(), r["words"].shape[0], r["row_rid"].data_ptr(), r["row_len"].data_ptr(),
                            r["row_woff"].data_ptr(), r["row_hasn"].data_ptr(), r["row_rid"].shape[0])
 
 
 def import_shimmers(eng, l2_all):
     l2_all = l2_all.contiguous()
+    _handoff(l2_all.device)
     eng.set_shimmers_device(l2_all.data_ptr(), l2_all.shape[0])
 
 

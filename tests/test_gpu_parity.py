@@ -330,6 +330,7 @@ def test_routed_exchange_matches_reference(sim1, workdir, ref_dir):
         parts.append(M.export_reads(engs[r], dev))
         counts.append(M.export_counts(engs[r], dev))
     all_counts = torch.cat(counts).contiguous()
+    torch.cuda.synchronize()  # torch's stream -> the library's stream (the engine is handed raw pointers below)
     has_first, sends, splits = [], [], []
     for r in range(T):
         engs[r].counts_set_device(all_counts.data_ptr(), int(all_counts.shape[0]))
@@ -347,6 +348,7 @@ def test_routed_exchange_matches_reference(sim1, workdir, ref_dir):
     M.import_reads(ovl, reads)
     for d in range(T):  # owner of chunk d + 1
         recv = torch.cat([sends[src][int(splits[src][d]): int(splits[src][d + 1])] for src in range(T)]).contiguous()
+        torch.cuda.synchronize()  # (without it the library may read recv before torch.cat has written it: seen once as missing records)
         ov = ovl.overlap_routed(recv.data_ptr(), int(recv.shape[0]), total_chunk=T)
         want = F.normalise_ovlp(F.read_ovlp(ro[d]))
         assert len(ov) == len(want) and ov.tobytes() == want.tobytes(), f"chunk {d + 1}"
