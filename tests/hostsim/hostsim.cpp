@@ -25,6 +25,7 @@
 #include "../../peregrine_b200/csrc/dedup.cuh"
 #include "../../peregrine_b200/csrc/fasta_reader.hpp"
 #include <unordered_set>
+#include <random>
 
 using namespace pgb;
 
@@ -694,9 +695,149 @@ static int cmd_fastaidx(const char *lst, size_t block) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ lane-group row walk (model)
+// k_replay_group (kernels.cuh) lets G lanes probe G candidates of a bucket row at once and then applies the row's sequential
+// semantics (src/shmr_overlap.c:97-176: stop at bestn overlaps, an accepted CONTAINED ends the row, CONTAINS marks the candidate)
+// with ballots.  This is the same decision logic on the CPU, against the product's sequential replay_bucket on random buckets in
+// which every read occurs once: the set of visited candidates (table updates, requests, records) and their order must be equal.
+struct RowEvent { uint32_t i, j, kind; };  // kind: 1 = table update (accepted, with its type << 4), 2 = alignment request
+struct ModelCtx {
+  std::unordered_map<uint64_t, uint64_t> E;       // pair -> rank << 2 | type (time-stamped rid_pairs)
+  std::unordered_map<uint64_t, match_t> aln;      // (i, j) -> known alignment
+  std::vector<uint32_t> rlen_by_rid;
+  std::vector<RowEvent> ev;
+  uint32_t rank = 0;
+  uint32_t rlen(uint32_t rid) const { return rlen_by_rid[rid]; }
+  void pair_get(uint64_t p, uint64_t *vold, uint64_t *vnew) const {
+    *vnew = ~0ULL;
+    auto it = E.find(p);
+    *vold = it == E.end() ? ~0ULL : it->second;
+  }
+  void pair_set(uint64_t p, uint64_t v) { ev.push_back(RowEvent{(uint32_t)(p >> 32), (uint32_t)p, 1u | (uint32_t)(v & 3) << 4}); }
+  bool aln_get(uint32_t i, uint32_t j, match_t *m) const {
+    auto it = aln.find(((uint64_t)i << 32) | j);
+    if (it == aln.end()) return false;
+    *m = it->second;
+    return true;
+  }
+  void aln_request(uint32_t i, uint32_t j, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t) { ev.push_back(RowEvent{i, j, 2}); }
+  void emit(uint32_t, const ovlp_rec &) {}
+};
+static int cmd_grouprow(int argc, char **argv) {
+  const int trials = argc > 2 ? atoi(argv[2]) : 20000;
+  std::mt19937_64 rng(99);
+  size_t n_rows_cut = 0, n_rows_ended = 0, n_contains = 0, n_events = 0;
+  for (int trial = 0; trial < trials; trial++) {
+    const int Gs[4] = {4, 8, 16, 32};
+    const uint32_t G = (uint32_t)Gs[trial & 3], n = 2 + (uint32_t)(rng() % 62), bestn = 1 + (uint32_t)(rng() % 6), rank = 1000;
+    // a bucket: n records of n different reads, descending positions as the reference's qsort leaves them
+    ModelCtx c;
+    c.rank = rank;
+    c.rlen_by_rid.assign(n + 1, 0);
+    std::vector<uint64_t> y0(n);
+    std::vector<uint8_t> dir(n), cont_seq(n);
+    for (uint32_t t = 0; t < n; t++) {
+      c.rlen_by_rid[t] = 9000 + (uint32_t)(rng() % 9000);
+      const uint32_t pos = 8000 - t * (uint32_t)(1 + rng() % 100) % 7000;
+      y0[t] = ((uint64_t)t << 32) | ((uint64_t)pos << 1) | (rng() & 1);
+      dir[t] = (uint8_t)(rng() & 1);
+    }
+    // what the tables hold: some pairs already in rid_pairs with a lower rank (hits), some alignments known (various outcomes)
+    for (uint32_t i = 0; i < n; i++)
+      for (uint32_t j = i + 1; j < n; j++) {
+        const uint32_t r = (uint32_t)(rng() % 100);
+        if (r < 25) c.E[((uint64_t)i << 32) | j] = ((uint64_t)(rng() % rank) << 2) | (rng() % 3);
+        else if (r < 85) {
+          match_t m;
+          predict_match(c.rlen_by_rid[i], c.rlen_by_rid[j], 100, &m);
+          const uint32_t o = (uint32_t)(rng() % 4);
+          if (o == 0) m.q_end = m.t_end = 100;                                         // rejected (short)
+          if (o == 1) { m.q_bgn = 0; m.q_end = (int)c.rlen_by_rid[i]; m.t_end = (int)c.rlen_by_rid[j]; }  // containment
+          c.aln[((uint64_t)i << 32) | j] = m;
+        }
+      }
+    // sequential walk (the product's replay_bucket)
+    ModelCtx cs = c;
+    uint32_t unk_s = 0;
+    const uint32_t acc_s = replay_bucket(cs, rank, y0.data(), dir.data(), n, cont_seq.data(), bestn, false, &unk_s);
+    // lane-group walk
+    ModelCtx cg = c;
+    std::vector<uint8_t> ct(n, 0);
+    uint32_t acc_g = 0, unk_g = 0;
+    for (uint32_t k0 = n - 1; k0 > 0; k0--) {
+      const uint32_t i = k0 - 1;
+      if (ct[i]) continue;
+      const uint32_t rid0 = (uint32_t)(y0[i] >> 32), pos0 = (uint32_t)((y0[i] & 0xFFFFFFFFULL) >> 1) + 1, rlen0 = cg.rlen(rid0);
+      uint32_t overlap_count = 0;
+      bool row_done = false;
+      for (uint32_t base = i + 1; base < n && overlap_count < bestn && !row_done; base += G) {
+        uint32_t incm = 0, endm = 0;
+        struct Lane { bool valid, hit, known, accepted; uint32_t type, j, rid1, pos1; uint64_t ridp; match_t m; } L[32];
+        for (uint32_t gl = 0; gl < G; gl++) {
+          Lane &l = L[gl];
+          l = Lane();
+          l.j = base + gl;
+          l.valid = l.j < n && !ct[l.j];
+          l.known = true;
+          if (!l.valid) continue;
+          l.rid1 = (uint32_t)(y0[l.j] >> 32);
+          l.ridp = rid0 < l.rid1 ? ((uint64_t)rid0 << 32) | l.rid1 : ((uint64_t)l.rid1 << 32) | rid0;
+          uint64_t v, vnew;
+          cg.pair_get(l.ridp, &v, &vnew);
+          l.hit = v != ~0ULL && (uint32_t)(v >> 2) < rank;
+          if (l.hit) { l.type = (uint32_t)(v & 3); }
+          else {
+            l.pos1 = (uint32_t)((y0[l.j] & 0xFFFFFFFFULL) >> 1) + 1;
+            const uint32_t rlen1 = cg.rlen(l.rid1);
+            l.known = cg.aln_get(i, l.j, &l.m);
+            if (!l.known) predict_match(rlen0, rlen1, pos0 - l.pos1, &l.m);
+            l.accepted = classify_match(l.m, rlen0, rlen1, rlen0 - pos0 + l.pos1, rlen1, &l.type);
+          }
+          if (l.type == OVL_OVERLAP && (l.hit || l.accepted)) incm |= 1u << gl;
+          if (!l.hit && l.accepted && l.type == OVL_CONTAINED) endm |= 1u << gl;
+        }
+        const uint32_t need = bestn - overlap_count;
+        uint32_t cut = G;
+        if ((uint32_t)__builtin_popcount(incm) >= need) {  // __fns(incm, 0, need): the need-th set bit
+          uint32_t seen = 0;
+          for (uint32_t b = 0; b < G; b++) if ((incm >> b) & 1u) { if (++seen == need) { cut = b; break; } }
+        }
+        if (endm) { const uint32_t e = (uint32_t)__builtin_ctz(endm); if (e <= cut) { cut = e; row_done = true; n_rows_ended++; } }
+        if (cut < G) n_rows_cut++;
+        for (uint32_t gl = 0; gl < G && gl <= cut; gl++) {
+          Lane &l = L[gl];
+          if (!l.valid || l.hit) continue;
+          if (!l.known) { unk_g++; cg.aln_request(i, l.j, 0, 0, 0, 0, 0); }
+          if (l.accepted) {
+            if (l.type == OVL_CONTAINS) { ct[l.j] = 1; n_contains++; }
+            cg.pair_set(l.ridp, ((uint64_t)rank << 2) | l.type);
+            acc_g++;
+          }
+        }
+        uint32_t vis = cut >= G - 1 ? (G == 32 ? ~0u : (1u << G) - 1) : ((2u << cut) - 1u);
+        overlap_count += (uint32_t)__builtin_popcount(incm & vis);
+        if (row_done) ct[i] = 1;
+      }
+    }
+    // the sequential walk issues request and update of one candidate in the same order; compare the event streams
+    bool same = acc_s == acc_g && unk_s == unk_g && cs.ev.size() == cg.ev.size() && memcmp(cont_seq.data(), ct.data(), n) == 0;
+    for (size_t e = 0; same && e < cs.ev.size(); e++) same = cs.ev[e].i == cg.ev[e].i && cs.ev[e].j == cg.ev[e].j && cs.ev[e].kind == cg.ev[e].kind;
+    n_events += cs.ev.size();
+    if (!same) {
+      fprintf(stderr, "group walk differs: trial %d G %u n %u bestn %u: accepted %u vs %u, unknown %u vs %u, events %zu vs %zu\n", trial, G, n, bestn, acc_s,
+              acc_g, unk_s, unk_g, cs.ev.size(), cg.ev.size());
+      return 3;
+    }
+  }
+  printf("grouprow: %d buckets, %zu events, %zu row chunks ended by a cut-off (%zu by a CONTAINED result), %zu CONTAINS marks: identical to the sequential walk\n",
+         trials, n_events, n_rows_cut, n_rows_ended, n_contains);
+  return n_events > 0 && n_rows_cut > n_rows_ended && n_rows_ended > 0 && n_contains > 0 ? 0 : 4;
+}
+
 int main(int argc, char **argv) {
-  if (argc < 2) { fprintf(stderr, "usage: hostsim sketch|match|overlap|dedup|fastaidx ...\n"); return 1; }
+  if (argc < 2) { fprintf(stderr, "usage: hostsim sketch|match|overlap|grouprow|dedup|fastaidx ...\n"); return 1; }
   if (!strcmp(argv[1], "dedup")) return cmd_dedup();
+  if (!strcmp(argv[1], "grouprow")) return cmd_grouprow(argc, argv);
   if (!strcmp(argv[1], "fastaidx") && argc > 2) return cmd_fastaidx(argv[2], argc > 3 ? (size_t)strtoull(argv[3], 0, 10) : 0);
   load_ref();
   if (!strcmp(argv[1], "sketch")) return cmd_sketch(argc, argv);

@@ -197,6 +197,8 @@ def test_kernel_logic_on_host(workdir, ref_dir):
     # ... and the check can fail: without the positions before a bad strip the splice is wrong
     r = subprocess.run([hs, "sketch", pb, "80", "16", "6"], env=dict(env, PGB_SPLICE_REACH="0"), stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
     assert r.returncode == 3 and b"mismatching=0\n" not in [x for x in r.stdout.splitlines(True) if x.startswith(b"strip model")][0]
+    # the lane-group bucket walk of k_replay_group: its cut-off logic against the sequential replay_bucket on random buckets
+    subprocess.check_call([hs, "grouprow", "20000"], stdout=subprocess.DEVNULL)
     subprocess.check_call([hs, "match", p, "1500", "50"], env=env, stdout=subprocess.DEVNULL)
     rp = D.ref_index(ref_dir, p, os.path.join(workdir, "adv_h/ref"), T=2, extra=["-m", "0", "-k", "18", "-w", "120", "-r", "3"])
     ro = D.ref_overlap(ref_dir, p, rp, 2, os.path.join(workdir, "adv_h/ref"), T=1)
